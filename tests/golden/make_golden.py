@@ -1,0 +1,244 @@
+#!/usr/bin/env python
+"""
+Generate the golden fixtures in tests/golden/ by running the REAL reference.
+
+Runs only in the build container (needs /root/reference, read-only).  The reference is
+pure Python; it is imported with stub modules for its missing third-party imports
+(laspy for LMC; matplotlib / mpl_toolkits for CS) -- no reference code is copied, the
+fixtures hold only inputs and the reference's outputs.
+
+    python tests/golden/make_golden.py            # rewrites tests/golden/*.npz + MANIFEST.json
+
+LMC = /root/reference/lidar_motion_compensation.py
+CS  = /root/reference/livox_mid70_complete_simulator.py
+"""
+import contextlib
+import hashlib
+import io
+import json
+import logging
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("LMC_REFERENCE_DIR", "/root/reference")
+
+
+def import_reference():
+    """Import both reference modules with stubs for absent third-party packages."""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    sys.modules.setdefault('laspy', types.ModuleType('laspy'))
+    for m in ['matplotlib', 'matplotlib.pyplot', 'matplotlib.animation', 'mpl_toolkits',
+              'mpl_toolkits.mplot3d']:
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.modules['matplotlib.animation'].FuncAnimation = object
+    sys.modules['mpl_toolkits.mplot3d'].Axes3D = object
+    logging.disable(logging.CRITICAL)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import lidar_motion_compensation as LMC
+        import livox_mid70_complete_simulator as CS
+    return LMC, CS
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# the five anchor configs of SURVEY.md section 4
+CONFIGS = {
+    'C1a': dict(trajectory_type='linear', environment_complexity='simple', duration=60.0, max_speed=25.0, lidar_fps=10),
+    'C1b': dict(trajectory_type='linear', environment_complexity='simple', duration=60.0, max_speed=25.0, lidar_fps=15),
+    'C2a': dict(trajectory_type='figure_eight', environment_complexity='complex', duration=60.0, max_speed=12.0, lidar_fps=10),
+    'C2b': dict(trajectory_type='figure_eight', environment_complexity='complex', duration=120.0, max_speed=12.0, lidar_fps=10),
+    'C3':  dict(trajectory_type='circular', environment_complexity='medium', duration=30.0, max_speed=5.0, lidar_fps=20),
+}
+# which frames are stored in full (None = all)
+KEEP = {'C1a': None, 'C2a': 10, 'C3': 8}
+
+
+def run_lmc(LMC, cfg):
+    sim = LMC.LiDARMotionSimulator(dict(cfg))
+    with contextlib.redirect_stdout(io.StringIO()):
+        res = sim.run_simulation()
+    return sim, res
+
+
+def lmc_fixture(LMC, name, manifest):
+    sim, res = run_lmc(LMC, CONFIGS[name])
+    raws = [s['points_local'] for s in res['raw_scans']]
+    al = res['aligned_pointclouds']
+    counts = np.array([len(r) for r in raws], np.int64)
+    raw_all, al_all = np.vstack(raws), np.vstack(al)
+    traj = res['trajectory']
+    frame_t = np.array([s['timestamp'] for s in res['raw_scans']], np.float64)
+    # the reference's own pose index per frame (LMC:804-806), recovered from the pose it stored
+    pos_used = np.array([s['sensor_pose']['position'] for s in res['raw_scans']])
+    eul_used = np.array([s['sensor_pose']['orientation'] for s in res['raw_scans']])
+    pose_idx = np.array([int(np.flatnonzero((traj['position_gps'] == p).all(1))[0]) for p in pos_used], np.int32)
+    entry = dict(config=CONFIGS[name], frames=len(raws), traj_samples=len(traj['time']),
+                 total_points=int(counts.sum()), empty_frames=int((counts == 0).sum()),
+                 single_point_frames=int((counts == 1).sum()),
+                 max_points_per_frame=int(counts.max()), raw_sha256=sha(raw_all), aligned_sha256=sha(al_all))
+    manifest['lmc'][name] = entry
+    if name not in KEEP:
+        return
+    keep = KEEP[name]
+    if keep is None:
+        ids = np.arange(len(raws))
+    else:
+        ids = np.unique(np.linspace(0, len(raws) - 1, keep).astype(int))
+    sel_counts = counts[ids]
+    off = np.zeros(len(ids) + 1, np.int64)
+    np.cumsum(sel_counts, out=off[1:])
+    np.savez_compressed(
+        os.path.join(HERE, f'lmc_{name}.npz'),
+        frame_ids=ids.astype(np.int32), frame_off=off,
+        raw=np.vstack([raws[i] for i in ids]), aligned=np.vstack([al[i] for i in ids]),
+        pose_position=pos_used[ids], pose_euler=eul_used[ids],
+        traj_time=traj['time'], traj_position_gps=traj['position_gps'],
+        traj_orientation_imu=traj['orientation_imu'],
+        frame_t_all=frame_t, pose_idx_all=pose_idx, counts_all=counts)
+    entry['fixture'] = f'lmc_{name}.npz'
+    entry['fixture_frames'] = int(len(ids))
+
+
+def lmc_edge_fixture(LMC, manifest):
+    """Reference transform_pointcloud (LMC:772-776) on ragged / tiny frames: n = 0, 1 (NumPy
+    routes a 3x1 right-hand side through gemv: different FMA order), 2, 3, ... and large
+    translations."""
+    rng = np.random.default_rng(5)
+    sim = LMC.LiDARMotionSimulator()
+    counts = [0, 1, 2, 1, 3, 0, 0, 1, 17, 64, 1, 1000, 1, 0]
+    raws, outs, pos, eul = [], [], [], []
+    for n in counts:
+        p = np.column_stack([rng.uniform(-90, 90, (n, 3)), rng.uniform(0.1, 0.9, n)]).reshape(n, 4)
+        t = rng.uniform(-1500, 1500, 3); e = rng.normal(0, 0.7, 3)
+        raws.append(p); pos.append(t); eul.append(e)
+        outs.append(sim.transform_pointcloud(p, {'translation': t, 'rotation': e}))
+    off = np.zeros(len(counts) + 1, np.int64)
+    np.cumsum(counts, out=off[1:])
+    np.savez_compressed(os.path.join(HERE, 'lmc_edge.npz'), raw=np.vstack(raws), aligned=np.vstack(outs),
+                        frame_off=off, pose_position=np.array(pos), pose_euler=np.array(eul))
+    manifest['lmc_edge'] = dict(frames=len(counts), points=int(off[-1]), aligned_sha256=sha(np.vstack(outs)))
+
+
+def lvx_type2_fixture(LMC, manifest):
+    """Reference per-point packer LMC:252-272 on adversarial + random rows."""
+    rng = np.random.default_rng(20261018)
+    rows = [rng.uniform(-90, 90, (4000, 3))]
+    rows.append(rng.uniform(-1, 1, (500, 3)) * 1e-3)                     # sub-millimetre
+    k = rng.integers(-90000, 90000, (1500, 3))
+    rows.append(k / 1000.0)                                              # exact-mm decimals (x*1000 may land 1 ulp under)
+    rows.append((k[:500] + 0.5) / 1000.0)
+    rows.append(rng.uniform(-4e6, 4e6, (300, 3)))                        # clip to int32 range
+    rows.append(np.array([[2147483.647, -2147483.648, 0.0], [2147483.648, -2147483.649, -0.0],
+                          [np.inf, -np.inf, 1e300], [0.0009999999, -0.0009999999, 5e-324]]))
+    xyz = np.vstack(rows)
+    inten = rng.uniform(0, 1, len(xyz))
+    inten[:50] = rng.uniform(-0.5, 1.5, 50)                              # clip of reflectivity
+    inten[50:60] = [0.0, 1.0, 0.999999999, 1 / 255, 2 / 255, 254.9999 / 255, 0.5, 0.25, 1e-9, 0.00392156862745098]
+    pts = np.column_stack([xyz, inten])
+    w = LMC.LivoxLVXWriter()
+    buf = io.BytesIO()
+    for p in pts:
+        w._write_point_data_type2(buf, p)
+    out = np.frombuffer(buf.getvalue(), np.uint8).reshape(-1, 14)
+    np.savez_compressed(os.path.join(HERE, 'lvx_type2.npz'), pts=pts, records=out)
+    manifest['lvx_type2'] = dict(points=len(pts), records_sha256=sha(out))
+
+
+def lvx_file_fixture(LMC, manifest):
+    """Whole-file bytes of LivoxLVXWriter.write_compatible_lvx (LMC:58-250) on tiny frames."""
+    rng = np.random.default_rng(7)
+    counts = [0, 1, 95, 96, 97, 200, 0, 3]
+    frames, raw = [], []
+    for i, n in enumerate(counts):
+        p = np.column_stack([rng.uniform(-50, 50, (n, 3)), rng.uniform(0, 1, n)]).reshape(n, 4)
+        frames.append({'frame_id': i, 'timestamp': i * 0.1, 'points': p})
+        raw.append(p)
+    path = os.path.join(HERE, '_tmp.lvx')
+    with contextlib.redirect_stdout(io.StringIO()):
+        ok = LMC.LivoxLVXWriter().write_compatible_lvx(path, frames)
+    assert ok
+    data = np.fromfile(path, np.uint8)
+    os.remove(path)
+    off = np.zeros(len(counts) + 1, np.int64)
+    np.cumsum(counts, out=off[1:])
+    np.savez_compressed(os.path.join(HERE, 'lvx_file.npz'), raw=np.vstack(raw), frame_off=off,
+                        timestamps=np.arange(len(counts)) * 0.1, file_bytes=data)
+    manifest['lvx_file'] = dict(frames=len(counts), bytes=int(len(data)), sha256=sha(data))
+
+
+def modeb_fixture(CS, manifest):
+    """Reference MotionCompensator.compensate_point_cloud (CS:1435-1536) + LVX2 packer
+    (CS:365-374) on synthetic Mid-70-shaped frames against the reference's own 200 Hz
+    IMUSimulator output (CS:1191-1246)."""
+    rng = np.random.default_rng(99)
+    cfg = {'random_seed': 42, 'duration': 2.0, 'trajectory_type': 'figure_eight', 'max_speed': 12.0}
+    tg = CS.TrajectoryGenerator('figure_eight', seed=42)
+    traj = tg.generate_trajectory(2.0, dt=0.1, max_speed=12.0)
+    imu = CS.IMUSimulator(cfg).simulate_imu_data(traj, 2.0)
+    imu_ts = np.array([s.timestamp for s in imu], np.int64)
+    # make the motion non-trivial: the simulated gyro of a 2 s figure-eight is small, so add a
+    # deterministic swell (still goes through the reference code unchanged)
+    swell = 0.8 * np.sin(np.arange(len(imu))[:, None] * np.array([0.05, 0.031, 0.07]))
+    for s, d in zip(imu, swell):
+        s.gyro_x += d[0]; s.gyro_y += d[1]; s.gyro_z += d[2]
+    imu_gyro = np.array([[s.gyro_x, s.gyro_y, s.gyro_z] for s in imu], np.float64)
+    mc = CS.MotionCompensator({'enable_motion_compensation': True})
+    # frames: one before the first IMU sample (clamp), three inside, one past the end (clamp)
+    frame_starts = [-50_000_000, 100_000_000, 700_000_000, 1_234_567_891, 1_990_000_000]
+    counts = [300, 700, 701, 1, 400]
+    all_pts, all_ts, all_out, all_tag = [], [], [], []
+    lvx2 = io.BytesIO()
+    w = CS.LivoxLVXWriter('lvx2')
+    for fs, n in zip(frame_starts, counts):
+        az = np.radians(rng.uniform(-35.2, 35.2, n)); el = np.radians(rng.uniform(-38.6, 38.6, n))
+        r = rng.uniform(0.05, 90, n)
+        xyz = np.column_stack([r * np.cos(el) * np.cos(az), r * np.cos(el) * np.sin(az), r * np.sin(el)])
+        inten = rng.integers(0, 256, n)
+        step = 100_000_000 // max(n, 1)
+        ts = fs + np.arange(n, dtype=np.int64) * step + rng.integers(0, 7, n)
+        tag = rng.integers(0, 2, n)
+        pts = [CS.LiDARPoint(x=float(xyz[i, 0]), y=float(xyz[i, 1]), z=float(xyz[i, 2]), intensity=int(inten[i]),
+                             timestamp=int(ts[i]), ring=i % 16, tag=int(tag[i])) for i in range(n)]
+        comp = mc.compensate_point_cloud(pts, imu, fs, 100_000_000)
+        out = np.array([[p.x, p.y, p.z, p.intensity] for p in comp], np.float64).reshape(n, 4)
+        all_pts.append(np.column_stack([xyz, inten.astype(np.float64)])); all_ts.append(ts)
+        all_out.append(out); all_tag.append(tag.astype(np.uint8))
+        fbuf = io.BytesIO()
+        w._write_frame_lvx2(fbuf, {'points': comp, 'timestamp': fs if fs > 0 else 0}, 0)
+        lvx2.write(fbuf.getvalue()[24 + 21:])       # skip 24-B frame header + 21-B package header
+    off = np.zeros(len(counts) + 1, np.int64)
+    np.cumsum(counts, out=off[1:])
+    rec = np.frombuffer(lvx2.getvalue(), np.uint8).reshape(-1, 14)
+    np.savez_compressed(os.path.join(HERE, 'modeb.npz'), pts=np.vstack(all_pts), ts=np.concatenate(all_ts),
+                        tag=np.concatenate(all_tag), frame_off=off, frame_start=np.array(frame_starts, np.int64),
+                        imu_ts=imu_ts, imu_gyro=imu_gyro, compensated=np.vstack(all_out), lvx2_records=rec)
+    manifest['modeb'] = dict(points=int(off[-1]), imu_samples=len(imu), compensated_sha256=sha(np.vstack(all_out)),
+                             lvx2_sha256=sha(rec))
+
+
+def main():
+    LMC, CS = import_reference()
+    manifest = {'generator': 'tests/golden/make_golden.py', 'numpy': np.__version__,
+                'scipy': __import__('scipy').__version__, 'lmc': {}}
+    for name in CONFIGS:
+        lmc_fixture(LMC, name, manifest)
+        print(name, manifest['lmc'][name]['total_points'], manifest['lmc'][name]['raw_sha256'][:16],
+              manifest['lmc'][name]['aligned_sha256'][:16])
+    lmc_edge_fixture(LMC, manifest)
+    lvx_type2_fixture(LMC, manifest)
+    lvx_file_fixture(LMC, manifest)
+    modeb_fixture(CS, manifest)
+    with open(os.path.join(HERE, 'MANIFEST.json'), 'w') as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+    print('wrote', sorted(os.listdir(HERE)))
+
+
+if __name__ == '__main__':
+    main()
