@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""
+bench.py -- compensated points/s of the motion-compensation hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--variant V5] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[3], SURVEY.md 8d "M-1H"): a synthetic 1 h Mid-70 stream, 36 000
+frames x 10 000 points = 3.6e8 points, figure-eight trajectory sampled at 200 Hz (720 001 pose
+samples) with GPS/IMU noise.  One "step" = one pass of the fused kernel over the whole stream:
+per-point binary search of the timestamp + SLERP/lerp pose interpolation + f64 rigid transform +
+LVX int32-mm quantisation (variant V5, 50 algorithmic bytes per point).
+
+At N > 1 every rank processes its own 1 h frame range of an N-hour stream (frame-sharded, weak
+scaling, no data-path collective); the merged-cloud all-gather is timed separately and reported
+under "merge".  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "compensated points/sec"
+UNIT = "points/s"
+N_FRAMES, PTS_PER_FRAME, SEED = 36_000, 10_000, 4242
+
+# algorithmic bytes per point (pose/sample tables and frame_off excluded)
+VARIANTS = {
+    #        mode      f64    ts   lvx    las   B/pt
+    "V0": ("rigid", True, None, False, False, 64),
+    "V1": ("rigid", False, None, False, False, 32),
+    "V2": ("rigid", False, None, True, False, 46),
+    "V3": ("rigid", False, None, False, True, 46),
+    "V4": ("slerp", False, "u32", False, False, 36),
+    "V5": ("slerp", False, "u32", True, False, 50),
+    "V5las": ("slerp", False, "u32", False, True, 50),
+    "V4b": ("gyro", False, "u32", False, False, 36),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", default="V5", choices=sorted(VARIANTS))
+    ap.add_argument("--frames", type=int, default=N_FRAMES)
+    ap.add_argument("--ppf", type=int, default=PTS_PER_FRAME)
+    ap.add_argument("--path", default="auto", choices=["auto", "direct", "tma"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-frames", type=int, default=1000)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks during the timed region (NVML; same fields as the recipe's nvidia-smi line)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index: int, period: float = 0.02):
+        self.samples, self.reasons, self.power = [], set(), []
+        self.max_mhz = None
+        self.period, self._stop, self._t = period, threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:                    # noqa: BLE001
+            self.nv, self.err = None, repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:                 # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:                     # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self._t is not None:
+            self._stop.set()
+            self._t.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0,
+                    "note": getattr(self, "err", "no samples")}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "power_w_max": max(self.power) if self.power else None}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:                          # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU path (NumPy port) on this box's host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, frames, ppf):
+    from oracle import cpu_baseline as cb
+    threads = cb.default_threads()
+    sample = cb.make_sample(frames, ppf)
+    for _ in range(min(warmup, 1)):
+        cb.run_port(sample, threads)
+    times = [cb.run_port(sample, threads) for _ in range(steps)]
+    t = float(np.mean(times))
+    return dict(value=sample['n_points'] / t, seconds_per_step=t, cores=threads, n_points=sample['n_points'],
+                sample=f"{frames} frames x {ppf} pts of the M-1H stream per step (f64 (n,4), NumPy/SciPy port of LMC:802-832 + vstack + LVX mm quantise)")
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20))
+    r = cpu_reference_run(steps, args.warmup, args.cpu_frames, args.ppf)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["seconds_per_step"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "M-1H synthetic 1 h Mid-70 stream (36000 frames x 10000 pts), bounded sample per step",
+                   "variant": "reference CPU path: hold-next pose per frame + transform_pointcloud + vstack + LVX int32-mm"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------
+def main_b200(args):
+    import torch
+    import torch.distributed as dist
+    from livox_motion_compensation_sim_b200 import _build, _capi as C, ops, synth
+    from livox_motion_compensation_sim_b200.pipeline import HostStream, StreamingAligner
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if not os.path.exists(_build.LIB_PATH):
+        if rank == 0:
+            _build.build_library()
+        if world > 1:
+            dist.barrier()
+    if args.path != "auto":
+        C.set_path(C.PATH_DIRECT if args.path == "direct" else C.PATH_TMA)
+
+    F, P = args.frames, args.ppf
+    # rank r owns hour r of an N-hour stream: same shape, different seed
+    st = synth.make_stream(F, P, SEED + 17 * rank, device=dev, dtype=torch.float32)
+    N = st.n_points
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)   # noqa: E731
+    off_d, fs_d, sts_d, seg_d = d(st.frame_off), d(st.frame_start), d(st.sample_ts), d(st.seg)
+    gyro_d = d(np.random.default_rng(3).normal(0, 0.2, (len(st.sample_ts), 3)))
+    # Mode A pose table through the device lookup kernel (a1)
+    pose_d, _ = ops.pose_lookup_hold_next(d(st.gps_t), d(st.gps_Rt), d(st.frame_t))
+    pts64 = None
+
+    def make_step(variant):
+        nonlocal pts64
+        mode, f64, ts, lvx, las, bpp = VARIANTS[variant]
+        pts = st.pts
+        if f64:
+            if pts64 is None:
+                pts64 = st.pts.to(torch.float64)
+            pts = pts64
+        out = torch.empty_like(pts)
+        into = ops.ExportBuffers(status=torch.zeros(1, dtype=torch.int32, device=dev))
+        if lvx:
+            into.lvx14 = torch.empty((N, 14), dtype=torch.uint8, device=dev)
+        if las:
+            into.las_x, into.las_y, into.las_z = (torch.empty(N, dtype=torch.int32, device=dev) for _ in range(3))
+            into.las_intensity = torch.empty(N, dtype=torch.uint16, device=dev)
+        spec = ops.ExportSpec(lvx=lvx, las=las, las_scale=(0.001,) * 3, into=into) if (lvx or las) else None
+        if mode == "rigid":
+            fn = lambda: ops.align_rigid(pts, off_d, pose_d, out=out, export=spec)                       # noqa: E731
+        elif mode == "slerp":
+            fn = lambda: ops.deskew_slerp(pts, st.ts_off, off_d, fs_d, sts_d, seg_d, out=out, export=spec)  # noqa: E731
+        else:
+            fn = lambda: ops.deskew_gyro(pts, st.ts_off, off_d, fs_d, sts_d, gyro_d, out=out, export=spec)  # noqa: E731
+        return fn, bpp, (out, into)
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        evs[0].record()
+        for i in range(steps):
+            fn()
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            dist.barrier()
+        per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+        total_ms = evs[0].elapsed_time(evs[steps])
+        if world > 1:
+            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms, per, clocks
+
+    # ---- headline: resident inputs, CUDA events, max over ranks ------------------------------------
+    fn, bpp, keep = make_step(args.variant)
+    sampler = ClockSampler(local)
+    total_ms, per, clocks = timed(fn, args.steps, max(args.warmup, 3), sampler)
+    ms_per_step = total_ms / args.steps
+    value = world * N / (ms_per_step * 1e-3)
+    kern_ms = float(np.mean(per))                     # one fused kernel per step on this stream
+    peak, peak_src = measured_peak()
+    achieved = N * bpp / (kern_ms * 1e-3) / 1e9
+    flags = keep[1].flags()
+    del keep, fn
+
+    # ---- other variants (short runs; context for the roofline) ---------------------------------------
+    sweep = {}
+    if not args.no_sweep:
+        for v in VARIANTS:
+            if v == args.variant:
+                continue
+            try:
+                f2, b2, k2 = make_step(v)
+                tms, _, _ = timed(f2, 10, 3)
+                sweep[v] = {"points_per_s": world * N / (tms / 10 * 1e-3), "GBps_per_gpu": N * b2 / (tms / 10 * 1e-3) / 1e9,
+                            "frac": N * b2 / (tms / 10 * 1e-3) / 1e9 / peak, "bytes_per_point": b2}
+                del f2, k2
+            except Exception as e:                # noqa: BLE001
+                sweep[v] = {"error": repr(e)}
+            torch.cuda.empty_cache()
+    pts64 = None
+    torch.cuda.empty_cache()
+
+    # ---- merged-cloud all-gather (the one exchange step), timed separately ---------------------------
+    merge = None
+    if world > 1:
+        per_rank = N
+        mo = torch.empty((world * per_rank, 4), dtype=torch.float32, device=dev)
+        mine = mo[rank * per_rank:(rank + 1) * per_rank]
+        mine.copy_(st.pts)
+        for _ in range(2):
+            dist.all_gather_into_tensor(mo, mine)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        reps = 3
+        for _ in range(reps):
+            dist.all_gather_into_tensor(mo, mine)
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ag_ms = float(t.item())
+        merge = {"what": "NCCL all_gather_into_tensor of the aligned float4 cloud into every rank's merged buffer",
+                 "ms": ag_ms, "bytes_received_per_rank": (world - 1) * per_rank * 16,
+                 "ingress_GBps_per_rank": (world - 1) * per_rank * 16 / (ag_ms * 1e-3) / 1e9,
+                 "points_per_s_kernel_plus_merge": world * N / ((ms_per_step + ag_ms) * 1e-3)}
+        del mo, mine
+
+    # ---- end to end: pinned host buffers in, pinned host buffers out ---------------------------------
+    e2e = None
+    if not args.no_e2e:
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:                          # noqa: BLE001
+            avail = 64 << 30
+        bytes_per_pt_host = 16 + 4 + 16 + 14
+        budget = min(avail // (3 * max(world, 1)), N * bytes_per_pt_host)
+        fe = max(1, min(F, int(budget // (bytes_per_pt_host * P))))
+        ne = fe * P
+        hs = HostStream(pts=torch.empty((ne, 4), dtype=torch.float32).pin_memory(),
+                        ts_off=torch.empty(ne, dtype=torch.uint32).pin_memory(),
+                        out=torch.empty((ne, 4), dtype=torch.float32).pin_memory(),
+                        lvx14=torch.empty((ne, 14), dtype=torch.uint8).pin_memory(),
+                        frame_off=st.frame_off[:fe + 1], frame_start=st.frame_start[:fe])
+        hs.pts.copy_(st.pts[:ne]); hs.ts_off.copy_(st.ts_off[:ne])
+        torch.cuda.synchronize()
+        sa = StreamingAligner(dev, hs.frame_off, hs.frame_start, mode="slerp", sample_ts=sts_d, seg=seg_d, lvx=True)
+        sa.run(hs); torch.cuda.synchronize()          # warm-up
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.e2e_steps):
+            sa.run(hs)
+        e1.record(); torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / args.e2e_steps
+        ems = e0.elapsed_time(e1) / args.e2e_steps
+        if world > 1:
+            t = torch.tensor([ems], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        # spot check: the pipelined host result equals the resident-data result
+        chk = ops.deskew_slerp(st.pts[:P], st.ts_off[:P], d(st.frame_off[:2]), fs_d[:1].contiguous(), sts_d, seg_d)[0]
+        assert torch.equal(chk.cpu(), hs.out[:P]), "e2e pipeline result differs from the resident-data result"
+        e2e = {"value": world * ne / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": sa.h2d_bytes, "d2h_bytes_per_step": sa.d2h_bytes,
+               "ms_per_step": ems, "wall_ms_per_step": wall * 1e3, "points_per_step_per_gpu": ne, "kernel_launches_per_step": sa.launches,
+               "what": "StreamingAligner.run: pinned host float4+u32 ts -> chunked H2D / fused Mode C + LVX kernel / D2H of float4 + 14-B records, 3 streams",
+               "h2d_GBps": sa.h2d_bytes / (ems * 1e-3) / 1e9, "d2h_GBps": sa.d2h_bytes / (ems * 1e-3) / 1e9}
+        del hs, sa
+    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_reference_run(3, 1, args.cpu_frames, P)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        try:
+            from oracle import cpu_baseline as cb
+            cpu["c_port_mode_c_1thread_points_per_s"] = cb.run_c_port_mode_c()
+        except Exception as e:                     # noqa: BLE001
+            cpu["c_port_error"] = repr(e)
+
+    if rank == 0:
+        mode, f64, ts, lvx, las, _ = VARIANTS[args.variant]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"M-1H synthetic 1 h Mid-70 stream: {F} frames x {P} pts = {N} points per GPU, 200 Hz pose samples ({len(st.sample_ts)}), seed {SEED}",
+                       "variant": f"{args.variant}: mode={mode} io={'f64' if f64 else 'f32 float4'} ts={ts} lvx={lvx} las={las}, f64 arithmetic",
+                       "bytes_per_point": bpp, "kernel_path": "tma" if C.get_path() == C.PATH_TMA else "direct",
+                       "l2": f"inputs {N * (16 + 4) / 1e9:.1f} GB >> 126 MB L2: no flush needed", "parallelism": f"frame-sharded x{world}",
+                       "status_flags": flags},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms,
+                         "algorithmic_bytes_per_launch": N * bpp, "frac_of_nominal_8TBps": achieved / 8000.0},
+            "clocks": clocks, "gpu_launches": args.steps, "e2e": e2e, "cpu_baseline": cpu,
+        }
+        if merge:
+            line["merge"] = merge
+        if sweep:
+            line["variants"] = sweep
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_b200(a)

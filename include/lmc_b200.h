@@ -1,0 +1,158 @@
+/*
+ * lmc_b200.h -- C ABI of liblmc_b200.so: the B200 (sm_100a) motion-compensation hot path of
+ * manishborikar92/livox-motion-compensation-sim.
+ *
+ * The reference is pure Python and has NO plugin / FFI layer: its boundary
+ * for this path is the Python method surface.  Every entry point below therefore cites the
+ * reference *method* it replaces; the ctypes binding a maintainer would add on the reference side
+ * is shown in INTEGRATION.md.
+ *
+ *   LMC = lidar_motion_compensation.py        CS = livox_mid70_complete_simulator.py
+ *
+ * Conventions
+ *   - every data pointer is a caller-owned DEVICE pointer (e.g. torch.Tensor.data_ptr()) unless
+ *     the parameter name ends in _host; the library never allocates or frees caller-visible memory
+ *   - point arrays, record arrays and LAS arrays must be 32-byte aligned at index 0
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all calls are
+ *     asynchronous and stream-ordered, re-entrant across streams and devices
+ *   - return value: LMC_OK or a negative LMC_ERR_*; lmc_last_error() gives a thread-local message.
+ *     No exceptions cross the ABI, and there is no CPU fallback: without a usable sm_100 device the
+ *     calls fail with LMC_ERR_CUDA.
+ *   - frames are CSR rows: frame f owns points [frame_off[f], frame_off[f+1]) of the flat arrays,
+ *     frame-major, which is exactly np.vstack order (LMC:888).  Empty frames are zero-length rows.
+ *   - [p_begin, p_end) selects the slice of points this call processes (a rank's shard of the
+ *     merged cloud); pass 0, n_points for everything.  Results are written at the same global
+ *     indices, so frame-sharded ranks fill disjoint slices of one merged buffer.
+ */
+#ifndef LMC_B200_H
+#define LMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LMC_VERSION           100      /* 0.1.0 */
+
+#define LMC_OK                  0
+#define LMC_ERR_INVALID        -1      /* bad argument (NULL, negative size, bad enum)            */
+#define LMC_ERR_ALIGN          -2      /* pointer not 32-byte aligned                             */
+#define LMC_ERR_CUDA           -3      /* CUDA runtime error / no sm_100 device                   */
+
+/* bits OR-ed into *status by the quantising epilogues (where the reference would raise) */
+#define LMC_FLAG_NAN            1u     /* int(nan): ValueError in LMC:257 / CS:368                */
+#define LMC_FLAG_OVERFLOW       2u     /* struct.pack('<i') / laspy OverflowError / u8 range      */
+
+/* lvx_mode */
+#define LMC_LVX_TYPE2_OF_INPUT  0      /* LMC:252-272 on the RAW sensor-frame input point (LMC:977):
+                                          trunc(clip(x*1000, int32 range)), refl=trunc(clip(i*255,0,255)), tag 0 */
+#define LMC_LVX2_OF_OUTPUT      1      /* CS:365-374 on the COMPENSATED output point:
+                                          trunc(x*1000) (no clip), intensity and tag bytes copied */
+/* las_intensity_mode */
+#define LMC_LAS_INTENSITY_UNIT  0      /* LMC:961   (i * 65535).astype(uint16)                    */
+#define LMC_LAS_INTENSITY_RAW   1      /* CS:1686   i.astype(uint16)                              */
+
+/*
+ * Optional fused export epilogues.  Any output pointer may be NULL (that export is skipped); a NULL
+ * lmc_export* skips all of them.  All arrays are indexed by global point index.
+ */
+typedef struct lmc_export {
+    uint8_t*  lvx14;              /* (n_points, 14) little-endian <iiiBB records                      */
+    int32_t   lvx_mode;           /* LMC_LVX_*                                                        */
+    const uint8_t* tag;           /* (n_points) tag byte for LMC_LVX2_OF_OUTPUT, NULL = 0             */
+    int32_t*  las_x;              /* (n_points) LAS integer X = rint((x - offset) / scale)            */
+    int32_t*  las_y;
+    int32_t*  las_z;
+    uint16_t* las_intensity;      /* (n_points)                                                       */
+    int32_t   las_intensity_mode; /* LMC_LAS_INTENSITY_*                                              */
+    double    las_scale[3];       /* laspy header default 0.01 (LMC:953), 0.001 set at CS:1679-1681   */
+    double    las_offset[3];      /* 0                                                                */
+    uint32_t* status;             /* device u32, OR of LMC_FLAG_*; NULL = not reported                */
+} lmc_export;
+
+int         lmc_version(void);
+const char* lmc_last_error(void);
+/* sm count / compute capability of the current device; fails unless it is sm_100 */
+int         lmc_device_query(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+/* 0 = direct (256-bit LDG/STG) kernels, 1 = TMA bulk-copy pipelined kernels (default where built) */
+int         lmc_set_path(int32_t path);
+int         lmc_get_path(void);
+
+/*
+ * (a1) frame pose lookup, replaces the per-frame Python at LMC:802-812:
+ *   idx_f = min(np.searchsorted(traj_t, frame_t[f]), n_t - 1)       ("hold-next", no interpolation)
+ *   pose_Rt[f] = traj_Rt[idx_f]     (12 doubles: R row-major as SciPy builds it at LMC:774, then t)
+ * pose_idx (optional, int32[n_frames]) receives idx_f.
+ */
+int lmc_pose_lookup_hold_next(const double* traj_t, int64_t n_t, const double* traj_Rt,
+                              const double* frame_t, int32_t n_frames,
+                              double* pose_Rt, int32_t* pose_idx, void* stream);
+
+/*
+ * (a2)+(a3) LiDARMotionSimulator.transform_pointcloud over all frames + merged-cloud assembly,
+ * replaces LMC:772-776 called from LMC:826-832 and np.vstack at LMC:886-889.
+ *   out[i, :3] = R_f @ pts[i, :3] + t_f ;  out[i, 3] = pts[i, 3]       (f = frame of point i)
+ * float64 arithmetic in the reference's operation order: bit-exact for (n,4) f64 input.
+ * _f32: same arithmetic on float4 points up-cast to f64 in registers, result rounded to f32.
+ * `out` may be NULL when only exports are wanted.
+ */
+int lmc_align_rigid_f64(const double* pts_n4, const int64_t* frame_off, const double* pose_Rt,
+                        double* out_n4, int64_t n_points, int32_t n_frames,
+                        int64_t p_begin, int64_t p_end, const lmc_export* ex, void* stream);
+int lmc_align_rigid_f32(const float* pts_n4, const int64_t* frame_off, const double* pose_Rt,
+                        float* out_n4, int64_t n_points, int32_t n_frames,
+                        int64_t p_begin, int64_t p_end, const lmc_export* ex, void* stream);
+
+/*
+ * (a6)-(a8) MotionCompensator.compensate_point_cloud, replaces CS:1435-1536 (per-point IMU bracket
+ * search CS:1482-1516, gyro lerp, Rx(-a)Ry(-b)Rz(-c) CS:1518-1536).  Rotation only.
+ *   _f64: pts (n,4) f64 [x y z intensity], ts int64 ns per point
+ *   _f32: pts float4, ts_off uint32 ns offset from frame_start[f]
+ * imu_ts int64[n_imu] sorted, imu_gyro f64 (n_imu,3).  n_imu == 0: points are copied (CS:1439).
+ */
+int lmc_deskew_gyro_f64(const double* pts_n4, const int64_t* ts, const int64_t* frame_off,
+                        const int64_t* frame_start, const int64_t* imu_ts, const double* imu_gyro,
+                        int64_t n_imu, double* out_n4, int64_t n_points, int32_t n_frames,
+                        int64_t p_begin, int64_t p_end, const lmc_export* ex, void* stream);
+int lmc_deskew_gyro_f32(const float* pts_n4, const uint32_t* ts_off, const int64_t* frame_off,
+                        const int64_t* frame_start, const int64_t* imu_ts, const double* imu_gyro,
+                        int64_t n_imu, float* out_n4, int64_t n_points, int32_t n_frames,
+                        int64_t p_begin, int64_t p_end, const lmc_export* ex, void* stream);
+
+/*
+ * Mode C: per-point pose-interp deskew (north_star; sketched without a body at
+ * docs/Master Guide.md:339-367; no reference implementation -> parity unpinned).
+ *   k = bracket(sample_ts, ts) ; alpha = (ts - t_k)/(t_{k+1} - t_k)
+ *   out = SLERP(R_k, R_{k+1}, alpha) p + lerp(pos_k, pos_{k+1}, alpha)
+ * seg: (n_samples, 20) f64 per-sample table [R_k(9) pos_k(3) axis_k(3) theta_k dpos_k(3) pad]
+ *      (built by the host wrapper, see livox_motion_compensation_sim_b200/frames.py).
+ * hold_idx (optional int32[n_frames]): every point of frame f takes sample hold_idx[f], alpha = 0
+ *      -> Mode A expressed in Mode C (bit-identical to lmc_align_rigid_* for frames of >= 2 points).
+ *   _f64: ts int64 ns per point (frame_start unused, may be NULL)
+ *   _f32: ts_off uint32 ns offsets from frame_start[f]
+ */
+int lmc_deskew_slerp_f64(const double* pts_n4, const int64_t* ts, const int64_t* frame_off,
+                         const int64_t* frame_start, const int64_t* sample_ts, const double* seg,
+                         int64_t n_samples, const int32_t* hold_idx, double* out_n4,
+                         int64_t n_points, int32_t n_frames,
+                         int64_t p_begin, int64_t p_end, const lmc_export* ex, void* stream);
+int lmc_deskew_slerp_f32(const float* pts_n4, const uint32_t* ts_off, const int64_t* frame_off,
+                         const int64_t* frame_start, const int64_t* sample_ts, const double* seg,
+                         int64_t n_samples, const int32_t* hold_idx, float* out_n4,
+                         int64_t n_points, int32_t n_frames,
+                         int64_t p_begin, int64_t p_end, const lmc_export* ex, void* stream);
+
+/*
+ * (a4)/(a5)/(a9)/(a10) stand-alone quantisers (no transform): LivoxLVXWriter._write_point_data_type2
+ * LMC:252-272, the LVX2 packer CS:365-374 and the LAS integer packing behind LMC:957-961 /
+ * CS:1683-1686.  `ex` selects outputs and modes exactly as in the fused calls; for lvx_mode both
+ * values read the given points.
+ */
+int lmc_quantize_f64(const double* pts_n4, int64_t n_points, const lmc_export* ex, void* stream);
+int lmc_quantize_f32(const float* pts_n4, int64_t n_points, const lmc_export* ex, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMC_B200_H */

@@ -1,0 +1,83 @@
+"""ctypes binding of include/lmc_b200.h.  There is no fallback: if liblmc_b200.so is missing or a
+call fails, this raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from ._build import LIB_PATH
+
+OK, ERR_INVALID, ERR_ALIGN, ERR_CUDA = 0, -1, -2, -3
+FLAG_NAN, FLAG_OVERFLOW = 1, 2
+LVX_TYPE2_OF_INPUT, LVX2_OF_OUTPUT = 0, 1
+LAS_INTENSITY_UNIT, LAS_INTENSITY_RAW = 0, 1
+PATH_DIRECT, PATH_TMA = 0, 1
+
+vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+
+
+class LmcExport(ctypes.Structure):
+    """struct lmc_export (include/lmc_b200.h)"""
+    _fields_ = [
+        ("lvx14", vp), ("lvx_mode", i32), ("tag", vp),
+        ("las_x", vp), ("las_y", vp), ("las_z", vp), ("las_intensity", vp),
+        ("las_intensity_mode", i32),
+        ("las_scale", ctypes.c_double * 3), ("las_offset", ctypes.c_double * 3),
+        ("status", vp),
+    ]
+
+
+class LmcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"liblmc_b200 error {code}: {msg}")
+        self.code = code
+
+
+_SIGNATURES = {
+    "lmc_version": ([], ctypes.c_int),
+    "lmc_last_error": ([], ctypes.c_char_p),
+    "lmc_device_query": ([vp, vp, vp], ctypes.c_int),
+    "lmc_set_path": ([i32], ctypes.c_int),
+    "lmc_get_path": ([], ctypes.c_int),
+    "lmc_pose_lookup_hold_next": ([vp, i64, vp, vp, i32, vp, vp, vp], ctypes.c_int),
+    "lmc_align_rigid_f64": ([vp, vp, vp, vp, i64, i32, i64, i64, vp, vp], ctypes.c_int),
+    "lmc_align_rigid_f32": ([vp, vp, vp, vp, i64, i32, i64, i64, vp, vp], ctypes.c_int),
+    "lmc_deskew_gyro_f64": ([vp, vp, vp, vp, vp, vp, i64, vp, i64, i32, i64, i64, vp, vp], ctypes.c_int),
+    "lmc_deskew_gyro_f32": ([vp, vp, vp, vp, vp, vp, i64, vp, i64, i32, i64, i64, vp, vp], ctypes.c_int),
+    "lmc_deskew_slerp_f64": ([vp, vp, vp, vp, vp, vp, i64, vp, vp, i64, i32, i64, i64, vp, vp], ctypes.c_int),
+    "lmc_deskew_slerp_f32": ([vp, vp, vp, vp, vp, vp, i64, vp, vp, i64, i32, i64, i64, vp, vp], ctypes.c_int),
+    "lmc_quantize_f64": ([vp, i64, vp, vp], ctypes.c_int),
+    "lmc_quantize_f32": ([vp, i64, vp, vp], ctypes.c_int),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load liblmc_b200.so (built in-tree by __graft_entry__.build() / _build.build_library())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m livox_motion_compensation_sim_b200._build` "
+                "(nvcc, sm_100a). There is no CPU fallback for this path.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (args, res) in _SIGNATURES.items():
+            fn = getattr(L, name)           # AttributeError if the library does not export it
+            fn.argtypes, fn.restype = args, res
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise LmcError(rc, lib().lmc_last_error().decode(errors="replace"))
+
+
+def set_path(path: int) -> None:
+    check(lib().lmc_set_path(int(path)))
+
+
+def get_path() -> int:
+    return int(lib().lmc_get_path())

@@ -1,0 +1,206 @@
+// lmc_capi.cu -- the extern "C" boundary declared in include/lmc_b200.h.
+// Plain pointers and sizes in, int status out; no exceptions, no allocation of caller-visible
+// memory, no CPU fallback (every call needs an sm_100 device).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "lmc_device.cuh"
+
+namespace lmc {
+cudaError_t launch_direct(bool f64, int mode, const Params& P, cudaStream_t st);
+cudaError_t launch_tma(bool f64, int mode, const Params& P, cudaStream_t st, bool* handled);
+cudaError_t launch_pose_lookup(const double*, int64_t, const double*, const double*, int32_t, double*, int32_t*, cudaStream_t);
+}
+
+namespace {
+
+thread_local char g_err[512] = "";
+int g_path = 1;                                    // 1 = TMA pipeline where available, 0 = direct
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(LMC_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
+
+// the kernels are built for sm_100a only: refuse anything else loudly (no fallback path exists)
+int check_device() {
+    static thread_local int ok_dev = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if (dev == ok_dev) return LMC_OK;
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+    if (major != 10) return fail(LMC_ERR_CUDA, "device %d is sm_%d0; liblmc_b200 is built for sm_100a only", dev, major);
+    ok_dev = dev;
+    return LMC_OK;
+}
+
+int fill_export(lmc::Params& P, const lmc_export* ex) {
+    P.lvx14 = nullptr; P.tag = nullptr; P.las_x = P.las_y = P.las_z = nullptr; P.las_int = nullptr; P.status = nullptr;
+    P.lvx_mode = 0; P.las_int_mode = 0;
+    for (int c = 0; c < 3; ++c) { P.las_scale[c] = 0.01; P.las_off[c] = 0.0; }
+    if (!ex) return LMC_OK;
+    if (ex->lvx_mode != LMC_LVX_TYPE2_OF_INPUT && ex->lvx_mode != LMC_LVX2_OF_OUTPUT) return fail(LMC_ERR_INVALID, "bad lvx_mode %d", ex->lvx_mode);
+    if (ex->las_intensity_mode != LMC_LAS_INTENSITY_UNIT && ex->las_intensity_mode != LMC_LAS_INTENSITY_RAW)
+        return fail(LMC_ERR_INVALID, "bad las_intensity_mode %d", ex->las_intensity_mode);
+    const bool any_xyz = ex->las_x || ex->las_y || ex->las_z;
+    if (any_xyz && !(ex->las_x && ex->las_y && ex->las_z)) return fail(LMC_ERR_INVALID, "las_x/las_y/las_z must be given together");
+    if (any_xyz) for (int c = 0; c < 3; ++c)
+        if (!(ex->las_scale[c] > 0.0)) return fail(LMC_ERR_INVALID, "las_scale[%d] must be > 0", c);
+    if (!aligned32(ex->lvx14) || !aligned32(ex->las_x) || !aligned32(ex->las_y) || !aligned32(ex->las_z) || !aligned32(ex->las_intensity))
+        return fail(LMC_ERR_ALIGN, "export arrays must be 32-byte aligned");
+    P.lvx14 = ex->lvx14; P.lvx_mode = ex->lvx_mode; P.tag = ex->tag;
+    P.las_x = ex->las_x; P.las_y = ex->las_y; P.las_z = ex->las_z; P.las_int = ex->las_intensity;
+    P.las_int_mode = ex->las_intensity_mode; P.status = ex->status;
+    for (int c = 0; c < 3; ++c) { P.las_scale[c] = ex->las_scale[c]; P.las_off[c] = ex->las_offset[c]; }
+    return LMC_OK;
+}
+
+int run(bool f64, int mode, lmc::Params& P, const lmc_export* ex, void* stream) {
+    int rc = check_device();
+    if (rc != LMC_OK) return rc;
+    if (P.n_points < 0 || P.n_frames < 0) return fail(LMC_ERR_INVALID, "negative size");
+    if (P.p_begin < 0 || P.p_end > P.n_points || P.p_begin > P.p_end) return fail(LMC_ERR_INVALID, "bad point range [%lld, %lld) of %lld",
+        (long long)P.p_begin, (long long)P.p_end, (long long)P.n_points);
+    if (P.p_begin == P.p_end) return LMC_OK;
+    if (!P.pts) return fail(LMC_ERR_INVALID, "pts is NULL");
+    if (P.out == P.pts) return fail(LMC_ERR_INVALID, "in-place operation is not supported");
+    if (!aligned32(P.pts) || !aligned32(P.out)) return fail(LMC_ERR_ALIGN, "point arrays must be 32-byte aligned");
+    if (mode != lmc::kQuantOnly && !P.frame_off) return fail(LMC_ERR_INVALID, "frame_off is NULL");
+    if (mode != lmc::kQuantOnly && P.n_frames < 1) return fail(LMC_ERR_INVALID, "points without frames");
+    rc = fill_export(P, ex);
+    if (rc != LMC_OK) return rc;
+    if (!P.out && !P.lvx14 && !P.las_x && !P.las_int) return fail(LMC_ERR_INVALID, "no output requested");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    bool handled = false;
+    if (g_path == 1) {
+        e = lmc::launch_tma(f64, mode, P, st, &handled);
+        if (handled) return e == cudaSuccess ? LMC_OK : cuda_fail(e, "launch (tma path)");
+    }
+    e = lmc::launch_direct(f64, mode, P, st);
+    return e == cudaSuccess ? LMC_OK : cuda_fail(e, "launch (direct path)");
+}
+
+lmc::Params base_params(const void* pts, void* out, int64_t n_points, int32_t n_frames, int64_t p_begin, int64_t p_end) {
+    lmc::Params P;
+    memset(&P, 0, sizeof P);
+    P.pts = pts; P.out = out; P.n_points = n_points; P.n_frames = n_frames; P.p_begin = p_begin; P.p_end = p_end;
+    return P;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lmc_version(void) { return LMC_VERSION; }
+const char* lmc_last_error(void) { return g_err; }
+
+int lmc_device_query(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+    int dev = 0, v = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if (sm_count) { e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return cuda_fail(e, "attr"); *sm_count = v; }
+    if (cc_major) { e = cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev); if (e != cudaSuccess) return cuda_fail(e, "attr"); *cc_major = v; }
+    if (cc_minor) { e = cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev); if (e != cudaSuccess) return cuda_fail(e, "attr"); *cc_minor = v; }
+    return check_device();
+}
+
+int lmc_set_path(int32_t path) {
+    if (path != 0 && path != 1) return fail(LMC_ERR_INVALID, "path must be 0 (direct) or 1 (tma)");
+    g_path = path;
+    return LMC_OK;
+}
+int lmc_get_path(void) { return g_path; }
+
+int lmc_pose_lookup_hold_next(const double* traj_t, int64_t n_t, const double* traj_Rt, const double* frame_t,
+                              int32_t n_frames, double* pose_Rt, int32_t* pose_idx, void* stream) {
+    int rc = check_device();
+    if (rc != LMC_OK) return rc;
+    if (n_frames < 0 || n_t < 1) return fail(LMC_ERR_INVALID, "need n_t >= 1, n_frames >= 0");
+    if (!traj_t || !traj_Rt || !frame_t || !pose_Rt) return fail(LMC_ERR_INVALID, "NULL argument");
+    if ((reinterpret_cast<uintptr_t>(traj_Rt) | reinterpret_cast<uintptr_t>(pose_Rt)) & 15u) return fail(LMC_ERR_ALIGN, "pose tables must be 16-byte aligned");
+    cudaError_t e = lmc::launch_pose_lookup(traj_t, n_t, traj_Rt, frame_t, n_frames, pose_Rt, pose_idx, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_pose_lookup");
+}
+
+#define LMC_RIGID_BODY(F64)                                                                              \
+    lmc::Params P = base_params(pts_n4, out_n4, n_points, n_frames, p_begin, p_end);                     \
+    if (!pose_Rt) return fail(LMC_ERR_INVALID, "pose_Rt is NULL");                                       \
+    if (reinterpret_cast<uintptr_t>(pose_Rt) & 15u) return fail(LMC_ERR_ALIGN, "pose_Rt must be 16-byte aligned"); \
+    P.frame_off = frame_off; P.pose_Rt = pose_Rt;                                                        \
+    return run(F64, lmc::kRigid, P, ex, stream);
+
+int lmc_align_rigid_f64(const double* pts_n4, const int64_t* frame_off, const double* pose_Rt, double* out_n4,
+                        int64_t n_points, int32_t n_frames, int64_t p_begin, int64_t p_end, const lmc_export* ex, void* stream) {
+    LMC_RIGID_BODY(true)
+}
+int lmc_align_rigid_f32(const float* pts_n4, const int64_t* frame_off, const double* pose_Rt, float* out_n4,
+                        int64_t n_points, int32_t n_frames, int64_t p_begin, int64_t p_end, const lmc_export* ex, void* stream) {
+    LMC_RIGID_BODY(false)
+}
+
+#define LMC_GYRO_BODY(F64, TS)                                                                           \
+    lmc::Params P = base_params(pts_n4, out_n4, n_points, n_frames, p_begin, p_end);                     \
+    if (n_imu < 0) return fail(LMC_ERR_INVALID, "n_imu < 0");                                            \
+    if (!TS || !frame_start) return fail(LMC_ERR_INVALID, "timestamps / frame_start are NULL");          \
+    if (n_imu > 0 && (!imu_ts || !imu_gyro)) return fail(LMC_ERR_INVALID, "imu tables are NULL");        \
+    if (reinterpret_cast<uintptr_t>(TS) & 15u) return fail(LMC_ERR_ALIGN, "timestamps must be 16-byte aligned"); \
+    P.frame_off = frame_off; P.frame_start = frame_start; P.ts = TS;                                     \
+    P.samp_ts = imu_ts; P.samp_tab = imu_gyro; P.n_samp = n_imu;                                         \
+    return run(F64, lmc::kGyro, P, ex, stream);
+
+int lmc_deskew_gyro_f64(const double* pts_n4, const int64_t* ts, const int64_t* frame_off, const int64_t* frame_start,
+                        const int64_t* imu_ts, const double* imu_gyro, int64_t n_imu, double* out_n4,
+                        int64_t n_points, int32_t n_frames, int64_t p_begin, int64_t p_end, const lmc_export* ex, void* stream) {
+    LMC_GYRO_BODY(true, ts)
+}
+int lmc_deskew_gyro_f32(const float* pts_n4, const uint32_t* ts_off, const int64_t* frame_off, const int64_t* frame_start,
+                        const int64_t* imu_ts, const double* imu_gyro, int64_t n_imu, float* out_n4,
+                        int64_t n_points, int32_t n_frames, int64_t p_begin, int64_t p_end, const lmc_export* ex, void* stream) {
+    LMC_GYRO_BODY(false, ts_off)
+}
+
+#define LMC_SLERP_BODY(F64, TS, NEED_FS)                                                                 \
+    lmc::Params P = base_params(pts_n4, out_n4, n_points, n_frames, p_begin, p_end);                     \
+    if (n_samples < 1 || !sample_ts || !seg) return fail(LMC_ERR_INVALID, "need a non-empty sample table"); \
+    if (!hold_idx && !TS) return fail(LMC_ERR_INVALID, "timestamps are NULL");                           \
+    if (!hold_idx && NEED_FS && !frame_start) return fail(LMC_ERR_INVALID, "frame_start is NULL");       \
+    if ((reinterpret_cast<uintptr_t>(TS) | reinterpret_cast<uintptr_t>(seg)) & 15u) return fail(LMC_ERR_ALIGN, "timestamps / seg must be 16-byte aligned"); \
+    P.frame_off = frame_off; P.frame_start = frame_start; P.ts = TS;                                     \
+    P.samp_ts = sample_ts; P.samp_tab = seg; P.n_samp = n_samples; P.hold_idx = hold_idx;                \
+    return run(F64, lmc::kSlerp, P, ex, stream);
+
+int lmc_deskew_slerp_f64(const double* pts_n4, const int64_t* ts, const int64_t* frame_off, const int64_t* frame_start,
+                         const int64_t* sample_ts, const double* seg, int64_t n_samples, const int32_t* hold_idx,
+                         double* out_n4, int64_t n_points, int32_t n_frames, int64_t p_begin, int64_t p_end,
+                         const lmc_export* ex, void* stream) {
+    LMC_SLERP_BODY(true, ts, false)
+}
+int lmc_deskew_slerp_f32(const float* pts_n4, const uint32_t* ts_off, const int64_t* frame_off, const int64_t* frame_start,
+                         const int64_t* sample_ts, const double* seg, int64_t n_samples, const int32_t* hold_idx,
+                         float* out_n4, int64_t n_points, int32_t n_frames, int64_t p_begin, int64_t p_end,
+                         const lmc_export* ex, void* stream) {
+    LMC_SLERP_BODY(false, ts_off, true)
+}
+
+int lmc_quantize_f64(const double* pts_n4, int64_t n_points, const lmc_export* ex, void* stream) {
+    lmc::Params P = base_params(pts_n4, nullptr, n_points, 0, 0, n_points);
+    if (!ex) return fail(LMC_ERR_INVALID, "ex is NULL");
+    return run(true, lmc::kQuantOnly, P, ex, stream);
+}
+int lmc_quantize_f32(const float* pts_n4, int64_t n_points, const lmc_export* ex, void* stream) {
+    lmc::Params P = base_params(pts_n4, nullptr, n_points, 0, 0, n_points);
+    if (!ex) return fail(LMC_ERR_INVALID, "ex is NULL");
+    return run(false, lmc::kQuantOnly, P, ex, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+"""Host-side plumbing around the device path: flattening the reference's per-frame arrays into
+one frame-major buffer + CSR offsets, and building the small per-frame / per-sample pose tables.
+
+The pose tables are tiny (<= 720 001 rows for a 1 h stream at 200 Hz) and are built on the host
+with SciPy exactly as the reference builds its rotation matrices (LMC:774
+``R.from_euler('xyz', rpy).as_matrix()``), so the f64 matrices the kernels consume are bit-identical
+to the reference's.  Everything per-point happens on the GPU.
+
+LMC = lidar_motion_compensation.py        CS = livox_mid70_complete_simulator.py
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+from scipy.spatial.transform import Rotation
+
+SEG_STRIDE = 20        # doubles per Mode C sample row (include/lmc_b200.h)
+
+
+def flatten_frames(frames: Sequence[np.ndarray], dtype=np.float64) -> Tuple[np.ndarray, np.ndarray]:
+    """list of (n_f,4) arrays -> ((N,4) frame-major array, int64 CSR offsets[F+1]).
+
+    Frame-major concatenation is np.vstack order (LMC:888); empty frames (``np.array([]).reshape(0,4)``,
+    LMC:719/748) become zero-length rows."""
+    counts = np.fromiter((len(f) for f in frames), dtype=np.int64, count=len(frames))
+    off = np.zeros(len(frames) + 1, np.int64)
+    np.cumsum(counts, out=off[1:])
+    flat = np.empty((int(off[-1]), 4), dtype)
+    for f, b in zip(frames, off[:-1]):
+        if len(f):
+            flat[b:b + len(f)] = f
+    return flat, off
+
+
+def split_frames(flat: np.ndarray, frame_off: np.ndarray) -> List[np.ndarray]:
+    """Inverse of flatten_frames: per-frame views (no copies)."""
+    return [flat[frame_off[i]:frame_off[i + 1]] for i in range(len(frame_off) - 1)]
+
+
+def pose_table(position: np.ndarray, euler_xyz: np.ndarray) -> np.ndarray:
+    """(n,12) f64 rows [R row-major | t] with R = SciPy from_euler('xyz') as at LMC:774."""
+    position = np.asarray(position, np.float64).reshape(-1, 3)
+    euler_xyz = np.asarray(euler_xyz, np.float64).reshape(-1, 3)
+    Rm = Rotation.from_euler('xyz', euler_xyz).as_matrix().reshape(-1, 9)
+    return np.ascontiguousarray(np.concatenate([Rm, position], axis=1))
+
+
+def lidar_frame_times(duration: float, lidar_fps: float) -> np.ndarray:
+    """LMC:792-793 (linspace WITH endpoint: dt = duration/(n-1), not 1/fps)."""
+    return np.linspace(0, duration, int(duration * lidar_fps))
+
+
+def slerp_segment_table(sample_quat_xyzw: np.ndarray, sample_pos: np.ndarray) -> np.ndarray:
+    """Per-sample table consumed by lmc_deskew_slerp_*: for sample k
+    [R_k (9) | pos_k (3) | unit axis of R_k^-1 R_{k+1} (3) | angle | pos_{k+1}-pos_k (3) | pad]."""
+    q = np.asarray(sample_quat_xyzw, np.float64).reshape(-1, 4)
+    pos = np.asarray(sample_pos, np.float64).reshape(-1, 3)
+    S = len(q)
+    rot = Rotation.from_quat(q)
+    seg = np.zeros((S, SEG_STRIDE), np.float64)
+    seg[:, 0:9] = rot.as_matrix().reshape(S, 9)
+    seg[:, 9:12] = pos
+    seg[:, 12] = 1.0
+    if S > 1:
+        rv = (rot[:-1].inv() * rot[1:]).as_rotvec()
+        th = np.linalg.norm(rv, axis=1)
+        nz = th > 0
+        seg[:-1][nz, 12:15] = rv[nz] / th[nz, None]
+        seg[:-1, 15] = th
+        seg[:-1, 16:19] = pos[1:] - pos[:-1]
+    return seg
+
+
+def partition_frames(frame_off: np.ndarray, world_size: int) -> np.ndarray:
+    """Contiguous frame ranges balanced by POINTS: returns int64[world_size+1] frame
+    cut indices; rank r owns frames [cuts[r], cuts[r+1]) = points [off[cuts[r]], off[cuts[r+1]])."""
+    frame_off = np.asarray(frame_off, np.int64)
+    F, N = len(frame_off) - 1, int(frame_off[-1])
+    targets = (np.arange(1, world_size, dtype=np.float64) * N / world_size)
+    cuts = np.searchsorted(frame_off, targets, side='left')
+    # choose the nearer of the two neighbouring frame boundaries
+    for i, t in enumerate(targets):
+        c = int(cuts[i])
+        if c > 0 and abs(frame_off[c - 1] - t) <= abs(frame_off[min(c, F)] - t):
+            cuts[i] = c - 1
+    cuts = np.clip(cuts, 0, F)
+    cuts = np.maximum.accumulate(cuts)
+    return np.concatenate([[0], cuts, [F]]).astype(np.int64)

@@ -1,0 +1,187 @@
+"""Device operators: torch CUDA tensors in, hand-written sm_100a kernels through the C ABI
+(include/lmc_b200.h), torch tensors out.  torch is only the allocator / stream provider.
+
+No fallback: inputs must be CUDA tensors and liblmc_b200.so must load, otherwise these raise."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _capi as C
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: Optional[torch.Tensor], dtype, name: str, shape_tail=None) -> int:
+    if t is None:
+        return 0
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA tensor (this path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: must be contiguous")
+    if shape_tail is not None and tuple(t.shape[1:]) != tuple(shape_tail):
+        raise ValueError(f"{name}: expected shape (n,{','.join(map(str, shape_tail))}), got {tuple(t.shape)}")
+    return t.data_ptr()
+
+
+@dataclass
+class ExportBuffers:
+    """Integer-quantised export buffers produced by the fused epilogues."""
+    lvx14: Optional[torch.Tensor] = None          # (N,14) uint8   <iiiBB records
+    las_x: Optional[torch.Tensor] = None          # (N) int32
+    las_y: Optional[torch.Tensor] = None
+    las_z: Optional[torch.Tensor] = None
+    las_intensity: Optional[torch.Tensor] = None  # (N) uint16
+    status: Optional[torch.Tensor] = None         # (1) int32 bitmask of C.FLAG_*
+
+    def flags(self) -> int:
+        return 0 if self.status is None else int(self.status.item())
+
+    def raise_for_flags(self) -> None:
+        """Mirror the reference's failure modes: int(nan) -> ValueError (LMC:257),
+        struct.pack / laspy overflow -> OverflowError."""
+        f = self.flags()
+        if f & C.FLAG_NAN:
+            raise ValueError("cannot convert float NaN to integer")
+        if f & C.FLAG_OVERFLOW:
+            raise OverflowError("quantised value out of range for the export format")
+
+
+@dataclass
+class ExportSpec:
+    lvx: bool = False
+    lvx_mode: int = C.LVX_TYPE2_OF_INPUT
+    tag: Optional[torch.Tensor] = None
+    las: bool = False
+    las_scale: Sequence[float] = (0.01, 0.01, 0.01)      # laspy header default (LMC:953)
+    las_offset: Sequence[float] = (0.0, 0.0, 0.0)
+    las_intensity_mode: int = C.LAS_INTENSITY_UNIT
+    into: Optional[ExportBuffers] = None                 # reuse caller buffers (merged cloud shards)
+
+
+def _make_export(spec: Optional[ExportSpec], n: int, device):
+    if spec is None or not (spec.lvx or spec.las):
+        return None, None
+    b = spec.into if spec.into is not None else ExportBuffers()
+    if spec.lvx and b.lvx14 is None:
+        b.lvx14 = torch.empty((n, 14), dtype=torch.uint8, device=device)
+    if spec.las and b.las_x is None:
+        b.las_x = torch.empty(n, dtype=torch.int32, device=device)
+        b.las_y = torch.empty(n, dtype=torch.int32, device=device)
+        b.las_z = torch.empty(n, dtype=torch.int32, device=device)
+        b.las_intensity = torch.empty(n, dtype=torch.uint16, device=device)
+    if b.status is None:
+        b.status = torch.zeros(1, dtype=torch.int32, device=device)
+    ex = C.LmcExport()
+    ex.lvx14 = _req(b.lvx14, torch.uint8, "lvx14", (14,)) if spec.lvx else 0
+    ex.lvx_mode = int(spec.lvx_mode)
+    ex.tag = _req(spec.tag, torch.uint8, "tag")
+    if spec.las:
+        ex.las_x = _req(b.las_x, torch.int32, "las_x")
+        ex.las_y = _req(b.las_y, torch.int32, "las_y")
+        ex.las_z = _req(b.las_z, torch.int32, "las_z")
+        ex.las_intensity = _req(b.las_intensity, torch.uint16, "las_intensity")
+    ex.las_intensity_mode = int(spec.las_intensity_mode)
+    for c in range(3):
+        ex.las_scale[c] = float(spec.las_scale[c])
+        ex.las_offset[c] = float(spec.las_offset[c])
+    ex.status = b.status.data_ptr()
+    return ex, b
+
+
+def _layout(pts: torch.Tensor):
+    if pts.dtype == torch.float64:
+        return True
+    if pts.dtype == torch.float32:
+        return False
+    raise TypeError(f"points must be float64 (parity layout) or float32 (throughput layout), got {pts.dtype}")
+
+
+def _range(n, p_range):
+    if p_range is None:
+        return 0, n
+    return int(p_range[0]), int(p_range[1])
+
+
+def pose_lookup_hold_next(traj_t: torch.Tensor, traj_Rt: torch.Tensor, frame_t: torch.Tensor):
+    """(a1) LMC:802-812 on the device. Returns (pose_Rt (F,12) f64, pose_idx (F) int32)."""
+    F = frame_t.shape[0]
+    pose = torch.empty((F, 12), dtype=torch.float64, device=frame_t.device)
+    idx = torch.empty(F, dtype=torch.int32, device=frame_t.device)
+    C.check(C.lib().lmc_pose_lookup_hold_next(
+        _req(traj_t, torch.float64, "traj_t"), traj_t.shape[0], _req(traj_Rt, torch.float64, "traj_Rt", (12,)),
+        _req(frame_t, torch.float64, "frame_t"), F, pose.data_ptr(), idx.data_ptr(), _stream_ptr()))
+    return pose, idx
+
+
+def align_rigid(pts: torch.Tensor, frame_off: torch.Tensor, pose_Rt: torch.Tensor, *, out: Optional[torch.Tensor] = None,
+                export: Optional[ExportSpec] = None, p_range=None, want_out: bool = True):
+    """(a2)+(a3) LMC:772-776 over all frames, frame-major (LMC:888). Returns (aligned, ExportBuffers|None)."""
+    f64 = _layout(pts)
+    n, F = pts.shape[0], frame_off.shape[0] - 1
+    if pose_Rt.shape[0] != F:
+        raise ValueError("pose_Rt must have one row per frame")
+    if out is None and want_out:
+        out = torch.empty_like(pts)
+    ex, bufs = _make_export(export, n, pts.device)
+    b, e = _range(n, p_range)
+    fn = C.lib().lmc_align_rigid_f64 if f64 else C.lib().lmc_align_rigid_f32
+    C.check(fn(_req(pts, pts.dtype, "pts", (4,)), _req(frame_off, torch.int64, "frame_off"),
+               _req(pose_Rt, torch.float64, "pose_Rt", (12,)), _req(out, pts.dtype, "out", (4,)),
+               n, F, b, e, None if ex is None else C.ctypes.byref(ex), _stream_ptr()))
+    return out, bufs
+
+
+def deskew_gyro(pts: torch.Tensor, ts: torch.Tensor, frame_off: torch.Tensor, frame_start: torch.Tensor,
+                imu_ts: torch.Tensor, imu_gyro: torch.Tensor, *, out: Optional[torch.Tensor] = None,
+                export: Optional[ExportSpec] = None, p_range=None, want_out: bool = True):
+    """(a6)-(a8) CS:1435-1536. f64 points take int64 ns timestamps, f32 points uint32 ns offsets."""
+    f64 = _layout(pts)
+    n, F = pts.shape[0], frame_off.shape[0] - 1
+    if out is None and want_out:
+        out = torch.empty_like(pts)
+    ex, bufs = _make_export(export, n, pts.device)
+    b, e = _range(n, p_range)
+    fn = C.lib().lmc_deskew_gyro_f64 if f64 else C.lib().lmc_deskew_gyro_f32
+    C.check(fn(_req(pts, pts.dtype, "pts", (4,)), _req(ts, torch.int64 if f64 else torch.uint32, "ts"),
+               _req(frame_off, torch.int64, "frame_off"), _req(frame_start, torch.int64, "frame_start"),
+               _req(imu_ts, torch.int64, "imu_ts"), _req(imu_gyro, torch.float64, "imu_gyro", (3,)), imu_ts.shape[0],
+               _req(out, pts.dtype, "out", (4,)), n, F, b, e, None if ex is None else C.ctypes.byref(ex), _stream_ptr()))
+    return out, bufs
+
+
+def deskew_slerp(pts: torch.Tensor, ts: Optional[torch.Tensor], frame_off: torch.Tensor, frame_start: Optional[torch.Tensor],
+                 sample_ts: torch.Tensor, seg: torch.Tensor, *, hold_idx: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None, export: Optional[ExportSpec] = None, p_range=None, want_out: bool = True):
+    """Mode C: per-point bracket search + SLERP + lerp (+ optional hold-next = Mode A)."""
+    f64 = _layout(pts)
+    n, F = pts.shape[0], frame_off.shape[0] - 1
+    if out is None and want_out:
+        out = torch.empty_like(pts)
+    ex, bufs = _make_export(export, n, pts.device)
+    b, e = _range(n, p_range)
+    fn = C.lib().lmc_deskew_slerp_f64 if f64 else C.lib().lmc_deskew_slerp_f32
+    C.check(fn(_req(pts, pts.dtype, "pts", (4,)), _req(ts, torch.int64 if f64 else torch.uint32, "ts"),
+               _req(frame_off, torch.int64, "frame_off"), _req(frame_start, torch.int64, "frame_start"),
+               _req(sample_ts, torch.int64, "sample_ts"), _req(seg, torch.float64, "seg", (20,)), sample_ts.shape[0],
+               _req(hold_idx, torch.int32, "hold_idx"), _req(out, pts.dtype, "out", (4,)), n, F, b, e,
+               None if ex is None else C.ctypes.byref(ex), _stream_ptr()))
+    return out, bufs
+
+
+def quantize(pts: torch.Tensor, export: ExportSpec) -> ExportBuffers:
+    """(a4)/(a5)/(a9)/(a10) stand-alone quantisers over an (N,4) point array."""
+    f64 = _layout(pts)
+    n = pts.shape[0]
+    ex, bufs = _make_export(export, n, pts.device)
+    if ex is None:
+        raise ValueError("quantize: export spec selects no output")
+    fn = C.lib().lmc_quantize_f64 if f64 else C.lib().lmc_quantize_f32
+    C.check(fn(_req(pts, pts.dtype, "pts", (4,)), n, C.ctypes.byref(ex), _stream_ptr()))
+    return bufs

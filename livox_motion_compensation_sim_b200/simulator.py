@@ -1,0 +1,272 @@
+"""
+Host-side mirror of the reference's ``LiDARMotionSimulator`` for the motion-compensation hot
+path (pose lookup -> per-point transform -> merge -> quantise), B200-native underneath.
+
+Same constructor, config keys, ``ValueError`` messages, ``transform_pointcloud`` operator,
+``results`` dict contract and output file names as /root/reference/lidar_motion_compensation.py
+(LMC).  What changes is *how* the alignment runs: the reference's per-frame Python loop
+(LMC:802-832) becomes ONE batched device call over a frame-major point buffer + CSR offsets.
+
+Out of scope here: the trajectory / environment / scanner
+generators and the plots.  ``run_simulation`` therefore takes a ``frame_source`` that supplies the
+trajectory and the per-frame raw scans -- in an integration that is the reference's own generator
+methods (see INTEGRATION.md for the three-line mix-in).
+
+There is no CPU fallback: a CUDA device and liblmc_b200.so are required.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _capi as C
+from . import frames as FR
+from . import ops
+from .lvx import build_lvx_v11_file
+
+COMPENSATION_MODES = ("frame_rigid",)      # Mode A; Modes B/C live in compensator.py / ops.deskew_slerp
+
+
+class LiDARMotionSimulator:
+    # ------------------------------------------------------------------ construction (LMC:275-359)
+    def __init__(self, config: Optional[Dict] = None):
+        self.config = self.default_config()
+        if config:
+            self._validate_config(config)
+            self.config.update(config)          # unknown keys accepted silently, as in LMC:285
+        np.random.seed(self.config['random_seed'])          # LMC:288 (generators upstream rely on it)
+        self.device = torch.device(self.config.get('device', 'cuda:0'))
+        self._performance_stats = {'scan_times': [], 'transform_times': [], 'total_points_processed': 0}
+
+    def default_config(self):
+        """All 22 reference keys with the reference's defaults (LMC:297-330) + B200 knobs."""
+        return {
+            'duration': 60.0, 'lidar_fps': 10, 'imu_rate': 100, 'gps_rate': 5, 'random_seed': 42,
+            'max_speed': 15.0, 'max_angular_vel': 0.5, 'trajectory_type': 'figure_eight',
+            'fov_horizontal': 70.0, 'fov_vertical': 77.2, 'range_max': 90.0, 'range_min': 0.05,
+            'points_per_frame': 96000, 'angular_resolution': 0.28,
+            'gps_noise_std': 0.03, 'imu_accel_noise': 0.1, 'imu_gyro_noise': 0.01, 'lidar_range_noise': 0.02,
+            'environment_complexity': 'medium', 'ground_height': 0.0, 'obstacle_density': 0.1,
+            # --- additional keys (defaults reproduce the reference's behaviour) ---
+            'device': 'cuda:0',
+            'io_dtype': 'float64',               # 'float64' = reference-exact layout, 'float32' = throughput layout
+            'strict_reference_merge': True,      # LMC:887-891: no merged_aligned if any frame is empty
+            'las_scale': (0.01, 0.01, 0.01),     # laspy header default used by LMC:953
+            'las_offset': (0.0, 0.0, 0.0),
+        }
+
+    def _validate_config(self, config: Dict) -> None:
+        """Same checks and messages as LMC:332-359."""
+        for key in ['duration', 'lidar_fps', 'max_speed', 'range_max', 'range_min', 'points_per_frame']:
+            if key in config and not isinstance(config[key], (int, float)):
+                raise ValueError(f"Configuration '{key}' must be numeric")
+        if 'lidar_fps' in config and config['lidar_fps'] <= 0:
+            raise ValueError("LiDAR frame rate must be positive")
+        if 'duration' in config and config['duration'] <= 0:
+            raise ValueError("Simulation duration must be positive")
+        if 'max_speed' in config and config['max_speed'] < 0:
+            raise ValueError("Maximum speed cannot be negative")
+        if 'range_max' in config and 'range_min' in config:
+            if config['range_max'] <= config['range_min']:
+                raise ValueError("Maximum range must be greater than minimum range")
+
+    # ------------------------------------------------------------------ device helpers
+    def _np_dtype(self):
+        return np.float64 if self.config.get('io_dtype', 'float64') == 'float64' else np.float32
+
+    def _to_dev(self, a: np.ndarray, dtype=None) -> torch.Tensor:
+        t = torch.from_numpy(np.ascontiguousarray(a if dtype is None else a.astype(dtype, copy=False)))
+        return t.to(self.device, non_blocking=False)
+
+    # ------------------------------------------------------------------ (a1) LMC:802-812
+    def lookup_frame_poses(self, trajectory: Dict, lidar_times: np.ndarray):
+        """Hold-next pose per frame on the device. Returns (pose_Rt device (F,12), pose_idx np int32)."""
+        traj_Rt = FR.pose_table(trajectory['position_gps'], trajectory['orientation_imu'])
+        pose, idx = ops.pose_lookup_hold_next(self._to_dev(np.asarray(trajectory['time'], np.float64)),
+                                              self._to_dev(traj_Rt),
+                                              self._to_dev(np.asarray(lidar_times, np.float64)))
+        return pose, idx.cpu().numpy()
+
+    # ------------------------------------------------------------------ (a2) LMC:772-776
+    def transform_pointcloud(self, points, transformation):
+        """Apply transformation to point cloud -- same contract as LMC:772-776: (n,4) f64 in, new
+        (n,4) f64 out, input untouched, empty in -> empty out.  Runs as a one-frame device batch."""
+        points = np.asarray(points, np.float64)
+        n = len(points)
+        if n == 0:
+            return np.column_stack([np.zeros((0, 3)), np.zeros(0)])
+        pose = FR.pose_table(np.asarray(transformation['translation'], np.float64),
+                             np.asarray(transformation['rotation'], np.float64))
+        off = torch.tensor([0, n], dtype=torch.int64, device=self.device)
+        out, _ = ops.align_rigid(self._to_dev(points), off, self._to_dev(pose))
+        return out.cpu().numpy()
+
+    # ------------------------------------------------------------------ (a2)+(a3) batched
+    def align_frames(self, frames: Sequence[np.ndarray], positions: np.ndarray, eulers: np.ndarray,
+                     export: Optional[ops.ExportSpec] = None):
+        """The reference's frame loop body LMC:826-832 for every frame at once.
+
+        Returns (merged (N,4) host array, frame_off, ExportBuffers|None).  The merged array is
+        frame-major == np.vstack(aligned) (LMC:888); per-frame results are views of it."""
+        dt = self._np_dtype()
+        flat, off = FR.flatten_frames(frames, dt)
+        pose = FR.pose_table(positions, eulers)
+        if len(flat) == 0:
+            return flat.copy(), off, None
+        out, bufs = ops.align_rigid(self._to_dev(flat), self._to_dev(off), self._to_dev(pose), export=export)
+        self._performance_stats['total_points_processed'] += len(flat)
+        return out.cpu().numpy(), off, bufs
+
+    # ------------------------------------------------------------------ LMC:778-858
+    def run_simulation(self, frame_source=None):
+        """Run the simulation with the alignment step on the B200.
+
+        ``frame_source`` supplies what the (out-of-scope) generators produce:
+          .trajectory                -> dict with 'time','position','velocity','orientation',
+                                        'position_gps','orientation_imu'  (LMC:396-428)
+          .scan(i, t, sensor_pose)   -> (n,4) f64 raw sensor-frame points   (LMC:701-770)
+          .environment (optional)
+        Returns the reference's results dict (LMC:852-858)."""
+        if frame_source is None:
+            raise NotImplementedError(
+                "trajectory / environment / scanner generators are outside the accelerated hot path "
+                "(SURVEY.md section 2 rows 8-11); pass a frame_source, or mix this class into the "
+                "reference's LiDARMotionSimulator as shown in INTEGRATION.md")
+        trajectory = frame_source.trajectory
+        lidar_times = FR.lidar_frame_times(self.config['duration'], self.config['lidar_fps'])
+        _, pose_idx = self.lookup_frame_poses(trajectory, lidar_times)
+
+        all_scans, motion_data = [], []
+        for i, t in enumerate(lidar_times):
+            k = int(pose_idx[i])
+            sensor_pose = {'position': trajectory['position_gps'][k],
+                           'orientation': trajectory['orientation_imu'][k],
+                           'velocity': trajectory['velocity'][k]}
+            scan = frame_source.scan(i, t, sensor_pose)
+            all_scans.append({'frame_id': i, 'timestamp': t, 'points_local': scan, 'sensor_pose': sensor_pose})
+            motion_data.append(self._motion_row(i, t, sensor_pose))
+        aligned = self.align_scans(all_scans)
+        return {'raw_scans': all_scans, 'aligned_pointclouds': aligned, 'motion_data': motion_data,
+                'trajectory': trajectory, 'environment': getattr(frame_source, 'environment', None)}
+
+    @staticmethod
+    def _motion_row(i, t, sensor_pose):
+        """LMC:835-847."""
+        p, o, v = sensor_pose['position'], sensor_pose['orientation'], sensor_pose['velocity']
+        return {'frame_id': i, 'timestamp': t,
+                'gps_lat': p[1] / 111320.0 + 40.0,
+                'gps_lon': p[0] / (111320.0 * np.cos(np.radians(40.0))) - 74.0,
+                'gps_alt': p[2], 'imu_roll': o[0], 'imu_pitch': o[1], 'imu_yaw': o[2],
+                'vel_x': v[0], 'vel_y': v[1], 'vel_z': v[2]}
+
+    def align_scans(self, raw_scans: List[dict], export: Optional[ops.ExportSpec] = None) -> List[np.ndarray]:
+        """Batched LMC:826-832 over the reference's raw_scans list; keeps the merged buffer and the
+        export buffers on ``self`` (last_merged / last_frame_off / last_export)."""
+        frames = [s['points_local'] for s in raw_scans]
+        pos = np.array([s['sensor_pose']['position'] for s in raw_scans], np.float64).reshape(-1, 3)
+        eul = np.array([s['sensor_pose']['orientation'] for s in raw_scans], np.float64).reshape(-1, 3)
+        merged, off, bufs = self.align_frames(frames, pos, eul, export=export)
+        self.last_merged, self.last_frame_off, self.last_export = merged, off, bufs
+        return FR.split_frames(merged, off)
+
+    # ------------------------------------------------------------------ (a3) LMC:886-899
+    def merge_results(self, results) -> Dict[str, Optional[np.ndarray]]:
+        """merged_aligned / merged_raw with the reference's guards."""
+        aligned = results['aligned_pointclouds']
+        out: Dict[str, Optional[np.ndarray]] = {'merged_aligned': None, 'merged_raw': None}
+        strict = self.config.get('strict_reference_merge', True)
+        if aligned and (all(len(pc) > 0 for pc in aligned) or not strict):
+            base = getattr(self, 'last_merged', None)
+            same = base is not None and len(aligned) and aligned[0].base is base
+            out['merged_aligned'] = base if same else np.vstack(aligned)
+        else:
+            print("Warning: No aligned point clouds to merge")
+        raw = [s['points_local'] for s in results['raw_scans'] if len(s['points_local']) > 0]
+        if raw:
+            out['merged_raw'] = np.vstack(raw)
+        else:
+            print("Warning: No raw point clouds to merge")
+        return out
+
+    # ------------------------------------------------------------------ (a4) LMC:252-272 / 965-990
+    def quantize_lvx(self, results) -> tuple:
+        """int32-millimetre LVX type-2 records of the RAW scans (LMC:973-978), on the device.
+        Returns ((N,14) uint8 host array, frame_off)."""
+        flat, off = FR.flatten_frames([s['points_local'] for s in results['raw_scans']], np.float64)
+        if len(flat) == 0:
+            return np.zeros((0, 14), np.uint8), off
+        bufs = ops.quantize(self._to_dev(flat), ops.ExportSpec(lvx=True, lvx_mode=C.LVX_TYPE2_OF_INPUT))
+        bufs.raise_for_flags()
+        return bufs.lvx14.cpu().numpy(), off
+
+    # ------------------------------------------------------------------ (a5) LMC:950-963
+    def quantize_las(self, points: np.ndarray):
+        """LAS integer X/Y/Z + uint16 intensity of the merged cloud (parity unpinned: laspy)."""
+        bufs = ops.quantize(self._to_dev(np.asarray(points, np.float64)),
+                            ops.ExportSpec(las=True, las_scale=self.config['las_scale'],
+                                           las_offset=self.config['las_offset'],
+                                           las_intensity_mode=C.LAS_INTENSITY_UNIT))
+        bufs.raise_for_flags()
+        return (bufs.las_x.cpu().numpy(), bufs.las_y.cpu().numpy(), bufs.las_z.cpu().numpy(),
+                bufs.las_intensity.cpu().numpy())
+
+    # ------------------------------------------------------------------ LMC:860-930 (hot-path outputs)
+    def save_results(self, results, output_dir='lidar_simulation_output'):
+        """Writes the reference's hot-path outputs under the reference's names:
+        aligned_scans_pcd/aligned_frame_%04d.pcd, raw_scans_pcd/frame_%04d.pcd, merged_aligned.pcd,
+        merged_raw_overlapped.pcd, lidar_data.lvx, and the LAS integer buffers as
+        merged_aligned.las_ints.npz (the LAS container itself is laspy's, out of scope)."""
+        os.makedirs(output_dir, exist_ok=True)
+        print(f"Saving results to {output_dir}...")
+        pcd_dir = os.path.join(output_dir, 'raw_scans_pcd'); os.makedirs(pcd_dir, exist_ok=True)
+        for scan in results['raw_scans']:
+            self.save_pcd(scan['points_local'], os.path.join(pcd_dir, f'frame_{scan["frame_id"]:04d}.pcd'))
+        aligned_dir = os.path.join(output_dir, 'aligned_scans_pcd'); os.makedirs(aligned_dir, exist_ok=True)
+        for i, pc in enumerate(results['aligned_pointclouds']):
+            self.save_pcd(pc, os.path.join(aligned_dir, f'aligned_frame_{i:04d}.pcd'))
+        merged = self.merge_results(results)
+        if merged['merged_aligned'] is not None:
+            self.save_pcd(merged['merged_aligned'], os.path.join(output_dir, 'merged_aligned.pcd'))
+        if merged['merged_raw'] is not None:
+            self.save_pcd(merged['merged_raw'], os.path.join(output_dir, 'merged_raw_overlapped.pcd'))
+        try:
+            if merged['merged_aligned'] is None:
+                raise UnboundLocalError("merged_aligned")           # what LMC:903 hits when the merge was skipped
+            X, Y, Z, I = self.quantize_las(merged['merged_aligned'])
+            np.savez(os.path.join(output_dir, 'merged_aligned.las_ints.npz'), X=X, Y=Y, Z=Z, intensity=I,
+                     scale=np.asarray(self.config['las_scale']), offset=np.asarray(self.config['las_offset']))
+            print("LAS integer buffers saved successfully")
+        except Exception as e:                                       # LMC:905-906 swallows and prints
+            print(f"Could not save LAS format: {e}")
+        try:
+            self.save_lvx(results, os.path.join(output_dir, 'lidar_data'))
+            print("LVX formats saved successfully")
+        except Exception as e:                                       # LMC:913-914
+            print(f"Could not save LVX formats: {e}")
+        print("Results saved successfully!")
+        return output_dir
+
+    def save_pcd(self, points, filename):
+        """ASCII PCD, byte-identical to LMC:932-948 ('%.6f' per field)."""
+        points = np.asarray(points, np.float64).reshape(-1, 4)
+        n = len(points)
+        header = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z intensity\n"
+                  "SIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\n"
+                  f"WIDTH {n}\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS {n}\nDATA ascii\n")
+        with open(filename, 'w') as f:
+            f.write(header)
+            if n:
+                np.savetxt(f, points, fmt='%.6f %.6f %.6f %.6f')
+
+    def save_lvx(self, results, base_filename):
+        """lidar_data.lvx with the LVX v1.1 container of LMC:58-250 around device-quantised records."""
+        rec, off = self.quantize_lvx(results)
+        ts = np.array([s['timestamp'] for s in results['raw_scans']], np.float64)
+        ids = np.array([s['frame_id'] for s in results['raw_scans']], np.int64)
+        data = build_lvx_v11_file(rec, off, ts, ids)
+        with open(f"{base_filename}.lvx", 'wb') as f:
+            f.write(data.tobytes())
+        return True

@@ -1,0 +1,419 @@
+"""
+GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI
+(include/lmc_b200.h via ctypes), against
+  (1) the committed golden fixtures produced by the REAL reference (tests/golden/), and
+  (2) the CPU oracle (oracle/lmc_oracle.c) on seeded synthetic Mid-70-shaped inputs.
+
+Bars (BASELINE.json north_star): integer export buffers and point order bit-exact; float xyz within
+1e-4 m per coordinate -- and, stronger, Mode A f64 output is required to be BIT-IDENTICAL to the
+reference's NumPy path.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import lmc_oracle as orc                                      # noqa: E402  (checker only)
+from livox_motion_compensation_sim_b200 import _capi as C                 # noqa: E402
+from livox_motion_compensation_sim_b200 import frames as FR               # noqa: E402
+from livox_motion_compensation_sim_b200 import ops, synth                 # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+MAN = json.load(open(os.path.join(GOLDEN, "MANIFEST.json")))
+DEV = "cuda:0"
+TOL_M = 1e-4            # north_star float tolerance (metres, per coordinate)
+
+
+def dev(a, dtype=None):
+    a = np.ascontiguousarray(a if dtype is None else np.asarray(a).astype(dtype))
+    return torch.from_numpy(a).to(DEV)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(params=[C.PATH_DIRECT, C.PATH_TMA], ids=["direct", "tma"])
+def path(request):
+    C.set_path(request.param)
+    yield request.param
+    C.set_path(C.PATH_TMA)
+
+
+# ------------------------------------------------------------------------------------------
+# Mode A against the reference's own outputs
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["lmc_C1a.npz", "lmc_C2a.npz", "lmc_C3.npz", "lmc_edge.npz"])
+def test_mode_a_f64_bit_exact_vs_reference(golden, name, path):
+    g = golden(name)
+    pose = FR.pose_table(g['pose_position'], g['pose_euler'])
+    out, _ = ops.align_rigid(dev(g['raw']), dev(g['frame_off']), dev(pose))
+    out = out.cpu().numpy()
+    assert out.tobytes() == g['aligned'].tobytes()
+
+
+def test_c1a_whole_run_sha(golden):
+    """configs[0] (highway_simple wording, 10 fps): every frame of the reference run, 94 % of them
+    empty, through one batched launch -> sha256 of the merged cloud equals the reference's."""
+    g = golden("lmc_C1a.npz")
+    pose = FR.pose_table(g['pose_position'], g['pose_euler'])
+    out, _ = ops.align_rigid(dev(g['raw']), dev(g['frame_off']), dev(pose))
+    assert sha(out.cpu().numpy()) == MAN['lmc']['C1a']['aligned_sha256']
+
+
+@pytest.mark.parametrize("name", ["lmc_C1a.npz", "lmc_C2a.npz", "lmc_C3.npz"])
+def test_pose_lookup_on_device(golden, name):
+    g = golden(name)
+    traj_Rt = FR.pose_table(g['traj_position_gps'], g['traj_orientation_imu'])
+    pose, idx = ops.pose_lookup_hold_next(dev(g['traj_time']), dev(traj_Rt), dev(g['frame_t_all']))
+    assert np.array_equal(idx.cpu().numpy(), g['pose_idx_all'])
+    ids = g['frame_ids']
+    want = FR.pose_table(g['pose_position'], g['pose_euler'])
+    assert pose.cpu().numpy()[ids].tobytes() == want.tobytes()
+
+
+def test_lookup_then_align_equals_reference(golden):
+    """(a1) + (a2) chained on the device == the reference's aligned frames."""
+    g = golden("lmc_C2a.npz")
+    traj_Rt = FR.pose_table(g['traj_position_gps'], g['traj_orientation_imu'])
+    pose_all, _ = ops.pose_lookup_hold_next(dev(g['traj_time']), dev(traj_Rt), dev(g['frame_t_all']))
+    pose = pose_all[torch.from_numpy(g['frame_ids'].astype(np.int64)).to(DEV)].contiguous()
+    out, _ = ops.align_rigid(dev(g['raw']), dev(g['frame_off']), pose)
+    assert out.cpu().numpy().tobytes() == g['aligned'].tobytes()
+
+
+# ------------------------------------------------------------------------------------------
+# quantisers against the reference's own bytes
+# ------------------------------------------------------------------------------------------
+def test_lvx_type2_records_vs_reference(golden, path):
+    g = golden("lvx_type2.npz")
+    b = ops.quantize(dev(g['pts']), ops.ExportSpec(lvx=True, lvx_mode=C.LVX_TYPE2_OF_INPUT))
+    assert b.flags() == 0
+    assert np.array_equal(b.lvx14.cpu().numpy(), g['records'])
+
+
+def test_lvx_nan_raises_like_reference():
+    pts = np.array([[1.0, np.nan, 2.0, 0.5]] * 3)
+    b = ops.quantize(dev(pts), ops.ExportSpec(lvx=True))
+    assert b.flags() & C.FLAG_NAN
+    with pytest.raises(ValueError):
+        b.raise_for_flags()
+
+
+def test_las_quantiser_vs_oracle(path):
+    rng = np.random.default_rng(3)
+    n = 200_001
+    pts = np.column_stack([rng.uniform(-2000, 2000, (n, 3)), rng.uniform(0, 1, n)])
+    k = rng.integers(-100000, 100000, (5000, 3))
+    pts[:5000, :3] = (k + 0.5) * 0.01
+    for scale, off, mode in [([0.01] * 3, [0.0] * 3, 0), ([0.001] * 3, [0.0, 1.5, -3.25], 0), ([0.001] * 3, [0.0] * 3, 1)]:
+        p = pts.copy()
+        if mode == 1:
+            p[:, 3] = rng.integers(0, 256, n)
+        b = ops.quantize(dev(p), ops.ExportSpec(las=True, las_scale=scale, las_offset=off, las_intensity_mode=mode))
+        X, Y, Z, I, fl = orc.C.quantize_las(p, scale, off, mode)
+        assert b.flags() == fl == 0
+        assert np.array_equal(b.las_x.cpu().numpy(), X) and np.array_equal(b.las_y.cpu().numpy(), Y)
+        assert np.array_equal(b.las_z.cpu().numpy(), Z)
+        assert np.array_equal(b.las_intensity.cpu().numpy().view(np.uint16), I)
+    b = ops.quantize(dev(np.array([[3e7, 0, 0, 0.5]] * 2)), ops.ExportSpec(las=True))
+    assert b.flags() & C.FLAG_OVERFLOW
+
+
+# ------------------------------------------------------------------------------------------
+# fused transform + quantise on synthetic Mid-70-shaped frames (M-SWEEP shapes, reduced totals)
+# ------------------------------------------------------------------------------------------
+def _ragged_counts(rng, F, mean):
+    c = rng.integers(0, 2 * mean, F)
+    c[rng.integers(0, F, max(F // 10, 1))] = 0          # empty frames
+    c[rng.integers(0, F, max(F // 20, 1))] = 1          # single-point frames (gemv order)
+    return c
+
+
+@pytest.mark.parametrize("ppf,F", [(10_000, 40), (100_000, 6), (1_000_000, 2), ("ragged", 300)])
+@pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
+def test_fused_rigid_lvx_las_vs_oracle(ppf, F, f64, path):
+    rng = np.random.default_rng(777)
+    counts = _ragged_counts(rng, F, 700) if ppf == "ragged" else ppf
+    st = synth.make_stream(F, counts, 777, device=DEV, dtype=torch.float64 if f64 else torch.float32)
+    pose = st.gps_Rt[orc.pose_lookup_hold_next_np(st.gps_t, st.frame_t)]
+    spec = ops.ExportSpec(lvx=True, lvx_mode=C.LVX_TYPE2_OF_INPUT, las=True, las_scale=(0.001,) * 3,
+                          las_offset=(0.0, 0.0, 0.0), las_intensity_mode=C.LAS_INTENSITY_UNIT)
+    out, b = ops.align_rigid(st.pts, dev(st.frame_off), dev(pose), export=spec)
+    pts64 = st.pts.cpu().numpy().astype(np.float64)
+    want = orc.C.align_rigid_f64(pts64, st.frame_off, pose, threads=4)
+    got = out.cpu().numpy()
+    if f64:
+        assert got.tobytes() == want.tobytes()
+    else:
+        assert np.array_equal(got, want.astype(np.float32))        # f64 math, one rounding to f32
+        assert np.abs(got.astype(np.float64) - want).max() <= TOL_M
+    rec, fl = orc.C.quantize_lvx_type2(pts64)
+    X, Y, Z, I, fl2 = orc.C.quantize_las(want, [0.001] * 3, [0.0] * 3, 0)
+    assert b.flags() == (fl | fl2)
+    assert np.array_equal(b.lvx14.cpu().numpy(), rec)
+    assert np.array_equal(b.las_x.cpu().numpy(), X) and np.array_equal(b.las_y.cpu().numpy(), Y)
+    assert np.array_equal(b.las_z.cpu().numpy(), Z)
+    assert np.array_equal(b.las_intensity.cpu().numpy().view(np.uint16), I)
+
+
+def test_point_range_shards_compose(path):
+    """Frame-sharded ranks writing disjoint [p_begin, p_end) slices of one merged buffer give the
+    same bytes as one launch (odd, unaligned cut points on purpose)."""
+    rng = np.random.default_rng(5)
+    F = 120
+    st = synth.make_stream(F, _ragged_counts(rng, F, 900), 5, device=DEV, dtype=torch.float32)
+    pose = dev(st.gps_Rt[orc.pose_lookup_hold_next_np(st.gps_t, st.frame_t)])
+    off = dev(st.frame_off)
+    spec = lambda into=None: ops.ExportSpec(lvx=True, las=True, las_scale=(0.01,) * 3, into=into)
+    whole, bw = ops.align_rigid(st.pts, off, pose, export=spec())
+    cuts = FR.partition_frames(st.frame_off, 3)
+    pcuts = st.frame_off[cuts]
+    out = torch.zeros_like(whole)
+    into = ops.ExportBuffers(lvx14=torch.zeros_like(bw.lvx14), las_x=torch.zeros_like(bw.las_x), las_y=torch.zeros_like(bw.las_y),
+                             las_z=torch.zeros_like(bw.las_z), las_intensity=torch.zeros_like(bw.las_intensity))
+    for r in range(3):
+        ops.align_rigid(st.pts, off, pose, out=out, export=spec(into), p_range=(pcuts[r], pcuts[r + 1]))
+    assert torch.equal(out, whole)
+    assert torch.equal(into.lvx14, bw.lvx14) and torch.equal(into.las_x, bw.las_x)
+    assert torch.equal(into.las_z, bw.las_z) and torch.equal(into.las_intensity.view(torch.int16), bw.las_intensity.view(torch.int16))
+    # a slice must not touch bytes outside its range
+    out2 = torch.full_like(whole, -7.0)
+    ops.align_rigid(st.pts, off, pose, out=out2, p_range=(1001, 2003))
+    assert torch.equal(out2[1001:2003], whole[1001:2003])
+    assert bool((out2[:1001] == -7.0).all()) and bool((out2[2003:] == -7.0).all())
+
+
+# ------------------------------------------------------------------------------------------
+# Mode B against the reference's own outputs, and against the oracle on synthetic streams
+# ------------------------------------------------------------------------------------------
+def test_mode_b_vs_reference(golden, path):
+    g = golden("modeb.npz")
+    spec = ops.ExportSpec(lvx=True, lvx_mode=C.LVX2_OF_OUTPUT, tag=dev(g['tag']))
+    out, b = ops.deskew_gyro(dev(g['pts']), dev(g['ts']), dev(g['frame_off']), dev(g['frame_start']),
+                             dev(g['imu_ts']), dev(g['imu_gyro']), export=spec)
+    got = out.cpu().numpy()
+    err = np.abs(got - g['compensated']).max()
+    assert err <= TOL_M
+    assert err <= 1e-11                     # device sincos vs glibc: a few ulp at 90 m range
+    rec = b.lvx14.cpu().numpy()
+    mism = int((rec != g['lvx2_records']).any(axis=1).sum())
+    print(f"mode B: max |d| = {err:.3e} m, LVX2 record mismatches = {mism} / {len(rec)}")
+    assert mism == 0
+    assert b.flags() == 0
+    assert np.array_equal(got[:, 3], g['pts'][:, 3])
+
+
+def test_mode_b_empty_imu_copies(golden):
+    g = golden("modeb.npz")
+    out, _ = ops.deskew_gyro(dev(g['pts']), dev(g['ts']), dev(g['frame_off']), dev(g['frame_start']),
+                             torch.zeros(0, dtype=torch.int64, device=DEV), torch.zeros((0, 3), dtype=torch.float64, device=DEV))
+    assert out.cpu().numpy().tobytes() == g['pts'].tobytes()
+
+
+@pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
+def test_mode_b_synthetic_vs_oracle(f64, path):
+    F, P = 30, 10_000
+    st = synth.make_stream(F, P, 31, device=DEV, dtype=torch.float64 if f64 else torch.float32)
+    rng = np.random.default_rng(8)
+    imu_ts = st.sample_ts[: (F * 20 - 7)]                  # stream runs past the last IMU sample
+    gyro = rng.normal(0, 0.3, (len(imu_ts), 3))
+    ts64 = (st.frame_start[np.repeat(np.arange(F), P)] + st.ts_off.cpu().numpy().astype(np.int64))
+    pts64 = st.pts.cpu().numpy().astype(np.float64)
+    pts64[:, 3] = np.floor(pts64[:, 3] * 255)              # LiDARPoint.intensity is an int 0..255
+    pts_d = dev(pts64 if f64 else pts64.astype(np.float32))
+    spec = ops.ExportSpec(lvx=True, lvx_mode=C.LVX2_OF_OUTPUT, las=True, las_scale=(0.001,) * 3,
+                          las_intensity_mode=C.LAS_INTENSITY_RAW)
+    ts_d = dev(ts64) if f64 else st.ts_off
+    out, b = ops.deskew_gyro(pts_d, ts_d, dev(st.frame_off), dev(st.frame_start), dev(imu_ts), dev(gyro), export=spec)
+    want = orc.C.deskew_gyro_f64(pts64, ts64, st.frame_off, st.frame_start, imu_ts, gyro)
+    got = out.cpu().numpy().astype(np.float64)
+    assert np.abs(got - want).max() <= (1e-10 if f64 else TOL_M)
+    rec, _ = orc.C.quantize_lvx2(want)
+    mism = int((b.lvx14.cpu().numpy() != rec).any(axis=1).sum())
+    X, Y, Z, I, _ = orc.C.quantize_las(want, [0.001] * 3, [0.0] * 3, 1)
+    mism_las = int((b.las_x.cpu().numpy() != X).sum() + (b.las_y.cpu().numpy() != Y).sum() + (b.las_z.cpu().numpy() != Z).sum())
+    print(f"mode B synthetic: LVX2 mismatches {mism}, LAS int mismatches {mism_las} of {len(rec)} pts")
+    assert mism <= 2 and mism_las <= 2      # trig ulp can flip an integer with p ~ 1e-10 per coordinate
+    assert np.array_equal(b.las_intensity.cpu().numpy().view(np.uint16), I)
+
+
+# ------------------------------------------------------------------------------------------
+# Mode C (parity unpinned by the reference): C oracle, scipy Slerp oracle, hold-next identity
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
+def test_mode_c_vs_oracles(f64, path):
+    F = 40
+    rng = np.random.default_rng(13)
+    counts = np.full(F, 10_000); counts[3] = 0; counts[7] = 1; counts[11] = 2047
+    st = synth.make_stream(F, counts, 13, device=DEV, dtype=torch.float64 if f64 else torch.float32)
+    S = len(st.sample_ts) - 40                              # last frames run past the table (clamp)
+    sample_ts, seg = st.sample_ts[:S], st.seg[:S]
+    fstart = st.frame_start - 3_000_000                     # first points precede the table (clamp)
+    fidx = np.repeat(np.arange(F), counts)
+    ts64 = fstart[fidx] + st.ts_off.cpu().numpy().astype(np.int64)
+    pts64 = st.pts.cpu().numpy().astype(np.float64)
+    spec = ops.ExportSpec(lvx=True, lvx_mode=C.LVX_TYPE2_OF_INPUT, las=True, las_scale=(0.001,) * 3)
+    ts_d = dev(ts64) if f64 else st.ts_off
+    out, b = ops.deskew_slerp(st.pts, ts_d, dev(st.frame_off), dev(fstart), dev(sample_ts), dev(seg), export=spec)
+    got = out.cpu().numpy().astype(np.float64)
+    want = orc.C.deskew_slerp_f64(pts64, ts64, st.frame_off, sample_ts, seg)
+    ref2 = orc.slerp_deskew_scipy(pts64, ts64, sample_ts, st.sample_quat[:S], st.sample_pos[:S])
+    assert np.abs(want - ref2).max() <= 1e-9               # C oracle == independent scipy Slerp + lerp
+    assert np.abs(got - want).max() <= (1e-10 if f64 else TOL_M)
+    if not f64:
+        assert (got.astype(np.float32) != want.astype(np.float32)).sum() <= 4
+    rec, _ = orc.C.quantize_lvx_type2(pts64)
+    assert np.array_equal(b.lvx14.cpu().numpy(), rec)       # LVX of the raw points: exact
+    X, Y, Z, I, _ = orc.C.quantize_las(want, [0.001] * 3, [0.0] * 3, 0)
+    mism = int((b.las_x.cpu().numpy() != X).sum() + (b.las_y.cpu().numpy() != Y).sum() + (b.las_z.cpu().numpy() != Z).sum())
+    print(f"mode C: LAS int mismatches {mism} of {3 * len(X)}")
+    assert mism <= 2
+    assert np.array_equal(b.las_intensity.cpu().numpy().view(np.uint16), I)
+
+
+def test_mode_c_hold_next_is_mode_a():
+    """Mode A == Mode C with the interpolation weight forced to hold-next: bit-identical."""
+    F = 25
+    st = synth.make_stream(F, 4096, 17, device=DEV, dtype=torch.float64)
+    hold = orc.C.pose_lookup_hold_next(st.sample_ts.astype(np.float64), st.frame_start.astype(np.float64))
+    pose = np.ascontiguousarray(st.seg[hold][:, :12])
+    a, _ = ops.align_rigid(st.pts, dev(st.frame_off), dev(pose))
+    c, _ = ops.deskew_slerp(st.pts, None, dev(st.frame_off), None, dev(st.sample_ts), dev(st.seg), hold_idx=dev(hold))
+    assert torch.equal(a, c)
+
+
+# ------------------------------------------------------------------------------------------
+# host-side mirrors of the reference API
+# ------------------------------------------------------------------------------------------
+def test_simulator_transform_pointcloud_contract(golden):
+    from livox_motion_compensation_sim_b200 import LiDARMotionSimulator
+    g = golden("lmc_edge.npz")
+    sim = LiDARMotionSimulator({'duration': 1.0})
+    off = g['frame_off']
+    for i in range(len(off) - 1):
+        p = g['raw'][off[i]:off[i + 1]]
+        keep = p.copy()
+        out = sim.transform_pointcloud(p, {'translation': g['pose_position'][i], 'rotation': g['pose_euler'][i]})
+        assert out.shape == (len(p), 4) and out.dtype == np.float64
+        assert out.tobytes() == g['aligned'][off[i]:off[i + 1]].tobytes()
+        assert np.array_equal(p, keep)
+
+
+def test_simulator_batched_alignment_and_outputs(golden, tmp_path):
+    from livox_motion_compensation_sim_b200 import LiDARMotionSimulator
+    g = golden("lmc_C2a.npz")
+    off = g['frame_off']
+    F = len(off) - 1
+    raw_scans = [{'frame_id': int(g['frame_ids'][i]), 'timestamp': float(g['frame_t_all'][g['frame_ids'][i]]),
+                  'points_local': g['raw'][off[i]:off[i + 1]],
+                  'sensor_pose': {'position': g['pose_position'][i], 'orientation': g['pose_euler'][i], 'velocity': np.zeros(3)}}
+                 for i in range(F)]
+    sim = LiDARMotionSimulator()
+    aligned = sim.align_scans(raw_scans)
+    assert len(aligned) == F
+    for i in range(F):
+        assert aligned[i].tobytes() == g['aligned'][off[i]:off[i + 1]].tobytes()
+    results = {'raw_scans': raw_scans, 'aligned_pointclouds': aligned, 'motion_data': [], 'trajectory': None, 'environment': None}
+    merged = sim.merge_results(results)
+    assert merged['merged_aligned'].tobytes() == g['aligned'].tobytes()
+    rec, _ = sim.quantize_lvx(results)
+    assert np.array_equal(rec, orc.C.quantize_lvx_type2(g['raw'])[0])
+    d = sim.save_results(results, str(tmp_path / "out"))
+    for f in ["merged_aligned.pcd", "merged_raw_overlapped.pcd", "lidar_data.lvx", "merged_aligned.las_ints.npz",
+              "aligned_scans_pcd/aligned_frame_0000.pcd", "raw_scans_pcd/frame_0000.pcd"]:
+        assert os.path.exists(os.path.join(d, f)), f
+    first = open(os.path.join(d, "aligned_scans_pcd/aligned_frame_0000.pcd")).read().splitlines()
+    p0 = g['aligned'][0]
+    assert first[11] == f"{p0[0]:.6f} {p0[1]:.6f} {p0[2]:.6f} {p0[3]:.6f}"
+
+
+def test_lvx_file_bytes_vs_reference(golden):
+    from livox_motion_compensation_sim_b200 import LiDARMotionSimulator
+    from livox_motion_compensation_sim_b200.lvx import build_lvx_v11_file
+    g = golden("lvx_file.npz")
+    off = g['frame_off']
+    sim = LiDARMotionSimulator()
+    results = {'raw_scans': [{'frame_id': i, 'timestamp': float(g['timestamps'][i]), 'points_local': g['raw'][off[i]:off[i + 1]]}
+                             for i in range(len(off) - 1)]}
+    rec, off2 = sim.quantize_lvx(results)
+    data = build_lvx_v11_file(rec, off2, g['timestamps'], np.arange(len(off) - 1))
+    assert np.array_equal(data, g['file_bytes'])
+
+
+def test_motion_compensator_list_api(golden):
+    from livox_motion_compensation_sim_b200 import MotionCompensator, LiDARPoint, IMUData
+    g = golden("modeb.npz")
+    off = g['frame_off']
+    imu = [IMUData(int(t), float(a), float(b), float(c), 0.0, 0.0, 0.0) for t, (a, b, c) in zip(g['imu_ts'], g['imu_gyro'])]
+    f = 1
+    sl = slice(off[f], off[f + 1])
+    pts = [LiDARPoint(float(p[0]), float(p[1]), float(p[2]), int(p[3]), int(t), i % 16, int(tg))
+           for i, (p, t, tg) in enumerate(zip(g['pts'][sl], g['ts'][sl], g['tag'][sl]))]
+    mc = MotionCompensator({'enable_motion_compensation': True})
+    out = mc.compensate_point_cloud(pts, imu, int(g['frame_start'][f]), 100_000_000)
+    got = np.array([[p.x, p.y, p.z] for p in out])
+    assert np.abs(got - g['compensated'][sl, :3]).max() <= 1e-11
+    assert [p.intensity for p in out] == [p.intensity for p in pts] and [p.tag for p in out] == [p.tag for p in pts]
+    assert MotionCompensator({'enable_motion_compensation': False}).compensate_point_cloud(pts, imu, 0, 1) is pts
+    assert mc.compensate_point_cloud(pts, [], 0, 1) is pts
+
+
+# ------------------------------------------------------------------------------------------
+# full-size stream: size-independent properties + spot checks against the oracle
+# ------------------------------------------------------------------------------------------
+def test_full_size_1h_stream_properties():
+    """BASELINE configs[3]: 36 000 frames x 10 000 pts = 3.6e8 points on one GPU, the north_star
+    kernel (Mode C + LVX + LAS).  Checked through (i) the oracle on 48 sampled frames, bit-exact
+    for the integer buffers, (ii) checksum-of-shards == checksum-of-whole, (iii) hold-next run ==
+    Mode A run (checksum)."""
+    F, P = 36_000, 10_000
+    st = synth.make_stream(F, P, 4242, device=DEV, dtype=torch.float32)
+    off_d, fs_d = dev(st.frame_off), dev(st.frame_start)
+    sts_d, seg_d = dev(st.sample_ts), dev(st.seg)
+    spec = ops.ExportSpec(lvx=True, las=True, las_scale=(0.001,) * 3)
+    out, b = ops.deskew_slerp(st.pts, st.ts_off, off_d, fs_d, sts_d, seg_d, export=spec)
+    torch.cuda.synchronize()
+    assert b.flags() == 0
+    rng = np.random.default_rng(0)
+    frames = np.concatenate([[0, 1, F - 1], rng.integers(0, F, 45)])
+    tot_mism = 0
+    for f in frames:
+        sl = slice(int(st.frame_off[f]), int(st.frame_off[f + 1]))
+        p64 = st.pts[sl].cpu().numpy().astype(np.float64)
+        ts64 = st.frame_start[f] + st.ts_off[sl].cpu().numpy().astype(np.int64)
+        want = orc.C.deskew_slerp_f64(p64, ts64, np.array([0, P], np.int64), st.sample_ts, st.seg)
+        got = out[sl].cpu().numpy()
+        assert np.abs(got.astype(np.float64) - want).max() <= TOL_M
+        assert np.array_equal(b.lvx14[sl].cpu().numpy(), orc.C.quantize_lvx_type2(p64)[0])
+        X, Y, Z, I, _ = orc.C.quantize_las(want, [0.001] * 3, [0.0] * 3, 0)
+        tot_mism += int((b.las_x[sl].cpu().numpy() != X).sum() + (b.las_y[sl].cpu().numpy() != Y).sum() + (b.las_z[sl].cpu().numpy() != Z).sum())
+        assert np.array_equal(b.las_intensity[sl].cpu().numpy().view(np.uint16), I)
+    print(f"1 h stream: LAS int mismatches on {len(frames)} sampled frames: {tot_mism} of {3 * P * len(frames)}")
+    assert tot_mism <= 2
+
+    def checksum(t):
+        return int(t.reshape(-1).view(torch.int32).sum(dtype=torch.int64).item())
+    whole = (checksum(out), checksum(b.lvx14), checksum(b.las_x))
+    # 8 frame-range shards into fresh buffers
+    out2 = torch.empty_like(out)
+    into = ops.ExportBuffers(lvx14=torch.empty_like(b.lvx14), las_x=torch.empty_like(b.las_x), las_y=torch.empty_like(b.las_y),
+                             las_z=torch.empty_like(b.las_z), las_intensity=torch.empty_like(b.las_intensity))
+    pcuts = st.frame_off[FR.partition_frames(st.frame_off, 8)]
+    for r in range(8):
+        ops.deskew_slerp(st.pts, st.ts_off, off_d, fs_d, sts_d, seg_d, out=out2,
+                         export=ops.ExportSpec(lvx=True, las=True, las_scale=(0.001,) * 3, into=into), p_range=(pcuts[r], pcuts[r + 1]))
+    assert (checksum(out2), checksum(into.lvx14), checksum(into.las_x)) == whole
+    del out2, into
+    # Mode A == Mode C(hold-next) at full size
+    hold = orc.C.pose_lookup_hold_next(st.sample_ts.astype(np.float64), st.frame_start.astype(np.float64))
+    a, _ = ops.align_rigid(st.pts, off_d, dev(np.ascontiguousarray(st.seg[hold][:, :12])))
+    c, _ = ops.deskew_slerp(st.pts, None, off_d, None, sts_d, seg_d, hold_idx=dev(hold))
+    assert checksum(a) == checksum(c)
+    assert torch.equal(a[:1_000_000], c[:1_000_000])

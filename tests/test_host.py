@@ -1,0 +1,184 @@
+"""CPU-only tests: host logic of the product package, the C-ABI surface (load + exported symbols,
+no compute calls), the LVX container layout against the reference's file bytes, and the
+frame-sharded merge over gloo with world_size 2."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from livox_motion_compensation_sim_b200 import _build, _capi, frames as FR
+from livox_motion_compensation_sim_b200.lvx import build_lvx_v11_file, frame_layout, FILE_HEADER
+from oracle import lmc_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    return _build.build_library()
+
+
+def test_capi_exports_every_declared_symbol(built_lib):
+    header = open(os.path.join(ROOT, "include", "lmc_b200.h")).read()
+    declared = set(re.findall(r"\b(lmc_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(built_lib)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/lmc_b200.h but not exported"
+    assert declared == set(_capi.EXPORTED_SYMBOLS)
+    assert _capi.lib().lmc_version() == 100
+
+
+def test_capi_struct_layout_matches_header():
+    # struct lmc_export: pointer/int interleaving -> check ctypes offsets against the C layout rules
+    E = _capi.LmcExport
+    assert E.lvx14.offset == 0 and E.lvx_mode.offset == 8 and E.tag.offset == 16
+    assert E.las_x.offset == 24 and E.las_intensity.offset == 48 and E.las_intensity_mode.offset == 56
+    assert E.las_scale.offset == 64 and E.las_offset.offset == 88 and E.status.offset == 112
+    assert ctypes.sizeof(E) == 120
+
+
+def test_capi_fails_loudly_without_gpu(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    L = _capi.lib()
+    rc = L.lmc_device_query(None, None, None)
+    assert rc == _capi.ERR_CUDA
+    with pytest.raises(_capi.LmcError):
+        _capi.check(rc)
+    from livox_motion_compensation_sim_b200 import ops
+    with pytest.raises(TypeError):                      # CPU tensors are refused: no CPU fallback
+        ops.align_rigid(torch.zeros((4, 4), dtype=torch.float64), torch.tensor([0, 4]), torch.zeros((1, 12), dtype=torch.float64))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "livox_motion_compensation_sim_b200")
+    for dp, _, fn in os.walk(pkg):
+        for f in fn:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "lmc_oracle" not in src or f.endswith((".cu", ".cuh")), f
+
+
+def test_config_contract():
+    import torch  # noqa: F401
+    from livox_motion_compensation_sim_b200.simulator import LiDARMotionSimulator
+    sim = LiDARMotionSimulator({'duration': 12.0, 'some_unknown_key': 1})
+    assert sim.config['duration'] == 12.0 and sim.config['some_unknown_key'] == 1
+    ref_defaults = {'duration': 60.0, 'lidar_fps': 10, 'imu_rate': 100, 'gps_rate': 5, 'random_seed': 42, 'max_speed': 15.0,
+                    'max_angular_vel': 0.5, 'trajectory_type': 'figure_eight', 'fov_horizontal': 70.0, 'fov_vertical': 77.2,
+                    'range_max': 90.0, 'range_min': 0.05, 'points_per_frame': 96000, 'angular_resolution': 0.28,
+                    'gps_noise_std': 0.03, 'imu_accel_noise': 0.1, 'imu_gyro_noise': 0.01, 'lidar_range_noise': 0.02,
+                    'environment_complexity': 'medium', 'ground_height': 0.0, 'obstacle_density': 0.1}
+    d = LiDARMotionSimulator().config
+    for k, v in ref_defaults.items():
+        assert d[k] == v
+    for bad, msg in [({'duration': 'x'}, "Configuration 'duration' must be numeric"), ({'lidar_fps': 0}, "LiDAR frame rate must be positive"),
+                     ({'duration': -1}, "Simulation duration must be positive"), ({'max_speed': -1}, "Maximum speed cannot be negative"),
+                     ({'range_max': 1, 'range_min': 2}, "Maximum range must be greater than minimum range")]:
+        with pytest.raises(ValueError, match=re.escape(msg)):
+            LiDARMotionSimulator(bad)
+    with pytest.raises(NotImplementedError):
+        sim.run_simulation()
+
+
+def test_frame_times_and_flatten():
+    t = FR.lidar_frame_times(60.0, 10)
+    assert len(t) == 600 and t[-1] == 60.0 and abs(t[1] - 60.0 / 599) < 1e-15        # linspace WITH endpoint (LMC:792)
+    frames = [np.zeros((0, 4)), np.ones((3, 4)), np.array([]).reshape(0, 4), 2 * np.ones((1, 4))]
+    flat, off = FR.flatten_frames(frames)
+    assert off.tolist() == [0, 0, 3, 3, 4] and flat.shape == (4, 4)
+    assert np.array_equal(flat, np.vstack(frames))
+    back = FR.split_frames(flat, off)
+    assert [len(b) for b in back] == [0, 3, 0, 1]
+
+
+def test_pose_table_is_scipy_exact(golden):
+    g = golden("lmc_edge.npz")
+    assert np.array_equal(FR.pose_table(g['pose_position'], g['pose_euler']), orc.pose_table_np(g['pose_position'], g['pose_euler']))
+    rng = np.random.default_rng(0)
+    from scipy.spatial.transform import Rotation
+    q = Rotation.from_euler('xyz', rng.normal(0, 1, (50, 3))).as_quat()
+    pos = rng.normal(0, 10, (50, 3))
+    assert np.array_equal(FR.slerp_segment_table(q, pos), orc.slerp_segment_table(q, pos))
+
+
+def test_partition_frames_balances_points():
+    rng = np.random.default_rng(1)
+    counts = rng.integers(0, 3000, 1000); counts[::7] = 0
+    off = np.concatenate([[0], np.cumsum(counts)])
+    for W in (1, 2, 3, 8):
+        cuts = FR.partition_frames(off, W)
+        assert cuts[0] == 0 and cuts[-1] == 1000 and np.all(np.diff(cuts) >= 0) and len(cuts) == W + 1
+        per = np.diff(off[cuts])
+        assert per.sum() == off[-1] and per.max() - per.min() <= 2 * 3000
+    off = np.arange(36001) * 10000
+    assert np.array_equal(np.diff(FR.partition_frames(off, 8)), np.full(8, 4500))
+
+
+def test_lvx_container_bytes_equal_reference_file(golden):
+    g = golden("lvx_file.npz")
+    rec, flags = orc.C.quantize_lvx_type2(g['raw'])          # records from the (pinned) oracle: no GPU needed here
+    assert flags == 0
+    data = build_lvx_v11_file(rec, g['frame_off'], g['timestamps'], np.arange(len(g['frame_off']) - 1))
+    assert np.array_equal(data, g['file_bytes'])
+    pk, pos = frame_layout(g['frame_off'])
+    assert pos[0] == FILE_HEADER == 88 and pk.tolist() == [0, 1, 1, 1, 2, 3, 0, 1]
+    with pytest.raises(ValueError):
+        build_lvx_v11_file(np.zeros((0, 14), np.uint8), np.array([0]), np.array([]), np.array([]))
+
+
+GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["LMC_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from livox_motion_compensation_sim_b200 import frames as FR
+from livox_motion_compensation_sim_b200.sharding import shard_ranges, all_gather_merged
+from oracle import lmc_oracle as orc
+dist.init_process_group("gloo")
+rank, W = dist.get_rank(), dist.get_world_size()
+for case in ("ragged", "equal"):
+    rng = np.random.default_rng(7)
+    F = 64
+    counts = rng.integers(0, 500, F) if case == "ragged" else np.full(F, 128)
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    N = int(off[-1])
+    pts = np.column_stack([rng.uniform(-90, 90, (N, 3)), rng.uniform(0, 1, N)])
+    pose = orc.pose_table_np(rng.uniform(-30, 30, (F, 3)), rng.normal(0, 0.5, (F, 3)))
+    whole = orc.C.align_rigid_f64(pts, off, pose)
+    rec_whole, _ = orc.C.quantize_lvx_type2(pts)
+    fcuts, pcuts = shard_ranges(off, W)
+    a, b = int(fcuts[rank]), int(fcuts[rank + 1])
+    # this rank computes only its frame range (the CPU oracle stands in for the kernel: host-logic test)
+    merged = torch.zeros((N, 4), dtype=torch.float64)
+    lvx = torch.zeros((N, 14), dtype=torch.uint8)
+    u16 = torch.zeros(N, dtype=torch.uint16)
+    sl = slice(int(pcuts[rank]), int(pcuts[rank + 1]))
+    loc_off = off[a:b + 1] - off[a]
+    merged[sl] = torch.from_numpy(orc.C.align_rigid_f64(pts[sl], loc_off, pose[a:b]))
+    lvx[sl] = torch.from_numpy(rec_whole[sl])
+    u16[sl] = torch.from_numpy((np.arange(N)[sl] % 65536).astype(np.uint16))
+    all_gather_merged([merged, lvx, u16, None], pcuts)
+    assert merged.numpy().tobytes() == whole.tobytes(), case          # == np.vstack order, no permutation
+    assert np.array_equal(lvx.numpy(), rec_whole), case
+    assert np.array_equal(u16.numpy(), (np.arange(N) % 65536).astype(np.uint16)), case
+dist.destroy_process_group()
+print("OK", rank)
+'''
+
+
+def test_frame_sharded_merge_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    env = dict(os.environ, LMC_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("OK") == 2
