@@ -366,7 +366,7 @@ def main_b200(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"M-1H synthetic 1 h Mid-70 stream: {F} frames x {P} pts = {N} points per GPU, 200 Hz pose samples ({len(st.sample_ts)}), seed {SEED}",
                        "variant": f"{args.variant}: mode={mode} io={'f64' if f64 else 'f32 float4'} ts={ts} lvx={lvx} las={las}, f64 arithmetic",
-                       "bytes_per_point": bpp, "kernel_path": "tma" if C.get_path() == C.PATH_TMA else "direct",
+                       "bytes_per_point": bpp, "kernel_path": {0: "direct", 1: "auto (persistent TMA pipeline at this size)", 2: "tma"}[C.get_path()],
                        "l2": f"inputs {N * (16 + 4) / 1e9:.1f} GB >> 126 MB L2: no flush needed", "parallelism": f"frame-sharded x{world}",
                        "status_flags": flags},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -75,7 +75,8 @@ int         lmc_version(void);
 const char* lmc_last_error(void);
 /* sm count / compute capability of the current device; fails unless it is sm_100 */
 int         lmc_device_query(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
-/* 0 = direct (256-bit LDG/STG) kernels, 1 = TMA bulk-copy pipelined kernels (default where built) */
+/* kernel path: 0 = direct (one tile per CTA, 256-bit LDG/STG), 1 = auto (default: persistent TMA
+ * bulk-copy pipeline on inputs that fill the GPU, direct otherwise), 2 = TMA pipeline always */
 int         lmc_set_path(int32_t path);
 int         lmc_get_path(void);
 
@@ -123,9 +124,9 @@ int lmc_deskew_gyro_f32(const float* pts_n4, const uint32_t* ts_off, const int64
 /*
  * Mode C: per-point pose-interp deskew (north_star; sketched without a body at
  * docs/Master Guide.md:339-367; no reference implementation -> parity unpinned).
- *   k = bracket(sample_ts, ts) ; alpha = (ts - t_k)/(t_{k+1} - t_k)
+ *   k = bracket(sample_ts, ts) ; alpha = (ts - t_k) * inv_dt_k      (inv_dt_k = 1/(t_{k+1} - t_k) from seg)
  *   out = SLERP(R_k, R_{k+1}, alpha) p + lerp(pos_k, pos_{k+1}, alpha)
- * seg: (n_samples, 20) f64 per-sample table [R_k(9) pos_k(3) axis_k(3) theta_k dpos_k(3) pad]
+ * seg: (n_samples, 20) f64 per-sample table [R_k(9) pos_k(3) axis_k(3) theta_k dpos_k(3) inv_dt_k]
  *      (built by the host wrapper, see livox_motion_compensation_sim_b200/frames.py).
  * hold_idx (optional int32[n_frames]): every point of frame f takes sample hold_idx[f], alpha = 0
  *      -> Mode A expressed in Mode C (bit-identical to lmc_align_rigid_* for frames of >= 2 points).

@@ -11,7 +11,7 @@ OK, ERR_INVALID, ERR_ALIGN, ERR_CUDA = 0, -1, -2, -3
 FLAG_NAN, FLAG_OVERFLOW = 1, 2
 LVX_TYPE2_OF_INPUT, LVX2_OF_OUTPUT = 0, 1
 LAS_INTENSITY_UNIT, LAS_INTENSITY_RAW = 0, 1
-PATH_DIRECT, PATH_TMA = 0, 1
+PATH_DIRECT, PATH_AUTO, PATH_TMA = 0, 1, 2
 
 vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
 

@@ -8,14 +8,14 @@
 
 namespace lmc {
 cudaError_t launch_direct(bool f64, int mode, const Params& P, cudaStream_t st);
-cudaError_t launch_tma(bool f64, int mode, const Params& P, cudaStream_t st, bool* handled);
+cudaError_t launch_tma(bool f64, int mode, const Params& P, cudaStream_t st, bool force, bool* handled);
 cudaError_t launch_pose_lookup(const double*, int64_t, const double*, const double*, int32_t, double*, int32_t*, cudaStream_t);
 }
 
 namespace {
 
 thread_local char g_err[512] = "";
-int g_path = 1;                                    // 1 = TMA pipeline where available, 0 = direct
+int g_path = 1;                                    // 0 = direct, 1 = auto (TMA pipeline on large inputs), 2 = TMA always
 
 int fail(int code, const char* fmt, ...) {
     va_list ap; va_start(ap, fmt);
@@ -46,7 +46,7 @@ int check_device() {
 int fill_export(lmc::Params& P, const lmc_export* ex) {
     P.lvx14 = nullptr; P.tag = nullptr; P.las_x = P.las_y = P.las_z = nullptr; P.las_int = nullptr; P.status = nullptr;
     P.lvx_mode = 0; P.las_int_mode = 0;
-    for (int c = 0; c < 3; ++c) { P.las_scale[c] = 0.01; P.las_off[c] = 0.0; }
+    for (int c = 0; c < 3; ++c) { P.las_scale[c] = 0.01; P.las_rcp[c] = 1.0 / 0.01; P.las_off[c] = 0.0; }
     if (!ex) return LMC_OK;
     if (ex->lvx_mode != LMC_LVX_TYPE2_OF_INPUT && ex->lvx_mode != LMC_LVX2_OF_OUTPUT) return fail(LMC_ERR_INVALID, "bad lvx_mode %d", ex->lvx_mode);
     if (ex->las_intensity_mode != LMC_LAS_INTENSITY_UNIT && ex->las_intensity_mode != LMC_LAS_INTENSITY_RAW)
@@ -60,7 +60,7 @@ int fill_export(lmc::Params& P, const lmc_export* ex) {
     P.lvx14 = ex->lvx14; P.lvx_mode = ex->lvx_mode; P.tag = ex->tag;
     P.las_x = ex->las_x; P.las_y = ex->las_y; P.las_z = ex->las_z; P.las_int = ex->las_intensity;
     P.las_int_mode = ex->las_intensity_mode; P.status = ex->status;
-    for (int c = 0; c < 3; ++c) { P.las_scale[c] = ex->las_scale[c]; P.las_off[c] = ex->las_offset[c]; }
+    for (int c = 0; c < 3; ++c) { P.las_scale[c] = ex->las_scale[c]; P.las_rcp[c] = 1.0 / ex->las_scale[c]; P.las_off[c] = ex->las_offset[c]; }
     return LMC_OK;
 }
 
@@ -82,8 +82,8 @@ int run(bool f64, int mode, lmc::Params& P, const lmc_export* ex, void* stream) 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
     bool handled = false;
-    if (g_path == 1) {
-        e = lmc::launch_tma(f64, mode, P, st, &handled);
+    if (g_path >= 1) {
+        e = lmc::launch_tma(f64, mode, P, st, g_path == 2, &handled);
         if (handled) return e == cudaSuccess ? LMC_OK : cuda_fail(e, "launch (tma path)");
     }
     e = lmc::launch_direct(f64, mode, P, st);
@@ -115,7 +115,7 @@ int lmc_device_query(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
 }
 
 int lmc_set_path(int32_t path) {
-    if (path != 0 && path != 1) return fail(LMC_ERR_INVALID, "path must be 0 (direct) or 1 (tma)");
+    if (path < 0 || path > 2) return fail(LMC_ERR_INVALID, "path must be 0 (direct), 1 (auto) or 2 (tma)");
     g_path = path;
     return LMC_OK;
 }

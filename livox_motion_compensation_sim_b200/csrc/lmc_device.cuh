@@ -13,12 +13,8 @@
 
 namespace lmc {
 
-constexpr int kThreads        = 256;                       // 8 warps per CTA
-constexpr int kPairsPerThread = 2;                         // each thread owns 2 pairs of consecutive points
-constexpr int kTilePairs      = kThreads * kPairsPerThread;
-constexpr int kTile           = 2 * kTilePairs;            // 1024 points per tile
-constexpr int kMaxBnd         = 62;                        // frame boundaries cached per tile
-constexpr int kSegStride      = 20;                        // doubles per Mode C sample row
+constexpr int kMaxBnd    = 30;        // frame boundaries cached per tile (more -> per-point global search)
+constexpr int kSegStride = 20;        // doubles per Mode C sample row
 
 enum Mode : int { kRigid = 0, kGyro = 1, kSlerp = 2, kQuantOnly = 3 };
 
@@ -44,11 +40,20 @@ struct Params {
     int32_t*        las_z;
     uint16_t*       las_int;
     uint32_t*       status;
-    double          las_scale[3], las_off[3];
+    double          las_scale[3], las_rcp[3], las_off[3];      // las_rcp = 1/scale (host, correctly rounded)
     int32_t         lvx_mode, las_int_mode;
 };
 
 struct Pt { double x, y, z, w; };
+
+// frames intersecting one tile of points, staged in shared memory
+struct TileMeta {
+    int64_t edge[kMaxBnd + 2];    // frame_off[f_lo .. f_lo + nb + 1]
+    int32_t f_lo;                 // frame of the tile's first point
+    int32_t nb;                   // frame boundaries inside the tile
+    int32_t overflow;             // more than kMaxBnd boundaries: per-point global search
+    int32_t pad;
+};
 
 // ------------------------------------------------------------------------------------------
 // 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256).  Points are streamed exactly once, so
@@ -101,14 +106,45 @@ __device__ __forceinline__ void rigid_apply(const double (&M)[12], bool single, 
     o.w = p.w;
 }
 
+// sin(x) and 1 - cos(x).  Deskew angles are tiny (gyro * 0.1 s, or one 5 ms pose segment), so for
+// |x| <= 0.5 a Taylor polynomial without range reduction is exact to < 1 ulp (next terms: 2e-20,
+// 6e-22 relative); larger arguments take the library path.
+__device__ __forceinline__ void sin_vercos(double x, double& s, double& v) {
+    if (fabs(x) <= 0.5) {
+        const double u = x * x;
+        double ps = -7.6471637318198164759e-13;                  // -1/15!
+        ps = fma(ps, u, 1.6059043836821614599e-10);              //  1/13!
+        ps = fma(ps, u, -2.5052108385441718775e-08);             // -1/11!
+        ps = fma(ps, u, 2.7557319223985890653e-06);              //  1/9!
+        ps = fma(ps, u, -1.9841269841269841270e-04);             // -1/7!
+        ps = fma(ps, u, 8.3333333333333333333e-03);              //  1/5!
+        ps = fma(ps, u, -1.6666666666666666667e-01);             // -1/3!
+        s = fma(x * u, ps, x);
+        double pc = -4.7794773323873852974e-14;                  // -1/16!
+        pc = fma(pc, u, 1.1470745597729724714e-11);              //  1/14!
+        pc = fma(pc, u, -2.0876756987868098979e-09);             // -1/12!
+        pc = fma(pc, u, 2.7557319223985890653e-07);              //  1/10!
+        pc = fma(pc, u, -2.4801587301587301587e-05);             // -1/8!
+        pc = fma(pc, u, 1.3888888888888888889e-03);              //  1/6!
+        pc = fma(pc, u, -4.1666666666666666667e-02);             // -1/4!
+        pc = fma(pc, u, 0.5);
+        v = u * pc;
+    } else {
+        double c;
+        sincos(x, &s, &c);
+        v = 1.0 - c;
+    }
+}
+
 // (a8) CS:1518-1536  Rx(-rx) @ Ry(-ry) @ Rz(-rz), both 3x3 products in dgemm order, then
 // (CS:1465) M @ p in gemv order.  The structural zeros/ones of the factors are kept as literal
 // operands so signed zeros and non-finite inputs behave exactly like the reference's dgemm.
 __device__ __forceinline__ void gyro_rotate(double ax, double ay, double az, const Pt& p, Pt& o) {
-    double sa, ca, sb, cb, sc, cc;
-    sincos(-ax, &sa, &ca);
-    sincos(-ay, &sb, &cb);
-    sincos(-az, &sc, &cc);
+    double sa, va, sb, vb, sc, vc;
+    sin_vercos(-ax, sa, va);
+    sin_vercos(-ay, sb, vb);
+    sin_vercos(-az, sc, vc);
+    const double ca = 1.0 - va, cb = 1.0 - vb, cc = 1.0 - vc;
     const double Rx[9] = { 1.0, 0.0, 0.0,   0.0, ca, -sa,   0.0, sa, ca };
     const double Ry[9] = { cb, 0.0, sb,   0.0, 1.0, 0.0,   -sb, 0.0, cb };
     const double Rz[9] = { cc, -sc, 0.0,   sc, cc, 0.0,   0.0, 0.0, 1.0 };
@@ -132,9 +168,8 @@ __device__ __forceinline__ void gyro_rotate(double ax, double ay, double az, con
 // Mode C per-point evaluation (definition: oracle/lmc_oracle.c::orc_deskew_slerp_f64)
 __device__ __forceinline__ void slerp_apply(const double (&s)[kSegStride], double alpha, const Pt& p, Pt& o) {
     const double th = __dmul_rn(alpha, s[15]);
-    double sn, cs;
-    sincos(th, &sn, &cs);
-    const double v = __dsub_rn(1.0, cs);
+    double sn, v;
+    sin_vercos(th, sn, v);
     const double nx = s[12], ny = s[13], nz = s[14];
     const double c1x = __fma_rn(ny, p.z, -__dmul_rn(nz, p.y));
     const double c1y = __fma_rn(nz, p.x, -__dmul_rn(nx, p.z));
@@ -152,56 +187,62 @@ __device__ __forceinline__ void slerp_apply(const double (&s)[kSegStride], doubl
 }
 
 // ------------------------------------------------------------------------------------------
-// Quantisers
+// Quantisers.  cvt.rzi.s32.f64 saturates, which IS np.clip to the int32 range followed by
+// truncation, so the clip costs nothing; NaN (where the reference raises) sets a status bit.
 // ------------------------------------------------------------------------------------------
 // (a4) LMC:257-259   int(np.clip(v * 1000, -2147483648, 2147483647))
 __device__ __forceinline__ int32_t q_mm_clip(double v, uint32_t& fl) {
-    double m = __dmul_rn(v, 1000.0);
-    if (m != m) { fl |= LMC_FLAG_NAN; return 0; }
-    m = fmin(fmax(m, -2147483648.0), 2147483647.0);
-    return __double2int_rz(m);
+    const double m = __dmul_rn(v, 1000.0);
+    if (m != m) fl |= LMC_FLAG_NAN;
+    return __double2int_rz(m);                      // NaN -> 0, +-big -> INT_MAX / INT_MIN
 }
 // (a4) LMC:266       int(np.clip(i * 255, 0, 255))
 __device__ __forceinline__ uint32_t q_refl(double w, uint32_t& fl) {
-    double m = __dmul_rn(w, 255.0);
-    if (m != m) { fl |= LMC_FLAG_NAN; return 0; }
-    m = fmin(fmax(m, 0.0), 255.0);
-    return (uint32_t)__double2int_rz(m);
+    const double m = __dmul_rn(w, 255.0);
+    if (m != m) fl |= LMC_FLAG_NAN;
+    return min(__double2uint_rz(m), 255u);          // negative -> 0 (saturating), NaN -> 0
 }
 // (a9) CS:368-370    int(v * 1000)  -- no clip; '<iii' packing raises outside int32
 __device__ __forceinline__ int32_t q_mm_noclip(double v, uint32_t& fl) {
-    double m = __dmul_rn(v, 1000.0);
-    if (m != m) { fl |= LMC_FLAG_NAN; return 0; }
+    const double m = __dmul_rn(v, 1000.0);
+    if (m != m) fl |= LMC_FLAG_NAN;
     if (m >= 2147483648.0 || m <= -2147483649.0) fl |= LMC_FLAG_OVERFLOW;
-    return __double2int_rz(m);                      // saturates
+    return __double2int_rz(m);
 }
 // (a9) CS:373        struct.pack('<B', point.intensity)
 __device__ __forceinline__ uint32_t q_u8_copy(double w, uint32_t& fl) {
-    if (w != w) { fl |= LMC_FLAG_NAN; return 0; }
-    if (w < 0.0 || w > 255.0) { fl |= LMC_FLAG_OVERFLOW; return w < 0.0 ? 0u : 255u; }
-    return (uint32_t)__double2int_rz(w);
+    if (w != w) fl |= LMC_FLAG_NAN;
+    if (w < 0.0 || w > 255.0) fl |= LMC_FLAG_OVERFLOW;
+    return min(__double2uint_rz(w), 255u);
 }
-// (a5)/(a10) laspy: np.round((v - offset) / scale) -> int32   (parity unpinned, see header)
-__device__ __forceinline__ int32_t q_las(double v, double scale, double off, uint32_t& fl) {
-    double d = __ddiv_rn(__dsub_rn(v, off), scale);
-    if (d != d) { fl |= LMC_FLAG_NAN; return 0; }
-    if (d >= 2147483647.5 || d < -2147483648.5) fl |= LMC_FLAG_OVERFLOW;
-    return __double2int_rn(d);                      // round-half-even, saturates
+// (a5)/(a10) laspy: np.round((v - offset) / scale) -> int32   (parity unpinned, see header).
+// The quotient is formed with the host-rounded reciprocal and two Markstein corrections
+// (q += fma(-s, q, a) * rcp), which yields the correctly rounded a / s -- identical to the IEEE
+// division the restatement uses, at 5 FP64 ops instead of a ~25-instruction division sequence.
+__device__ __forceinline__ int32_t q_las(double v, double scale, double rcp, double off, uint32_t& fl) {
+    const double a = __dsub_rn(v, off);
+    double q = __dmul_rn(a, rcp);
+    if (fabs(q) < 1.0e300) {                        // finite, far from overflow: refine
+        q = __fma_rn(__fma_rn(-scale, q, a), rcp, q);
+        q = __fma_rn(__fma_rn(-scale, q, a), rcp, q);
+    }
+    if (q != q) fl |= LMC_FLAG_NAN;
+    if (q >= 2147483647.5 || q < -2147483648.5) fl |= LMC_FLAG_OVERFLOW;
+    return __double2int_rn(q);                      // round-half-even, saturates
 }
 // LMC:961 (w*65535).astype(uint16) | CS:1686 w.astype(uint16): truncate, wrap modulo 2^16
 __device__ __forceinline__ uint32_t q_las_intensity(double w, int mode, uint32_t& fl) {
-    double m = mode == LMC_LAS_INTENSITY_UNIT ? __dmul_rn(w, 65535.0) : w;
-    if (m != m) { fl |= LMC_FLAG_NAN; return 0; }
+    const double m = mode == LMC_LAS_INTENSITY_UNIT ? __dmul_rn(w, 65535.0) : w;
+    if (m != m) fl |= LMC_FLAG_NAN;
     if (m >= 9.2e18 || m <= -9.2e18) { fl |= LMC_FLAG_OVERFLOW; return 0; }
     return (uint32_t)(__double2ll_rz(m) & 0xffff);
 }
 
 // ------------------------------------------------------------------------------------------
-// Warp-cooperative searches over sorted int64 tables (frame_off, imu_ts, sample_ts).
-// All 32 lanes must call these together.
+// Searches over sorted int64 tables (frame_off, imu_ts, sample_ts)
 // ------------------------------------------------------------------------------------------
-// count of elements <= key  (== np.searchsorted(a, key, side='right')); key is warp-uniform.
-// 32-ary search: each round probes 32 positions with one coalesced-ish load + ballot.
+// Warp-cooperative count of elements <= key (== np.searchsorted(a, key, side='right')); key is
+// warp-uniform and all 32 lanes must call.  32-ary search: one probe load + ballot per round.
 __device__ __forceinline__ int64_t warp_count_le(const int64_t* __restrict__ a, int64_t n, int64_t key, int lane) {
     int64_t lo = 0, hi = n;                       // answer in [lo, hi]
     while (hi - lo > 32) {
@@ -219,24 +260,267 @@ __device__ __forceinline__ int64_t warp_count_le(const int64_t* __restrict__ a, 
     return lo + __popc(__ballot_sync(0xffffffffu, le));
 }
 
-__device__ __forceinline__ int64_t warp_min_i64(int64_t v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { int64_t t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
-    return v;
-}
-__device__ __forceinline__ int64_t warp_max_i64(int64_t v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { int64_t t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
-    return v;
-}
-
-// per-lane binary search restricted to [lo, hi]: count of a[i] <= key
+// per-thread binary search restricted to [lo, hi]: count of a[i] <= key
 __device__ __forceinline__ int64_t count_le_in(const int64_t* __restrict__ a, int64_t lo, int64_t hi, int64_t key) {
     while (lo < hi) {
         const int64_t mid = lo + ((hi - lo) >> 1);
         if (__ldg(a + mid) <= key) lo = mid + 1; else hi = mid;
     }
     return lo;
+}
+
+// Sample-table bracket for one timestamp: k = (count of ts <= t) - 1 in [-1, S-1], i.e. the
+// `before` sample of CS:1482-1494.  Guess-and-verify: a table sampled at a (nearly) constant rate
+// is hit directly by k ~ (t - t0) * rate, the verification loads (ts[k], ts[k+1]) are the ones the
+// interpolation weight needs anyway, and any table that defeats the guess falls back to a binary
+// search -- the result is always the exact bracket.
+struct Bracket { int64_t k, tb, ta; };            // tb = ts[k], ta = ts[k+1] where they exist
+__device__ __forceinline__ Bracket bracket_of(const int64_t* __restrict__ ts, int64_t S, int64_t t, int64_t t0, double rate) {
+    Bracket b;
+    int64_t k = __double2ll_rz(__dmul_rn((double)(t - t0), rate));
+    k = k < 0 ? 0 : (k > S - 1 ? S - 1 : k);
+    int64_t tk = __ldg(ts + k);
+    if (tk <= t) {                                 // walk right to the last sample <= t
+        int steps = 0;
+        b.ta = 0;
+        while (k + 1 < S) {
+            const int64_t tn = __ldg(ts + k + 1);
+            if (tn > t) { b.ta = tn; break; }
+            k += 1; tk = tn;
+            if (++steps == 4) {                    // the guess was far off: finish with a binary search
+                k = count_le_in(ts, k + 1, S, t) - 1;
+                tk = __ldg(ts + k);
+                if (k + 1 < S) b.ta = __ldg(ts + k + 1);
+                break;
+            }
+        }
+        b.k = k; b.tb = tk;
+    } else {                                       // walk left to the first sample <= t
+        int steps = 0;
+        b.ta = tk;
+        while (true) {
+            if (k == 0) { k = -1; tk = 0; break; }
+            k -= 1;
+            const int64_t tp = __ldg(ts + k);
+            if (tp <= t) { tk = tp; break; }
+            b.ta = tp;
+            if (++steps == 4) {
+                k = count_le_in(ts, 0, k, t) - 1;
+                tk = k >= 0 ? __ldg(ts + k) : 0;
+                b.ta = __ldg(ts + k + 1);
+                break;
+            }
+        }
+        b.k = k; b.tb = tk;
+    }
+    return b;
+}
+
+// frame of point p (global index) + whether that frame holds exactly one point
+__device__ __forceinline__ int32_t frame_of(const Params& P, const TileMeta& tm, int64_t p, bool& single) {
+    if (!tm.overflow) {
+        int lo = 0, hi = tm.nb;                     // count of edge[1..nb] <= p
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (tm.edge[1 + mid] <= p) lo = mid + 1; else hi = mid; }
+        single = (tm.edge[lo + 1] - tm.edge[lo]) == 1;
+        return tm.f_lo + lo;
+    }
+    const int64_t f = count_le_in(P.frame_off, 0, (int64_t)P.n_frames + 1, p) - 1;
+    single = (__ldg(P.frame_off + f + 1) - __ldg(P.frame_off + f)) == 1;
+    return (int32_t)f;
+}
+
+// One warp fills TileMeta for points [first, last].  hint >= 0 is a frame known to start at or
+// before `first` (the previous tile's last frame when a CTA walks consecutive tiles): the frame of
+// `first` is then usually found in the next 32 offsets with a single load.
+__device__ __forceinline__ void tile_meta(const Params& P, int64_t first, int64_t last, TileMeta& tm, int lane, int64_t hint = -1) {
+    const int64_t F = P.n_frames;
+    int64_t f_lo = -1;
+    if (hint >= 0) {
+        const int64_t j = hint + 1 + lane;
+        const int64_t v = j <= F ? __ldg(P.frame_off + j) : INT64_MAX;
+        const int c = __popc(__ballot_sync(0xffffffffu, v <= first));
+        if (c < 32) f_lo = hint + c;
+    }
+    if (f_lo < 0) f_lo = warp_count_le(P.frame_off, F + 1, first, lane) - 1;   // count >= 1 since frame_off[0] = 0
+    int nb = 0; bool done = false; int overflow = 0;
+    if (lane == 0) tm.edge[0] = __ldg(P.frame_off + f_lo);
+    for (int64_t j0 = f_lo + 1; !done; j0 += 32) {
+        const int64_t j = j0 + lane;
+        const int64_t v = j <= F ? __ldg(P.frame_off + j) : INT64_MAX;
+        const unsigned m = __ballot_sync(0xffffffffu, v <= last);       // true-prefix (sorted)
+        const int c = __popc(m);
+        if (lane <= c && nb + lane < kMaxBnd + 1) tm.edge[1 + nb + lane] = v;   // boundaries + closing edge
+        nb += c;
+        done = c < 32;
+        if (nb > kMaxBnd) { overflow = 1; done = true; }
+    }
+    if (lane == 0) { tm.f_lo = (int32_t)f_lo; tm.nb = nb; tm.overflow = overflow; }
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-thread compute context: caches the pose / sample row of the previous point (consecutive
+// points almost always share it) and evaluates one point.
+// ------------------------------------------------------------------------------------------
+template <bool F64, int MODE>
+struct PointCtx {
+    double  tab[MODE == kSlerp ? kSegStride : 12];
+    int64_t key = -1;            // frame (Mode A) or sample index (Mode C) held in tab
+    int64_t t0 = 0;              // Mode B/C: first sample time and mean sample rate for the bracket guess
+    double  rate = 0.0;
+
+    __device__ __forceinline__ void init(const Params& P) {
+        if constexpr (MODE == kGyro || MODE == kSlerp) {
+            if (P.n_samp > 0) {
+                t0 = __ldg(P.samp_ts);
+                const int64_t span = __ldg(P.samp_ts + P.n_samp - 1) - t0;
+                rate = span > 0 ? (double)(P.n_samp - 1) / (double)span : 0.0;
+            }
+        }
+    }
+
+    // f / single: frame of the point and whether it is a one-point frame (frame_of);
+    // tsraw: int64 ns (f64 layout) or uint32 ns offset from the frame start (f32 layout)
+    __device__ __forceinline__ void point(const Params& P, int32_t f, bool single, int64_t tsraw, const Pt& in, Pt& out) {
+        if constexpr (MODE == kQuantOnly) { out = in; return; }
+        if constexpr (MODE == kRigid) {
+            if (f != key) {
+                const double2* pr = reinterpret_cast<const double2*>(P.pose_Rt + 12 * (int64_t)f);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) { const double2 v = __ldg(pr + q); tab[2 * q] = v.x; tab[2 * q + 1] = v.y; }
+                key = f;
+            }
+            rigid_apply(tab, single, in, out);
+        } else if constexpr (MODE == kGyro) {
+            // (a6)/(a7): per-point bracket in imu_ts, gyro lerp, small-angle rotation
+            const int64_t S = P.n_samp;
+            if (S == 0) { out = in; return; }                         // CS:1439-1440: no IMU data -> unchanged
+            const int64_t fs = __ldg(P.frame_start + f);
+            const int64_t t = F64 ? tsraw : tsraw + fs;
+            const Bracket b = bracket_of(P.samp_ts, S, t, t0, rate);
+            double g0, g1, g2;
+            if (b.k < 0 || b.k >= S - 1) {                            // CS:1495-1496: clamp to the existing end sample
+                const double* g = P.samp_tab + 3 * (b.k < 0 ? 0 : S - 1);
+                g0 = __ldg(g); g1 = __ldg(g + 1); g2 = __ldg(g + 2);
+            } else {
+                const double alpha = __ddiv_rn((double)(t - b.tb), (double)(b.ta - b.tb));     // CS:1503 (true division)
+                const double* gb = P.samp_tab + 3 * b.k;
+                const double b0 = __ldg(gb), b1 = __ldg(gb + 1), b2 = __ldg(gb + 2);
+                const double a0 = __ldg(gb + 3), a1 = __ldg(gb + 4), a2 = __ldg(gb + 5);
+                g0 = __dadd_rn(b0, __dmul_rn(alpha, __dsub_rn(a0, b0)));                       // CS:1507-1509
+                g1 = __dadd_rn(b1, __dmul_rn(alpha, __dsub_rn(a1, b1)));
+                g2 = __dadd_rn(b2, __dmul_rn(alpha, __dsub_rn(a2, b2)));
+            }
+            const double dt = __dmul_rn((double)(t - fs), 1e-9);                               // CS:1454
+            gyro_rotate(__dmul_rn(g0, dt), __dmul_rn(g1, dt), __dmul_rn(g2, dt), in, out);
+        } else if constexpr (MODE == kSlerp) {
+            const int64_t S = P.n_samp;
+            int64_t k; double alpha = 0.0;
+            if (P.hold_idx != nullptr) k = __ldg(P.hold_idx + f);
+            else {
+                const int64_t t = F64 ? tsraw : tsraw + __ldg(P.frame_start + f);
+                const Bracket b = bracket_of(P.samp_ts, S, t, t0, rate);
+                k = b.k;
+                if (k < 0) k = 0;
+                else if (k >= S - 1) k = S - 1;
+                else alpha = (double)(t - b.tb);                       // times inv_dt_k below
+            }
+            if (k != key) {
+                const double2* sr = reinterpret_cast<const double2*>(P.samp_tab + kSegStride * k);
+#pragma unroll
+                for (int q = 0; q < kSegStride / 2; ++q) { const double2 v = __ldg(sr + q); tab[2 * q] = v.x; tab[2 * q + 1] = v.y; }
+                key = k;
+            }
+            alpha = __dmul_rn(alpha, tab[19]);
+            slerp_apply(tab, alpha, in, out);
+        }
+    }
+};
+
+// LVX record words of one point: x, y, z as u32 and (reflectivity | tag << 8)
+template <int MODE>
+__device__ __forceinline__ void lvx_words(const Params& P, const Pt& in, const Pt& out, uint32_t tagbyte,
+                                          uint32_t& x, uint32_t& y, uint32_t& z, uint32_t& rt, uint32_t& fl) {
+    if (P.lvx_mode == LMC_LVX_TYPE2_OF_INPUT) {                       // LMC:252-272 on the raw point
+        x = (uint32_t)q_mm_clip(in.x, fl); y = (uint32_t)q_mm_clip(in.y, fl); z = (uint32_t)q_mm_clip(in.z, fl);
+        rt = q_refl(in.w, fl);                                         // tag byte = 0
+    } else {                                                           // CS:365-374 on the compensated point
+        x = (uint32_t)q_mm_noclip(out.x, fl); y = (uint32_t)q_mm_noclip(out.y, fl); z = (uint32_t)q_mm_noclip(out.z, fl);
+        rt = q_u8_copy(out.w, fl) | (tagbyte << 8);
+    }
+}
+
+// 28 bytes of two consecutive records as 7 aligned words
+__device__ __forceinline__ void lvx_pair_words(uint32_t* w, const uint32_t (&x)[2], const uint32_t (&y)[2],
+                                               const uint32_t (&z)[2], const uint32_t (&rt)[2]) {
+    w[0] = x[0]; w[1] = y[0]; w[2] = z[0];
+    w[3] = rt[0] | (x[1] << 16);
+    w[4] = (x[1] >> 16) | (y[1] << 16);
+    w[5] = (y[1] >> 16) | (z[1] << 16);
+    w[6] = (z[1] >> 16) | (rt[1] << 16);
+}
+
+// ---- point pair load / store ------------------------------------------------------------
+template <bool F64, bool FULL>
+__device__ __forceinline__ void load_pair(const void* base, int64_t p, bool va, bool vb, Pt& a, Pt& b) {
+    if constexpr (F64) {
+        const double* src = reinterpret_cast<const double*>(base) + 4 * p;
+        if (FULL || va) ldg256(src, a.x, a.y, a.z, a.w);
+        if (FULL || vb) ldg256(src + 4, b.x, b.y, b.z, b.w);
+    } else {
+        const float* src = reinterpret_cast<const float*>(base) + 4 * p;
+        if (FULL || (va && vb)) {
+            float v[8];
+            ldg256(src, v);
+            a = { (double)v[0], (double)v[1], (double)v[2], (double)v[3] };
+            b = { (double)v[4], (double)v[5], (double)v[6], (double)v[7] };
+        } else {
+            if (va) { const float4 v = __ldg(reinterpret_cast<const float4*>(src));     a = { (double)v.x, (double)v.y, (double)v.z, (double)v.w }; }
+            if (vb) { const float4 v = __ldg(reinterpret_cast<const float4*>(src) + 1); b = { (double)v.x, (double)v.y, (double)v.z, (double)v.w }; }
+        }
+    }
+}
+
+template <bool F64, bool FULL>
+__device__ __forceinline__ void store_pair(void* base, int64_t p, bool va, bool vb, const Pt& a, const Pt& b) {
+    if constexpr (F64) {
+        double* dst = reinterpret_cast<double*>(base) + 4 * p;
+        if (FULL || va) stg256(dst, a.x, a.y, a.z, a.w);
+        if (FULL || vb) stg256(dst + 4, b.x, b.y, b.z, b.w);
+    } else {
+        float* dst = reinterpret_cast<float*>(base) + 4 * p;
+        if (FULL || (va && vb)) {
+            const float v[8] = { (float)a.x, (float)a.y, (float)a.z, (float)a.w, (float)b.x, (float)b.y, (float)b.z, (float)b.w };
+            stg256(dst, v);
+        } else {
+            if (va) *reinterpret_cast<float4*>(dst)     = make_float4((float)a.x, (float)a.y, (float)a.z, (float)a.w);
+            if (vb) *reinterpret_cast<float4*>(dst + 4) = make_float4((float)b.x, (float)b.y, (float)b.z, (float)b.w);
+        }
+    }
+}
+
+// LAS integer stores of one pair (SoA, 64-bit per array for a full pair)
+template <bool FULL>
+__device__ __forceinline__ void store_las_pair(const Params& P, int64_t p, bool va, bool vb, const Pt& a, const Pt& b, uint32_t& fl) {
+    if (P.las_x != nullptr) {
+        int32_t X[2] = {0, 0}, Y[2] = {0, 0}, Z[2] = {0, 0};
+        if (FULL || va) { X[0] = q_las(a.x, P.las_scale[0], P.las_rcp[0], P.las_off[0], fl); Y[0] = q_las(a.y, P.las_scale[1], P.las_rcp[1], P.las_off[1], fl); Z[0] = q_las(a.z, P.las_scale[2], P.las_rcp[2], P.las_off[2], fl); }
+        if (FULL || vb) { X[1] = q_las(b.x, P.las_scale[0], P.las_rcp[0], P.las_off[0], fl); Y[1] = q_las(b.y, P.las_scale[1], P.las_rcp[1], P.las_off[1], fl); Z[1] = q_las(b.z, P.las_scale[2], P.las_rcp[2], P.las_off[2], fl); }
+        if (FULL || (va && vb)) {
+            *reinterpret_cast<int2*>(P.las_x + p) = make_int2(X[0], X[1]);
+            *reinterpret_cast<int2*>(P.las_y + p) = make_int2(Y[0], Y[1]);
+            *reinterpret_cast<int2*>(P.las_z + p) = make_int2(Z[0], Z[1]);
+        } else {
+            if (va) { P.las_x[p] = X[0]; P.las_y[p] = Y[0]; P.las_z[p] = Z[0]; }
+            if (vb) { P.las_x[p + 1] = X[1]; P.las_y[p + 1] = Y[1]; P.las_z[p + 1] = Z[1]; }
+        }
+    }
+    if (P.las_int != nullptr) {
+        uint32_t i0 = 0, i1 = 0;
+        if (FULL || va) i0 = q_las_intensity(a.w, P.las_int_mode, fl);
+        if (FULL || vb) i1 = q_las_intensity(b.w, P.las_int_mode, fl);
+        if (FULL || (va && vb)) *reinterpret_cast<uint32_t*>(P.las_int + p) = i0 | (i1 << 16);
+        else { if (va) P.las_int[p] = (uint16_t)i0; if (vb) P.las_int[p + 1] = (uint16_t)i1; }
+    }
 }
 
 }  // namespace lmc

@@ -1,5 +1,294 @@
-// lmc_tma.cu -- TMA bulk-copy pipelined kernels (placeholder: not built yet, direct path is used)
+// lmc_tma.cu -- persistent, warp-specialised streaming kernels (the default path on large inputs).
+//
+// One CTA per SM, 15 consumer warps + 1 producer warp, each CTA walks a contiguous run of tiles.
+//
+//   producer warp   per tile: find the frames intersecting the tile (one coalesced read of the CSR
+//                   offsets after the previous tile's frame), then ONE elected lane issues TMA bulk
+//                   copies (cp.async.bulk global -> shared, UBLKCP) for the tile's points / timestamps
+//                   / tag bytes into a 4-stage ring; completion is signalled on an mbarrier with
+//                   expect_tx.  Up to 4 x 42 KB are in flight per SM, independent of registers.
+//   consumer warps  wait on the stage's "full" mbarrier, pull their point pairs out of shared memory,
+//                   resolve frames, release the stage ("empty" mbarrier) and only then do the f64
+//                   work: pose / sample-row fetch (L1 broadcast), transform, quantise.  Results leave
+//                   straight from registers as 256-bit stores (aligned cloud) and 64-bit SoA stores
+//                   (LAS ints); the 14-byte LVX records are transposed through a warp-private shared
+//                   slab (7 words per point pair, conflict-free) into 16-byte coalesced stores, so the
+//                   output side needs no CTA-wide barrier at all.
+//
+// Edge tiles (a shard's ragged first / last tile) skip TMA and take guarded global loads.
 #include "lmc_device.cuh"
+
 namespace lmc {
-cudaError_t launch_tma(bool, int, const Params&, cudaStream_t, bool* handled) { *handled = false; return cudaSuccess; }
+
+constexpr int kCW            = 15;                       // consumer warps (15 + producer = 512 threads -> 128 regs each)
+constexpr int kStreamThreads = 32 * (kCW + 1);           // + producer warp
+constexpr int kStages        = 4;
+
+template <bool F64> struct StreamCfg {
+    static constexpr int PPT      = F64 ? 1 : 2;                 // point pairs per consumer thread per tile
+    static constexpr int TP       = kCW * 32 * 2 * PPT;          // points per tile: 960 (f64) / 1920 (f32)
+    static constexpr int PT_BYTES = F64 ? 32 : 16;
+    static constexpr int TS_BYTES = F64 ? 8 : 4;
+    static constexpr int PTS_STAGE = TP * PT_BYTES;              // 30 KB either way
+    static constexpr int TS_STAGE  = TP * TS_BYTES;              // 7.5 KB either way
+    static constexpr int TAG_STAGE = TP;                         //  1-2 KB
+    static constexpr int STAGE     = PTS_STAGE + TS_STAGE + TAG_STAGE;
+    static constexpr int LVX_SLAB  = PPT * 64 * 14;              // bytes per consumer warp
+    static constexpr int SMEM      = kStages * STAGE + kCW * LVX_SLAB + kStages * (int)sizeof(TileMeta) + kStages * 32 + 2 * kStages * 8 + 128;
+};
+
+struct TileInfo { int64_t base, lim_lo, lim_hi; int32_t full, pad; };     // 32 bytes
+
+// ---- mbarrier / bulk-copy PTX ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra D;\n\tbra W;\n\tD:\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA, 1-D): 16-byte aligned addresses, size multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- one tile on the consumer side ------------------------------------------------------------
+template <bool F64, int MODE, bool FULL>
+__device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti, const TileMeta& tm,
+                                             const uint8_t* s_pts, const uint8_t* s_ts, const uint8_t* s_tag,
+                                             uint8_t* slab, uint64_t* empty_bar, PointCtx<F64, MODE>& ctx,
+                                             uint32_t& fl, int cw, int lane)
+{
+    using Cfg = StreamCfg<F64>;
+    constexpr int PPT = Cfg::PPT;
+    const bool has_ts = (MODE == kGyro || MODE == kSlerp) && P.ts != nullptr;
+    const bool has_tag = P.lvx14 != nullptr && P.tag != nullptr && P.lvx_mode == LMC_LVX2_OF_OUTPUT;
+    const int64_t base = ti.base;
+
+    Pt in[PPT][2];
+    bool valid[PPT][2];
+    int64_t tsv[PPT][2];
+    uint32_t tagv[PPT];
+    int32_t fr[PPT][2];
+    bool single[PPT][2];
+
+    // ---- registers <- stage (full tile) or <- global (edge tile) --------------------------------
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int q = (cw * PPT + j) * 32 + lane;            // pair index inside the tile
+        const int64_t p = base + 2 * q;
+        const bool va = FULL || (p >= ti.lim_lo && p < ti.lim_hi), vb = FULL || (p + 1 >= ti.lim_lo && p + 1 < ti.lim_hi);
+        valid[j][0] = va; valid[j][1] = vb;
+        in[j][0] = in[j][1] = Pt{ 0.0, 0.0, 0.0, 0.0 };
+        tsv[j][0] = tsv[j][1] = 0; tagv[j] = 0;
+        if constexpr (FULL) {
+            if constexpr (F64) {
+                const double2* s = reinterpret_cast<const double2*>(s_pts) + 4 * q;
+                const double2 a0 = s[0], a1 = s[1], b0 = s[2], b1 = s[3];
+                in[j][0] = { a0.x, a0.y, a1.x, a1.y }; in[j][1] = { b0.x, b0.y, b1.x, b1.y };
+                if (has_ts) { const longlong2 t = reinterpret_cast<const longlong2*>(s_ts)[q]; tsv[j][0] = t.x; tsv[j][1] = t.y; }
+            } else {
+                const float4* s = reinterpret_cast<const float4*>(s_pts) + 2 * q;
+                const float4 a = s[0], b = s[1];
+                in[j][0] = { (double)a.x, (double)a.y, (double)a.z, (double)a.w };
+                in[j][1] = { (double)b.x, (double)b.y, (double)b.z, (double)b.w };
+                if (has_ts) { const uint2 t = reinterpret_cast<const uint2*>(s_ts)[q]; tsv[j][0] = t.x; tsv[j][1] = t.y; }
+            }
+            if (has_tag) tagv[j] = reinterpret_cast<const uint16_t*>(s_tag)[q];
+        } else {
+            load_pair<F64, false>(P.pts, p, va, vb, in[j][0], in[j][1]);
+            if (has_ts) {
+                if constexpr (F64) { const int64_t* t = reinterpret_cast<const int64_t*>(P.ts) + p; if (va) tsv[j][0] = __ldg(t); if (vb) tsv[j][1] = __ldg(t + 1); }
+                else { const uint32_t* t = reinterpret_cast<const uint32_t*>(P.ts) + p; if (va) tsv[j][0] = __ldg(t); if (vb) tsv[j][1] = __ldg(t + 1); }
+            }
+            if (has_tag) { if (va) tagv[j] |= __ldg(P.tag + p); if (vb) tagv[j] |= (uint32_t)__ldg(P.tag + p + 1) << 8; }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            fr[j][h] = 0; single[j][h] = false;
+            if constexpr (MODE != kQuantOnly) { if (FULL || valid[j][h]) fr[j][h] = frame_of(P, tm, p + h, single[j][h]); }
+        }
+    }
+    // everything this warp needs from the stage is in registers: hand the slot back to the producer
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar);
+
+    // ---- f64 work + stores, one point pair at a time (short live ranges) ----------------------
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int q = (cw * PPT + j) * 32 + lane;
+        const int64_t p = base + 2 * q;
+        const bool va = valid[j][0], vb = valid[j][1];
+        Pt o0 = in[j][0], o1 = in[j][1];
+        if (FULL || va) ctx.point(P, fr[j][0], single[j][0], tsv[j][0], in[j][0], o0);
+        if (FULL || vb) ctx.point(P, fr[j][1], single[j][1], tsv[j][1], in[j][1], o1);
+        if (P.out != nullptr) store_pair<F64, FULL>(P.out, p, va, vb, o0, o1);
+        store_las_pair<FULL>(P, p, va, vb, o0, o1, fl);
+        if (P.lvx14 != nullptr) {
+            uint32_t x[2] = {0, 0}, y[2] = {0, 0}, z[2] = {0, 0}, rt[2] = {0, 0};
+            if (FULL || va) lvx_words<MODE>(P, in[j][0], o0, tagv[j] & 0xffu, x[0], y[0], z[0], rt[0], fl);
+            if (FULL || vb) lvx_words<MODE>(P, in[j][1], o1, (tagv[j] >> 8) & 0xffu, x[1], y[1], z[1], rt[1], fl);
+            lvx_pair_words(reinterpret_cast<uint32_t*>(slab) + 7 * (j * 32 + lane), x, y, z, rt);
+        }
+    }
+    if (P.lvx14 != nullptr) {
+        __syncwarp();
+        // the warp's PPT x 64 records are contiguous in the output: 16-byte coalesced stores
+        const int64_t wfirst = base + 2 * (int64_t)(cw * PPT) * 32;          // first point of the warp's block
+        uint8_t* g = P.lvx14 + 14 * wfirst;
+        constexpr int NB = PPT * 64 * 14;
+        if constexpr (FULL) {
+            for (int i = lane; i < NB / 16; i += 32) reinterpret_cast<uint4*>(g)[i] = reinterpret_cast<const uint4*>(slab)[i];
+        } else {
+            int64_t lo = ti.lim_lo - wfirst, hi = ti.lim_hi - wfirst;
+            lo = lo < 0 ? 0 : lo; hi = hi > PPT * 64 ? PPT * 64 : hi;
+            if (lo < hi) {
+                const int b0 = (int)lo * 14, b1 = (int)hi * 14;
+                int a0 = (b0 + 15) & ~15; if (a0 > b1) a0 = b1;
+                int a1 = b1 & ~15;        if (a1 < a0) a1 = a0;
+                for (int i = a0 / 16 + lane; i < a1 / 16; i += 32) reinterpret_cast<uint4*>(g)[i] = reinterpret_cast<const uint4*>(slab)[i];
+                for (int i = b0 + lane; i < a0; i += 32) g[i] = slab[i];
+                for (int i = a1 + lane; i < b1; i += 32) g[i] = slab[i];
+            }
+        }
+        __syncwarp();                                                         // slab is reused by the next tile
+    }
+}
+
+template <bool F64, int MODE>
+__global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_constant__ Params P, int64_t tile0, int64_t n_tiles)
+{
+    using Cfg = StreamCfg<F64>;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    uint8_t*  s_stage = smem;                                                   // kStages x STAGE
+    uint8_t*  s_slab  = s_stage + kStages * Cfg::STAGE;                         // kCW x LVX_SLAB
+    TileMeta* s_meta  = reinterpret_cast<TileMeta*>(s_slab + kCW * Cfg::LVX_SLAB);
+    TileInfo* s_info  = reinterpret_cast<TileInfo*>(s_meta + kStages);
+    uint64_t* s_full  = reinterpret_cast<uint64_t*>(s_info + kStages);
+    uint64_t* s_empty = s_full + kStages;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t t_begin = n_tiles * (int64_t)blockIdx.x / gridDim.x;
+    const int64_t t_end   = n_tiles * (int64_t)(blockIdx.x + 1) / gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(s_full + s, 1); mbar_init(s_empty + s, kCW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const bool has_ts = (MODE == kGyro || MODE == kSlerp) && P.ts != nullptr;
+    const bool has_tag = P.lvx14 != nullptr && P.tag != nullptr && P.lvx_mode == LMC_LVX2_OF_OUTPUT;
+
+    if (warp == kCW) {
+        // ================================ producer warp ==========================================
+        int s = 0; uint32_t ph = 0;
+        int64_t hint = -1;
+        for (int64_t t = t_begin; t < t_end; ++t) {
+            mbar_wait(s_empty + s, ph ^ 1);                                      // slot free (first lap passes)
+            const int64_t base = tile0 + t * Cfg::TP;
+            const int64_t lim_lo = base > P.p_begin ? base : P.p_begin;
+            const int64_t lim_hi = base + Cfg::TP < P.p_end ? base + Cfg::TP : P.p_end;
+            const bool full = lim_lo == base && lim_hi == base + Cfg::TP;
+            if constexpr (MODE != kQuantOnly) {
+                tile_meta(P, lim_lo, lim_hi - 1, s_meta[s], lane, hint);
+                __syncwarp();
+                hint = (int64_t)s_meta[s].f_lo + (s_meta[s].overflow ? 0 : s_meta[s].nb);   // frame of the tile's last point
+            }
+            if (lane == 0) {
+                s_info[s] = TileInfo{ base, lim_lo, lim_hi, full ? 1 : 0, 0 };
+                uint8_t* st = s_stage + s * Cfg::STAGE;
+                if (full) {
+                    const uint32_t bytes = Cfg::PTS_STAGE + (has_ts ? Cfg::TS_STAGE : 0) + (has_tag ? Cfg::TAG_STAGE : 0);
+                    mbar_arrive_expect_tx(s_full + s, bytes);
+                    bulk_g2s(st, reinterpret_cast<const uint8_t*>(P.pts) + base * Cfg::PT_BYTES, Cfg::PTS_STAGE, s_full + s);
+                    if (has_ts)  bulk_g2s(st + Cfg::PTS_STAGE, reinterpret_cast<const uint8_t*>(P.ts) + base * Cfg::TS_BYTES, Cfg::TS_STAGE, s_full + s);
+                    if (has_tag) bulk_g2s(st + Cfg::PTS_STAGE + Cfg::TS_STAGE, P.tag + base, Cfg::TAG_STAGE, s_full + s);
+                } else {
+                    mbar_arrive(s_full + s);                                       // edge tile: consumers read global memory
+                }
+            }
+            __syncwarp();
+            if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+    } else {
+        // ================================ consumer warps =========================================
+        PointCtx<F64, MODE> ctx;
+        ctx.init(P);
+        uint32_t fl = 0;
+        uint8_t* slab = s_slab + warp * Cfg::LVX_SLAB;
+        int s = 0; uint32_t ph = 0;
+        for (int64_t t = t_begin; t < t_end; ++t) {
+            mbar_wait(s_full + s, ph);
+            const TileInfo ti = s_info[s];
+            const uint8_t* st = s_stage + s * Cfg::STAGE;
+            if (ti.full) consume_tile<F64, MODE, true>(P, ti, s_meta[s], st, st + Cfg::PTS_STAGE, st + Cfg::PTS_STAGE + Cfg::TS_STAGE, slab, s_empty + s, ctx, fl, warp, lane);
+            else         consume_tile<F64, MODE, false>(P, ti, s_meta[s], st, st + Cfg::PTS_STAGE, st + Cfg::PTS_STAGE + Cfg::TS_STAGE, slab, s_empty + s, ctx, fl, warp, lane);
+            if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+        if (fl != 0 && P.status != nullptr) atomicOr(P.status, fl);
+    }
+}
+
+// ---- launcher ----------------------------------------------------------------------------------
+static int sm_count_cached() {
+    static thread_local int dev_cached = -1, sms = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (dev != dev_cached) {
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        dev_cached = dev;
+    }
+    return sms;
+}
+
+template <bool F64, int MODE>
+static cudaError_t launch_stream(const Params& P, cudaStream_t st, bool force, bool* handled) {
+    using Cfg = StreamCfg<F64>;
+    const int sms = sm_count_cached();
+    if (sms <= 0) return cudaErrorInvalidDevice;
+    const int64_t tile0 = (P.p_begin / Cfg::TP) * Cfg::TP;                       // tiles aligned in GLOBAL index space
+    const int64_t n_tiles = (P.p_end - tile0 + Cfg::TP - 1) / Cfg::TP;
+    if (!force && n_tiles < 2 * (int64_t)sms) { *handled = false; return cudaSuccess; }   // too small to fill a persistent grid
+    *handled = true;
+    // TMA sources must be 16-byte aligned: guaranteed by the 32-byte rule for points, checked here for the rest
+    if (P.ts != nullptr && (reinterpret_cast<uintptr_t>(P.ts) & 15u)) { *handled = false; return cudaSuccess; }
+    if (P.tag != nullptr && (reinterpret_cast<uintptr_t>(P.tag) & 15u)) { *handled = false; return cudaSuccess; }
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(k_stream<F64, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_dev = dev;
+    }
+    const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+    k_stream<F64, MODE><<<grid, kStreamThreads, Cfg::SMEM, st>>>(P, tile0, n_tiles);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tma(bool f64, int mode, const Params& P, cudaStream_t st, bool force, bool* handled) {
+    *handled = false;
+    if (P.p_end <= P.p_begin) { *handled = true; return cudaSuccess; }
+    switch (mode) {
+    case kRigid:     return f64 ? launch_stream<true, kRigid>(P, st, force, handled)     : launch_stream<false, kRigid>(P, st, force, handled);
+    case kGyro:      return f64 ? launch_stream<true, kGyro>(P, st, force, handled)      : launch_stream<false, kGyro>(P, st, force, handled);
+    case kSlerp:     return f64 ? launch_stream<true, kSlerp>(P, st, force, handled)     : launch_stream<false, kSlerp>(P, st, force, handled);
+    case kQuantOnly: return f64 ? launch_stream<true, kQuantOnly>(P, st, force, handled) : launch_stream<false, kQuantOnly>(P, st, force, handled);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace lmc

@@ -51,9 +51,9 @@ def lidar_frame_times(duration: float, lidar_fps: float) -> np.ndarray:
     return np.linspace(0, duration, int(duration * lidar_fps))
 
 
-def slerp_segment_table(sample_quat_xyzw: np.ndarray, sample_pos: np.ndarray) -> np.ndarray:
+def slerp_segment_table(sample_quat_xyzw: np.ndarray, sample_pos: np.ndarray, sample_ts: np.ndarray) -> np.ndarray:
     """Per-sample table consumed by lmc_deskew_slerp_*: for sample k
-    [R_k (9) | pos_k (3) | unit axis of R_k^-1 R_{k+1} (3) | angle | pos_{k+1}-pos_k (3) | pad]."""
+    [R_k (9) | pos_k (3) | unit axis of R_k^-1 R_{k+1} (3) | angle | pos_{k+1}-pos_k (3) | 1/(t_{k+1}-t_k)]."""
     q = np.asarray(sample_quat_xyzw, np.float64).reshape(-1, 4)
     pos = np.asarray(sample_pos, np.float64).reshape(-1, 3)
     S = len(q)
@@ -69,6 +69,8 @@ def slerp_segment_table(sample_quat_xyzw: np.ndarray, sample_pos: np.ndarray) ->
         seg[:-1][nz, 12:15] = rv[nz] / th[nz, None]
         seg[:-1, 15] = th
         seg[:-1, 16:19] = pos[1:] - pos[:-1]
+        dts = np.diff(np.asarray(sample_ts, np.int64)).astype(np.float64)
+        seg[:-1, 19] = np.where(dts > 0, 1.0 / np.where(dts > 0, dts, 1.0), 0.0)
     return seg
 
 

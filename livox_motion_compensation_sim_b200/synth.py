@@ -66,7 +66,7 @@ def make_tables(n_frames: int, seed: int, fps: float = 10.0, sample_rate: float 
     pos = pos + rng.normal(0, 0.03, pos.shape)
     eul = eul + rng.normal(0, 0.01, eul.shape)
     quat = Rotation.from_euler('xyz', eul).as_quat()
-    seg = FR.slerp_segment_table(quat, pos)
+    seg = FR.slerp_segment_table(quat, pos, sample_ts)
     frame_start = (np.arange(n_frames, dtype=np.int64) * int(round(1e9 / fps)))
     frame_t = frame_start * 1e-9
     n_t = max(int(duration * gps_rate), 2)

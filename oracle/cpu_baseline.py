@@ -85,7 +85,7 @@ def run_c_port_mode_c(n_frames: int = 60, pts_per_frame: int = 10_000):
     S = n_frames * 20 + 1
     sample_ts = np.arange(S, dtype=np.int64) * 5_000_000
     quat = Rotation.from_euler('xyz', np.cumsum(rng.normal(0, 0.01, (S, 3)), axis=0)).as_quat()
-    seg = orc.slerp_segment_table(quat, np.cumsum(rng.normal(0, 0.05, (S, 3)), axis=0))
+    seg = orc.slerp_segment_table(quat, np.cumsum(rng.normal(0, 0.05, (S, 3)), axis=0), sample_ts)
     off = np.arange(n_frames + 1, dtype=np.int64) * pts_per_frame
     ts = np.repeat(np.arange(n_frames, dtype=np.int64) * 100_000_000, pts_per_frame) + np.tile(np.arange(pts_per_frame, dtype=np.int64) * 10_000, n_frames)
     orc.C.deskew_slerp_f64(pts[:1000], ts[:1000], np.array([0, 1000]), sample_ts, seg)

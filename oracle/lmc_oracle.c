@@ -279,13 +279,14 @@ void orc_deskew_gyro_f64(const double* pts, const int64_t* ts, const int64_t* fr
  * is a body-less sketch).  Definition (validated against scipy Slerp + lerp in
  * oracle/lmc_oracle.py::slerp_deskew_scipy):
  *   k = bracket_right(sample_ts, ts)  (same bracket rule as a7, clamped at both ends)
- *   alpha = (ts - t_k) / (t_{k+1} - t_k)
+ *   alpha = (ts - t_k) * inv_dt_k,  inv_dt_k = 1.0 / (double)(t_{k+1} - t_k) from the table
+ *           (a per-segment reciprocal instead of a per-point division: <= 1 ulp from the quotient)
  *   R(ts) = R_k * exp(alpha * rotvec(R_k^-1 R_{k+1}))      == scipy Slerp
  *   pos(ts) = pos_k + alpha * (pos_{k+1} - pos_k)
  *   out = R(ts) p + pos(ts)
  * seg is the per-segment table, SEG_STRIDE doubles per sample k:
  *   [0..8] R_k row-major, [9..11] pos_k, [12..14] unit axis n_k, [15] theta_k,
- *   [16..18] dpos_k = pos_{k+1}-pos_k, [19] pad.   Last sample: theta = 0, dpos = 0.
+ *   [16..18] dpos_k = pos_{k+1}-pos_k, [19] inv_dt_k.   Last sample: theta = 0, dpos = 0, inv_dt = 0.
  * hold_idx != NULL: every point of frame f uses sample hold_idx[f] with alpha = 0
  * (Mode A expressed in Mode C: must equal orc_align_rigid_f64 bit-for-bit for n_f >= 2).
  * ---------------------------------------------------------------------------------- */
@@ -305,7 +306,7 @@ void orc_deskew_slerp_f64(const double* pts, const int64_t* ts, const int64_t* f
                 k = bracket_right(sample_ts, n_samples, ts[i]);
                 if (k < 0) k = 0;
                 else if (k >= n_samples - 1) k = n_samples - 1;
-                else alpha = (double)(ts[i] - sample_ts[k]) / (double)(sample_ts[k + 1] - sample_ts[k]);
+                else alpha = (double)(ts[i] - sample_ts[k]) * seg[ORC_SEG_STRIDE * k + 19];
             }
             const double* s = seg + ORC_SEG_STRIDE * k;
             double th = alpha * s[15];

@@ -43,7 +43,7 @@ def sha(a):
 def path(request):
     C.set_path(request.param)
     yield request.param
-    C.set_path(C.PATH_TMA)
+    C.set_path(C.PATH_AUTO)
 
 
 # ------------------------------------------------------------------------------------------

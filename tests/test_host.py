@@ -106,7 +106,8 @@ def test_pose_table_is_scipy_exact(golden):
     from scipy.spatial.transform import Rotation
     q = Rotation.from_euler('xyz', rng.normal(0, 1, (50, 3))).as_quat()
     pos = rng.normal(0, 10, (50, 3))
-    assert np.array_equal(FR.slerp_segment_table(q, pos), orc.slerp_segment_table(q, pos))
+    ts = np.cumsum(rng.integers(1, 9_000_000, 50)).astype(np.int64)
+    assert np.array_equal(FR.slerp_segment_table(q, pos, ts), orc.slerp_segment_table(q, pos, ts))
 
 
 def test_partition_frames_balances_points():
