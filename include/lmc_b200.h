@@ -126,7 +126,8 @@ int lmc_deskew_gyro_f32(const float* pts_n4, const uint32_t* ts_off, const int64
  * docs/Master Guide.md:339-367; no reference implementation -> parity unpinned).
  *   k = bracket(sample_ts, ts) ; alpha = (ts - t_k) * inv_dt_k      (inv_dt_k = 1/(t_{k+1} - t_k) from seg)
  *   out = SLERP(R_k, R_{k+1}, alpha) p + lerp(pos_k, pos_{k+1}, alpha)
- * seg: (n_samples, 20) f64 per-sample table [R_k(9) pos_k(3) axis_k(3) theta_k dpos_k(3) inv_dt_k]
+ * seg: (n_samples, 22) f64 per-sample table [R_k(9) pos_k(3) axis_k(3) theta_k dpos_k(3) inv_dt_k
+ *      t_k t_{k+1}] -- the last two are the raw int64 timestamps stored in double slots
  *      (built by the host wrapper, see livox_motion_compensation_sim_b200/frames.py).
  * hold_idx (optional int32[n_frames]): every point of frame f takes sample hold_idx[f], alpha = 0
  *      -> Mode A expressed in Mode C (bit-identical to lmc_align_rigid_* for frames of >= 2 points).

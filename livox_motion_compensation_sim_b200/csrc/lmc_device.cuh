@@ -14,7 +14,7 @@
 namespace lmc {
 
 constexpr int kMaxBnd    = 30;        // frame boundaries cached per tile (more -> per-point global search)
-constexpr int kSegStride = 20;        // doubles per Mode C sample row
+constexpr int kSegStride = 22;        // doubles per Mode C sample row
 
 enum Mode : int { kRigid = 0, kGyro = 1, kSlerp = 2, kQuantOnly = 3 };
 
@@ -49,6 +49,7 @@ struct Pt { double x, y, z, w; };
 // frames intersecting one tile of points, staged in shared memory
 struct TileMeta {
     int64_t edge[kMaxBnd + 2];    // frame_off[f_lo .. f_lo + nb + 1]
+    int64_t fstart[kMaxBnd + 2];  // frame_start[f_lo .. f_lo + nb] (Mode B/C), staged with the edges
     int32_t f_lo;                 // frame of the tile's first point
     int32_t nb;                   // frame boundaries inside the tile
     int32_t overflow;             // more than kMaxBnd boundaries: per-point global search
@@ -109,26 +110,26 @@ __device__ __forceinline__ void rigid_apply(const double (&M)[12], bool single, 
 // sin(x) and 1 - cos(x).  Deskew angles are tiny (gyro * 0.1 s, or one 5 ms pose segment), so for
 // |x| <= 0.5 a Taylor polynomial without range reduction is exact to < 1 ulp (next terms: 2e-20,
 // 6e-22 relative); larger arguments take the library path.
+__constant__ double kSinC[7] = { -7.6471637318198164759e-13 /* -1/15! */, 1.6059043836821614599e-10, -2.5052108385441718775e-08,
+                                 2.7557319223985890653e-06, -1.9841269841269841270e-04, 8.3333333333333333333e-03,
+                                 -1.6666666666666666667e-01 /* -1/3! */ };
+__constant__ double kCosC[8] = { -4.7794773323873852974e-14 /* -1/16! */, 1.1470745597729724714e-11, -2.0876756987868098979e-09,
+                                 2.7557319223985890653e-07, -2.4801587301587301587e-05, 1.3888888888888888889e-03,
+                                 -4.1666666666666666667e-02, 0.5 /* 1/2! */ };
+// branch-free polynomial part, valid for |x| <= 0.5
+__device__ __forceinline__ void sin_vercos_small(double x, double& s, double& v) {
+    const double u = x * x;
+    double ps = kSinC[0], pc = kCosC[0];
+#pragma unroll
+    for (int i = 1; i < 7; ++i) ps = fma(ps, u, kSinC[i]);
+#pragma unroll
+    for (int i = 1; i < 8; ++i) pc = fma(pc, u, kCosC[i]);
+    s = fma(x * u, ps, x);
+    v = u * pc;
+}
 __device__ __forceinline__ void sin_vercos(double x, double& s, double& v) {
     if (fabs(x) <= 0.5) {
-        const double u = x * x;
-        double ps = -7.6471637318198164759e-13;                  // -1/15!
-        ps = fma(ps, u, 1.6059043836821614599e-10);              //  1/13!
-        ps = fma(ps, u, -2.5052108385441718775e-08);             // -1/11!
-        ps = fma(ps, u, 2.7557319223985890653e-06);              //  1/9!
-        ps = fma(ps, u, -1.9841269841269841270e-04);             // -1/7!
-        ps = fma(ps, u, 8.3333333333333333333e-03);              //  1/5!
-        ps = fma(ps, u, -1.6666666666666666667e-01);             // -1/3!
-        s = fma(x * u, ps, x);
-        double pc = -4.7794773323873852974e-14;                  // -1/16!
-        pc = fma(pc, u, 1.1470745597729724714e-11);              //  1/14!
-        pc = fma(pc, u, -2.0876756987868098979e-09);             // -1/12!
-        pc = fma(pc, u, 2.7557319223985890653e-07);              //  1/10!
-        pc = fma(pc, u, -2.4801587301587301587e-05);             // -1/8!
-        pc = fma(pc, u, 1.3888888888888888889e-03);              //  1/6!
-        pc = fma(pc, u, -4.1666666666666666667e-02);             // -1/4!
-        pc = fma(pc, u, 0.5);
-        v = u * pc;
+        sin_vercos_small(x, s, v);
     } else {
         double c;
         sincos(x, &s, &c);
@@ -166,10 +167,11 @@ __device__ __forceinline__ void gyro_rotate(double ax, double ay, double az, con
 }
 
 // Mode C per-point evaluation (definition: oracle/lmc_oracle.c::orc_deskew_slerp_f64)
+template <bool SMALL = false>
 __device__ __forceinline__ void slerp_apply(const double (&s)[kSegStride], double alpha, const Pt& p, Pt& o) {
     const double th = __dmul_rn(alpha, s[15]);
     double sn, v;
-    sin_vercos(th, sn, v);
+    if (SMALL) sin_vercos_small(th, sn, v); else sin_vercos(th, sn, v);
     const double nx = s[12], ny = s[13], nz = s[14];
     const double c1x = __fma_rn(ny, p.z, -__dmul_rn(nz, p.y));
     const double c1y = __fma_rn(nz, p.x, -__dmul_rn(nx, p.z));
@@ -319,8 +321,12 @@ __device__ __forceinline__ Bracket bracket_of(const int64_t* __restrict__ ts, in
 // frame of point p (global index) + whether that frame holds exactly one point
 __device__ __forceinline__ int32_t frame_of(const Params& P, const TileMeta& tm, int64_t p, bool& single) {
     if (!tm.overflow) {
-        int lo = 0, hi = tm.nb;                     // count of edge[1..nb] <= p
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (tm.edge[1 + mid] <= p) lo = mid + 1; else hi = mid; }
+        int lo;
+        if (tm.nb <= 1) lo = (tm.nb == 1 && tm.edge[1] <= p) ? 1 : 0;    // a tile rarely holds more than one boundary
+        else {
+            lo = 0; int hi = tm.nb;                 // count of edge[1..nb] <= p
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (tm.edge[1 + mid] <= p) lo = mid + 1; else hi = mid; }
+        }
         single = (tm.edge[lo + 1] - tm.edge[lo]) == 1;
         return tm.f_lo + lo;
     }
@@ -354,12 +360,87 @@ __device__ __forceinline__ void tile_meta(const Params& P, int64_t first, int64_
         done = c < 32;
         if (nb > kMaxBnd) { overflow = 1; done = true; }
     }
+    if (P.frame_start != nullptr && !overflow)
+        for (int j = lane; j <= nb; j += 32) tm.fstart[j] = __ldg(P.frame_start + f_lo + j);
     if (lane == 0) { tm.f_lo = (int32_t)f_lo; tm.nb = nb; tm.overflow = overflow; }
+}
+// frame_start of frame f, from the staged copy when the tile has one
+__device__ __forceinline__ int64_t frame_start_of(const Params& P, const TileMeta& tm, int32_t f) {
+    return tm.overflow ? __ldg(P.frame_start + f) : tm.fstart[f - tm.f_lo];
 }
 
 // ------------------------------------------------------------------------------------------
-// Per-thread compute context: caches the pose / sample row of the previous point (consecutive
-// points almost always share it) and evaluates one point.
+// General per-point evaluation: every corner case (clamps, ragged brackets, big angles, one-point
+// frames).  Self-contained (fetches its own pose / sample row), so the out-of-line copy used by
+// the rare fall-backs does not force the callers' cached tables out of registers.
+//   f / single: frame of the point and whether it is a one-point frame (frame_of)
+//   fs: the frame's start time (Mode B/C); tsraw: int64 ns (f64 layout) or uint32 ns offset from fs
+// ------------------------------------------------------------------------------------------
+template <bool F64, int MODE>
+__device__ __forceinline__ Pt point_eval(const Params& P, int32_t f, bool single, int64_t fs, int64_t tsraw, const Pt& in,
+                                         int64_t t0, double rate) {
+    Pt out = in;
+    if constexpr (MODE == kRigid) {
+        double M[12];
+        const double2* pr = reinterpret_cast<const double2*>(P.pose_Rt + 12 * (int64_t)f);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) { const double2 v = __ldg(pr + q); M[2 * q] = v.x; M[2 * q + 1] = v.y; }
+        rigid_apply(M, single, in, out);
+    } else if constexpr (MODE == kGyro) {
+        // (a6)/(a7): per-point bracket in imu_ts, gyro lerp, small-angle rotation
+        const int64_t S = P.n_samp;
+        if (S == 0) return out;                                        // CS:1439-1440: no IMU data -> unchanged
+        const int64_t t = F64 ? tsraw : tsraw + fs;
+        const Bracket b = bracket_of(P.samp_ts, S, t, t0, rate);
+        double g0, g1, g2;
+        if (b.k < 0 || b.k >= S - 1) {                                // CS:1495-1496: clamp to the existing end sample
+            const double* g = P.samp_tab + 3 * (b.k < 0 ? 0 : S - 1);
+            g0 = __ldg(g); g1 = __ldg(g + 1); g2 = __ldg(g + 2);
+        } else {
+            const double alpha = __ddiv_rn((double)(t - b.tb), (double)(b.ta - b.tb));         // CS:1503 (true division)
+            const double* gb = P.samp_tab + 3 * b.k;
+            const double b0 = __ldg(gb), b1 = __ldg(gb + 1), b2 = __ldg(gb + 2);
+            const double a0 = __ldg(gb + 3), a1 = __ldg(gb + 4), a2 = __ldg(gb + 5);
+            g0 = __dadd_rn(b0, __dmul_rn(alpha, __dsub_rn(a0, b0)));                           // CS:1507-1509
+            g1 = __dadd_rn(b1, __dmul_rn(alpha, __dsub_rn(a1, b1)));
+            g2 = __dadd_rn(b2, __dmul_rn(alpha, __dsub_rn(a2, b2)));
+        }
+        const double dt = __dmul_rn((double)(t - fs), 1e-9);                                   // CS:1454
+        gyro_rotate(__dmul_rn(g0, dt), __dmul_rn(g1, dt), __dmul_rn(g2, dt), in, out);
+    } else if constexpr (MODE == kSlerp) {
+        const int64_t S = P.n_samp;
+        int64_t k; double alpha = 0.0;
+        if (P.hold_idx != nullptr) k = __ldg(P.hold_idx + f);
+        else {
+            const int64_t t = F64 ? tsraw : tsraw + fs;
+            const Bracket b = bracket_of(P.samp_ts, S, t, t0, rate);
+            k = b.k;
+            if (k < 0) k = 0;
+            else if (k >= S - 1) k = S - 1;
+            else alpha = (double)(t - b.tb);                           // times inv_dt_k below
+        }
+        double row[kSegStride];
+        const double2* sr = reinterpret_cast<const double2*>(P.samp_tab + kSegStride * k);
+#pragma unroll
+        for (int q = 0; q < kSegStride / 2; ++q) { const double2 v = __ldg(sr + q); row[2 * q] = v.x; row[2 * q + 1] = v.y; }
+        alpha = __dmul_rn(alpha, row[19]);
+        slerp_apply(row, alpha, in, out);
+    }
+    return out;
+}
+template <bool F64, int MODE>
+__device__ __noinline__ Pt point_eval_slow(const Params& P, int32_t f, bool single, int64_t fs, int64_t tsraw, Pt in,
+                                           int64_t t0, double rate) {
+    return point_eval<F64, MODE>(P, f, single, fs, tsraw, in, t0, rate);
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-thread context for PAIRS of consecutive points: caches the pose / sample row of the previous
+// pair (consecutive points almost always share it).  pair() takes a straight-line fast path -- no
+// branches between the two points, so their FP64 chains overlap -- when both points share a frame
+// pose (Mode A) or a pose segment whose own [t_k, t_{k+1}) verifies the bracket guess (Mode C); any
+// other case goes to point_eval().  Both routes execute the same operations in the same order, so
+// the results are bit-identical.
 // ------------------------------------------------------------------------------------------
 template <bool F64, int MODE>
 struct PointCtx {
@@ -378,61 +459,53 @@ struct PointCtx {
         }
     }
 
-    // f / single: frame of the point and whether it is a one-point frame (frame_of);
-    // tsraw: int64 ns (f64 layout) or uint32 ns offset from the frame start (f32 layout)
-    __device__ __forceinline__ void point(const Params& P, int32_t f, bool single, int64_t tsraw, const Pt& in, Pt& out) {
-        if constexpr (MODE == kQuantOnly) { out = in; return; }
+    __device__ __forceinline__ Pt one(const Params& P, int32_t f, bool single, int64_t fs, int64_t tsraw, const Pt& in) const {
+        if constexpr (MODE == kQuantOnly) return in;
+        else if constexpr (MODE == kGyro) return point_eval<F64, MODE>(P, f, single, fs, tsraw, in, t0, rate);   // no fast path yet: inline
+        else return point_eval_slow<F64, MODE>(P, f, single, fs, tsraw, in, t0, rate);
+    }
+
+    __device__ __forceinline__ void pair(const Params& P, const int32_t (&f)[2], const bool (&single)[2], const int64_t (&fs)[2],
+                                         const int64_t (&tsraw)[2], const Pt (&in)[2], Pt (&out)[2]) {
         if constexpr (MODE == kRigid) {
-            if (f != key) {
-                const double2* pr = reinterpret_cast<const double2*>(P.pose_Rt + 12 * (int64_t)f);
+            if (f[0] == f[1] && !single[0]) {
+                if (f[0] != key) {
+                    const double2* pr = reinterpret_cast<const double2*>(P.pose_Rt + 12 * (int64_t)f[0]);
 #pragma unroll
-                for (int q = 0; q < 6; ++q) { const double2 v = __ldg(pr + q); tab[2 * q] = v.x; tab[2 * q + 1] = v.y; }
-                key = f;
+                    for (int q = 0; q < 6; ++q) { const double2 v = __ldg(pr + q); tab[2 * q] = v.x; tab[2 * q + 1] = v.y; }
+                    key = f[0];
+                }
+                rigid_apply(tab, false, in[0], out[0]);
+                rigid_apply(tab, false, in[1], out[1]);
+                return;
             }
-            rigid_apply(tab, single, in, out);
-        } else if constexpr (MODE == kGyro) {
-            // (a6)/(a7): per-point bracket in imu_ts, gyro lerp, small-angle rotation
-            const int64_t S = P.n_samp;
-            if (S == 0) { out = in; return; }                         // CS:1439-1440: no IMU data -> unchanged
-            const int64_t fs = __ldg(P.frame_start + f);
-            const int64_t t = F64 ? tsraw : tsraw + fs;
-            const Bracket b = bracket_of(P.samp_ts, S, t, t0, rate);
-            double g0, g1, g2;
-            if (b.k < 0 || b.k >= S - 1) {                            // CS:1495-1496: clamp to the existing end sample
-                const double* g = P.samp_tab + 3 * (b.k < 0 ? 0 : S - 1);
-                g0 = __ldg(g); g1 = __ldg(g + 1); g2 = __ldg(g + 2);
-            } else {
-                const double alpha = __ddiv_rn((double)(t - b.tb), (double)(b.ta - b.tb));     // CS:1503 (true division)
-                const double* gb = P.samp_tab + 3 * b.k;
-                const double b0 = __ldg(gb), b1 = __ldg(gb + 1), b2 = __ldg(gb + 2);
-                const double a0 = __ldg(gb + 3), a1 = __ldg(gb + 4), a2 = __ldg(gb + 5);
-                g0 = __dadd_rn(b0, __dmul_rn(alpha, __dsub_rn(a0, b0)));                       // CS:1507-1509
-                g1 = __dadd_rn(b1, __dmul_rn(alpha, __dsub_rn(a1, b1)));
-                g2 = __dadd_rn(b2, __dmul_rn(alpha, __dsub_rn(a2, b2)));
-            }
-            const double dt = __dmul_rn((double)(t - fs), 1e-9);                               // CS:1454
-            gyro_rotate(__dmul_rn(g0, dt), __dmul_rn(g1, dt), __dmul_rn(g2, dt), in, out);
-        } else if constexpr (MODE == kSlerp) {
-            const int64_t S = P.n_samp;
-            int64_t k; double alpha = 0.0;
-            if (P.hold_idx != nullptr) k = __ldg(P.hold_idx + f);
-            else {
-                const int64_t t = F64 ? tsraw : tsraw + __ldg(P.frame_start + f);
-                const Bracket b = bracket_of(P.samp_ts, S, t, t0, rate);
-                k = b.k;
-                if (k < 0) k = 0;
-                else if (k >= S - 1) k = S - 1;
-                else alpha = (double)(t - b.tb);                       // times inv_dt_k below
-            }
-            if (k != key) {
-                const double2* sr = reinterpret_cast<const double2*>(P.samp_tab + kSegStride * k);
-#pragma unroll
-                for (int q = 0; q < kSegStride / 2; ++q) { const double2 v = __ldg(sr + q); tab[2 * q] = v.x; tab[2 * q + 1] = v.y; }
-                key = k;
-            }
-            alpha = __dmul_rn(alpha, tab[19]);
-            slerp_apply(tab, alpha, in, out);
         }
+        if constexpr (MODE == kSlerp) {
+            const int64_t S = P.n_samp;
+            if (P.hold_idx == nullptr && S >= 2) {
+                const int64_t ta = F64 ? tsraw[0] : tsraw[0] + fs[0];
+                const int64_t tb = F64 ? tsraw[1] : tsraw[1] + fs[1];
+                int64_t k = __double2ll_rz(__dmul_rn((double)(ta - t0), rate));     // bracket guess from the mean rate
+                k = k < 0 ? 0 : (k > S - 2 ? S - 2 : k);
+                if (k != key) {
+                    const double2* sr = reinterpret_cast<const double2*>(P.samp_tab + kSegStride * k);
+#pragma unroll
+                    for (int q = 0; q < kSegStride / 2; ++q) { const double2 v = __ldg(sr + q); tab[2 * q] = v.x; tab[2 * q + 1] = v.y; }
+                    key = k;
+                }
+                const int64_t tk = __double_as_longlong(tab[20]), tn = __double_as_longlong(tab[21]);
+                // the row's own [t_k, t_{k+1}) verifies the guess for both points at once
+                if (tk <= ta && ta < tn && tk <= tb && tb < tn && tab[15] <= 0.49) {
+                    const double a0 = __dmul_rn((double)(ta - tk), tab[19]);
+                    const double a1 = __dmul_rn((double)(tb - tk), tab[19]);
+                    slerp_apply<true>(tab, a0, in[0], out[0]);
+                    slerp_apply<true>(tab, a1, in[1], out[1]);
+                    return;
+                }
+            }
+        }
+        out[0] = one(P, f[0], single[0], fs[0], tsraw[0], in[0]);
+        out[1] = one(P, f[1], single[1], fs[1], tsraw[1], in[1]);
     }
 };
 

@@ -73,17 +73,24 @@ __device__ __forceinline__ void tile_body(const Params& P, int64_t base, int64_t
     PointCtx<F64, MODE> ctx;
     ctx.init(P);
 #pragma unroll
-    for (int j = 0; j < kPairsPerThread; ++j)
+    for (int j = 0; j < kPairsPerThread; ++j) {
+        int32_t f[2] = {0, 0}; bool single[2] = {false, false}; int64_t fs[2] = {0, 0};
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             outp[j][h] = in[j][h];
-            if (FULL || valid[j][h]) {
-                bool single = false;
-                int32_t f = 0;
-                if constexpr (MODE != kQuantOnly) f = frame_of(P, s_tm, base + 2 * (tid + j * kThreads) + h, single);
-                ctx.point(P, f, single, tsv[j][h], in[j][h], outp[j][h]);
+            if constexpr (MODE != kQuantOnly) {
+                if (FULL || valid[j][h]) {
+                    f[h] = frame_of(P, s_tm, base + 2 * (tid + j * kThreads) + h, single[h]);
+                    if constexpr (MODE == kGyro || MODE == kSlerp) { if (P.frame_start != nullptr) fs[h] = frame_start_of(P, s_tm, f[h]); }
+                }
             }
         }
+        if (FULL || (valid[j][0] && valid[j][1])) ctx.pair(P, f, single, fs, tsv[j], in[j], outp[j]);
+        else {
+            if (valid[j][0]) outp[j][0] = ctx.one(P, f[0], single[0], fs[0], tsv[j][0], in[j][0]);
+            if (valid[j][1]) outp[j][1] = ctx.one(P, f[1], single[1], fs[1], tsv[j][1], in[j][1]);
+        }
+    }
 
     // ---- 4. stores + export epilogues ---------------------------------------------------------
 #pragma unroll
@@ -121,7 +128,7 @@ __device__ __forceinline__ void tile_body(const Params& P, int64_t base, int64_t
 }
 
 template <bool F64, int MODE>
-__global__ void __launch_bounds__(kThreads) k_fused(const __grid_constant__ Params P)
+__global__ void __launch_bounds__(kThreads, 2) k_fused(const __grid_constant__ Params P)
 {
     __shared__ __align__(16) uint32_t s_lvx[kTilePairs * 7];      // 1024 x 14 B records
     __shared__ TileMeta s_tm;

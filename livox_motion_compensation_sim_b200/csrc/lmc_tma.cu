@@ -16,6 +16,7 @@
 //                   output side needs no CTA-wide barrier at all.
 //
 // Edge tiles (a shard's ragged first / last tile) skip TMA and take guarded global loads.
+#include <type_traits>
 #include "lmc_device.cuh"
 
 namespace lmc {
@@ -76,12 +77,15 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
     const bool has_tag = P.lvx14 != nullptr && P.tag != nullptr && P.lvx_mode == LMC_LVX2_OF_OUTPUT;
     const int64_t base = ti.base;
 
-    Pt in[PPT][2];
+    // raw inputs stay in their storage type (float4 for the f32 layout) until the pair is computed
+    using Raw = typename std::conditional<F64, Pt, float4>::type;
+    Raw raw[PPT][2];
     bool valid[PPT][2];
     int64_t tsv[PPT][2];
     uint32_t tagv[PPT];
     int32_t fr[PPT][2];
     bool single[PPT][2];
+    int64_t fsv[PPT][2];
 
     // ---- registers <- stage (full tile) or <- global (edge tile) --------------------------------
 #pragma unroll
@@ -90,24 +94,29 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
         const int64_t p = base + 2 * q;
         const bool va = FULL || (p >= ti.lim_lo && p < ti.lim_hi), vb = FULL || (p + 1 >= ti.lim_lo && p + 1 < ti.lim_hi);
         valid[j][0] = va; valid[j][1] = vb;
-        in[j][0] = in[j][1] = Pt{ 0.0, 0.0, 0.0, 0.0 };
         tsv[j][0] = tsv[j][1] = 0; tagv[j] = 0;
         if constexpr (FULL) {
             if constexpr (F64) {
                 const double2* s = reinterpret_cast<const double2*>(s_pts) + 4 * q;
-                const double2 a0 = s[0], a1 = s[1], b0 = s[2], b1 = s[3];
-                in[j][0] = { a0.x, a0.y, a1.x, a1.y }; in[j][1] = { b0.x, b0.y, b1.x, b1.y };
+                const double2 pa0 = s[0], pa1 = s[1], pb0 = s[2], pb1 = s[3];
+                raw[j][0] = Pt{ pa0.x, pa0.y, pa1.x, pa1.y }; raw[j][1] = Pt{ pb0.x, pb0.y, pb1.x, pb1.y };
                 if (has_ts) { const longlong2 t = reinterpret_cast<const longlong2*>(s_ts)[q]; tsv[j][0] = t.x; tsv[j][1] = t.y; }
             } else {
                 const float4* s = reinterpret_cast<const float4*>(s_pts) + 2 * q;
-                const float4 a = s[0], b = s[1];
-                in[j][0] = { (double)a.x, (double)a.y, (double)a.z, (double)a.w };
-                in[j][1] = { (double)b.x, (double)b.y, (double)b.z, (double)b.w };
+                raw[j][0] = s[0]; raw[j][1] = s[1];
                 if (has_ts) { const uint2 t = reinterpret_cast<const uint2*>(s_ts)[q]; tsv[j][0] = t.x; tsv[j][1] = t.y; }
             }
             if (has_tag) tagv[j] = reinterpret_cast<const uint16_t*>(s_tag)[q];
         } else {
-            load_pair<F64, false>(P.pts, p, va, vb, in[j][0], in[j][1]);
+            if constexpr (F64) {
+                raw[j][0] = raw[j][1] = Pt{ 0.0, 0.0, 0.0, 0.0 };
+                load_pair<true, false>(P.pts, p, va, vb, raw[j][0], raw[j][1]);
+            } else {
+                raw[j][0] = raw[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4* src = reinterpret_cast<const float4*>(P.pts) + p;
+                if (va) raw[j][0] = __ldg(src);
+                if (vb) raw[j][1] = __ldg(src + 1);
+            }
             if (has_ts) {
                 if constexpr (F64) { const int64_t* t = reinterpret_cast<const int64_t*>(P.ts) + p; if (va) tsv[j][0] = __ldg(t); if (vb) tsv[j][1] = __ldg(t + 1); }
                 else { const uint32_t* t = reinterpret_cast<const uint32_t*>(P.ts) + p; if (va) tsv[j][0] = __ldg(t); if (vb) tsv[j][1] = __ldg(t + 1); }
@@ -116,8 +125,19 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            fr[j][h] = 0; single[j][h] = false;
-            if constexpr (MODE != kQuantOnly) { if (FULL || valid[j][h]) fr[j][h] = frame_of(P, tm, p + h, single[j][h]); }
+            fr[j][h] = 0; single[j][h] = false; fsv[j][h] = 0;
+            if constexpr (MODE != kQuantOnly) {
+                if (FULL || valid[j][h]) {
+                    fr[j][h] = frame_of(P, tm, p + h, single[j][h]);
+                    if constexpr (MODE == kGyro || MODE == kSlerp) {
+                        if (P.frame_start != nullptr) {
+                            const int64_t fs = frame_start_of(P, tm, fr[j][h]);
+                            if constexpr (MODE == kSlerp && !F64) tsv[j][h] += fs;        // absolute time now; fs no longer needed
+                            else fsv[j][h] = fs;
+                        }
+                    }
+                }
+            }
         }
     }
     // everything this warp needs from the stage is in registers: hand the slot back to the producer
@@ -130,15 +150,24 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
         const int q = (cw * PPT + j) * 32 + lane;
         const int64_t p = base + 2 * q;
         const bool va = valid[j][0], vb = valid[j][1];
-        Pt o0 = in[j][0], o1 = in[j][1];
-        if (FULL || va) ctx.point(P, fr[j][0], single[j][0], tsv[j][0], in[j][0], o0);
-        if (FULL || vb) ctx.point(P, fr[j][1], single[j][1], tsv[j][1], in[j][1], o1);
-        if (P.out != nullptr) store_pair<F64, FULL>(P.out, p, va, vb, o0, o1);
-        store_las_pair<FULL>(P, p, va, vb, o0, o1, fl);
+        Pt in[2];
+        if constexpr (F64) { in[0] = raw[j][0]; in[1] = raw[j][1]; }
+        else {
+            in[0] = Pt{ (double)raw[j][0].x, (double)raw[j][0].y, (double)raw[j][0].z, (double)raw[j][0].w };
+            in[1] = Pt{ (double)raw[j][1].x, (double)raw[j][1].y, (double)raw[j][1].z, (double)raw[j][1].w };
+        }
+        Pt o[2] = { in[0], in[1] };
+        if (FULL || (va && vb)) ctx.pair(P, fr[j], single[j], fsv[j], tsv[j], in, o);
+        else {
+            if (va) o[0] = ctx.one(P, fr[j][0], single[j][0], fsv[j][0], tsv[j][0], in[0]);
+            if (vb) o[1] = ctx.one(P, fr[j][1], single[j][1], fsv[j][1], tsv[j][1], in[1]);
+        }
+        if (P.out != nullptr) store_pair<F64, FULL>(P.out, p, va, vb, o[0], o[1]);
+        store_las_pair<FULL>(P, p, va, vb, o[0], o[1], fl);
         if (P.lvx14 != nullptr) {
             uint32_t x[2] = {0, 0}, y[2] = {0, 0}, z[2] = {0, 0}, rt[2] = {0, 0};
-            if (FULL || va) lvx_words<MODE>(P, in[j][0], o0, tagv[j] & 0xffu, x[0], y[0], z[0], rt[0], fl);
-            if (FULL || vb) lvx_words<MODE>(P, in[j][1], o1, (tagv[j] >> 8) & 0xffu, x[1], y[1], z[1], rt[1], fl);
+            if (FULL || va) lvx_words<MODE>(P, in[0], o[0], tagv[j] & 0xffu, x[0], y[0], z[0], rt[0], fl);
+            if (FULL || vb) lvx_words<MODE>(P, in[1], o[1], (tagv[j] >> 8) & 0xffu, x[1], y[1], z[1], rt[1], fl);
             lvx_pair_words(reinterpret_cast<uint32_t*>(slab) + 7 * (j * 32 + lane), x, y, z, rt);
         }
     }
@@ -170,8 +199,7 @@ template <bool F64, int MODE>
 __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_constant__ Params P, int64_t tile0, int64_t n_tiles)
 {
     using Cfg = StreamCfg<F64>;
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    extern __shared__ __align__(128) uint8_t smem[];                            // no static smem in this kernel: base is aligned
     uint8_t*  s_stage = smem;                                                   // kStages x STAGE
     uint8_t*  s_slab  = s_stage + kStages * Cfg::STAGE;                         // kCW x LVX_SLAB
     TileMeta* s_meta  = reinterpret_cast<TileMeta*>(s_slab + kCW * Cfg::LVX_SLAB);

@@ -169,7 +169,7 @@ def deskew_slerp(pts: torch.Tensor, ts: Optional[torch.Tensor], frame_off: torch
     fn = C.lib().lmc_deskew_slerp_f64 if f64 else C.lib().lmc_deskew_slerp_f32
     C.check(fn(_req(pts, pts.dtype, "pts", (4,)), _req(ts, torch.int64 if f64 else torch.uint32, "ts"),
                _req(frame_off, torch.int64, "frame_off"), _req(frame_start, torch.int64, "frame_start"),
-               _req(sample_ts, torch.int64, "sample_ts"), _req(seg, torch.float64, "seg", (20,)), sample_ts.shape[0],
+               _req(sample_ts, torch.int64, "sample_ts"), _req(seg, torch.float64, "seg", (22,)), sample_ts.shape[0],
                _req(hold_idx, torch.int32, "hold_idx"), _req(out, pts.dtype, "out", (4,)), n, F, b, e,
                None if ex is None else C.ctypes.byref(ex), _stream_ptr()))
     return out, bufs
