@@ -58,11 +58,12 @@ def lib() -> ctypes.CDLL:
     """Load liblmc_b200.so (built in-tree by __graft_entry__.build() / _build.build_library())."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("LMC_B200_LIB", LIB_PATH)       # experiments: alternative builds of the same ABI
+        if not os.path.exists(path):
             raise RuntimeError(
-                f"{LIB_PATH} is missing: build it with `python -m livox_motion_compensation_sim_b200._build` "
+                f"{path} is missing: build it with `python -m livox_motion_compensation_sim_b200._build` "
                 "(nvcc, sm_100a). There is no CPU fallback for this path.")
-        L = ctypes.CDLL(LIB_PATH)
+        L = ctypes.CDLL(path)
         for name, (args, res) in _SIGNATURES.items():
             fn = getattr(L, name)           # AttributeError if the library does not export it
             fn.argtypes, fn.restype = args, res

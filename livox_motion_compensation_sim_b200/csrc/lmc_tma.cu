@@ -21,9 +21,15 @@
 
 namespace lmc {
 
-constexpr int kCW            = 15;                       // consumer warps (15 + producer = 512 threads -> 128 regs each)
+#ifndef LMC_CW
+#define LMC_CW 15
+#endif
+#ifndef LMC_STAGES
+#define LMC_STAGES 4
+#endif
+constexpr int kCW            = LMC_CW;                   // consumer warps (15 + producer = 512 threads -> 128 regs each)
 constexpr int kStreamThreads = 32 * (kCW + 1);           // + producer warp
-constexpr int kStages        = 4;
+constexpr int kStages        = LMC_STAGES;
 
 template <bool F64> struct StreamCfg {
     static constexpr int PPT      = F64 ? 1 : 2;                 // point pairs per consumer thread per tile
@@ -77,97 +83,102 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
     const bool has_tag = P.lvx14 != nullptr && P.tag != nullptr && P.lvx_mode == LMC_LVX2_OF_OUTPUT;
     const int64_t base = ti.base;
 
-    // raw inputs stay in their storage type (float4 for the f32 layout) until the pair is computed
-    using Raw = typename std::conditional<F64, Pt, float4>::type;
-    Raw raw[PPT][2];
-    bool valid[PPT][2];
-    int64_t tsv[PPT][2];
-    uint32_t tagv[PPT];
-    int32_t fr[PPT][2];
-    bool single[PPT][2];
-    int64_t fsv[PPT][2];
+    // tile-level frame facts in registers: a tile rarely holds more than one frame boundary
+    int32_t m_nb = 0, m_flo = 0; bool m_simple = true;
+    int64_t m_e0 = 0, m_e1 = 0, m_e2 = 0, m_fs0 = 0, m_fs1 = 0;
+    if constexpr (MODE != kQuantOnly) {
+        m_nb = tm.nb; m_flo = tm.f_lo;
+        m_simple = !tm.overflow && m_nb <= 1;
+        if (m_simple) {
+            m_e0 = tm.edge[0]; m_e1 = tm.edge[1]; m_e2 = tm.edge[m_nb + 1];
+            if ((MODE == kGyro || MODE == kSlerp) && P.frame_start != nullptr) { m_fs0 = tm.fstart[0]; m_fs1 = tm.fstart[m_nb]; }
+        }
+    }
 
-    // ---- registers <- stage (full tile) or <- global (edge tile) --------------------------------
+    // one point pair at a time: stage -> registers -> f64 work -> stores (short live ranges); the
+    // stage is handed back to the producer as soon as the LAST pair has been pulled out of it
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
         const int q = (cw * PPT + j) * 32 + lane;            // pair index inside the tile
         const int64_t p = base + 2 * q;
         const bool va = FULL || (p >= ti.lim_lo && p < ti.lim_hi), vb = FULL || (p + 1 >= ti.lim_lo && p + 1 < ti.lim_hi);
-        valid[j][0] = va; valid[j][1] = vb;
-        tsv[j][0] = tsv[j][1] = 0; tagv[j] = 0;
+        Pt in[2];
+        float wraw[2] = {0.f, 0.f};
+        int64_t tsv[2] = {0, 0};
+        uint32_t tagv = 0;
+        in[0] = in[1] = Pt{ 0.0, 0.0, 0.0, 0.0 };
         if constexpr (FULL) {
             if constexpr (F64) {
                 const double2* s = reinterpret_cast<const double2*>(s_pts) + 4 * q;
                 const double2 pa0 = s[0], pa1 = s[1], pb0 = s[2], pb1 = s[3];
-                raw[j][0] = Pt{ pa0.x, pa0.y, pa1.x, pa1.y }; raw[j][1] = Pt{ pb0.x, pb0.y, pb1.x, pb1.y };
-                if (has_ts) { const longlong2 t = reinterpret_cast<const longlong2*>(s_ts)[q]; tsv[j][0] = t.x; tsv[j][1] = t.y; }
+                in[0] = Pt{ pa0.x, pa0.y, pa1.x, pa1.y }; in[1] = Pt{ pb0.x, pb0.y, pb1.x, pb1.y };
+                if (has_ts) { const longlong2 t = reinterpret_cast<const longlong2*>(s_ts)[q]; tsv[0] = t.x; tsv[1] = t.y; }
             } else {
                 const float4* s = reinterpret_cast<const float4*>(s_pts) + 2 * q;
-                raw[j][0] = s[0]; raw[j][1] = s[1];
-                if (has_ts) { const uint2 t = reinterpret_cast<const uint2*>(s_ts)[q]; tsv[j][0] = t.x; tsv[j][1] = t.y; }
+                const float4 ra = s[0], rb = s[1];
+                in[0] = Pt{ (double)ra.x, (double)ra.y, (double)ra.z, (double)ra.w };
+                in[1] = Pt{ (double)rb.x, (double)rb.y, (double)rb.z, (double)rb.w };
+                wraw[0] = ra.w; wraw[1] = rb.w;
+                if (has_ts) { const uint2 t = reinterpret_cast<const uint2*>(s_ts)[q]; tsv[0] = t.x; tsv[1] = t.y; }
             }
-            if (has_tag) tagv[j] = reinterpret_cast<const uint16_t*>(s_tag)[q];
+            if (has_tag) tagv = reinterpret_cast<const uint16_t*>(s_tag)[q];
         } else {
-            if constexpr (F64) {
-                raw[j][0] = raw[j][1] = Pt{ 0.0, 0.0, 0.0, 0.0 };
-                load_pair<true, false>(P.pts, p, va, vb, raw[j][0], raw[j][1]);
-            } else {
-                raw[j][0] = raw[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4* src = reinterpret_cast<const float4*>(P.pts) + p;
-                if (va) raw[j][0] = __ldg(src);
-                if (vb) raw[j][1] = __ldg(src + 1);
-            }
+            load_pair<F64, false>(P.pts, p, va, vb, in[0], in[1]);
+            wraw[0] = (float)in[0].w; wraw[1] = (float)in[1].w;
             if (has_ts) {
-                if constexpr (F64) { const int64_t* t = reinterpret_cast<const int64_t*>(P.ts) + p; if (va) tsv[j][0] = __ldg(t); if (vb) tsv[j][1] = __ldg(t + 1); }
-                else { const uint32_t* t = reinterpret_cast<const uint32_t*>(P.ts) + p; if (va) tsv[j][0] = __ldg(t); if (vb) tsv[j][1] = __ldg(t + 1); }
+                if constexpr (F64) { const int64_t* t = reinterpret_cast<const int64_t*>(P.ts) + p; if (va) tsv[0] = __ldg(t); if (vb) tsv[1] = __ldg(t + 1); }
+                else { const uint32_t* t = reinterpret_cast<const uint32_t*>(P.ts) + p; if (va) tsv[0] = __ldg(t); if (vb) tsv[1] = __ldg(t + 1); }
             }
-            if (has_tag) { if (va) tagv[j] |= __ldg(P.tag + p); if (vb) tagv[j] |= (uint32_t)__ldg(P.tag + p + 1) << 8; }
+            if (has_tag) { if (va) tagv |= __ldg(P.tag + p); if (vb) tagv |= (uint32_t)__ldg(P.tag + p + 1) << 8; }
         }
+        int32_t fr[2] = {0, 0}; bool single[2] = {false, false}; int64_t fsv[2] = {0, 0};
+        if constexpr (MODE != kQuantOnly) {
+            if (m_simple) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            fr[j][h] = 0; single[j][h] = false; fsv[j][h] = 0;
-            if constexpr (MODE != kQuantOnly) {
-                if (FULL || valid[j][h]) {
-                    fr[j][h] = frame_of(P, tm, p + h, single[j][h]);
-                    if constexpr (MODE == kGyro || MODE == kSlerp) {
-                        if (P.frame_start != nullptr) {
-                            const int64_t fs = frame_start_of(P, tm, fr[j][h]);
-                            if constexpr (MODE == kSlerp && !F64) tsv[j][h] += fs;        // absolute time now; fs no longer needed
-                            else fsv[j][h] = fs;
-                        }
+                for (int h = 0; h < 2; ++h) {
+                    const bool second = m_nb == 1 && m_e1 <= p + h;
+                    fr[h] = m_flo + (second ? 1 : 0);
+                    if constexpr (MODE == kRigid) single[h] = second ? (m_e2 - m_e1 == 1) : (m_e1 - m_e0 == 1);
+                    fsv[h] = second ? m_fs1 : m_fs0;
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (FULL || (h == 0 ? va : vb)) {
+                        fr[h] = frame_of(P, tm, p + h, single[h]);
+                        if ((MODE == kGyro || MODE == kSlerp) && P.frame_start != nullptr) fsv[h] = frame_start_of(P, tm, fr[h]);
                     }
+            }
+        }
+        if (j == PPT - 1) {                                  // everything this warp needs from the stage is in registers
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar);
+        }
+
+        Pt o[2] = { in[0], in[1] };
+        if (FULL || (va && vb)) ctx.pair(P, fr, single, fsv, tsv, in, o);
+        else {
+            if (va) o[0] = ctx.one(P, fr[0], single[0], fsv[0], tsv[0], in[0]);
+            if (vb) o[1] = ctx.one(P, fr[1], single[1], fsv[1], tsv[1], in[1]);
+        }
+        if (P.out != nullptr) {
+            if constexpr (F64) store_pair<true, FULL>(P.out, p, va, vb, o[0], o[1]);
+            else {
+                float* dst = reinterpret_cast<float*>(P.out) + 4 * p;
+                if (FULL || (va && vb)) {
+                    const float v[8] = { (float)o[0].x, (float)o[0].y, (float)o[0].z, wraw[0], (float)o[1].x, (float)o[1].y, (float)o[1].z, wraw[1] };
+                    stg256(dst, v);
+                } else {
+                    if (va) *reinterpret_cast<float4*>(dst)     = make_float4((float)o[0].x, (float)o[0].y, (float)o[0].z, wraw[0]);
+                    if (vb) *reinterpret_cast<float4*>(dst + 4) = make_float4((float)o[1].x, (float)o[1].y, (float)o[1].z, wraw[1]);
                 }
             }
         }
-    }
-    // everything this warp needs from the stage is in registers: hand the slot back to the producer
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty_bar);
-
-    // ---- f64 work + stores, one point pair at a time (short live ranges) ----------------------
-#pragma unroll
-    for (int j = 0; j < PPT; ++j) {
-        const int q = (cw * PPT + j) * 32 + lane;
-        const int64_t p = base + 2 * q;
-        const bool va = valid[j][0], vb = valid[j][1];
-        Pt in[2];
-        if constexpr (F64) { in[0] = raw[j][0]; in[1] = raw[j][1]; }
-        else {
-            in[0] = Pt{ (double)raw[j][0].x, (double)raw[j][0].y, (double)raw[j][0].z, (double)raw[j][0].w };
-            in[1] = Pt{ (double)raw[j][1].x, (double)raw[j][1].y, (double)raw[j][1].z, (double)raw[j][1].w };
-        }
-        Pt o[2] = { in[0], in[1] };
-        if (FULL || (va && vb)) ctx.pair(P, fr[j], single[j], fsv[j], tsv[j], in, o);
-        else {
-            if (va) o[0] = ctx.one(P, fr[j][0], single[j][0], fsv[j][0], tsv[j][0], in[0]);
-            if (vb) o[1] = ctx.one(P, fr[j][1], single[j][1], fsv[j][1], tsv[j][1], in[1]);
-        }
-        if (P.out != nullptr) store_pair<F64, FULL>(P.out, p, va, vb, o[0], o[1]);
         store_las_pair<FULL>(P, p, va, vb, o[0], o[1], fl);
         if (P.lvx14 != nullptr) {
             uint32_t x[2] = {0, 0}, y[2] = {0, 0}, z[2] = {0, 0}, rt[2] = {0, 0};
-            if (FULL || va) lvx_words<MODE>(P, in[0], o[0], tagv[j] & 0xffu, x[0], y[0], z[0], rt[0], fl);
-            if (FULL || vb) lvx_words<MODE>(P, in[1], o[1], (tagv[j] >> 8) & 0xffu, x[1], y[1], z[1], rt[1], fl);
+            if (FULL || va) lvx_words<MODE>(P, in[0], o[0], tagv & 0xffu, x[0], y[0], z[0], rt[0], fl);
+            if (FULL || vb) lvx_words<MODE>(P, in[1], o[1], (tagv >> 8) & 0xffu, x[1], y[1], z[1], rt[1], fl);
             lvx_pair_words(reinterpret_cast<uint32_t*>(slab) + 7 * (j * 32 + lane), x, y, z, rt);
         }
     }
