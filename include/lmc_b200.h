@@ -127,7 +127,8 @@ int lmc_deskew_gyro_f32(const float* pts_n4, const uint32_t* ts_off, const int64
  *   k = bracket(sample_ts, ts) ; alpha = (ts - t_k) * inv_dt_k      (inv_dt_k = 1/(t_{k+1} - t_k) from seg)
  *   out = SLERP(R_k, R_{k+1}, alpha) p + lerp(pos_k, pos_{k+1}, alpha)
  * seg: (n_samples, 22) f64 per-sample table [R_k(9) pos_k(3) axis_k(3) theta_k dpos_k(3) inv_dt_k
- *      t_k t_{k+1}] -- the last two are the raw int64 timestamps stored in double slots
+ *      t_k dt_k] -- the last two are raw int64 values (t_k, t_{k+1} - t_k) stored in double slots;
+ *      n_samples must be < 2^31
  *      (built by the host wrapper, see livox_motion_compensation_sim_b200/frames.py).
  * hold_idx (optional int32[n_frames]): every point of frame f takes sample hold_idx[f], alpha = 0
  *      -> Mode A expressed in Mode C (bit-identical to lmc_align_rigid_* for frames of >= 2 points).

@@ -445,7 +445,7 @@ __device__ __noinline__ Pt point_eval_slow(const Params& P, int32_t f, bool sing
 template <bool F64, int MODE>
 struct PointCtx {
     double  tab[MODE == kSlerp ? kSegStride : 12];
-    int64_t key = -1;            // frame (Mode A) or sample index (Mode C) held in tab
+    int32_t key = -1;            // frame (Mode A) or sample index (Mode C) held in tab
     int64_t t0 = 0;              // Mode B/C: first sample time and mean sample rate for the bracket guess
     double  rate = 0.0;
 
@@ -465,11 +465,13 @@ struct PointCtx {
         else return point_eval_slow<F64, MODE>(P, f, single, fs, tsraw, in, t0, rate);
     }
 
+    // LEAN: the launcher has checked hold_idx == NULL, 2 <= n_samp < 2^31 (Mode C) -- no runtime tests here
+    template <bool LEAN = false>
     __device__ __forceinline__ void pair(const Params& P, const int32_t (&f)[2], const bool (&single)[2], const int64_t (&fs)[2],
                                          const int64_t (&tsraw)[2], const Pt (&in)[2], Pt (&out)[2]) {
         if constexpr (MODE == kRigid) {
             if (f[0] == f[1] && !single[0]) {
-                if (f[0] != key) {
+                if (f[0] != (int32_t)key) {
                     const double2* pr = reinterpret_cast<const double2*>(P.pose_Rt + 12 * (int64_t)f[0]);
 #pragma unroll
                     for (int q = 0; q < 6; ++q) { const double2 v = __ldg(pr + q); tab[2 * q] = v.x; tab[2 * q + 1] = v.y; }
@@ -482,22 +484,25 @@ struct PointCtx {
         }
         if constexpr (MODE == kSlerp) {
             const int64_t S = P.n_samp;
-            if (P.hold_idx == nullptr && S >= 2) {
+            if (LEAN || (P.hold_idx == nullptr && S >= 2 && S < 0x7fffffffLL)) {
                 const int64_t ta = F64 ? tsraw[0] : tsraw[0] + fs[0];
                 const int64_t tb = F64 ? tsraw[1] : tsraw[1] + fs[1];
-                int64_t k = __double2ll_rz(__dmul_rn((double)(ta - t0), rate));     // bracket guess from the mean rate
-                k = k < 0 ? 0 : (k > S - 2 ? S - 2 : k);
-                if (k != key) {
-                    const double2* sr = reinterpret_cast<const double2*>(P.samp_tab + kSegStride * k);
+                // bracket guess from the mean sample rate (saturating conversion, then clamp to a real segment)
+                int32_t k = __double2int_rz(__dmul_rn((double)(ta - t0), rate));
+                k = max(0, min(k, (int32_t)S - 2));
+                if (k != (int32_t)key) {
+                    const double2* sr = reinterpret_cast<const double2*>(P.samp_tab + (int64_t)kSegStride * k);
 #pragma unroll
                     for (int q = 0; q < kSegStride / 2; ++q) { const double2 v = __ldg(sr + q); tab[2 * q] = v.x; tab[2 * q + 1] = v.y; }
                     key = k;
                 }
-                const int64_t tk = __double_as_longlong(tab[20]), tn = __double_as_longlong(tab[21]);
-                // the row's own [t_k, t_{k+1}) verifies the guess for both points at once
-                if (tk <= ta && ta < tn && tk <= tb && tb < tn && tab[15] <= 0.49) {
-                    const double a0 = __dmul_rn((double)(ta - tk), tab[19]);
-                    const double a1 = __dmul_rn((double)(tb - tk), tab[19]);
+                const int64_t tk = __double_as_longlong(tab[20]);
+                const uint64_t dtk = (uint64_t)__double_as_longlong(tab[21]);
+                const int64_t da = ta - tk, db = tb - tk;
+                // the row's own [t_k, t_k + dt_k) verifies the guess for both points at once
+                if ((uint64_t)da < dtk && (uint64_t)db < dtk && tab[15] <= 0.49) {
+                    const double a0 = __dmul_rn((double)da, tab[19]);
+                    const double a1 = __dmul_rn((double)db, tab[19]);
                     slerp_apply<true>(tab, a0, in[0], out[0]);
                     slerp_apply<true>(tab, a1, in[1], out[1]);
                     return;

@@ -48,50 +48,65 @@ struct TileInfo { int64_t base, lim_lo, lim_hi; int32_t full, pad; };     // 32 
 
 // ---- mbarrier / bulk-copy PTX ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra D;\n\tbra W;\n\tD:\n\t}"
-        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+        :: "r"(bar), "r"(parity) : "memory");
 }
 // global -> shared bulk copy (TMA, 1-D): 16-byte aligned addresses, size multiple of 16
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// Export configuration known at compile time ("lean" kernels) or tested at run time (kExGeneric).
+// Lean variants also assume what the launcher has verified: LVX records are type-2-of-input without
+// tag bytes, timestamps / frame starts are present where the mode needs them, no hold_idx,
+// 2 <= n_samp < 2^31.
+constexpr int kExOut = 1, kExLvx = 2, kExLas = 4, kExGeneric = 8;
+
 // ---- one tile on the consumer side ------------------------------------------------------------
-template <bool F64, int MODE, bool FULL>
+template <bool F64, int MODE, int EX, bool FULL>
 __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti, const TileMeta& tm,
                                              const uint8_t* s_pts, const uint8_t* s_ts, const uint8_t* s_tag,
-                                             uint8_t* slab, uint64_t* empty_bar, PointCtx<F64, MODE>& ctx,
+                                             uint8_t* slab, uint32_t empty_bar, PointCtx<F64, MODE>& ctx,
                                              uint32_t& fl, int cw, int lane)
 {
     using Cfg = StreamCfg<F64>;
     constexpr int PPT = Cfg::PPT;
-    const bool has_ts = (MODE == kGyro || MODE == kSlerp) && P.ts != nullptr;
-    const bool has_tag = P.lvx14 != nullptr && P.tag != nullptr && P.lvx_mode == LMC_LVX2_OF_OUTPUT;
+    constexpr bool GEN = EX == kExGeneric;
+    const bool do_out = GEN ? P.out != nullptr : bool(EX & kExOut);
+    const bool do_lvx = GEN ? P.lvx14 != nullptr : bool(EX & kExLvx);
+    const bool do_las = GEN ? (P.las_x != nullptr || P.las_int != nullptr) : bool(EX & kExLas);
+    const bool has_ts = (MODE == kGyro || MODE == kSlerp) && (GEN ? P.ts != nullptr : true);
+    const bool has_fs = (MODE == kGyro || MODE == kSlerp) && (GEN ? P.frame_start != nullptr : (MODE == kGyro || !F64));
+    const bool has_tag = GEN && do_lvx && P.tag != nullptr && P.lvx_mode == LMC_LVX2_OF_OUTPUT;
     const int64_t base = ti.base;
 
-    // tile-level frame facts in registers: a tile rarely holds more than one frame boundary
-    int32_t m_nb = 0, m_flo = 0; bool m_simple = true;
-    int64_t m_e0 = 0, m_e1 = 0, m_e2 = 0, m_fs0 = 0, m_fs1 = 0;
+    // tile-level frame facts in registers: a tile rarely holds more than one frame boundary.
+    // rel_e1 = tile-local index of the first point of the second frame (INT_MAX: none)
+    int32_t m_flo = 0, rel_e1 = 0x7fffffff; bool m_simple = true, m_single0 = false, m_single1 = false;
+    int64_t m_fs0 = 0, m_fs1 = 0;
     if constexpr (MODE != kQuantOnly) {
-        m_nb = tm.nb; m_flo = tm.f_lo;
-        m_simple = !tm.overflow && m_nb <= 1;
+        const int32_t nb = tm.nb;
+        m_flo = tm.f_lo;
+        m_simple = !tm.overflow && nb <= 1;
         if (m_simple) {
-            m_e0 = tm.edge[0]; m_e1 = tm.edge[1]; m_e2 = tm.edge[m_nb + 1];
-            if ((MODE == kGyro || MODE == kSlerp) && P.frame_start != nullptr) { m_fs0 = tm.fstart[0]; m_fs1 = tm.fstart[m_nb]; }
+            const int64_t e1 = tm.edge[1];
+            if (nb == 1) rel_e1 = (int32_t)(e1 - base);
+            if constexpr (MODE == kRigid) { m_single0 = e1 - tm.edge[0] == 1; m_single1 = tm.edge[nb + 1] - e1 == 1; }
+            if (has_fs) { m_fs0 = tm.fstart[0]; m_fs1 = tm.fstart[nb]; }
         }
     }
 
@@ -136,9 +151,9 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
             if (m_simple) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const bool second = m_nb == 1 && m_e1 <= p + h;
+                    const bool second = 2 * q + h >= rel_e1;
                     fr[h] = m_flo + (second ? 1 : 0);
-                    if constexpr (MODE == kRigid) single[h] = second ? (m_e2 - m_e1 == 1) : (m_e1 - m_e0 == 1);
+                    if constexpr (MODE == kRigid) single[h] = second ? m_single1 : m_single0;
                     fsv[h] = second ? m_fs1 : m_fs0;
                 }
             } else {
@@ -146,7 +161,7 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
                 for (int h = 0; h < 2; ++h)
                     if (FULL || (h == 0 ? va : vb)) {
                         fr[h] = frame_of(P, tm, p + h, single[h]);
-                        if ((MODE == kGyro || MODE == kSlerp) && P.frame_start != nullptr) fsv[h] = frame_start_of(P, tm, fr[h]);
+                        if (has_fs) fsv[h] = frame_start_of(P, tm, fr[h]);
                     }
             }
         }
@@ -156,12 +171,12 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
         }
 
         Pt o[2] = { in[0], in[1] };
-        if (FULL || (va && vb)) ctx.pair(P, fr, single, fsv, tsv, in, o);
+        if (FULL || (va && vb)) ctx.template pair<!GEN>(P, fr, single, fsv, tsv, in, o);
         else {
             if (va) o[0] = ctx.one(P, fr[0], single[0], fsv[0], tsv[0], in[0]);
             if (vb) o[1] = ctx.one(P, fr[1], single[1], fsv[1], tsv[1], in[1]);
         }
-        if (P.out != nullptr) {
+        if (do_out) {
             if constexpr (F64) store_pair<true, FULL>(P.out, p, va, vb, o[0], o[1]);
             else {
                 float* dst = reinterpret_cast<float*>(P.out) + 4 * p;
@@ -174,15 +189,24 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
                 }
             }
         }
-        store_las_pair<FULL>(P, p, va, vb, o[0], o[1], fl);
-        if (P.lvx14 != nullptr) {
+        if (do_las) store_las_pair<FULL>(P, p, va, vb, o[0], o[1], fl);
+        if (do_lvx) {
             uint32_t x[2] = {0, 0}, y[2] = {0, 0}, z[2] = {0, 0}, rt[2] = {0, 0};
-            if (FULL || va) lvx_words<MODE>(P, in[0], o[0], tagv & 0xffu, x[0], y[0], z[0], rt[0], fl);
-            if (FULL || vb) lvx_words<MODE>(P, in[1], o[1], (tagv >> 8) & 0xffu, x[1], y[1], z[1], rt[1], fl);
+            if constexpr (GEN) {
+                if (FULL || va) lvx_words<MODE>(P, in[0], o[0], tagv & 0xffu, x[0], y[0], z[0], rt[0], fl);
+                if (FULL || vb) lvx_words<MODE>(P, in[1], o[1], (tagv >> 8) & 0xffu, x[1], y[1], z[1], rt[1], fl);
+            } else {                                        // lean: LMC:252-272 on the raw input point
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (FULL || (h == 0 ? va : vb)) {
+                        x[h] = (uint32_t)q_mm_clip(in[h].x, fl); y[h] = (uint32_t)q_mm_clip(in[h].y, fl); z[h] = (uint32_t)q_mm_clip(in[h].z, fl);
+                        rt[h] = q_refl(in[h].w, fl);
+                    }
+            }
             lvx_pair_words(reinterpret_cast<uint32_t*>(slab) + 7 * (j * 32 + lane), x, y, z, rt);
         }
     }
-    if (P.lvx14 != nullptr) {
+    if (do_lvx) {
         __syncwarp();
         // the warp's PPT x 64 records are contiguous in the output: 16-byte coalesced stores
         const int64_t wfirst = base + 2 * (int64_t)(cw * PPT) * 32;          // first point of the warp's block
@@ -206,10 +230,11 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
     }
 }
 
-template <bool F64, int MODE>
+template <bool F64, int MODE, int EX>
 __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_constant__ Params P, int64_t tile0, int64_t n_tiles)
 {
     using Cfg = StreamCfg<F64>;
+    constexpr bool GEN = EX == kExGeneric;
     extern __shared__ __align__(128) uint8_t smem[];                            // no static smem in this kernel: base is aligned
     uint8_t*  s_stage = smem;                                                   // kStages x STAGE
     uint8_t*  s_slab  = s_stage + kStages * Cfg::STAGE;                         // kCW x LVX_SLAB
@@ -218,25 +243,27 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
     uint64_t* s_full  = reinterpret_cast<uint64_t*>(s_info + kStages);
     uint64_t* s_empty = s_full + kStages;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    asm volatile("" : "+r"(warp), "+r"(lane));                                  // keep them in registers (no S2R re-reads in the loop)
     const int64_t t_begin = n_tiles * (int64_t)blockIdx.x / gridDim.x;
     const int64_t t_end   = n_tiles * (int64_t)(blockIdx.x + 1) / gridDim.x;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(s_full + s, 1); mbar_init(s_empty + s, kCW); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(s_full + s), 1); mbar_init(smem_u32(s_empty + s), kCW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    const uint32_t full0 = smem_u32(s_full), empty0 = smem_u32(s_empty);       // barrier s lives at +8*s
 
-    const bool has_ts = (MODE == kGyro || MODE == kSlerp) && P.ts != nullptr;
-    const bool has_tag = P.lvx14 != nullptr && P.tag != nullptr && P.lvx_mode == LMC_LVX2_OF_OUTPUT;
+    const bool has_ts = (MODE == kGyro || MODE == kSlerp) && (GEN ? P.ts != nullptr : true);
+    const bool has_tag = GEN && P.lvx14 != nullptr && P.tag != nullptr && P.lvx_mode == LMC_LVX2_OF_OUTPUT;
 
     if (warp == kCW) {
         // ================================ producer warp ==========================================
         int s = 0; uint32_t ph = 0;
         int64_t hint = -1;
         for (int64_t t = t_begin; t < t_end; ++t) {
-            mbar_wait(s_empty + s, ph ^ 1);                                      // slot free (first lap passes)
+            mbar_wait(empty0 + 8 * s, ph ^ 1);                                   // slot free (first lap passes)
             const int64_t base = tile0 + t * Cfg::TP;
             const int64_t lim_lo = base > P.p_begin ? base : P.p_begin;
             const int64_t lim_hi = base + Cfg::TP < P.p_end ? base + Cfg::TP : P.p_end;
@@ -251,12 +278,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
                 uint8_t* st = s_stage + s * Cfg::STAGE;
                 if (full) {
                     const uint32_t bytes = Cfg::PTS_STAGE + (has_ts ? Cfg::TS_STAGE : 0) + (has_tag ? Cfg::TAG_STAGE : 0);
-                    mbar_arrive_expect_tx(s_full + s, bytes);
-                    bulk_g2s(st, reinterpret_cast<const uint8_t*>(P.pts) + base * Cfg::PT_BYTES, Cfg::PTS_STAGE, s_full + s);
-                    if (has_ts)  bulk_g2s(st + Cfg::PTS_STAGE, reinterpret_cast<const uint8_t*>(P.ts) + base * Cfg::TS_BYTES, Cfg::TS_STAGE, s_full + s);
-                    if (has_tag) bulk_g2s(st + Cfg::PTS_STAGE + Cfg::TS_STAGE, P.tag + base, Cfg::TAG_STAGE, s_full + s);
+                    mbar_arrive_expect_tx(full0 + 8 * s, bytes);
+                    bulk_g2s(st, reinterpret_cast<const uint8_t*>(P.pts) + base * Cfg::PT_BYTES, Cfg::PTS_STAGE, full0 + 8 * s);
+                    if (has_ts)  bulk_g2s(st + Cfg::PTS_STAGE, reinterpret_cast<const uint8_t*>(P.ts) + base * Cfg::TS_BYTES, Cfg::TS_STAGE, full0 + 8 * s);
+                    if (has_tag) bulk_g2s(st + Cfg::PTS_STAGE + Cfg::TS_STAGE, P.tag + base, Cfg::TAG_STAGE, full0 + 8 * s);
                 } else {
-                    mbar_arrive(s_full + s);                                       // edge tile: consumers read global memory
+                    mbar_arrive(full0 + 8 * s);                                    // edge tile: consumers read global memory
                 }
             }
             __syncwarp();
@@ -270,11 +297,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
         uint8_t* slab = s_slab + warp * Cfg::LVX_SLAB;
         int s = 0; uint32_t ph = 0;
         for (int64_t t = t_begin; t < t_end; ++t) {
-            mbar_wait(s_full + s, ph);
+            mbar_wait(full0 + 8 * s, ph);
             const TileInfo ti = s_info[s];
             const uint8_t* st = s_stage + s * Cfg::STAGE;
-            if (ti.full) consume_tile<F64, MODE, true>(P, ti, s_meta[s], st, st + Cfg::PTS_STAGE, st + Cfg::PTS_STAGE + Cfg::TS_STAGE, slab, s_empty + s, ctx, fl, warp, lane);
-            else         consume_tile<F64, MODE, false>(P, ti, s_meta[s], st, st + Cfg::PTS_STAGE, st + Cfg::PTS_STAGE + Cfg::TS_STAGE, slab, s_empty + s, ctx, fl, warp, lane);
+            if (ti.full) consume_tile<F64, MODE, EX, true>(P, ti, s_meta[s], st, st + Cfg::PTS_STAGE, st + Cfg::PTS_STAGE + Cfg::TS_STAGE, slab, empty0 + 8 * s, ctx, fl, warp, lane);
+            else         consume_tile<F64, MODE, EX, false>(P, ti, s_meta[s], st, st + Cfg::PTS_STAGE, st + Cfg::PTS_STAGE + Cfg::TS_STAGE, slab, empty0 + 8 * s, ctx, fl, warp, lane);
             if (++s == kStages) { s = 0; ph ^= 1; }
         }
         if (fl != 0 && P.status != nullptr) atomicOr(P.status, fl);
@@ -293,6 +320,21 @@ static int sm_count_cached() {
     return sms;
 }
 
+template <bool F64, int MODE, int EX>
+static cudaError_t launch_stream_ex(const Params& P, cudaStream_t st, int grid, int64_t tile0, int64_t n_tiles) {
+    using Cfg = StreamCfg<F64>;
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(k_stream<F64, MODE, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        if (e != cudaSuccess) return e;
+        attr_dev = dev;
+    }
+    k_stream<F64, MODE, EX><<<grid, kStreamThreads, Cfg::SMEM, st>>>(P, tile0, n_tiles);
+    return cudaGetLastError();
+}
+
 template <bool F64, int MODE>
 static cudaError_t launch_stream(const Params& P, cudaStream_t st, bool force, bool* handled) {
     using Cfg = StreamCfg<F64>;
@@ -301,21 +343,24 @@ static cudaError_t launch_stream(const Params& P, cudaStream_t st, bool force, b
     const int64_t tile0 = (P.p_begin / Cfg::TP) * Cfg::TP;                       // tiles aligned in GLOBAL index space
     const int64_t n_tiles = (P.p_end - tile0 + Cfg::TP - 1) / Cfg::TP;
     if (!force && n_tiles < 2 * (int64_t)sms) { *handled = false; return cudaSuccess; }   // too small to fill a persistent grid
-    *handled = true;
     // TMA sources must be 16-byte aligned: guaranteed by the 32-byte rule for points, checked here for the rest
     if (P.ts != nullptr && (reinterpret_cast<uintptr_t>(P.ts) & 15u)) { *handled = false; return cudaSuccess; }
     if (P.tag != nullptr && (reinterpret_cast<uintptr_t>(P.tag) & 15u)) { *handled = false; return cudaSuccess; }
-    static thread_local int attr_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (attr_dev != dev) {
-        cudaError_t e = cudaFuncSetAttribute(k_stream<F64, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-        if (e != cudaSuccess) return e;
-        attr_dev = dev;
-    }
+    *handled = true;
     const int grid = (int)(n_tiles < sms ? n_tiles : sms);
-    k_stream<F64, MODE><<<grid, kStreamThreads, Cfg::SMEM, st>>>(P, tile0, n_tiles);
-    return cudaGetLastError();
+    // lean (compile-time export configuration) variants for the common cases of Mode A / Mode C
+    if constexpr (MODE == kRigid || MODE == kSlerp) {
+        const int mask = (P.out ? kExOut : 0) | (P.lvx14 ? kExLvx : 0) | ((P.las_x || P.las_int) ? kExLas : 0);
+        bool lean = (!P.lvx14 || (P.lvx_mode == LMC_LVX_TYPE2_OF_INPUT)) && (!(mask & kExLas) || (P.las_x && P.las_int));
+        if (MODE == kSlerp) lean = lean && P.hold_idx == nullptr && P.ts != nullptr && P.n_samp >= 2 && P.n_samp < 0x7fffffffLL &&
+                                   (F64 || P.frame_start != nullptr);
+        if (lean) {
+            if (mask == kExOut)            return launch_stream_ex<F64, MODE, kExOut>(P, st, grid, tile0, n_tiles);
+            if (mask == (kExOut | kExLvx)) return launch_stream_ex<F64, MODE, kExOut | kExLvx>(P, st, grid, tile0, n_tiles);
+            if (mask == (kExOut | kExLas)) return launch_stream_ex<F64, MODE, kExOut | kExLas>(P, st, grid, tile0, n_tiles);
+        }
+    }
+    return launch_stream_ex<F64, MODE, kExGeneric>(P, st, grid, tile0, n_tiles);
 }
 
 cudaError_t launch_tma(bool f64, int mode, const Params& P, cudaStream_t st, bool force, bool* handled) {

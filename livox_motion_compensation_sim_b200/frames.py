@@ -53,7 +53,7 @@ def lidar_frame_times(duration: float, lidar_fps: float) -> np.ndarray:
 
 def slerp_segment_table(sample_quat_xyzw: np.ndarray, sample_pos: np.ndarray, sample_ts: np.ndarray) -> np.ndarray:
     """Per-sample table consumed by lmc_deskew_slerp_*: for sample k
-    [R_k (9) | pos_k (3) | unit axis of R_k^-1 R_{k+1} (3) | angle | pos_{k+1}-pos_k (3) | 1/(t_{k+1}-t_k) | t_k bits | t_{k+1} bits]."""
+    [R_k (9) | pos_k (3) | unit axis of R_k^-1 R_{k+1} (3) | angle | pos_{k+1}-pos_k (3) | 1/(t_{k+1}-t_k) | t_k bits | (t_{k+1}-t_k) bits]."""
     q = np.asarray(sample_quat_xyzw, np.float64).reshape(-1, 4)
     pos = np.asarray(sample_pos, np.float64).reshape(-1, 3)
     S = len(q)
@@ -71,11 +71,12 @@ def slerp_segment_table(sample_quat_xyzw: np.ndarray, sample_pos: np.ndarray, sa
         seg[:-1, 16:19] = pos[1:] - pos[:-1]
         dts = np.diff(np.asarray(sample_ts, np.int64)).astype(np.float64)
         seg[:-1, 19] = np.where(dts > 0, 1.0 / np.where(dts > 0, dts, 1.0), 0.0)
-    # columns 20/21: t_k and t_{k+1} as raw int64 bits (the row then verifies its own bracket)
+    # columns 20/21: t_k and dt_k = t_{k+1} - t_k as raw int64 bits (the row then verifies its own bracket)
     tsi = np.asarray(sample_ts, np.int64)
     seg[:, 20] = tsi.view(np.float64)
-    seg[:-1, 21] = tsi[1:].view(np.float64)
-    seg[-1, 21] = tsi[-1:].view(np.float64)[0]
+    dti = np.zeros(S, np.int64)
+    dti[:-1] = np.diff(tsi)
+    seg[:, 21] = dti.view(np.float64)
     return seg
 
 

@@ -286,7 +286,7 @@ void orc_deskew_gyro_f64(const double* pts, const int64_t* ts, const int64_t* fr
  *   out = R(ts) p + pos(ts)
  * seg is the per-segment table, SEG_STRIDE doubles per sample k:
  *   [0..8] R_k row-major, [9..11] pos_k, [12..14] unit axis n_k, [15] theta_k,
- *   [16..18] dpos_k = pos_{k+1}-pos_k, [19] inv_dt_k, [20],[21] t_k / t_{k+1} as raw int64 bits (unused
+ *   [16..18] dpos_k = pos_{k+1}-pos_k, [19] inv_dt_k, [20],[21] t_k / dt_k as raw int64 bits (unused
  *   here: the device kernel verifies its bracket guess against them).  Last sample: theta = dpos = inv_dt = 0.
  * hold_idx != NULL: every point of frame f uses sample hold_idx[f] with alpha = 0
  * (Mode A expressed in Mode C: must equal orc_align_rigid_f64 bit-for-bit for n_f >= 2).
