@@ -166,6 +166,26 @@ __device__ __forceinline__ void gyro_rotate(double ax, double ay, double az, con
     o.w = p.w;
 }
 
+// The same rotation for |angles| <= 0.49 rad with the structural zeros / ones of Rx, Ry, Rz folded
+// away: every surviving operation is the one the dgemm chain of gyro_rotate() performs on non-zero
+// operands (x*0 terms and "+0" additions dropped), so results agree bit-for-bit except possibly in the
+// sign of an exact zero.  14 FP64 ops for the matrix instead of 54, branch-free.
+__device__ __forceinline__ void gyro_rotate_small(double ax, double ay, double az, const Pt& p, Pt& o) {
+    double sa, va, sb, vb, sc, vc;
+    sin_vercos_small(-ax, sa, va);
+    sin_vercos_small(-ay, sb, vb);
+    sin_vercos_small(-az, sc, vc);
+    const double ca = 1.0 - va, cb = 1.0 - vb, cc = 1.0 - vc;
+    const double t10 = __dmul_rn(sa, sb), t20 = -__dmul_rn(ca, sb);         // (Rx Ry)[1][0], [2][0]
+    const double m00 = __dmul_rn(cb, cc), m01 = -__dmul_rn(cb, sc), m02 = sb;
+    const double m10 = __fma_rn(ca, sc, __dmul_rn(t10, cc)), m11 = __fma_rn(ca, cc, -__dmul_rn(t10, sc)), m12 = -__dmul_rn(sa, cb);
+    const double m20 = __fma_rn(sa, sc, __dmul_rn(t20, cc)), m21 = __fma_rn(sa, cc, -__dmul_rn(t20, sc)), m22 = __dmul_rn(ca, cb);
+    o.x = dot_gemv(m00, p.x, m01, p.y, m02, p.z);
+    o.y = dot_gemv(m10, p.x, m11, p.y, m12, p.z);
+    o.z = dot_gemv(m20, p.x, m21, p.y, m22, p.z);
+    o.w = p.w;
+}
+
 // Mode C per-point evaluation (definition: oracle/lmc_oracle.c::orc_deskew_slerp_f64)
 template <bool SMALL = false>
 __device__ __forceinline__ void slerp_apply(const double (&s)[kSegStride], double alpha, const Pt& p, Pt& o) {
@@ -461,7 +481,6 @@ struct PointCtx {
 
     __device__ __forceinline__ Pt one(const Params& P, int32_t f, bool single, int64_t fs, int64_t tsraw, const Pt& in) const {
         if constexpr (MODE == kQuantOnly) return in;
-        else if constexpr (MODE == kGyro) return point_eval<F64, MODE>(P, f, single, fs, tsraw, in, t0, rate);   // no fast path yet: inline
         else return point_eval_slow<F64, MODE>(P, f, single, fs, tsraw, in, t0, rate);
     }
 
@@ -506,6 +525,59 @@ struct PointCtx {
                     slerp_apply<true>(tab, a0, in[0], out[0]);
                     slerp_apply<true>(tab, a1, in[1], out[1]);
                     return;
+                }
+            }
+        }
+        if constexpr (MODE == kGyro) {
+            // (a6)-(a8) CS:1435-1536 for two points bracketed by the same IMU sample pair
+            const int64_t S = P.n_samp;
+            if (S >= 2 && S < 0x7fffffffLL) {
+                const int64_t ta = F64 ? tsraw[0] : tsraw[0] + fs[0];
+                const int64_t tb = F64 ? tsraw[1] : tsraw[1] + fs[1];
+                int32_t k = __double2int_rz(__dmul_rn((double)(ta - t0), rate));
+                k = max(0, min(k, (int32_t)S - 2));
+                if (k != key) {
+                    const int64_t tk = __ldg(P.samp_ts + k), tn = __ldg(P.samp_ts + k + 1);
+                    const double* g = P.samp_tab + 3 * (int64_t)k;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const double gb = __ldg(g + c), ga = __ldg(g + 3 + c);
+                        tab[c] = gb;
+                        tab[3 + c] = __dsub_rn(ga, gb);                               // CS:1507 (after - before)
+                    }
+                    tab[6] = __longlong_as_double(tk);
+                    tab[7] = __longlong_as_double(tn - tk);
+                    tab[8] = (double)(tn - tk);
+                    tab[9] = tn > tk ? 1.0 / tab[8] : 0.0;                            // correctly rounded reciprocal (IEEE division)
+                    key = k;
+                }
+                const int64_t tk = __double_as_longlong(tab[6]);
+                const uint64_t dtk = (uint64_t)__double_as_longlong(tab[7]);
+                const int64_t dd[2] = { ta - tk, tb - tk };
+                if ((uint64_t)dd[0] < dtk && (uint64_t)dd[1] < dtk) {
+                    double ang[2][3];
+                    double amax = 0.0;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        // alpha = (t - t_before) / (t_after - t_before) (CS:1503): reciprocal + two Markstein
+                        // corrections = the correctly rounded quotient
+                        const double a = (double)dd[h];
+                        double q = __dmul_rn(a, tab[9]);
+                        q = __fma_rn(__fma_rn(-tab[8], q, a), tab[9], q);
+                        q = __fma_rn(__fma_rn(-tab[8], q, a), tab[9], q);
+                        const double dt = __dmul_rn((double)((h == 0 ? ta : tb) - fs[h]), 1e-9);      // CS:1454
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const double gc = __dadd_rn(tab[c], __dmul_rn(q, tab[3 + c]));             // CS:1507-1509
+                            ang[h][c] = __dmul_rn(gc, dt);                                            // CS:1457-1458
+                            amax = fmax(amax, fabs(ang[h][c]));
+                        }
+                    }
+                    if (amax <= 0.49) {
+                        gyro_rotate_small(ang[0][0], ang[0][1], ang[0][2], in[0], out[0]);
+                        gyro_rotate_small(ang[1][0], ang[1][1], ang[1][2], in[1], out[1]);
+                        return;
+                    }
                 }
             }
         }

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     asm volatile("" : "+r"(warp), "+r"(lane));                                  // keep them in registers (no S2R re-reads in the loop)
     const int64_t t_begin = n_tiles * (int64_t)blockIdx.x / gridDim.x;
-    const int64_t t_end   = n_tiles * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    const int32_t my_tiles = (int32_t)(n_tiles * (int64_t)(blockIdx.x + 1) / gridDim.x - t_begin);   // <= 2^31 tiles per CTA
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(s_full + s), 1); mbar_init(smem_u32(s_empty + s), kCW); }
@@ -262,9 +262,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
         // ================================ producer warp ==========================================
         int s = 0; uint32_t ph = 0;
         int64_t hint = -1;
-        for (int64_t t = t_begin; t < t_end; ++t) {
+        int64_t base = tile0 + t_begin * Cfg::TP;
+        for (int32_t it = 0; it < my_tiles; ++it, base += Cfg::TP) {
             mbar_wait(empty0 + 8 * s, ph ^ 1);                                   // slot free (first lap passes)
-            const int64_t base = tile0 + t * Cfg::TP;
             const int64_t lim_lo = base > P.p_begin ? base : P.p_begin;
             const int64_t lim_hi = base + Cfg::TP < P.p_end ? base + Cfg::TP : P.p_end;
             const bool full = lim_lo == base && lim_hi == base + Cfg::TP;
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
         uint32_t fl = 0;
         uint8_t* slab = s_slab + warp * Cfg::LVX_SLAB;
         int s = 0; uint32_t ph = 0;
-        for (int64_t t = t_begin; t < t_end; ++t) {
+        for (int32_t it = 0; it < my_tiles; ++it) {
             mbar_wait(full0 + 8 * s, ph);
             const TileInfo ti = s_info[s];
             const uint8_t* st = s_stage + s * Cfg::STAGE;
