@@ -155,6 +155,24 @@ int lmc_deskew_slerp_f32(const float* pts_n4, const uint32_t* ts_off, const int6
 int lmc_quantize_f64(const double* pts_n4, int64_t n_points, const lmc_export* ex, void* stream);
 int lmc_quantize_f32(const float* pts_n4, int64_t n_points, const lmc_export* ex, void* stream);
 
+/*
+ *  LivoxLVXWriter.write_compatible_lvx, replaces LMC:58-250: the complete LVX v1.1 file
+ * image -- 88-byte preamble, per frame a 24-byte header and ceil(n/96) packages of 22-byte header +
+ * 96 x 14-byte records (tail zero-padded) -- built on the device from the RAW points (LMC:977), with
+ * the record arithmetic of LMC:252-272.  frame_pos[f] = byte offset of frame f in the file
+ * (frame_pos[0] = 88, frame_pos[n_frames] = file size = capacity of file_out), frame_time in seconds
+ * (package timestamp = int(t * 1e9), LMC:177), frame_id = the reference's frame_id.
+ * max_frame_points = max over frames of the point count (sizes the launch grid).
+ */
+int lmc_lvx_v11_build_f64(const double* pts_n4, const int64_t* frame_off, const int64_t* frame_pos,
+                          const double* frame_time, const int64_t* frame_id, uint8_t* file_out,
+                          int64_t n_points, int32_t n_frames, int64_t max_frame_points,
+                          uint32_t* status, void* stream);
+int lmc_lvx_v11_build_f32(const float* pts_n4, const int64_t* frame_off, const int64_t* frame_pos,
+                          const double* frame_time, const int64_t* frame_id, uint8_t* file_out,
+                          int64_t n_points, int32_t n_frames, int64_t max_frame_points,
+                          uint32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,8 @@ namespace lmc {
 cudaError_t launch_direct(bool f64, int mode, const Params& P, cudaStream_t st);
 cudaError_t launch_tma(bool f64, int mode, const Params& P, cudaStream_t st, bool force, bool* handled);
 cudaError_t launch_pose_lookup(const double*, int64_t, const double*, const double*, int32_t, double*, int32_t*, cudaStream_t);
+cudaError_t launch_lvx_v11(bool f64, const void* pts, const int64_t* frame_off, const int64_t* frame_pos, const double* frame_time,
+                           const int64_t* frame_id, uint8_t* out, int32_t n_frames, int64_t max_frame_points, uint32_t* status, cudaStream_t st);
 }
 
 namespace {
@@ -201,6 +203,29 @@ int lmc_quantize_f32(const float* pts_n4, int64_t n_points, const lmc_export* ex
     lmc::Params P = base_params(pts_n4, nullptr, n_points, 0, 0, n_points);
     if (!ex) return fail(LMC_ERR_INVALID, "ex is NULL");
     return run(false, lmc::kQuantOnly, P, ex, stream);
+}
+
+static int lvx_build(bool f64, const void* pts, const int64_t* frame_off, const int64_t* frame_pos, const double* frame_time,
+                     const int64_t* frame_id, uint8_t* file_out, int64_t n_points, int32_t n_frames, int64_t max_frame_points,
+                     uint32_t* status, void* stream) {
+    int rc = check_device();
+    if (rc != LMC_OK) return rc;
+    if (n_frames < 1 || n_points < 0 || max_frame_points < 0) return fail(LMC_ERR_INVALID, "need n_frames >= 1 (the reference refuses an empty frame list, LMC:75-76)");
+    if (!frame_off || !frame_pos || !frame_time || !frame_id || !file_out || (n_points > 0 && !pts)) return fail(LMC_ERR_INVALID, "NULL argument");
+    if (!aligned32(pts) || !aligned32(file_out)) return fail(LMC_ERR_ALIGN, "points and file buffer must be 32-byte aligned");
+    cudaError_t e = lmc::launch_lvx_v11(f64, pts, frame_off, frame_pos, frame_time, frame_id, file_out, n_frames, max_frame_points, status,
+                                        static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_lvx_v11");
+}
+int lmc_lvx_v11_build_f64(const double* pts_n4, const int64_t* frame_off, const int64_t* frame_pos, const double* frame_time,
+                          const int64_t* frame_id, uint8_t* file_out, int64_t n_points, int32_t n_frames, int64_t max_frame_points,
+                          uint32_t* status, void* stream) {
+    return lvx_build(true, pts_n4, frame_off, frame_pos, frame_time, frame_id, file_out, n_points, n_frames, max_frame_points, status, stream);
+}
+int lmc_lvx_v11_build_f32(const float* pts_n4, const int64_t* frame_off, const int64_t* frame_pos, const double* frame_time,
+                          const int64_t* frame_id, uint8_t* file_out, int64_t n_points, int32_t n_frames, int64_t max_frame_points,
+                          uint32_t* status, void* stream) {
+    return lvx_build(false, pts_n4, frame_off, frame_pos, frame_time, frame_id, file_out, n_points, n_frames, max_frame_points, status, stream);
 }
 
 }  // extern "C"

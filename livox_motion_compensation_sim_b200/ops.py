@@ -185,3 +185,20 @@ def quantize(pts: torch.Tensor, export: ExportSpec) -> ExportBuffers:
     fn = C.lib().lmc_quantize_f64 if f64 else C.lib().lmc_quantize_f32
     C.check(fn(_req(pts, pts.dtype, "pts", (4,)), n, C.ctypes.byref(ex), _stream_ptr()))
     return bufs
+
+
+def build_lvx_v11(pts: torch.Tensor, frame_off: torch.Tensor, frame_pos: torch.Tensor, frame_time: torch.Tensor,
+                  frame_id: torch.Tensor, max_frame_points: int):
+    """(N1) LMC:58-250 on the device: RAW points -> the complete LVX v1.1 file image (uint8 tensor).
+    frame_pos (int64[F+1], byte offsets incl. the 88-byte preamble) comes from lvx.frame_layout().
+    Returns (file bytes tensor, status flags tensor)."""
+    f64 = _layout(pts)
+    F = frame_off.shape[0] - 1
+    size = int(frame_pos[-1].item())
+    out = torch.empty(size, dtype=torch.uint8, device=pts.device)
+    status = torch.zeros(1, dtype=torch.int32, device=pts.device)
+    fn = C.lib().lmc_lvx_v11_build_f64 if f64 else C.lib().lmc_lvx_v11_build_f32
+    C.check(fn(_req(pts, pts.dtype, "pts", (4,)), _req(frame_off, torch.int64, "frame_off"), _req(frame_pos, torch.int64, "frame_pos"),
+               _req(frame_time, torch.float64, "frame_time"), _req(frame_id, torch.int64, "frame_id"), out.data_ptr(),
+               pts.shape[0], F, int(max_frame_points), status.data_ptr(), _stream_ptr()))
+    return out, status

@@ -25,7 +25,7 @@ import torch
 from . import _capi as C
 from . import frames as FR
 from . import ops
-from .lvx import build_lvx_v11_file
+from .lvx import build_lvx_v11_file, frame_layout
 
 COMPENSATION_MODES = ("frame_rigid",)      # Mode A; Modes B/C live in compensator.py / ops.deskew_slerp
 
@@ -263,10 +263,24 @@ class LiDARMotionSimulator:
 
     def save_lvx(self, results, base_filename):
         """lidar_data.lvx with the LVX v1.1 container of LMC:58-250 around device-quantised records."""
-        rec, off = self.quantize_lvx(results)
-        ts = np.array([s['timestamp'] for s in results['raw_scans']], np.float64)
-        ids = np.array([s['frame_id'] for s in results['raw_scans']], np.int64)
-        data = build_lvx_v11_file(rec, off, ts, ids)
+        data = self.build_lvx_bytes(results)
         with open(f"{base_filename}.lvx", 'wb') as f:
             f.write(data.tobytes())
         return True
+
+    def build_lvx_bytes(self, results) -> np.ndarray:
+        """The whole LVX v1.1 file image (LMC:58-250), quantised and laid out on the device."""
+        scans = results['raw_scans']
+        if not scans:
+            raise ValueError("No frame data provided")                      # LMC:75-76
+        flat, off = FR.flatten_frames([s['points_local'] for s in scans], np.float64)
+        ts = np.array([s['timestamp'] for s in scans], np.float64)
+        ids = np.array([s['frame_id'] for s in scans], np.int64)
+        _, fpos = frame_layout(off)
+        if len(flat) == 0:
+            return build_lvx_v11_file(np.zeros((0, 14), np.uint8), off, ts, ids)
+        data, status = ops.build_lvx_v11(self._to_dev(flat), self._to_dev(off), self._to_dev(fpos), self._to_dev(ts),
+                                         self._to_dev(ids), int(np.diff(off).max()))
+        bufs = ops.ExportBuffers(status=status)
+        bufs.raise_for_flags()
+        return data.cpu().numpy()

@@ -335,6 +335,8 @@ def test_simulator_batched_alignment_and_outputs(golden, tmp_path):
 
 
 def test_lvx_file_bytes_vs_reference(golden):
+    """(N1) whole LVX v1.1 file image built on the device == the reference writer's file, byte for byte
+    (frames of 0, 1, 95, 96, 97, 200 points: empty frames, exact and ragged package tails)."""
     from livox_motion_compensation_sim_b200 import LiDARMotionSimulator
     from livox_motion_compensation_sim_b200.lvx import build_lvx_v11_file
     g = golden("lvx_file.npz")
@@ -342,9 +344,30 @@ def test_lvx_file_bytes_vs_reference(golden):
     sim = LiDARMotionSimulator()
     results = {'raw_scans': [{'frame_id': i, 'timestamp': float(g['timestamps'][i]), 'points_local': g['raw'][off[i]:off[i + 1]]}
                              for i in range(len(off) - 1)]}
-    rec, off2 = sim.quantize_lvx(results)
-    data = build_lvx_v11_file(rec, off2, g['timestamps'], np.arange(len(off) - 1))
+    data = sim.build_lvx_bytes(results)
     assert np.array_equal(data, g['file_bytes'])
+    rec, off2 = sim.quantize_lvx(results)                    # host container around device records: same bytes
+    assert np.array_equal(build_lvx_v11_file(rec, off2, g['timestamps'], np.arange(len(off) - 1)), g['file_bytes'])
+
+
+@pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
+def test_lvx_file_device_builder_ragged(f64):
+    """Device-built LVX image vs the host layout around oracle records on a ragged stream with large
+    frames (multi-chunk), empty frames and odd frame ids / timestamps."""
+    from livox_motion_compensation_sim_b200.lvx import build_lvx_v11_file, frame_layout
+    rng = np.random.default_rng(21)
+    F = 57
+    counts = rng.integers(0, 3000, F); counts[5] = 0; counts[6] = 96 * 8; counts[7] = 96 * 8 + 1; counts[20] = 20_000; counts[-1] = 0
+    st = synth.make_stream(F, counts, 21, device=DEV, dtype=torch.float64 if f64 else torch.float32)
+    ts = np.sort(rng.uniform(0, 1e4, F)); ids = rng.integers(0, 2 ** 40, F).astype(np.int64)
+    _, fpos = frame_layout(st.frame_off)
+    data, status = ops.build_lvx_v11(st.pts, dev(st.frame_off), dev(fpos), dev(ts), dev(ids), int(counts.max()))
+    assert int(status.item()) == 0
+    rec, _ = orc.C.quantize_lvx_type2(st.pts.cpu().numpy().astype(np.float64))
+    want = build_lvx_v11_file(rec, st.frame_off, ts, ids)
+    got = data.cpu().numpy()
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
 
 
 def test_motion_compensator_list_api(golden):
