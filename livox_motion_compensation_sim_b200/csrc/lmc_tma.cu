@@ -24,27 +24,38 @@ namespace lmc {
 #ifndef LMC_CW
 #define LMC_CW 15
 #endif
-#ifndef LMC_STAGES
-#define LMC_STAGES 4
-#endif
 constexpr int kCW            = LMC_CW;                   // consumer warps (15 + producer = 512 threads -> 128 regs each)
 constexpr int kStreamThreads = 32 * (kCW + 1);           // + producer warp
-constexpr int kStages        = LMC_STAGES;
 
-template <bool F64> struct StreamCfg {
-    static constexpr int PPT      = F64 ? 1 : 2;                 // point pairs per consumer thread per tile
-    static constexpr int TP       = kCW * 32 * 2 * PPT;          // points per tile: 960 (f64) / 1920 (f32)
+// Tile shape per kernel family (measured on B200, see profiles/): Mode C on float4 points amortises its
+// per-tile bookkeeping best with 3 pairs per thread over a 3-stage ring; everything else runs 2 pairs
+// (f32) / 1 pair (f64) per thread over 4 stages.
+template <bool F64, int MODE> struct StreamCfg {
+    static constexpr int PPT      = F64 ? 1 : (MODE == kSlerp ? 3 : 2);   // point pairs per consumer thread per tile
+    static constexpr int STAGES   = (!F64 && MODE == kSlerp) ? 3 : 4;
+    static constexpr int TP       = kCW * 32 * 2 * PPT;          // points per tile: 960 (f64) / 1920 / 2880 (f32)
     static constexpr int PT_BYTES = F64 ? 32 : 16;
     static constexpr int TS_BYTES = F64 ? 8 : 4;
-    static constexpr int PTS_STAGE = TP * PT_BYTES;              // 30 KB either way
-    static constexpr int TS_STAGE  = TP * TS_BYTES;              // 7.5 KB either way
-    static constexpr int TAG_STAGE = TP;                         //  1-2 KB
+    static constexpr int PTS_STAGE = TP * PT_BYTES;
+    static constexpr int TS_STAGE  = TP * TS_BYTES;
+    static constexpr int TAG_STAGE = TP;
     static constexpr int STAGE     = PTS_STAGE + TS_STAGE + TAG_STAGE;
     static constexpr int LVX_SLAB  = PPT * 64 * 14;              // bytes per consumer warp
-    static constexpr int SMEM      = kStages * STAGE + kCW * LVX_SLAB + kStages * (int)sizeof(TileMeta) + kStages * 32 + 2 * kStages * 8 + 128;
+    static constexpr int SMEM      = STAGES * STAGE + kCW * LVX_SLAB + STAGES * (int)sizeof(TileMeta) + STAGES * 64 + 2 * STAGES * 8 + 128;
 };
 
-struct TileInfo { int64_t base, lim_lo, lim_hi; int32_t full, pad; };     // 32 bytes
+// Everything a consumer needs to know about a tile, prepared once by the producer (64 bytes = four
+// broadcast LDS.128): bounds, and -- when the tile holds at most one frame boundary ("simple", the
+// common case) -- the frame facts themselves, so consumers never touch TileMeta.
+struct TileInfo {
+    int64_t base, lim_lo, lim_hi;
+    int32_t full;                 // 1: whole tile inside [p_begin, p_end) and staged by TMA
+    int32_t f_lo;                 // frame of the tile's first point
+    int32_t rel_e1;               // tile-local index of the first point of frame f_lo + 1 (INT_MAX: none)
+    int32_t flags;                // bit 0 simple, bit 1 / 2: frame f_lo / f_lo + 1 holds exactly one point
+    int64_t fs0, fs1;             // frame_start of f_lo and f_lo + 1 (Mode B/C)
+    int64_t pad;
+};
 
 // ---- mbarrier / bulk-copy PTX ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -83,7 +94,7 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
                                              uint8_t* slab, uint32_t empty_bar, PointCtx<F64, MODE>& ctx,
                                              uint32_t& fl, int cw, int lane)
 {
-    using Cfg = StreamCfg<F64>;
+    using Cfg = StreamCfg<F64, MODE>;
     constexpr int PPT = Cfg::PPT;
     constexpr bool GEN = EX == kExGeneric;
     const bool do_out = GEN ? P.out != nullptr : bool(EX & kExOut);
@@ -94,21 +105,10 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
     const bool has_tag = GEN && do_lvx && P.tag != nullptr && P.lvx_mode == LMC_LVX2_OF_OUTPUT;
     const int64_t base = ti.base;
 
-    // tile-level frame facts in registers: a tile rarely holds more than one frame boundary.
-    // rel_e1 = tile-local index of the first point of the second frame (INT_MAX: none)
-    int32_t m_flo = 0, rel_e1 = 0x7fffffff; bool m_simple = true, m_single0 = false, m_single1 = false;
-    int64_t m_fs0 = 0, m_fs1 = 0;
-    if constexpr (MODE != kQuantOnly) {
-        const int32_t nb = tm.nb;
-        m_flo = tm.f_lo;
-        m_simple = !tm.overflow && nb <= 1;
-        if (m_simple) {
-            const int64_t e1 = tm.edge[1];
-            if (nb == 1) rel_e1 = (int32_t)(e1 - base);
-            if constexpr (MODE == kRigid) { m_single0 = e1 - tm.edge[0] == 1; m_single1 = tm.edge[nb + 1] - e1 == 1; }
-            if (has_fs) { m_fs0 = tm.fstart[0]; m_fs1 = tm.fstart[nb]; }
-        }
-    }
+    // tile-level frame facts (prepared by the producer) in registers
+    const int32_t m_flo = ti.f_lo, rel_e1 = ti.rel_e1;
+    const bool m_simple = MODE == kQuantOnly || (ti.flags & 1), m_single0 = ti.flags & 2, m_single1 = ti.flags & 4;
+    const int64_t m_fs0 = ti.fs0, m_fs1 = ti.fs1;
 
     // one point pair at a time: stage -> registers -> f64 work -> stores (short live ranges); the
     // stage is handed back to the producer as soon as the LAST pair has been pulled out of it
@@ -233,15 +233,15 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
 template <bool F64, int MODE, int EX>
 __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_constant__ Params P, int64_t tile0, int64_t n_tiles)
 {
-    using Cfg = StreamCfg<F64>;
+    using Cfg = StreamCfg<F64, MODE>;
     constexpr bool GEN = EX == kExGeneric;
     extern __shared__ __align__(128) uint8_t smem[];                            // no static smem in this kernel: base is aligned
-    uint8_t*  s_stage = smem;                                                   // kStages x STAGE
-    uint8_t*  s_slab  = s_stage + kStages * Cfg::STAGE;                         // kCW x LVX_SLAB
+    uint8_t*  s_stage = smem;                                                   // Cfg::STAGES x STAGE
+    uint8_t*  s_slab  = s_stage + Cfg::STAGES * Cfg::STAGE;                         // kCW x LVX_SLAB
     TileMeta* s_meta  = reinterpret_cast<TileMeta*>(s_slab + kCW * Cfg::LVX_SLAB);
-    TileInfo* s_info  = reinterpret_cast<TileInfo*>(s_meta + kStages);
-    uint64_t* s_full  = reinterpret_cast<uint64_t*>(s_info + kStages);
-    uint64_t* s_empty = s_full + kStages;
+    TileInfo* s_info  = reinterpret_cast<TileInfo*>(s_meta + Cfg::STAGES);
+    uint64_t* s_full  = reinterpret_cast<uint64_t*>(s_info + Cfg::STAGES);
+    uint64_t* s_empty = s_full + Cfg::STAGES;
 
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     asm volatile("" : "+r"(warp), "+r"(lane));                                  // keep them in registers (no S2R re-reads in the loop)
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
     const int32_t my_tiles = (int32_t)(n_tiles * (int64_t)(blockIdx.x + 1) / gridDim.x - t_begin);   // <= 2^31 tiles per CTA
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(smem_u32(s_full + s), 1); mbar_init(smem_u32(s_empty + s), kCW); }
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(smem_u32(s_full + s), 1); mbar_init(smem_u32(s_empty + s), kCW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -274,7 +274,22 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
                 hint = (int64_t)s_meta[s].f_lo + (s_meta[s].overflow ? 0 : s_meta[s].nb);   // frame of the tile's last point
             }
             if (lane == 0) {
-                s_info[s] = TileInfo{ base, lim_lo, lim_hi, full ? 1 : 0, 0 };
+                TileInfo inf{ base, lim_lo, lim_hi, full ? 1 : 0, 0, 0x7fffffff, 1, 0, 0, 0 };
+                if constexpr (MODE != kQuantOnly) {
+                    const TileMeta& tm = s_meta[s];
+                    const int32_t nb = tm.nb;
+                    const bool simple = !tm.overflow && nb <= 1;
+                    inf.f_lo = tm.f_lo;
+                    inf.flags = simple ? 1 : 0;
+                    if (simple) {
+                        const int64_t e1 = tm.edge[1];
+                        if (nb == 1) inf.rel_e1 = (int32_t)(e1 - base);
+                        if (e1 - tm.edge[0] == 1) inf.flags |= 2;
+                        if (tm.edge[nb + 1] - e1 == 1) inf.flags |= 4;
+                        if (P.frame_start != nullptr) { inf.fs0 = tm.fstart[0]; inf.fs1 = tm.fstart[nb]; }
+                    }
+                }
+                s_info[s] = inf;
                 uint8_t* st = s_stage + s * Cfg::STAGE;
                 if (full) {
                     const uint32_t bytes = Cfg::PTS_STAGE + (has_ts ? Cfg::TS_STAGE : 0) + (has_tag ? Cfg::TAG_STAGE : 0);
@@ -287,7 +302,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
                 }
             }
             __syncwarp();
-            if (++s == kStages) { s = 0; ph ^= 1; }
+            if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
     } else {
         // ================================ consumer warps =========================================
@@ -302,7 +317,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
             const uint8_t* st = s_stage + s * Cfg::STAGE;
             if (ti.full) consume_tile<F64, MODE, EX, true>(P, ti, s_meta[s], st, st + Cfg::PTS_STAGE, st + Cfg::PTS_STAGE + Cfg::TS_STAGE, slab, empty0 + 8 * s, ctx, fl, warp, lane);
             else         consume_tile<F64, MODE, EX, false>(P, ti, s_meta[s], st, st + Cfg::PTS_STAGE, st + Cfg::PTS_STAGE + Cfg::TS_STAGE, slab, empty0 + 8 * s, ctx, fl, warp, lane);
-            if (++s == kStages) { s = 0; ph ^= 1; }
+            if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
         if (fl != 0 && P.status != nullptr) atomicOr(P.status, fl);
     }
@@ -322,7 +337,7 @@ static int sm_count_cached() {
 
 template <bool F64, int MODE, int EX>
 static cudaError_t launch_stream_ex(const Params& P, cudaStream_t st, int grid, int64_t tile0, int64_t n_tiles) {
-    using Cfg = StreamCfg<F64>;
+    using Cfg = StreamCfg<F64, MODE>;
     static thread_local int attr_dev = -1;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -337,7 +352,7 @@ static cudaError_t launch_stream_ex(const Params& P, cudaStream_t st, int grid, 
 
 template <bool F64, int MODE>
 static cudaError_t launch_stream(const Params& P, cudaStream_t st, bool force, bool* handled) {
-    using Cfg = StreamCfg<F64>;
+    using Cfg = StreamCfg<F64, MODE>;
     const int sms = sm_count_cached();
     if (sms <= 0) return cudaErrorInvalidDevice;
     const int64_t tile0 = (P.p_begin / Cfg::TP) * Cfg::TP;                       // tiles aligned in GLOBAL index space
