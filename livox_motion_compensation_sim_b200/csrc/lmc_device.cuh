@@ -211,23 +211,23 @@ __device__ __forceinline__ void slerp_apply(const double (&s)[kSegStride], doubl
 // ------------------------------------------------------------------------------------------
 // Quantisers.  cvt.rzi.s32.f64 saturates, which IS np.clip to the int32 range followed by
 // truncation, so the clip costs nothing; NaN (where the reference raises) sets a status bit.
+// The NaN test is made on the INPUT value (v*1000 is NaN iff v is): testing the product instead
+// made ptxas keep -- and spill -- every product until a deferred compare.
 // ------------------------------------------------------------------------------------------
 // (a4) LMC:257-259   int(np.clip(v * 1000, -2147483648, 2147483647))
 __device__ __forceinline__ int32_t q_mm_clip(double v, uint32_t& fl) {
-    const double m = __dmul_rn(v, 1000.0);
-    if (m != m) fl |= LMC_FLAG_NAN;
-    return __double2int_rz(m);                      // NaN -> 0, +-big -> INT_MAX / INT_MIN
+    if (v != v) fl |= LMC_FLAG_NAN;
+    return __double2int_rz(__dmul_rn(v, 1000.0));   // NaN -> 0, +-big -> INT_MAX / INT_MIN
 }
 // (a4) LMC:266       int(np.clip(i * 255, 0, 255))
 __device__ __forceinline__ uint32_t q_refl(double w, uint32_t& fl) {
-    const double m = __dmul_rn(w, 255.0);
-    if (m != m) fl |= LMC_FLAG_NAN;
-    return min(__double2uint_rz(m), 255u);          // negative -> 0 (saturating), NaN -> 0
+    if (w != w) fl |= LMC_FLAG_NAN;
+    return min(__double2uint_rz(__dmul_rn(w, 255.0)), 255u);   // negative -> 0 (saturating), NaN -> 0
 }
 // (a9) CS:368-370    int(v * 1000)  -- no clip; '<iii' packing raises outside int32
 __device__ __forceinline__ int32_t q_mm_noclip(double v, uint32_t& fl) {
     const double m = __dmul_rn(v, 1000.0);
-    if (m != m) fl |= LMC_FLAG_NAN;
+    if (v != v) fl |= LMC_FLAG_NAN;
     if (m >= 2147483648.0 || m <= -2147483649.0) fl |= LMC_FLAG_OVERFLOW;
     return __double2int_rz(m);
 }
@@ -248,14 +248,14 @@ __device__ __forceinline__ int32_t q_las(double v, double scale, double rcp, dou
         q = __fma_rn(__fma_rn(-scale, q, a), rcp, q);
         q = __fma_rn(__fma_rn(-scale, q, a), rcp, q);
     }
-    if (q != q) fl |= LMC_FLAG_NAN;
+    if (v != v) fl |= LMC_FLAG_NAN;
     if (q >= 2147483647.5 || q < -2147483648.5) fl |= LMC_FLAG_OVERFLOW;
     return __double2int_rn(q);                      // round-half-even, saturates
 }
 // LMC:961 (w*65535).astype(uint16) | CS:1686 w.astype(uint16): truncate, wrap modulo 2^16
 __device__ __forceinline__ uint32_t q_las_intensity(double w, int mode, uint32_t& fl) {
     const double m = mode == LMC_LAS_INTENSITY_UNIT ? __dmul_rn(w, 65535.0) : w;
-    if (m != m) fl |= LMC_FLAG_NAN;
+    if (w != w) fl |= LMC_FLAG_NAN;
     if (m >= 9.2e18 || m <= -9.2e18) { fl |= LMC_FLAG_OVERFLOW; return 0; }
     return (uint32_t)(__double2ll_rz(m) & 0xffff);
 }
@@ -509,10 +509,14 @@ struct PointCtx {
                 // bracket guess from the mean sample rate (saturating conversion, then clamp to a real segment)
                 int32_t k = __double2int_rz(__dmul_rn((double)(ta - t0), rate));
                 k = max(0, min(k, (int32_t)S - 2));
-                if (k != (int32_t)key) {
-                    const double2* sr = reinterpret_cast<const double2*>(P.samp_tab + (int64_t)kSegStride * k);
+                const double2* sr = reinterpret_cast<const double2*>(P.samp_tab + (int64_t)kSegStride * k);
+                // Only the "front" of the row (axis, theta, dpos, 1/dt, t_k, dt_k = columns 12..21) is kept in
+                // registers across pairs; R_k and pos_k (columns 0..11) are re-read per pair from L1, where the
+                // row stays hot -- holding all 22 doubles plus two points in flight overflows 128 registers
+                // and the spills cost more LSU traffic than six broadcast loads.
+                if (k != key) {
 #pragma unroll
-                    for (int q = 0; q < kSegStride / 2; ++q) { const double2 v = __ldg(sr + q); tab[2 * q] = v.x; tab[2 * q + 1] = v.y; }
+                    for (int q = 6; q < kSegStride / 2; ++q) { const double2 v = __ldg(sr + q); tab[2 * q] = v.x; tab[2 * q + 1] = v.y; }
                     key = k;
                 }
                 const int64_t tk = __double_as_longlong(tab[20]);
@@ -520,10 +524,15 @@ struct PointCtx {
                 const int64_t da = ta - tk, db = tb - tk;
                 // the row's own [t_k, t_k + dt_k) verifies the guess for both points at once
                 if ((uint64_t)da < dtk && (uint64_t)db < dtk && tab[15] <= 0.49) {
-                    const double a0 = __dmul_rn((double)da, tab[19]);
-                    const double a1 = __dmul_rn((double)db, tab[19]);
-                    slerp_apply<true>(tab, a0, in[0], out[0]);
-                    slerp_apply<true>(tab, a1, in[1], out[1]);
+                    double row[kSegStride];
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) { const double2 v = __ldg(sr + q); row[2 * q] = v.x; row[2 * q + 1] = v.y; }
+#pragma unroll
+                    for (int q = 12; q < kSegStride; ++q) row[q] = tab[q];
+                    const double a0 = __dmul_rn((double)da, row[19]);
+                    const double a1 = __dmul_rn((double)db, row[19]);
+                    slerp_apply<true>(row, a0, in[0], out[0]);
+                    slerp_apply<true>(row, a1, in[1], out[1]);
                     return;
                 }
             }

@@ -114,6 +114,9 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
     // stage is handed back to the producer as soon as the LAST pair has been pulled out of it
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
+        // keep pair j+1's shared-memory loads behind pair j's work: hoisting all pairs' inputs to the top
+        // of the tile makes ptxas spill a dozen doubles per pair
+        if (j > 0) asm volatile("" ::: "memory");
         const int q = (cw * PPT + j) * 32 + lane;            // pair index inside the tile
         const int64_t p = base + 2 * q;
         const bool va = FULL || (p >= ti.lim_lo && p < ti.lim_hi), vb = FULL || (p + 1 >= ti.lim_lo && p + 1 < ti.lim_hi);
@@ -170,6 +173,20 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
             if (lane == 0) mbar_arrive(empty_bar);
         }
 
+        if constexpr (!GEN) {
+            // lean: the LVX record is LMC:252-272 on the RAW input point -- independent of the transform,
+            // so pack it first and let its temporaries die before the FP64-heavy part
+            if (do_lvx) {
+                uint32_t x[2] = {0, 0}, y[2] = {0, 0}, z[2] = {0, 0}, rt[2] = {0, 0};
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (FULL || (h == 0 ? va : vb)) {
+                        x[h] = (uint32_t)q_mm_clip(in[h].x, fl); y[h] = (uint32_t)q_mm_clip(in[h].y, fl); z[h] = (uint32_t)q_mm_clip(in[h].z, fl);
+                        rt[h] = q_refl(in[h].w, fl);
+                    }
+                lvx_pair_words(reinterpret_cast<uint32_t*>(slab) + 7 * (j * 32 + lane), x, y, z, rt);
+            }
+        }
         Pt o[2] = { in[0], in[1] };
         if (FULL || (va && vb)) ctx.template pair<!GEN>(P, fr, single, fsv, tsv, in, o);
         else {
@@ -190,20 +207,13 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
             }
         }
         if (do_las) store_las_pair<FULL>(P, p, va, vb, o[0], o[1], fl);
-        if (do_lvx) {
-            uint32_t x[2] = {0, 0}, y[2] = {0, 0}, z[2] = {0, 0}, rt[2] = {0, 0};
-            if constexpr (GEN) {
+        if constexpr (GEN) {
+            if (do_lvx) {
+                uint32_t x[2] = {0, 0}, y[2] = {0, 0}, z[2] = {0, 0}, rt[2] = {0, 0};
                 if (FULL || va) lvx_words<MODE>(P, in[0], o[0], tagv & 0xffu, x[0], y[0], z[0], rt[0], fl);
                 if (FULL || vb) lvx_words<MODE>(P, in[1], o[1], (tagv >> 8) & 0xffu, x[1], y[1], z[1], rt[1], fl);
-            } else {                                        // lean: LMC:252-272 on the raw input point
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    if (FULL || (h == 0 ? va : vb)) {
-                        x[h] = (uint32_t)q_mm_clip(in[h].x, fl); y[h] = (uint32_t)q_mm_clip(in[h].y, fl); z[h] = (uint32_t)q_mm_clip(in[h].z, fl);
-                        rt[h] = q_refl(in[h].w, fl);
-                    }
+                lvx_pair_words(reinterpret_cast<uint32_t*>(slab) + 7 * (j * 32 + lane), x, y, z, rt);
             }
-            lvx_pair_words(reinterpret_cast<uint32_t*>(slab) + 7 * (j * 32 + lane), x, y, z, rt);
         }
     }
     if (do_lvx) {
