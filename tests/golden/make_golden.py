@@ -173,6 +173,26 @@ def lvx_file_fixture(LMC, manifest):
     manifest['lvx_file'] = dict(frames=len(counts), bytes=int(len(data)), sha256=sha(data))
 
 
+def coord_chain_fixture(CS, manifest):
+    """(N3) Reference CoordinateTransformer (CS:153-233): sensor->vehicle default, a user-set
+    vehicle->local transform and their inverse, applied with transform_points (4x4 homogeneous)."""
+    rng = np.random.default_rng(314)
+    ct = CS.CoordinateTransformer()
+    ct.set_transformation(CS.CoordinateSystem.VEHICLE, CS.CoordinateSystem.LOCAL, [12.5, -3.25, 0.75], [0.02, -0.03, 1.1])
+    cases = [(CS.CoordinateSystem.SENSOR, CS.CoordinateSystem.VEHICLE), (CS.CoordinateSystem.VEHICLE, CS.CoordinateSystem.LOCAL),
+             (CS.CoordinateSystem.LOCAL, CS.CoordinateSystem.VEHICLE)]
+    pts, outs, mats, counts = [], [], [], []
+    for (a, b), n in zip(cases, [1500, 2, 777]):
+        p = rng.uniform(-90, 90, (n, 3))
+        o = ct.transform_points(p, a, b)
+        pts.append(p); outs.append(o); mats.append(ct.transformations[(a, b)]); counts.append(n)
+    off = np.zeros(len(counts) + 1, np.int64)
+    np.cumsum(counts, out=off[1:])
+    np.savez_compressed(os.path.join(HERE, 'coord_chain.npz'), pts=np.vstack(pts), out=np.vstack(outs),
+                        T=np.array(mats), frame_off=off)
+    manifest['coord_chain'] = dict(frames=len(counts), points=int(off[-1]), out_sha256=sha(np.vstack(outs)))
+
+
 def modeb_fixture(CS, manifest):
     """Reference MotionCompensator.compensate_point_cloud (CS:1435-1536) + LVX2 packer
     (CS:365-374) on synthetic Mid-70-shaped frames against the reference's own 200 Hz
@@ -235,6 +255,7 @@ def main():
     lvx_type2_fixture(LMC, manifest)
     lvx_file_fixture(LMC, manifest)
     modeb_fixture(CS, manifest)
+    coord_chain_fixture(CS, manifest)
     with open(os.path.join(HERE, 'MANIFEST.json'), 'w') as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     print('wrote', sorted(os.listdir(HERE)))

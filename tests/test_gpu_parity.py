@@ -388,6 +388,59 @@ def test_motion_compensator_list_api(golden):
     assert mc.compensate_point_cloud(pts, [], 0, 1) is pts
 
 
+def test_coordinate_transformer_mirror_vs_reference(golden):
+    """(N3) CS:153-233 mirror: matrices built on the host with the reference's NumPy calls, points
+    transformed by the Mode A kernel -> bit-exact against the reference's transform_points."""
+    from livox_motion_compensation_sim_b200.coords import CoordinateTransformer, CoordinateSystem as CSys, fold_chain, pose_rows_from_matrices
+    g = golden("coord_chain.npz")
+    off = g['frame_off']
+    ct = CoordinateTransformer()
+    ct.set_transformation(CSys.VEHICLE, CSys.LOCAL, [12.5, -3.25, 0.75], [0.02, -0.03, 1.1])
+    cases = [(CSys.SENSOR, CSys.VEHICLE), (CSys.VEHICLE, CSys.LOCAL), (CSys.LOCAL, CSys.VEHICLE)]
+    for i, (a, b) in enumerate(cases):
+        assert np.array_equal(ct.transformations[(a, b)], g['T'][i])
+        out = ct.transform_points(g['pts'][off[i]:off[i + 1]], a, b)
+        assert np.array_equal(out, g['out'][off[i]:off[i + 1]])
+    assert ct.transform_points(g['pts'][:5], 'utm', 'wgs84') is not None          # unknown pair: unchanged (CS:216-218)
+    # folding a chain into the pose table == applying the two transforms one after the other (to rounding)
+    p4 = np.column_stack([g['pts'][:1500], np.zeros(1500)])
+    # sensor->vehicle then vehicle->local, vs the folded single transform
+    seq = ct.transform_points(ct.transform_points(g['pts'][:1500], CSys.SENSOR, CSys.VEHICLE), CSys.VEHICLE, CSys.LOCAL)
+    fold, _ = ops.align_rigid(dev(p4), dev(np.array([0, 1500], np.int64)), dev(fold_chain(g['T'][1], pose_rows_from_matrices(g['T'][0][None]))))
+    assert np.abs(fold.cpu().numpy()[:, :3] - seq).max() <= 1e-11
+
+
+@pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
+def test_no_write_outside_buffers(f64, path):
+    """Home-made memcheck (compute-sanitizer is closed on this pool): every output lives inside a larger
+    allocation filled with a sentinel; after the fused kernel the guard bytes must be untouched.
+    Odd point count, ragged frames, shard range starting / ending mid-tile."""
+    rng = np.random.default_rng(77)
+    F = 90
+    counts = _ragged_counts(rng, F, 1500)
+    st = synth.make_stream(F, counts, 77, device=DEV, dtype=torch.float64 if f64 else torch.float32)
+    N = st.n_points
+    G = 4096                                                  # guard elements on both sides (keeps 32-byte alignment)
+    def guarded(shape_tail, dtype, fill):
+        full = torch.full((N + 2 * G,) + shape_tail, fill, dtype=dtype, device=DEV)
+        return full, full[G:G + N]
+    out_f, out = guarded((4,), st.pts.dtype, -123.0)
+    lvx_f, lvx = guarded((14,), torch.uint8, 0xAB)
+    lx_f, lx = guarded((), torch.int32, -77); ly_f, ly = guarded((), torch.int32, -77); lz_f, lz = guarded((), torch.int32, -77)
+    li_f, li = guarded((), torch.uint16, 0x5A5A)
+    into = ops.ExportBuffers(lvx14=lvx, las_x=lx, las_y=ly, las_z=lz, las_intensity=li)
+    fidx = np.repeat(np.arange(F), counts)
+    ts = dev(st.frame_start[fidx] + st.ts_off.cpu().numpy().astype(np.int64)) if f64 else st.ts_off
+    b, e = 1237, N - 911
+    ops.deskew_slerp(st.pts, ts, dev(st.frame_off), dev(st.frame_start), dev(st.sample_ts), dev(st.seg), out=out,
+                     export=ops.ExportSpec(lvx=True, las=True, las_scale=(0.001,) * 3, into=into), p_range=(b, e))
+    torch.cuda.synchronize()
+    for full, view, fill in [(out_f, out, -123.0), (lvx_f, lvx, 0xAB), (lx_f, lx, -77), (ly_f, ly, -77), (lz_f, lz, -77)]:
+        assert bool((full[:G + b] == fill).all()) and bool((full[G + e:] == fill).all())
+        assert not bool((view[b:e] == fill).all())
+    assert bool((li_f.view(torch.int16)[:G + b] == 0x5A5A).all()) and bool((li_f.view(torch.int16)[G + e:] == 0x5A5A).all())
+
+
 # ------------------------------------------------------------------------------------------
 # full-size stream: size-independent properties + spot checks against the oracle
 # ------------------------------------------------------------------------------------------
