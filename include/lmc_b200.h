@@ -173,6 +173,24 @@ int lmc_lvx_v11_build_f32(const float* pts_n4, const int64_t* frame_off, const i
                           int64_t n_points, int32_t n_frames, int64_t max_frame_points,
                           uint32_t* status, void* stream);
 
+/*
+ *  ASCII PCD point data, replaces the per-point Python loop of
+ * LiDARMotionSimulator.save_pcd (LMC:946-947): for every row of the (n,4) array the line
+ *     "%.6f %.6f %.6f %.6f\n"        (x y z intensity)
+ * byte-identical to CPython / C printf (correctly rounded, round-half-even on the exact binary value;
+ * "nan", "inf", "-inf" as Python prints them).  Lines have variable length, so it is a two-call
+ * protocol: _size fills tile_off (int64[ceil(n / LMC_PCD_TILE) + 1], byte offset of every tile of
+ * LMC_PCD_TILE points; the last entry is the total text size), the caller allocates text_out of that
+ * size, _write produces the bytes.  |values| >= 9.2e12 set LMC_FLAG_OVERFLOW in *status.
+ */
+#define LMC_PCD_TILE 256
+int lmc_pcd_ascii_size_f64(const double* pts_n4, int64_t n_points, int64_t* tile_off, void* stream);
+int lmc_pcd_ascii_size_f32(const float* pts_n4, int64_t n_points, int64_t* tile_off, void* stream);
+int lmc_pcd_ascii_write_f64(const double* pts_n4, int64_t n_points, const int64_t* tile_off,
+                            uint8_t* text_out, uint32_t* status, void* stream);
+int lmc_pcd_ascii_write_f32(const float* pts_n4, int64_t n_points, const int64_t* tile_off,
+                            uint8_t* text_out, uint32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@ FLAG_NAN, FLAG_OVERFLOW = 1, 2
 LVX_TYPE2_OF_INPUT, LVX2_OF_OUTPUT = 0, 1
 LAS_INTENSITY_UNIT, LAS_INTENSITY_RAW = 0, 1
 PATH_DIRECT, PATH_AUTO, PATH_TMA = 0, 1, 2
+PCD_TILE = 256
 
 vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
 
@@ -50,6 +51,10 @@ _SIGNATURES = {
     "lmc_quantize_f32": ([vp, i64, vp, vp], ctypes.c_int),
     "lmc_lvx_v11_build_f64": ([vp, vp, vp, vp, vp, vp, i64, i32, i64, vp, vp], ctypes.c_int),
     "lmc_lvx_v11_build_f32": ([vp, vp, vp, vp, vp, vp, i64, i32, i64, vp, vp], ctypes.c_int),
+    "lmc_pcd_ascii_size_f64": ([vp, i64, vp, vp], ctypes.c_int),
+    "lmc_pcd_ascii_size_f32": ([vp, i64, vp, vp], ctypes.c_int),
+    "lmc_pcd_ascii_write_f64": ([vp, i64, vp, vp, vp, vp], ctypes.c_int),
+    "lmc_pcd_ascii_write_f32": ([vp, i64, vp, vp, vp, vp], ctypes.c_int),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

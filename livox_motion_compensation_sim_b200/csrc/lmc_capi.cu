@@ -10,6 +10,8 @@ namespace lmc {
 cudaError_t launch_direct(bool f64, int mode, const Params& P, cudaStream_t st);
 cudaError_t launch_tma(bool f64, int mode, const Params& P, cudaStream_t st, bool force, bool* handled);
 cudaError_t launch_pose_lookup(const double*, int64_t, const double*, const double*, int32_t, double*, int32_t*, cudaStream_t);
+cudaError_t launch_pcd_size(bool f64, const void* pts, int64_t n, int64_t* tile_off, cudaStream_t st);
+cudaError_t launch_pcd_write(bool f64, const void* pts, int64_t n, const int64_t* tile_off, uint8_t* out, uint32_t* status, cudaStream_t st);
 cudaError_t launch_lvx_v11(bool f64, const void* pts, const int64_t* frame_off, const int64_t* frame_pos, const double* frame_time,
                            const int64_t* frame_id, uint8_t* out, int32_t n_frames, int64_t max_frame_points, uint32_t* status, cudaStream_t st);
 }
@@ -226,6 +228,31 @@ int lmc_lvx_v11_build_f32(const float* pts_n4, const int64_t* frame_off, const i
                           const int64_t* frame_id, uint8_t* file_out, int64_t n_points, int32_t n_frames, int64_t max_frame_points,
                           uint32_t* status, void* stream) {
     return lvx_build(false, pts_n4, frame_off, frame_pos, frame_time, frame_id, file_out, n_points, n_frames, max_frame_points, status, stream);
+}
+
+static int pcd_size(bool f64, const void* pts, int64_t n, int64_t* tile_off, void* stream) {
+    int rc = check_device();
+    if (rc != LMC_OK) return rc;
+    if (n < 0 || !tile_off || (n > 0 && !pts)) return fail(LMC_ERR_INVALID, "bad argument");
+    if (!aligned32(pts)) return fail(LMC_ERR_ALIGN, "points must be 32-byte aligned");
+    cudaError_t e = lmc::launch_pcd_size(f64, pts, n, tile_off, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_pcd_len / k_pcd_scan");
+}
+static int pcd_write(bool f64, const void* pts, int64_t n, const int64_t* tile_off, uint8_t* out, uint32_t* status, void* stream) {
+    int rc = check_device();
+    if (rc != LMC_OK) return rc;
+    if (n < 0 || !tile_off || (n > 0 && (!pts || !out))) return fail(LMC_ERR_INVALID, "bad argument");
+    if (!aligned32(pts) || !aligned32(out)) return fail(LMC_ERR_ALIGN, "points and text buffer must be 32-byte aligned");
+    cudaError_t e = lmc::launch_pcd_write(f64, pts, n, tile_off, out, status, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_pcd_write");
+}
+int lmc_pcd_ascii_size_f64(const double* pts_n4, int64_t n_points, int64_t* tile_off, void* stream) { return pcd_size(true, pts_n4, n_points, tile_off, stream); }
+int lmc_pcd_ascii_size_f32(const float* pts_n4, int64_t n_points, int64_t* tile_off, void* stream) { return pcd_size(false, pts_n4, n_points, tile_off, stream); }
+int lmc_pcd_ascii_write_f64(const double* pts_n4, int64_t n_points, const int64_t* tile_off, uint8_t* text_out, uint32_t* status, void* stream) {
+    return pcd_write(true, pts_n4, n_points, tile_off, text_out, status, stream);
+}
+int lmc_pcd_ascii_write_f32(const float* pts_n4, int64_t n_points, const int64_t* tile_off, uint8_t* text_out, uint32_t* status, void* stream) {
+    return pcd_write(false, pts_n4, n_points, tile_off, text_out, status, stream);
 }
 
 }  // extern "C"

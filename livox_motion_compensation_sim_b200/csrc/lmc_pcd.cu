@@ -1,0 +1,188 @@
+// lmc_pcd.cu --  ASCII PCD point data on the device: the per-point line of
+// LiDARMotionSimulator.save_pcd (LMC:946-947)
+//     f"{x:.6f} {y:.6f} {z:.6f} {intensity:.6f}\n"
+// for every row of an (N,4) array, byte-identical to CPython's formatting (correctly rounded,
+// round-half-even on the exact binary value -- the same rule as C printf).
+//
+// "%.6f" of a double exactly:  |v| = m * 2^e (m < 2^53)  ->  Q = round_half_even(m * 10^6 * 2^e)
+// with the 73-bit product m * 10^6 held in unsigned __int128; then Q / 10^6 and Q % 10^6 are the
+// integer and fractional digits.  Values with |v| >= 9.2e12 (Q would not fit 64 bits) are printed as
+// "inf"-free saturated text and flagged LMC_FLAG_OVERFLOW -- no point cloud coordinate gets there.
+//
+// Lines have variable length, so the text is produced in three launches:
+//   k_pcd_len    per tile of 256 points: total text bytes of the tile
+//   k_pcd_scan   one CTA: exclusive prefix sum of the tile sizes -> byte offset of every tile
+//   k_pcd_write  per tile: format again, lay the lines out in shared memory (block scan of the line
+//                lengths) and copy the tile's contiguous byte range out with 16-byte stores
+#include "lmc_device.cuh"
+
+namespace lmc {
+
+constexpr int kPcdTile    = 256;                    // points (= threads) per tile
+constexpr int kNumMax     = 1 + 13 + 1 + 6;         // sign + 13 integer digits + '.' + 6 decimals
+constexpr int kLineMax    = 4 * kNumMax + 4;        // 3 spaces + newline
+constexpr int kPcdImg     = ((kPcdTile * kLineMax + 32 + 15) / 16) * 16;
+
+struct Num { uint64_t q; uint32_t len; uint32_t kind; };   // kind 0 finite, 1 nan, 2 inf; bit 31 of len-free sign in `neg`
+
+// Q = round_half_even(|v| * 1e6), text length, special-value kind
+__device__ __forceinline__ uint32_t fmt_prepare(double v, uint64_t& q, bool& neg, uint32_t& kind, uint32_t& fl) {
+    const uint64_t bits = (uint64_t)__double_as_longlong(v);
+    neg = bits >> 63;
+    const uint32_t ex = (uint32_t)(bits >> 52) & 0x7ffu;
+    const uint64_t frac = bits & 0xfffffffffffffull;
+    if (ex == 0x7ff) { kind = frac ? 1u : 2u; q = 0; return frac ? 3u : (neg ? 4u : 3u); }   // "nan" | "inf" / "-inf"
+    kind = 0;
+    const uint64_t m = ex ? (frac | (1ull << 52)) : frac;
+    const int e = (ex ? (int)ex : 1) - 1075;
+    if (e >= 0) {                                    // integer-valued, >= 2^52: beyond the supported magnitude
+        fl |= LMC_FLAG_OVERFLOW; q = 9199999999999999999ull;
+    } else {
+        const int s = -e;
+        const unsigned __int128 P = (unsigned __int128)m * 1000000u;
+        if (s >= 127) q = 0;                         // < 2^-54 * 2^73-ish: far below half of the last place
+        else {
+            const unsigned __int128 Qw = P >> s;
+            if (Qw > (unsigned __int128)9199999999999999999ull) { fl |= LMC_FLAG_OVERFLOW; q = 9199999999999999999ull; }
+            else {
+                q = (uint64_t)Qw;
+                const unsigned __int128 rem = P - (Qw << s), half = (unsigned __int128)1 << (s - 1);
+                if (rem > half || (rem == half && (q & 1ull))) q += 1;
+            }
+        }
+    }
+    // digits of the integer part
+    const uint64_t ip = q / 1000000ull;
+    uint32_t nd = 1;
+    for (uint64_t t = ip; t >= 10; t /= 10) ++nd;
+    return (neg ? 1u : 0u) + nd + 7u;
+}
+
+__device__ __forceinline__ int fmt_write(uint8_t* dst, uint64_t q, bool neg, uint32_t kind, uint32_t len) {
+    if (kind) {
+        int o = 0;
+        if (kind == 2 && neg) dst[o++] = '-';
+        if (kind == 1) { dst[o] = 'n'; dst[o + 1] = 'a'; dst[o + 2] = 'n'; }
+        else           { dst[o] = 'i'; dst[o + 1] = 'n'; dst[o + 2] = 'f'; }
+        return o + 3;
+    }
+    uint64_t ip = q / 1000000ull;
+    uint32_t fp = (uint32_t)(q - ip * 1000000ull);
+    int o = (int)len;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { dst[--o] = (uint8_t)('0' + fp % 10u); fp /= 10u; }
+    dst[--o] = '.';
+    do { dst[--o] = (uint8_t)('0' + (uint32_t)(ip % 10ull)); ip /= 10ull; } while (ip);
+    if (neg) dst[--o] = '-';
+    return (int)len;
+}
+
+template <bool F64>
+__device__ __forceinline__ void load_row(const void* pts, int64_t i, double (&v)[4]) {
+    if constexpr (F64) { const double* s = reinterpret_cast<const double*>(pts) + 4 * i; ldg256(s, v[0], v[1], v[2], v[3]); }
+    else { const float4 f = __ldg(reinterpret_cast<const float4*>(pts) + i); v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w; }
+}
+
+__device__ __forceinline__ uint32_t block_scan_excl(uint32_t x, uint32_t* s_warp, uint32_t& total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < kPcdTile / 32; ++k) { const uint32_t t = s_warp[k]; if (k < w) base += t; tot += t; }
+    total = tot;
+    return base + inc - x;
+}
+
+template <bool F64>
+__global__ void __launch_bounds__(kPcdTile) k_pcd_len(const void* __restrict__ pts, int64_t n, int64_t* __restrict__ tile_off) {
+    __shared__ uint32_t s_warp[kPcdTile / 32];
+    const int64_t i = (int64_t)blockIdx.x * kPcdTile + threadIdx.x;
+    uint32_t len = 0, fl = 0;
+    if (i < n) {
+        double v[4];
+        load_row<F64>(pts, i, v);
+        len = 4;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { uint64_t q; bool neg; uint32_t kind; len += fmt_prepare(v[c], q, neg, kind, fl); }
+    }
+    uint32_t total;
+    block_scan_excl(len, s_warp, total);
+    if (threadIdx.x == 0) tile_off[blockIdx.x + 1] = total;       // sizes now, offsets after k_pcd_scan
+}
+
+// one CTA: tile_off[0] = 0; tile_off[t+1] = sum of sizes[0..t]   (in place)
+__global__ void __launch_bounds__(1024) k_pcd_scan(int64_t* __restrict__ tile_off, int64_t n_tiles) {
+    __shared__ int64_t s_part[1024];
+    const int t = threadIdx.x;
+    const int64_t per = (n_tiles + 1023) / 1024;
+    const int64_t b = t * per, e = b + per < n_tiles ? b + per : n_tiles;
+    int64_t sum = 0;
+    for (int64_t k = b; k < e; ++k) sum += tile_off[k + 1];
+    s_part[t] = sum;
+    __syncthreads();
+    if (t == 0) { int64_t acc = 0; for (int k = 0; k < 1024; ++k) { const int64_t v = s_part[k]; s_part[k] = acc; acc += v; } tile_off[0] = 0; }
+    __syncthreads();
+    int64_t acc = s_part[t];
+    for (int64_t k = b; k < e; ++k) { acc += tile_off[k + 1]; tile_off[k + 1] = acc; }
+}
+
+template <bool F64>
+__global__ void __launch_bounds__(kPcdTile) k_pcd_write(const void* __restrict__ pts, int64_t n, const int64_t* __restrict__ tile_off,
+                                                        uint8_t* __restrict__ out, uint32_t* __restrict__ status) {
+    __shared__ __align__(16) uint8_t s_img[kPcdImg];
+    __shared__ uint32_t s_warp[kPcdTile / 32];
+    const int tid = threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * kPcdTile + tid;
+    const int64_t dst0 = tile_off[blockIdx.x];
+    const int phase = (int)(dst0 & 15);
+    uint64_t q[4]; bool neg[4]; uint32_t kind[4], ln[4];
+    uint32_t len = 0, fl = 0;
+    if (i < n) {
+        double v[4];
+        load_row<F64>(pts, i, v);
+        len = 4;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { ln[c] = fmt_prepare(v[c], q[c], neg[c], kind[c], fl); len += ln[c]; }
+    }
+    uint32_t total;
+    const uint32_t off = block_scan_excl(len, s_warp, total);
+    if (i < n) {
+        uint8_t* d = s_img + phase + off;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { d += fmt_write(d, q[c], neg[c], kind[c], ln[c]); *d++ = c == 3 ? '\n' : ' '; }
+    }
+    __syncthreads();
+    uint8_t* g = out + (dst0 - phase);                              // 16-byte aligned
+    const int b0 = phase, b1 = phase + (int)total;
+    int a0 = (b0 + 15) & ~15; if (a0 > b1) a0 = b1;
+    int a1 = b1 & ~15;        if (a1 < a0) a1 = a0;
+    for (int k = a0 / 16 + tid; k < a1 / 16; k += kPcdTile) reinterpret_cast<uint4*>(g)[k] = reinterpret_cast<const uint4*>(s_img)[k];
+    for (int k = b0 + tid; k < a0; k += kPcdTile) g[k] = s_img[k];
+    for (int k = a1 + tid; k < b1; k += kPcdTile) g[k] = s_img[k];
+    if (fl != 0 && status != nullptr) atomicOr(status, fl);
+}
+
+cudaError_t launch_pcd_size(bool f64, const void* pts, int64_t n, int64_t* tile_off, cudaStream_t st) {
+    const int64_t tiles = (n + kPcdTile - 1) / kPcdTile;
+    if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+    if (tiles > 0) {
+        if (f64) k_pcd_len<true><<<(unsigned)tiles, kPcdTile, 0, st>>>(pts, n, tile_off);
+        else     k_pcd_len<false><<<(unsigned)tiles, kPcdTile, 0, st>>>(pts, n, tile_off);
+    }
+    k_pcd_scan<<<1, 1024, 0, st>>>(tile_off, tiles);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pcd_write(bool f64, const void* pts, int64_t n, const int64_t* tile_off, uint8_t* out, uint32_t* status, cudaStream_t st) {
+    const int64_t tiles = (n + kPcdTile - 1) / kPcdTile;
+    if (tiles == 0) return cudaSuccess;
+    if (f64) k_pcd_write<true><<<(unsigned)tiles, kPcdTile, 0, st>>>(pts, n, tile_off, out, status);
+    else     k_pcd_write<false><<<(unsigned)tiles, kPcdTile, 0, st>>>(pts, n, tile_off, out, status);
+    return cudaGetLastError();
+}
+
+}  // namespace lmc

@@ -202,3 +202,20 @@ def build_lvx_v11(pts: torch.Tensor, frame_off: torch.Tensor, frame_pos: torch.T
                _req(frame_time, torch.float64, "frame_time"), _req(frame_id, torch.int64, "frame_id"), out.data_ptr(),
                pts.shape[0], F, int(max_frame_points), status.data_ptr(), _stream_ptr()))
     return out, status
+
+
+def pcd_ascii_body(pts: torch.Tensor):
+    """(N2) LMC:946-947 on the device: one '%.6f %.6f %.6f %.6f\\n' line per row, byte-identical to the
+    reference's f-string formatting.  Returns (uint8 text tensor, status flags tensor)."""
+    f64 = _layout(pts)
+    n = pts.shape[0]
+    tiles = (n + C.PCD_TILE - 1) // C.PCD_TILE
+    tile_off = torch.empty(tiles + 1, dtype=torch.int64, device=pts.device)
+    status = torch.zeros(1, dtype=torch.int32, device=pts.device)
+    L = C.lib()
+    C.check((L.lmc_pcd_ascii_size_f64 if f64 else L.lmc_pcd_ascii_size_f32)(_req(pts, pts.dtype, "pts", (4,)), n, tile_off.data_ptr(), _stream_ptr()))
+    total = int(tile_off[-1].item())                       # the one host sync: the text buffer has to be sized
+    out = torch.empty(total, dtype=torch.uint8, device=pts.device)
+    C.check((L.lmc_pcd_ascii_write_f64 if f64 else L.lmc_pcd_ascii_write_f32)(_req(pts, pts.dtype, "pts", (4,)), n, tile_off.data_ptr(),
+                                                                              out.data_ptr(), status.data_ptr(), _stream_ptr()))
+    return out, status

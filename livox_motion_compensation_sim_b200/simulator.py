@@ -250,16 +250,20 @@ class LiDARMotionSimulator:
         return output_dir
 
     def save_pcd(self, points, filename):
-        """ASCII PCD, byte-identical to LMC:932-948 ('%.6f' per field)."""
+        """ASCII PCD, byte-identical to LMC:932-948 ('%.6f' per field); the point lines are formatted on the GPU."""
         points = np.asarray(points, np.float64).reshape(-1, 4)
         n = len(points)
         header = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z intensity\n"
                   "SIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\n"
                   f"WIDTH {n}\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS {n}\nDATA ascii\n")
-        with open(filename, 'w') as f:
-            f.write(header)
+        with open(filename, 'wb') as f:
+            f.write(header.encode('ascii'))
             if n:
-                np.savetxt(f, points, fmt='%.6f %.6f %.6f %.6f')
+                body, status = ops.pcd_ascii_body(self._to_dev(points))       # (N2) '%.6f' formatting on the device
+                if int(status.item()):                                        # |value| >= 9.2e12: leave it to the host formatter
+                    np.savetxt(f, points, fmt='%.6f %.6f %.6f %.6f')
+                else:
+                    f.write(body.cpu().numpy().tobytes())
 
     def save_lvx(self, results, base_filename):
         """lidar_data.lvx with the LVX v1.1 container of LMC:58-250 around device-quantised records."""

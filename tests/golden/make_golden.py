@@ -193,6 +193,26 @@ def coord_chain_fixture(CS, manifest):
     manifest['coord_chain'] = dict(frames=len(counts), points=int(off[-1]), out_sha256=sha(np.vstack(outs)))
 
 
+def pcd_fixture(LMC, manifest):
+    """(N2) Reference save_pcd (LMC:932-948) on adversarial values: exact ties (odd k / 128), carries,
+    negative zero, tiny / denormal, large magnitudes, nan / inf."""
+    rng = np.random.default_rng(2718)
+    vals = [rng.uniform(-90, 90, 4000), rng.uniform(-1, 1, 500) * 1e-6, np.arange(1, 400, 2) / 128.0, -np.arange(1, 400, 2) / 128.0,
+            np.array([0.0, -0.0, 0.9999995, 0.99999949999, 9.9999995, 99.9999995, -0.9999995, 1e-7, -1e-9, 5e-324, 2.5e-7, 7.5e-7,
+                      123456.7890125, -99999.9999995, 1e12, -8.5e12, 9.1e12, 0.5, 1.5e-6, 2.5e-6, 3.5e-6, 1048575.9999995,
+                      np.nan, np.inf, -np.inf, 1.0, -1.0, 1e6, 0.1, 0.2, 0.3]),
+            rng.uniform(-2000, 2000, 3000), rng.uniform(0, 1, 2000)]
+    v = np.concatenate(vals)
+    v = np.concatenate([v, np.zeros((-len(v)) % 4)])
+    pts = v.reshape(-1, 4)
+    path = os.path.join(HERE, '_tmp.pcd')
+    LMC.LiDARMotionSimulator().save_pcd(pts, path)
+    data = np.fromfile(path, np.uint8)
+    os.remove(path)
+    np.savez_compressed(os.path.join(HERE, 'pcd_ascii.npz'), pts=pts, file_bytes=data)
+    manifest['pcd_ascii'] = dict(points=len(pts), bytes=int(len(data)), sha256=sha(data))
+
+
 def modeb_fixture(CS, manifest):
     """Reference MotionCompensator.compensate_point_cloud (CS:1435-1536) + LVX2 packer
     (CS:365-374) on synthetic Mid-70-shaped frames against the reference's own 200 Hz
@@ -256,6 +276,7 @@ def main():
     lvx_file_fixture(LMC, manifest)
     modeb_fixture(CS, manifest)
     coord_chain_fixture(CS, manifest)
+    pcd_fixture(LMC, manifest)
     with open(os.path.join(HERE, 'MANIFEST.json'), 'w') as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     print('wrote', sorted(os.listdir(HERE)))

@@ -388,6 +388,41 @@ def test_motion_compensator_list_api(golden):
     assert mc.compensate_point_cloud(pts, [], 0, 1) is pts
 
 
+def test_pcd_ascii_vs_reference(golden, tmp_path):
+    """(N2) device '%.6f' formatting == the reference's save_pcd bytes (ties, carries, -0.0, denormals,
+    nan / inf), and the mirror's save_pcd writes the identical file."""
+    from livox_motion_compensation_sim_b200 import LiDARMotionSimulator
+    g = golden("pcd_ascii.npz")
+    ref = g['file_bytes'].tobytes()
+    body, status = ops.pcd_ascii_body(dev(g['pts']))
+    assert int(status.item()) == 0
+    got = body.cpu().numpy().tobytes()
+    assert ref.endswith(got) and got.count(b"\n") == len(g['pts'])
+    assert ref[:len(ref) - len(got)].endswith(b"DATA ascii\n")
+    f = tmp_path / "x.pcd"
+    LiDARMotionSimulator().save_pcd(g['pts'], str(f))
+    assert f.read_bytes() == ref
+    LiDARMotionSimulator().save_pcd(np.zeros((0, 4)), str(f))
+    assert f.read_bytes().endswith(b"POINTS 0\nDATA ascii\n")
+
+
+@pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
+def test_pcd_ascii_large_random(f64):
+    rng = np.random.default_rng(4)
+    n = 300_007
+    pts = np.column_stack([rng.uniform(-2000, 2000, (n, 3)), rng.uniform(0, 1, n)])
+    pts[::7, 0] = np.round(pts[::7, 0], 3); pts[::11, 1] = rng.integers(-100, 100, len(pts[::11])) / 128.0
+    if not f64:
+        pts = pts.astype(np.float32)
+    body, status = ops.pcd_ascii_body(dev(pts))
+    got = body.cpu().numpy().tobytes()
+    want = "".join("%.6f %.6f %.6f %.6f\n" % tuple(r) for r in pts.astype(np.float64)).encode()
+    assert int(status.item()) == 0 and got == want
+    big = np.array([[1e13, 0, 0, 0]] * 3)
+    _, status = ops.pcd_ascii_body(dev(big))
+    assert int(status.item()) & C.FLAG_OVERFLOW
+
+
 def test_coordinate_transformer_mirror_vs_reference(golden):
     """(N3) CS:153-233 mirror: matrices built on the host with the reference's NumPy calls, points
     transformed by the Mode A kernel -> bit-exact against the reference's transform_points."""
