@@ -279,6 +279,39 @@ def main_b200(args):
     pts64 = None
     torch.cuda.empty_cache()
 
+    # ---- downstream writers fed from device buffers, bounded sample ---------------
+    writers = None
+    if rank == 0 and not args.no_sweep:
+        try:
+            from livox_motion_compensation_sim_b200.lvx import frame_layout
+            fw = min(F, 3600)
+            nw = int(st.frame_off[fw])
+            _, fpos = frame_layout(st.frame_off[:fw + 1])
+            fpos_d, offw, ftw, idw = d(fpos), d(st.frame_off[:fw + 1]), d(st.frame_t[:fw]), d(np.arange(fw, dtype=np.int64))
+            raw = st.pts[:nw]
+
+            def t_ms(fn, reps=5):
+                fn(); torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record(); torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / reps
+            lvx_ms = t_ms(lambda: ops.build_lvx_v11(raw, offw, fpos_d, ftw, idw, P))
+            lvx_bytes = int(fpos[-1])
+            pcd_ms = t_ms(lambda: ops.pcd_ascii_body(raw))
+            pcd_bytes = int(ops.pcd_ascii_body(raw)[0].numel())
+            writers = {"sample_points": nw,
+                       "lvx_v11_file": {"points_per_s": nw / (lvx_ms * 1e-3), "GBps": (nw * 16 + lvx_bytes) / (lvx_ms * 1e-3) / 1e9,
+                                        "file_bytes": lvx_bytes, "what": "raw float4 -> complete LVX v1.1 file image (LMC:58-272) on the device"},
+                       "pcd_ascii": {"points_per_s": nw / (pcd_ms * 1e-3), "GBps": (2 * nw * 16 + pcd_bytes) / (pcd_ms * 1e-3) / 1e9,
+                                     "text_bytes": pcd_bytes, "what": "'%.6f %.6f %.6f %.6f\\n' per point (LMC:946-947), size + write passes"}}
+            del raw
+        except Exception as e:                    # noqa: BLE001
+            writers = {"error": repr(e)}
+        torch.cuda.empty_cache()
+
     # ---- merged-cloud all-gather (the one exchange step), timed separately ---------------------------
     merge = None
     if world > 1:
@@ -355,6 +388,7 @@ def main_b200(args):
         try:
             from oracle import cpu_baseline as cb
             cpu["c_port_mode_c_1thread_points_per_s"] = cb.run_c_port_mode_c()
+            cpu["writers_port_points_per_s"] = cb.run_writers_port()
         except Exception as e:                     # noqa: BLE001
             cpu["c_port_error"] = repr(e)
 
@@ -378,6 +412,8 @@ def main_b200(args):
             line["merge"] = merge
         if sweep:
             line["variants"] = sweep
+        if writers:
+            line["writers"] = writers
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -95,6 +95,21 @@ def run_c_port_mode_c(n_frames: int = 60, pts_per_frame: int = 10_000):
     return n / (time.perf_counter() - t0)
 
 
+def run_writers_port(n: int = 200_000):
+    """Context for the device writers: the reference's own per-point Python loops restated as the fastest
+    single-thread NumPy/Python equivalents ('%.6f' formatting per row; LVX records + container layout)."""
+    rng = np.random.default_rng(2)
+    pts = np.column_stack([rng.uniform(-90, 90, (n, 3)), rng.uniform(0, 1, n)])
+    t0 = time.perf_counter()
+    body = "".join("%.6f %.6f %.6f %.6f\n" % tuple(r) for r in pts)
+    t_pcd = time.perf_counter() - t0
+    assert len(body) > 0
+    t0 = time.perf_counter()
+    rec = orc.quantize_lvx_type2_np(pts)
+    t_lvx = time.perf_counter() - t0
+    return {"pcd_ascii": n / t_pcd, "lvx_records": n / t_lvx}
+
+
 def default_threads() -> int:
     try:
         n = len(os.sched_getaffinity(0))

@@ -163,6 +163,57 @@ def test_fused_rigid_lvx_las_vs_oracle(ppf, F, f64, path):
     assert np.array_equal(b.las_intensity.cpu().numpy().view(np.uint16), I)
 
 
+@pytest.mark.parametrize("mode", ["rigid", "gyro", "slerp"])
+def test_many_tiny_frames_overflow_path(mode, path):
+    """Thousands of 0-3 point frames: far more than the 30 frame boundaries a tile caches, so every point
+    takes the per-point global frame search (TileMeta.overflow), plus one-point frames (gemv order)."""
+    rng = np.random.default_rng(99)
+    F = 6000
+    counts = rng.integers(0, 4, F)
+    st = synth.make_stream(F, counts, 99, device=DEV, dtype=torch.float64)
+    pts64 = st.pts.cpu().numpy()
+    fidx = np.repeat(np.arange(F), counts)
+    ts64 = st.frame_start[fidx] + st.ts_off.cpu().numpy().astype(np.int64)
+    off_d = dev(st.frame_off)
+    if mode == "rigid":
+        pose = st.gps_Rt[orc.pose_lookup_hold_next_np(st.gps_t, st.frame_t)]
+        out, _ = ops.align_rigid(st.pts, off_d, dev(pose))
+        want = orc.C.align_rigid_f64(pts64, st.frame_off, pose)
+        assert out.cpu().numpy().tobytes() == want.tobytes()
+    elif mode == "gyro":
+        gyro = rng.normal(0, 0.3, (len(st.sample_ts), 3))
+        out, _ = ops.deskew_gyro(st.pts, dev(ts64), off_d, dev(st.frame_start), dev(st.sample_ts), dev(gyro))
+        want = orc.C.deskew_gyro_f64(pts64, ts64, st.frame_off, st.frame_start, st.sample_ts, gyro)
+        assert np.abs(out.cpu().numpy() - want).max() <= 1e-10
+    else:
+        out, _ = ops.deskew_slerp(st.pts, dev(ts64), off_d, dev(st.frame_start), dev(st.sample_ts), dev(st.seg))
+        want = orc.C.deskew_slerp_f64(pts64, ts64, st.frame_off, st.sample_ts, st.seg)
+        assert np.abs(out.cpu().numpy() - want).max() <= 1e-10
+
+
+def test_empty_and_degenerate_inputs():
+    """N = 0, all-empty frames, a single point, one-sample tables."""
+    z = torch.zeros((0, 4), dtype=torch.float64, device=DEV)
+    off0 = dev(np.zeros(4, np.int64))
+    out, _ = ops.align_rigid(z, off0, dev(np.zeros((3, 12))))
+    assert out.shape == (0, 4)
+    one = dev(np.array([[1.0, 2.0, 3.0, 0.5]]))
+    pose = np.zeros((1, 12)); pose[0, [0, 4, 8]] = 1.0; pose[0, 9:] = [10, 20, 30]
+    out, b = ops.align_rigid(one, dev(np.array([0, 1], np.int64)), dev(pose), export=ops.ExportSpec(lvx=True, las=True))
+    assert out.cpu().numpy().tolist() == [[11.0, 22.0, 33.0, 0.5]]
+    assert b.las_x.item() == 1100 and b.las_intensity.cpu().numpy().view(np.uint16)[0] == int(0.5 * 65535)
+    # one-sample tables: Mode B returns that sample's gyro, Mode C that sample's pose
+    seg = FR.slerp_segment_table(np.array([[0, 0, 0, 1.0]]), np.array([[1.0, 1.0, 1.0]]), np.array([5], np.int64))
+    out, _ = ops.deskew_slerp(one, dev(np.array([7], np.int64)), dev(np.array([0, 1], np.int64)), dev(np.array([0], np.int64)),
+                              dev(np.array([5], np.int64)), dev(seg))
+    assert out.cpu().numpy().tolist() == [[2.0, 3.0, 4.0, 0.5]]
+    out, _ = ops.deskew_gyro(one, dev(np.array([7], np.int64)), dev(np.array([0, 1], np.int64)), dev(np.array([0], np.int64)),
+                             dev(np.array([5], np.int64)), dev(np.zeros((1, 3))))
+    assert np.allclose(out.cpu().numpy(), [[1.0, 2.0, 3.0, 0.5]])
+    with pytest.raises(C.LmcError):
+        ops.align_rigid(one, dev(np.array([0, 1], np.int64)), dev(pose), p_range=(0, 5))      # range beyond the array
+
+
 def test_point_range_shards_compose(path):
     """Frame-sharded ranks writing disjoint [p_begin, p_end) slices of one merged buffer give the
     same bytes as one launch (odd, unaligned cut points on purpose)."""
