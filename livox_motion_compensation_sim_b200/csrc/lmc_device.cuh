@@ -107,17 +107,30 @@ __device__ __forceinline__ void rigid_apply(const double (&M)[12], bool single, 
     o.w = p.w;
 }
 
-// sin(x) and 1 - cos(x).  Deskew angles are tiny (gyro * 0.1 s, or one 5 ms pose segment), so for
-// |x| <= 0.5 a Taylor polynomial without range reduction is exact to < 1 ulp (next terms: 2e-20,
-// 6e-22 relative); larger arguments take the library path.
+// sin(x) and 1 - cos(x).  Deskew angles are tiny (gyro * 0.1 s, or one 5 ms pose segment), so Taylor
+// polynomials without range reduction are exact to < 1 ulp; |x| > 0.5 takes the library path.
 __constant__ double kSinC[7] = { -7.6471637318198164759e-13 /* -1/15! */, 1.6059043836821614599e-10, -2.5052108385441718775e-08,
                                  2.7557319223985890653e-06, -1.9841269841269841270e-04, 8.3333333333333333333e-03,
                                  -1.6666666666666666667e-01 /* -1/3! */ };
 __constant__ double kCosC[8] = { -4.7794773323873852974e-14 /* -1/16! */, 1.1470745597729724714e-11, -2.0876756987868098979e-09,
                                  2.7557319223985890653e-07, -2.4801587301587301587e-05, 1.3888888888888888889e-03,
                                  -4.1666666666666666667e-02, 0.5 /* 1/2! */ };
-// branch-free polynomial part, valid for |x| <= 0.5
-__device__ __forceinline__ void sin_vercos_small(double x, double& s, double& v) {
+// Branch-free polynomial parts.  kSmallAngle covers what deskew actually sees (one 5 ms pose segment,
+// gyro * 0.1 s): |x| <= 0.125 needs only degree 11 / 12 (next terms 1e-20, 3e-22 relative); up to 0.5 the
+// degree 15 / 16 version is used.  Which one is taken depends on x alone, so the straight-line fast paths
+// (which require every angle <= kSmallAngle) and the general path always agree bit-for-bit.
+constexpr double kSmallAngle = 0.125;
+__device__ __forceinline__ void sin_vercos_small(double x, double& s, double& v) {      // |x| <= kSmallAngle
+    const double u = x * x;
+    double ps = kSinC[2], pc = kCosC[2];
+#pragma unroll
+    for (int i = 3; i < 7; ++i) ps = fma(ps, u, kSinC[i]);
+#pragma unroll
+    for (int i = 3; i < 8; ++i) pc = fma(pc, u, kCosC[i]);
+    s = fma(x * u, ps, x);
+    v = u * pc;
+}
+__device__ __forceinline__ void sin_vercos_mid(double x, double& s, double& v) {        // |x| <= 0.5
     const double u = x * x;
     double ps = kSinC[0], pc = kCosC[0];
 #pragma unroll
@@ -128,8 +141,10 @@ __device__ __forceinline__ void sin_vercos_small(double x, double& s, double& v)
     v = u * pc;
 }
 __device__ __forceinline__ void sin_vercos(double x, double& s, double& v) {
-    if (fabs(x) <= 0.5) {
+    if (fabs(x) <= kSmallAngle) {
         sin_vercos_small(x, s, v);
+    } else if (fabs(x) <= 0.5) {
+        sin_vercos_mid(x, s, v);
     } else {
         double c;
         sincos(x, &s, &c);
@@ -166,7 +181,7 @@ __device__ __forceinline__ void gyro_rotate(double ax, double ay, double az, con
     o.w = p.w;
 }
 
-// The same rotation for |angles| <= 0.49 rad with the structural zeros / ones of Rx, Ry, Rz folded
+// The same rotation for |angles| <= kSmallAngle with the structural zeros / ones of Rx, Ry, Rz folded
 // away: every surviving operation is the one the dgemm chain of gyro_rotate() performs on non-zero
 // operands (x*0 terms and "+0" additions dropped), so results agree bit-for-bit except possibly in the
 // sign of an exact zero.  14 FP64 ops for the matrix instead of 54, branch-free.
@@ -523,7 +538,7 @@ struct PointCtx {
                 const uint64_t dtk = (uint64_t)__double_as_longlong(tab[21]);
                 const int64_t da = ta - tk, db = tb - tk;
                 // the row's own [t_k, t_k + dt_k) verifies the guess for both points at once
-                if ((uint64_t)da < dtk && (uint64_t)db < dtk && tab[15] <= 0.49) {
+                if ((uint64_t)da < dtk && (uint64_t)db < dtk && tab[15] <= kSmallAngle) {
                     double row[kSegStride];
 #pragma unroll
                     for (int q = 0; q < 6; ++q) { const double2 v = __ldg(sr + q); row[2 * q] = v.x; row[2 * q + 1] = v.y; }
@@ -582,7 +597,7 @@ struct PointCtx {
                             amax = fmax(amax, fabs(ang[h][c]));
                         }
                     }
-                    if (amax <= 0.49) {
+                    if (amax <= kSmallAngle) {
                         gyro_rotate_small(ang[0][0], ang[0][1], ang[0][2], in[0], out[0]);
                         gyro_rotate_small(ang[1][0], ang[1][1], ang[1][2], in[1], out[1]);
                         return;
