@@ -180,6 +180,7 @@ def main_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep NCCL's version banner off stdout (ONE JSON line)
         dist.init_process_group("nccl", device_id=dev)
     if not os.path.exists(_build.LIB_PATH):
         if rank == 0:
@@ -193,6 +194,7 @@ def main_b200(args):
     # rank r owns hour r of an N-hour stream: same shape, different seed
     st = synth.make_stream(F, P, SEED + 17 * rank, device=dev, dtype=torch.float32)
     N = st.n_points
+    n_samples = len(st.sample_ts)
     d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)   # noqa: E731
     off_d, fs_d, sts_d, seg_d = d(st.frame_off), d(st.frame_start), d(st.sample_ts), d(st.seg)
     gyro_d = d(np.random.default_rng(3).normal(0, 0.2, (len(st.sample_ts), 3)))
@@ -312,31 +314,6 @@ def main_b200(args):
             writers = {"error": repr(e)}
         torch.cuda.empty_cache()
 
-    # ---- merged-cloud all-gather (the one exchange step), timed separately ---------------------------
-    merge = None
-    if world > 1:
-        per_rank = N
-        mo = torch.empty((world * per_rank, 4), dtype=torch.float32, device=dev)
-        mine = mo[rank * per_rank:(rank + 1) * per_rank]
-        mine.copy_(st.pts)
-        for _ in range(2):
-            dist.all_gather_into_tensor(mo, mine)
-        torch.cuda.synchronize(); dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        reps = 3
-        for _ in range(reps):
-            dist.all_gather_into_tensor(mo, mine)
-        e1.record(); torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ag_ms = float(t.item())
-        merge = {"what": "NCCL all_gather_into_tensor of the aligned float4 cloud into every rank's merged buffer",
-                 "ms": ag_ms, "bytes_received_per_rank": (world - 1) * per_rank * 16,
-                 "ingress_GBps_per_rank": (world - 1) * per_rank * 16 / (ag_ms * 1e-3) / 1e9,
-                 "points_per_s_kernel_plus_merge": world * N / ((ms_per_step + ag_ms) * 1e-3)}
-        del mo, mine
-
     # ---- end to end: pinned host buffers in, pinned host buffers out ---------------------------------
     e2e = None
     if not args.no_e2e:
@@ -380,6 +357,66 @@ def main_b200(args):
                "what": "StreamingAligner.run: pinned host float4+u32 ts -> chunked H2D / fused Mode C + LVX kernel / D2H of float4 + 14-B records, 3 streams",
                "h2d_GBps": sa.h2d_bytes / (ems * 1e-3) / 1e9, "d2h_GBps": sa.d2h_bytes / (ems * 1e-3) / 1e9}
         del hs, sa
+    # ---- merged cloud (BASELINE configs[3] literally): ONE 1 h stream, frame-sharded over the N ranks, the
+    #      merged aligned cloud + LVX records assembled on every rank.  Strong scaling, reported under "merge":
+    #      (a) shard kernel + NCCL all-gather(v), (b) merged-cloud assembly fused into the kernel epilogue
+    #      (peer stores over NVLink into every rank's symmetric-memory copy).
+    merge = None
+    if world > 1:
+        try:
+            from livox_motion_compensation_sim_b200 import sharding
+            del st
+            torch.cuda.empty_cache()
+            sm_st = synth.make_stream(F, P, SEED, device=dev, dtype=torch.float32)          # the SAME stream on every rank
+            Nm = sm_st.n_points
+            offm, fsm = d(sm_st.frame_off), d(sm_st.frame_start)
+            fcuts, pcuts = sharding.shard_ranges(sm_st.frame_off, world)
+            pb, pe = int(pcuts[rank]), int(pcuts[rank + 1])
+            symm = sharding.SymmetricMerged(Nm, dev, lvx=True)
+            po, pl = symm.peer_ptrs()
+
+            def run_nccl():
+                ops.deskew_slerp(sm_st.pts, sm_st.ts_off, offm, fsm, sts_d, seg_d, out=symm.out,
+                                 export=ops.ExportSpec(lvx=True, into=ops.ExportBuffers(lvx14=symm.lvx14)), p_range=(pb, pe))
+                sharding.all_gather_merged([symm.out, symm.lvx14], pcuts)
+
+            def run_fused():
+                ops.deskew_slerp(sm_st.pts, sm_st.ts_off, offm, fsm, sts_d, seg_d, out=symm.out,
+                                 export=ops.ExportSpec(lvx=True, into=ops.ExportBuffers(lvx14=symm.lvx14), peer_out=po, peer_lvx14=pl),
+                                 p_range=(pb, pe))
+                symm.barrier()
+
+            def run_shard_only():
+                ops.deskew_slerp(sm_st.pts, sm_st.ts_off, offm, fsm, sts_d, seg_d, out=symm.out,
+                                 export=ops.ExportSpec(lvx=True, into=ops.ExportBuffers(lvx14=symm.lvx14)), p_range=(pb, pe))
+
+            def t_max_ms(fn, reps=5):
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize(); dist.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record(); torch.cuda.synchronize()
+                t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dist.barrier()
+                return float(t.item())
+            shard_ms, nccl_ms, fused_ms = t_max_ms(run_shard_only), t_max_ms(run_nccl), t_max_ms(run_fused)
+            recv = (Nm - (pe - pb)) * 30
+            merge = {"what": "ONE 1 h stream (3.6e8 pts) frame-sharded over the ranks; aligned float4 cloud + 14-B LVX records merged on every rank",
+                     "scaling": "strong", "points": Nm, "bytes_received_per_rank": recv,
+                     "shard_kernel_only": {"ms": shard_ms, "points_per_s": Nm / (shard_ms * 1e-3)},
+                     "kernel_plus_nccl_allgather": {"ms": nccl_ms, "points_per_s": Nm / (nccl_ms * 1e-3)},
+                     "fused_peer_store_epilogue": {"ms": fused_ms, "points_per_s": Nm / (fused_ms * 1e-3),
+                                                   "ingress_GBps_per_rank": recv / (fused_ms * 1e-3) / 1e9,
+                                                   "what": "same kernel, epilogue also stores into every peer's symmetric-memory copy over NVLink, then one cross-rank barrier"}}
+            del symm, sm_st
+        except Exception as e:                     # noqa: BLE001
+            merge = {"error": repr(e)}
+        torch.cuda.empty_cache()
+
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -398,7 +435,7 @@ def main_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"M-1H synthetic 1 h Mid-70 stream: {F} frames x {P} pts = {N} points per GPU, 200 Hz pose samples ({len(st.sample_ts)}), seed {SEED}",
+            "config": {"workload": f"M-1H synthetic 1 h Mid-70 stream: {F} frames x {P} pts = {N} points per GPU, 200 Hz pose samples ({n_samples}), seed {SEED}",
                        "variant": f"{args.variant}: mode={mode} io={'f64' if f64 else 'f32 float4'} ts={ts} lvx={lvx} las={las}, f64 arithmetic",
                        "bytes_per_point": bpp, "kernel_path": {0: "direct", 1: "auto (persistent TMA pipeline at this size)", 2: "tma"}[C.get_path()],
                        "l2": f"inputs {N * (16 + 4) / 1e9:.1f} GB >> 126 MB L2: no flush needed", "parallelism": f"frame-sharded x{world}",

@@ -69,7 +69,16 @@ typedef struct lmc_export {
     double    las_scale[3];       /* laspy header default 0.01 (LMC:953), 0.001 set at CS:1679-1681   */
     double    las_offset[3];      /* 0                                                                */
     uint32_t* status;             /* device u32, OR of LMC_FLAG_*; NULL = not reported                */
+    /* Merged-cloud assembly fused into the epilogue: when n_peers > 0 the aligned cloud and
+     * the LVX records are ALSO stored, at the same global point indices, into the other ranks' copies of
+     * the merged buffers (peer-mapped device pointers, e.g. torch symmetric memory buffer_ptrs) -- the
+     * all-gather happens over NVLink while the kernel computes.  A cross-rank barrier after the kernel
+     * makes the remote writes visible.  LAS arrays are not mirrored. */
+    int32_t   n_peers;            /* 0 .. LMC_MAX_PEERS                                              */
+    void*     peer_out[7];        /* same layout as out_n4 (NULL entries are skipped)                 */
+    uint8_t*  peer_lvx14[7];      /* same layout as lvx14                                             */
 } lmc_export;
+#define LMC_MAX_PEERS 7
 
 int         lmc_version(void);
 const char* lmc_last_error(void);

@@ -13,6 +13,7 @@ LVX_TYPE2_OF_INPUT, LVX2_OF_OUTPUT = 0, 1
 LAS_INTENSITY_UNIT, LAS_INTENSITY_RAW = 0, 1
 PATH_DIRECT, PATH_AUTO, PATH_TMA = 0, 1, 2
 PCD_TILE = 256
+MAX_PEERS = 7
 
 vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
 
@@ -25,6 +26,7 @@ class LmcExport(ctypes.Structure):
         ("las_intensity_mode", i32),
         ("las_scale", ctypes.c_double * 3), ("las_offset", ctypes.c_double * 3),
         ("status", vp),
+        ("n_peers", i32), ("peer_out", vp * 7), ("peer_lvx14", vp * 7),
     ]
 
 

@@ -49,7 +49,8 @@ int check_device() {
 
 int fill_export(lmc::Params& P, const lmc_export* ex) {
     P.lvx14 = nullptr; P.tag = nullptr; P.las_x = P.las_y = P.las_z = nullptr; P.las_int = nullptr; P.status = nullptr;
-    P.lvx_mode = 0; P.las_int_mode = 0;
+    P.lvx_mode = 0; P.las_int_mode = 0; P.n_peers = 0;
+    for (int r = 0; r < LMC_MAX_PEERS; ++r) { P.peer_out[r] = nullptr; P.peer_lvx[r] = nullptr; }
     for (int c = 0; c < 3; ++c) { P.las_scale[c] = 0.01; P.las_rcp[c] = 1.0 / 0.01; P.las_off[c] = 0.0; }
     if (!ex) return LMC_OK;
     if (ex->lvx_mode != LMC_LVX_TYPE2_OF_INPUT && ex->lvx_mode != LMC_LVX2_OF_OUTPUT) return fail(LMC_ERR_INVALID, "bad lvx_mode %d", ex->lvx_mode);
@@ -64,6 +65,12 @@ int fill_export(lmc::Params& P, const lmc_export* ex) {
     P.lvx14 = ex->lvx14; P.lvx_mode = ex->lvx_mode; P.tag = ex->tag;
     P.las_x = ex->las_x; P.las_y = ex->las_y; P.las_z = ex->las_z; P.las_int = ex->las_intensity;
     P.las_int_mode = ex->las_intensity_mode; P.status = ex->status;
+    if (ex->n_peers < 0 || ex->n_peers > LMC_MAX_PEERS) return fail(LMC_ERR_INVALID, "n_peers must be 0..%d", LMC_MAX_PEERS);
+    P.n_peers = ex->n_peers;
+    for (int r = 0; r < ex->n_peers; ++r) {
+        if (!aligned32(ex->peer_out[r]) || !aligned32(ex->peer_lvx14[r])) return fail(LMC_ERR_ALIGN, "peer buffers must be 32-byte aligned");
+        P.peer_out[r] = ex->peer_out[r]; P.peer_lvx[r] = ex->peer_lvx14[r];
+    }
     for (int c = 0; c < 3; ++c) { P.las_scale[c] = ex->las_scale[c]; P.las_rcp[c] = 1.0 / ex->las_scale[c]; P.las_off[c] = ex->las_offset[c]; }
     return LMC_OK;
 }
@@ -86,10 +93,11 @@ int run(bool f64, int mode, lmc::Params& P, const lmc_export* ex, void* stream) 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
     bool handled = false;
-    if (g_path >= 1) {
-        e = lmc::launch_tma(f64, mode, P, st, g_path == 2, &handled);
+    if (g_path >= 1 || P.n_peers > 0) {
+        e = lmc::launch_tma(f64, mode, P, st, g_path == 2 || P.n_peers > 0, &handled);
         if (handled) return e == cudaSuccess ? LMC_OK : cuda_fail(e, "launch (tma path)");
     }
+    if (P.n_peers > 0) return fail(LMC_ERR_INVALID, "peer stores need the streaming kernels (16-byte aligned timestamp / tag arrays)");
     e = lmc::launch_direct(f64, mode, P, st);
     return e == cudaSuccess ? LMC_OK : cuda_fail(e, "launch (direct path)");
 }

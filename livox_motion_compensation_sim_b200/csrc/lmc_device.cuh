@@ -42,6 +42,10 @@ struct Params {
     uint32_t*       status;
     double          las_scale[3], las_rcp[3], las_off[3];      // las_rcp = 1/scale (host, correctly rounded)
     int32_t         lvx_mode, las_int_mode;
+    // fused merged-cloud assembly: peer-mapped copies of out / lvx14 on the other ranks
+    int32_t         n_peers;
+    void*           peer_out[LMC_MAX_PEERS];
+    uint8_t*        peer_lvx[LMC_MAX_PEERS];
 };
 
 struct Pt { double x, y, z, w; };

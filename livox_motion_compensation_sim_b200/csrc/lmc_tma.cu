@@ -206,6 +206,11 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
                 }
             }
         }
+        if constexpr (GEN) {
+            // fused merged-cloud assembly: the same pair goes to every peer's copy of the merged buffer
+            for (int r = 0; r < P.n_peers; ++r)
+                if (P.peer_out[r] != nullptr) store_pair<F64, FULL>(P.peer_out[r], p, va, vb, o[0], o[1]);
+        }
         if (do_las) store_las_pair<FULL>(P, p, va, vb, o[0], o[1], fl);
         if constexpr (GEN) {
             if (do_lvx) {
@@ -234,6 +239,20 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
                 for (int i = a0 / 16 + lane; i < a1 / 16; i += 32) reinterpret_cast<uint4*>(g)[i] = reinterpret_cast<const uint4*>(slab)[i];
                 for (int i = b0 + lane; i < a0; i += 32) g[i] = slab[i];
                 for (int i = a1 + lane; i < b1; i += 32) g[i] = slab[i];
+            }
+        }
+        if constexpr (GEN) {
+            for (int r = 0; r < P.n_peers; ++r) {
+                uint8_t* gp = P.peer_lvx[r];
+                if (gp == nullptr) continue;
+                gp += 14 * wfirst;
+                if constexpr (FULL) {
+                    for (int i = lane; i < NB / 16; i += 32) reinterpret_cast<uint4*>(gp)[i] = reinterpret_cast<const uint4*>(slab)[i];
+                } else {
+                    int64_t lo = ti.lim_lo - wfirst, hi = ti.lim_hi - wfirst;
+                    lo = lo < 0 ? 0 : lo; hi = hi > PPT * 64 ? PPT * 64 : hi;
+                    for (int i = (int)lo * 14 + lane; i < (int)hi * 14; i += 32) gp[i] = slab[i];
+                }
             }
         }
         __syncwarp();                                                         // slab is reused by the next tile
@@ -376,7 +395,7 @@ static cudaError_t launch_stream(const Params& P, cudaStream_t st, bool force, b
     // lean (compile-time export configuration) variants for the common cases of Mode A / Mode C
     if constexpr (MODE == kRigid || MODE == kSlerp) {
         const int mask = (P.out ? kExOut : 0) | (P.lvx14 ? kExLvx : 0) | ((P.las_x || P.las_int) ? kExLas : 0);
-        bool lean = (!P.lvx14 || (P.lvx_mode == LMC_LVX_TYPE2_OF_INPUT)) && (!(mask & kExLas) || (P.las_x && P.las_int));
+        bool lean = P.n_peers == 0 && (!P.lvx14 || (P.lvx_mode == LMC_LVX_TYPE2_OF_INPUT)) && (!(mask & kExLas) || (P.las_x && P.las_int));
         if (MODE == kSlerp) lean = lean && P.hold_idx == nullptr && P.ts != nullptr && P.n_samp >= 2 && P.n_samp < 0x7fffffffLL &&
                                    (F64 || P.frame_start != nullptr);
         if (lean) {

@@ -63,10 +63,12 @@ class ExportSpec:
     las_offset: Sequence[float] = (0.0, 0.0, 0.0)
     las_intensity_mode: int = C.LAS_INTENSITY_UNIT
     into: Optional[ExportBuffers] = None                 # reuse caller buffers (merged cloud shards)
+    peer_out: Sequence[int] = ()                         # peer-mapped device pointers of the other ranks' `out` copies
+    peer_lvx14: Sequence[int] = ()                       # ... and of their lvx14 copies (fused merged-cloud assembly)
 
 
 def _make_export(spec: Optional[ExportSpec], n: int, device):
-    if spec is None or not (spec.lvx or spec.las):
+    if spec is None or not (spec.lvx or spec.las or spec.peer_out):
         return None, None
     b = spec.into if spec.into is not None else ExportBuffers()
     if spec.lvx and b.lvx14 is None:
@@ -92,6 +94,13 @@ def _make_export(spec: Optional[ExportSpec], n: int, device):
         ex.las_scale[c] = float(spec.las_scale[c])
         ex.las_offset[c] = float(spec.las_offset[c])
     ex.status = b.status.data_ptr()
+    npeer = max(len(spec.peer_out), len(spec.peer_lvx14))
+    if npeer > C.MAX_PEERS:
+        raise ValueError(f"at most {C.MAX_PEERS} peers")
+    ex.n_peers = npeer
+    for r in range(npeer):
+        ex.peer_out[r] = int(spec.peer_out[r]) if r < len(spec.peer_out) else None
+        ex.peer_lvx14[r] = int(spec.peer_lvx14[r]) if (spec.lvx and r < len(spec.peer_lvx14)) else None
     return ex, b
 
 

@@ -52,3 +52,33 @@ def all_gather_merged(buffers: Sequence[torch.Tensor], point_cuts: np.ndarray, g
                     works.append(dist.broadcast(raw[b:e], src=src, group=group, async_op=True))
     for w in works:
         w.wait()
+
+
+class SymmetricMerged:
+    """Merged-cloud buffers in NVLink-symmetric memory (torch.distributed._symmetric_memory): every rank
+    holds a full-size copy of the aligned cloud (and LVX records) and can address the other ranks' copies
+    directly.  Passing ``peer_spec()`` to the fused operators makes the kernel epilogue store each result
+    into every rank's copy (remote st.global over NVLink), so the all-gather overlaps the transform instead
+    of following it; ``barrier()`` after the launch makes the remote writes visible.  torch is only the
+    allocator / rendezvous plumbing here -- the data moves inside the sm_100a kernel."""
+
+    def __init__(self, n_points: int, device, *, dtype=torch.float32, lvx: bool = True, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.out = symm.empty((n_points, 4), dtype=dtype, device=device)
+        self.h_out = symm.rendezvous(self.out, self.group)
+        self.lvx14 = self.h_lvx = None
+        if lvx:
+            self.lvx14 = symm.empty((n_points, 14), dtype=torch.uint8, device=device)
+            self.h_lvx = symm.rendezvous(self.lvx14, self.group)
+
+    def peer_ptrs(self):
+        others = [r for r in range(self.world) if r != self.rank]
+        po = [int(self.h_out.buffer_ptrs[r]) for r in others]
+        pl = [int(self.h_lvx.buffer_ptrs[r]) for r in others] if self.h_lvx is not None else []
+        return po, pl
+
+    def barrier(self):
+        torch.cuda.current_stream().synchronize()
+        self.h_out.barrier()

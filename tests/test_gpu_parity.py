@@ -579,3 +579,17 @@ def test_full_size_1h_stream_properties():
     c, _ = ops.deskew_slerp(st.pts, None, off_d, None, sts_d, seg_d, hold_idx=dev(hold))
     assert checksum(a) == checksum(c)
     assert torch.equal(a[:1_000_000], c[:1_000_000])
+
+
+def test_fused_merge_multi_gpu():
+    """>= 2 GPUs only (skipped on the 1-GPU test box): peer-store epilogue == NCCL all-gather == single rank."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29641", os.path.join(root, "tests", "multi_gpu_fused_merge.py")],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, LMC_F="1500"))
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+    assert "OK world=2" in r.stdout
