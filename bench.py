@@ -457,9 +457,40 @@ def main_b200(args):
         dist.destroy_process_group()
 
 
+class _QuietStdout:
+    """Everything but the final JSON line goes to stderr -- including C-level writes to fd 1 such as
+    the 'NCCL version ...' banner printed at communicator creation -- so stdout carries ONE line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+_real_print = print
+
+
+def print(*a, **k):                       # noqa: A001  (the JSON line is printed while fd 1 is diverted: send it to the saved fd)
+    if _QUIET is not None:
+        sys.stdout.flush()
+        os.write(_QUIET.saved, (" ".join(str(x) for x in a) + "\n").encode())
+    else:
+        _real_print(*a, **k)
+
+
+_QUIET = None
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
-        main_reference(a)
-    else:
-        main_b200(a)
+    with _QuietStdout() as _QUIET:
+        if a.impl == "reference":
+            main_reference(a)
+        else:
+            main_b200(a)
