@@ -47,6 +47,10 @@ VARIANTS = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (ncu --set full, profiles/)
+NCU_TRAFFIC = {("V5", N_FRAMES, PTS_PER_FRAME): 18.107e9, ("V1", N_FRAMES, PTS_PER_FRAME): 11.482e9}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -441,7 +445,7 @@ def main_b200(args):
                        "l2": f"inputs {N * (16 + 4) / 1e9:.1f} GB >> 126 MB L2: no flush needed", "parallelism": f"frame-sharded x{world}",
                        "status_flags": flags},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms,
+                         "traffic": NCU_TRAFFIC.get((args.variant, F, P)), "traffic_source": "profiles/r01_ncu_v5_summary.md / r01_ncu_v1_summary.md (dram__bytes_read+write per launch, ncu --set full)" if (args.variant, F, P) in NCU_TRAFFIC else None, "peak_source": peak_src, "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": N * bpp, "frac_of_nominal_8TBps": achieved / 8000.0},
             "clocks": clocks, "gpu_launches": args.steps, "e2e": e2e, "cpu_baseline": cpu,
         }
