@@ -27,7 +27,6 @@ from . import frames as FR
 from . import ops
 from .lvx import build_lvx_v11_file, frame_layout
 
-COMPENSATION_MODES = ("frame_rigid",)      # Mode A; Modes B/C live in compensator.py / ops.deskew_slerp
 
 
 class LiDARMotionSimulator:
