@@ -488,6 +488,8 @@ def test_coordinate_transformer_mirror_vs_reference(golden):
         out = ct.transform_points(g['pts'][off[i]:off[i + 1]], a, b)
         assert np.array_equal(out, g['out'][off[i]:off[i + 1]])
     assert ct.transform_points(g['pts'][:5], 'utm', 'wgs84') is not None          # unknown pair: unchanged (CS:216-218)
+    one = ct.transform_points(g['pts'][:1], CSys.VEHICLE, CSys.LOCAL)               # single point: 1 ulp (4-term gemv order)
+    assert one.shape == (1, 3) and np.abs(one - (g['T'][1] @ np.append(g['pts'][0], 1.0))[:3]).max() <= 1e-12
     # folding a chain into the pose table == applying the two transforms one after the other (to rounding)
     p4 = np.column_stack([g['pts'][:1500], np.zeros(1500)])
     # sensor->vehicle then vehicle->local, vs the folded single transform
