@@ -25,7 +25,7 @@ import torch
 from . import _capi as C
 from . import frames as FR
 from . import ops
-from .lvx import build_lvx_v11_file, frame_layout
+from .lvx import frame_layout
 
 
 
@@ -259,10 +259,9 @@ class LiDARMotionSimulator:
             f.write(header.encode('ascii'))
             if n:
                 body, status = ops.pcd_ascii_body(self._to_dev(points))       # (N2) '%.6f' formatting on the device
-                if int(status.item()):                                        # |value| >= 9.2e12: leave it to the host formatter
-                    np.savetxt(f, points, fmt='%.6f %.6f %.6f %.6f')
-                else:
-                    f.write(body.cpu().numpy().tobytes())
+                if int(status.item()):
+                    raise OverflowError("save_pcd: |value| >= 9.2e12 is outside the device formatter's range")
+                f.write(body.cpu().numpy().tobytes())
 
     def save_lvx(self, results, base_filename):
         """lidar_data.lvx with the LVX v1.1 container of LMC:58-250 around device-quantised records."""
@@ -280,8 +279,6 @@ class LiDARMotionSimulator:
         ts = np.array([s['timestamp'] for s in scans], np.float64)
         ids = np.array([s['frame_id'] for s in scans], np.int64)
         _, fpos = frame_layout(off)
-        if len(flat) == 0:
-            return build_lvx_v11_file(np.zeros((0, 14), np.uint8), off, ts, ids)
         data, status = ops.build_lvx_v11(self._to_dev(flat), self._to_dev(off), self._to_dev(fpos), self._to_dev(ts),
                                          self._to_dev(ids), int(np.diff(off).max()))
         bufs = ops.ExportBuffers(status=status)

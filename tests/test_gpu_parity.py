@@ -455,6 +455,10 @@ def test_pcd_ascii_vs_reference(golden, tmp_path):
     assert f.read_bytes() == ref
     LiDARMotionSimulator().save_pcd(np.zeros((0, 4)), str(f))
     assert f.read_bytes().endswith(b"POINTS 0\nDATA ascii\n")
+    # all-empty frame list still yields a valid container (headers only), built on the device
+    empty = {'raw_scans': [{'frame_id': i, 'timestamp': 0.1 * i, 'points_local': np.zeros((0, 4))} for i in range(3)]}
+    img = LiDARMotionSimulator().build_lvx_bytes(empty)
+    assert len(img) == 88 + 3 * 24 and bytes(img[:10]) == b"livox_tech"
 
 
 @pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
