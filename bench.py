@@ -64,6 +64,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-frames", type=int, default=1000)
     return ap.parse_args()
@@ -182,6 +183,9 @@ def main_b200(args):
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from livox_motion_compensation_sim_b200.pipeline import bind_host_to_gpu
+    orig_affinity = os.sched_getaffinity(0)
+    numa_cpus = None if args.no_numa_bind else bind_host_to_gpu(local)      # pinned e2e buffers on the GPU's own socket
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep NCCL's version banner off stdout (ONE JSON line)
@@ -359,7 +363,8 @@ def main_b200(args):
         e2e = {"value": world * ne / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": sa.h2d_bytes, "d2h_bytes_per_step": sa.d2h_bytes,
                "ms_per_step": ems, "wall_ms_per_step": wall * 1e3, "points_per_step_per_gpu": ne, "kernel_launches_per_step": sa.launches,
                "what": "StreamingAligner.run: pinned host float4+u32 ts -> chunked H2D / fused Mode C + LVX kernel / D2H of float4 + 14-B records, 3 streams",
-               "h2d_GBps": sa.h2d_bytes / (ems * 1e-3) / 1e9, "d2h_GBps": sa.d2h_bytes / (ems * 1e-3) / 1e9}
+               "h2d_GBps": sa.h2d_bytes / (ems * 1e-3) / 1e9, "d2h_GBps": sa.d2h_bytes / (ems * 1e-3) / 1e9,
+               "host_cpus_bound": None if numa_cpus is None else len(numa_cpus)}
         del hs, sa
     # ---- merged cloud (BASELINE configs[3] literally): ONE 1 h stream, frame-sharded over the N ranks, the
     #      merged aligned cloud + LVX records assembled on every rank.  Strong scaling, reported under "merge":
@@ -424,6 +429,7 @@ def main_b200(args):
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        os.sched_setaffinity(0, orig_affinity)             # the CPU baseline gets every host core back
         r = cpu_reference_run(3, 1, args.cpu_frames, P)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
         try:

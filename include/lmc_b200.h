@@ -200,6 +200,25 @@ int lmc_pcd_ascii_write_f64(const double* pts_n4, int64_t n_points, const int64_
 int lmc_pcd_ascii_write_f32(const float* pts_n4, int64_t n_points, const int64_t* tile_off,
                             uint8_t* text_out, uint32_t* status, void* stream);
 
+/*
+ *  A complete LAS 1.2 / point-format-3 file image -- what save_las (LMC:950-963) and
+ * _export_las (CS:1671-1698) get from laspy -- built on the device: 227-byte public header (min / max
+ * reduced on the GPU) + 34-byte records.  PARITY UNPINNED (laspy absent): the file follows the LAS 1.2
+ * specification; X/Y/Z = rint((v - offset) / scale), intensity per las_intensity_mode, gps_time from
+ * the optional array (CS:1689) else 0, every other field 0.  file_out holds LMC_LAS_HEADER_BYTES +
+ * LMC_LAS_RECORD_BYTES * n_points bytes; minmax_scratch is 6 device int32 (any contents).
+ */
+#define LMC_LAS_HEADER_BYTES 227
+#define LMC_LAS_RECORD_BYTES 34
+int lmc_las_pf3_build_f64(const double* pts_n4, const double* gps_time, int64_t n_points,
+                          const double scale[3], const double offset[3], int32_t las_intensity_mode,
+                          int32_t year, int32_t day_of_year, uint8_t* file_out, int32_t* minmax_scratch,
+                          uint32_t* status, void* stream);
+int lmc_las_pf3_build_f32(const float* pts_n4, const double* gps_time, int64_t n_points,
+                          const double scale[3], const double offset[3], int32_t las_intensity_mode,
+                          int32_t year, int32_t day_of_year, uint8_t* file_out, int32_t* minmax_scratch,
+                          uint32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

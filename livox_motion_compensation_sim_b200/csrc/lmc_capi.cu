@@ -12,6 +12,7 @@ cudaError_t launch_tma(bool f64, int mode, const Params& P, cudaStream_t st, boo
 cudaError_t launch_pose_lookup(const double*, int64_t, const double*, const double*, int32_t, double*, int32_t*, cudaStream_t);
 cudaError_t launch_pcd_size(bool f64, const void* pts, int64_t n, int64_t* tile_off, cudaStream_t st);
 cudaError_t launch_pcd_write(bool f64, const void* pts, int64_t n, const int64_t* tile_off, uint8_t* out, uint32_t* status, cudaStream_t st);
+cudaError_t launch_las_pf3(bool f64, const LasParams& L, cudaStream_t st);
 cudaError_t launch_lvx_v11(bool f64, const void* pts, const int64_t* frame_off, const int64_t* frame_pos, const double* frame_time,
                            const int64_t* frame_id, uint8_t* out, int32_t n_frames, int64_t max_frame_points, uint32_t* status, cudaStream_t st);
 }
@@ -261,6 +262,36 @@ int lmc_pcd_ascii_write_f64(const double* pts_n4, int64_t n_points, const int64_
 }
 int lmc_pcd_ascii_write_f32(const float* pts_n4, int64_t n_points, const int64_t* tile_off, uint8_t* text_out, uint32_t* status, void* stream) {
     return pcd_write(false, pts_n4, n_points, tile_off, text_out, status, stream);
+}
+
+static int las_build(bool f64, const void* pts, const double* gps_time, int64_t n, const double* scale, const double* offset,
+                     int32_t mode, int32_t year, int32_t day, uint8_t* out, int32_t* mm, uint32_t* status, void* stream) {
+    int rc = check_device();
+    if (rc != LMC_OK) return rc;
+    if (n < 0 || n > 0xffffffffLL) return fail(LMC_ERR_INVALID, "LAS 1.2 holds at most 2^32 - 1 point records");
+    if (!out || !mm || !scale || !offset || (n > 0 && !pts)) return fail(LMC_ERR_INVALID, "NULL argument");
+    if (mode != LMC_LAS_INTENSITY_UNIT && mode != LMC_LAS_INTENSITY_RAW) return fail(LMC_ERR_INVALID, "bad las_intensity_mode");
+    if (!aligned32(pts) || !aligned32(out)) return fail(LMC_ERR_ALIGN, "points and file buffer must be 32-byte aligned");
+    lmc::LasParams L;
+    memset(&L, 0, sizeof L);
+    L.pts = pts; L.gps_time = gps_time; L.out = out; L.minmax = mm; L.status = status; L.n = n;
+    for (int c = 0; c < 3; ++c) {
+        if (!(scale[c] > 0.0)) return fail(LMC_ERR_INVALID, "scale[%d] must be > 0", c);
+        L.scale[c] = scale[c]; L.rcp[c] = 1.0 / scale[c]; L.off[c] = offset[c];
+    }
+    L.intensity_mode = mode; L.year = (uint16_t)year; L.day = (uint16_t)day;
+    cudaError_t e = lmc::launch_las_pf3(f64, L, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_las_records / k_las_header");
+}
+int lmc_las_pf3_build_f64(const double* pts_n4, const double* gps_time, int64_t n_points, const double scale[3], const double offset[3],
+                          int32_t las_intensity_mode, int32_t year, int32_t day_of_year, uint8_t* file_out, int32_t* minmax_scratch,
+                          uint32_t* status, void* stream) {
+    return las_build(true, pts_n4, gps_time, n_points, scale, offset, las_intensity_mode, year, day_of_year, file_out, minmax_scratch, status, stream);
+}
+int lmc_las_pf3_build_f32(const float* pts_n4, const double* gps_time, int64_t n_points, const double scale[3], const double offset[3],
+                          int32_t las_intensity_mode, int32_t year, int32_t day_of_year, uint8_t* file_out, int32_t* minmax_scratch,
+                          uint32_t* status, void* stream) {
+    return las_build(false, pts_n4, gps_time, n_points, scale, offset, las_intensity_mode, year, day_of_year, file_out, minmax_scratch, status, stream);
 }
 
 }  // extern "C"

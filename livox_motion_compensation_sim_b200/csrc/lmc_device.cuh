@@ -50,6 +50,20 @@ struct Params {
 
 struct Pt { double x, y, z, w; };
 
+// LAS 1.2 / PF3 file builder (lmc_las.cu)
+struct LasParams {
+    const void*   pts;
+    const double* gps_time;      // optional (CS:1689 gps_time = ts * 1e-9), NULL -> 0.0
+    uint8_t*      out;
+    int32_t*      minmax;        // device scratch: {minX, maxX, minY, maxY, minZ, maxZ}, pre-set to {MAX, MIN, ...}
+    uint32_t*     status;
+    int64_t       n;
+    double        scale[3], rcp[3], off[3];
+    int32_t       intensity_mode;
+    uint16_t      year, day;
+};
+
+
 // frames intersecting one tile of points, staged in shared memory
 struct TileMeta {
     int64_t edge[kMaxBnd + 2];    // frame_off[f_lo .. f_lo + nb + 1]

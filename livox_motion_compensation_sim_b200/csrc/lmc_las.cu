@@ -1,0 +1,129 @@
+// lmc_las.cu --  a complete LAS 1.2 / point-format-3 file image built on the device:
+// what `save_las` (LMC:950-963) / `_export_las` (CS:1671-1698) obtain from laspy.
+//
+// PARITY UNPINNED: laspy is neither vendored nor installed, so there are no reference bytes to
+// compare with.  The file follows the public LAS 1.2 specification: 227-byte public header block,
+// no VLRs, 34-byte PF3 records {X Y Z int32, intensity u16, return/flag byte, classification,
+// scan angle, user data, point source id u16, gps_time f64, R G B u16}.  X/Y/Z are the same
+// rint((v - offset) / scale) integers as the fused LAS epilogue (bit-exact against the restatement),
+// intensity follows the two call sites (LMC:961 unit scale, CS:1686 raw), every field the reference
+// never sets stays 0 (as laspy's zero-initialised record array would leave it), and the header's
+// min / max are the scaled extremes X*scale + offset (what laspy's update_header computes), reduced on
+// the GPU with integer atomics.
+//
+// Two launches: k_las_records (records + min/max reduction; the 227-byte data offset makes every
+// record start at an odd address, so each CTA assembles its contiguous byte range in shared memory at
+// the destination's 16-byte phase and copies it out with 16-byte stores), then k_las_header.
+#include "lmc_device.cuh"
+
+namespace lmc {
+
+constexpr int kLasHeader  = 227;
+constexpr int kLasRec     = 34;
+constexpr int kLasTile    = 512;                    // points per CTA
+constexpr int kLasThreads = 256;
+constexpr int kLasImg     = ((kLasTile * kLasRec + 32 + 15) / 16) * 16;
+
+__device__ __forceinline__ void put_le(uint8_t* p, uint64_t v, int nbytes) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (k < nbytes) p[k] = (uint8_t)(v >> (8 * k));
+}
+
+template <bool F64>
+__global__ void __launch_bounds__(kLasThreads) k_las_records(const __grid_constant__ LasParams L) {
+    __shared__ __align__(16) uint8_t s_img[kLasImg];
+    __shared__ int32_t s_mm[6];
+    const int tid = threadIdx.x;
+    const int64_t first = (int64_t)blockIdx.x * kLasTile;
+    const int cnt = (int)min((int64_t)kLasTile, L.n - first);
+    const int64_t dst0 = kLasHeader + first * kLasRec;
+    const int phase = (int)(dst0 & 15);
+    uint8_t* img = s_img + phase;
+    if (tid < 6) s_mm[tid] = (tid & 1) ? INT32_MIN : INT32_MAX;
+    __syncthreads();
+    uint32_t fl = 0;
+    int32_t mn[3] = { INT32_MAX, INT32_MAX, INT32_MAX }, mx[3] = { INT32_MIN, INT32_MIN, INT32_MIN };
+    for (int j = tid; j < cnt; j += kLasThreads) {
+        Pt p;
+        const int64_t i = first + j;
+        if constexpr (F64) { const double* s = reinterpret_cast<const double*>(L.pts) + 4 * i; ldg256(s, p.x, p.y, p.z, p.w); }
+        else { const float4 v = __ldg(reinterpret_cast<const float4*>(L.pts) + i); p = Pt{ (double)v.x, (double)v.y, (double)v.z, (double)v.w }; }
+        const int32_t X = q_las(p.x, L.scale[0], L.rcp[0], L.off[0], fl);
+        const int32_t Y = q_las(p.y, L.scale[1], L.rcp[1], L.off[1], fl);
+        const int32_t Z = q_las(p.z, L.scale[2], L.rcp[2], L.off[2], fl);
+        const uint32_t I = q_las_intensity(p.w, L.intensity_mode, fl);
+        mn[0] = min(mn[0], X); mx[0] = max(mx[0], X); mn[1] = min(mn[1], Y); mx[1] = max(mx[1], Y); mn[2] = min(mn[2], Z); mx[2] = max(mx[2], Z);
+        uint8_t* r = img + j * kLasRec;
+        put_le(r, (uint32_t)X, 4); put_le(r + 4, (uint32_t)Y, 4); put_le(r + 8, (uint32_t)Z, 4);
+        put_le(r + 12, I, 2);
+        put_le(r + 14, 0, 6);                                   // return byte, classification, scan angle, user data, point source id
+        const double g = L.gps_time ? __ldg(L.gps_time + i) : 0.0;
+        put_le(r + 20, (uint64_t)__double_as_longlong(g), 8);
+        put_le(r + 28, 0, 6);                                   // R G B
+    }
+    // block min / max -> one atomic per value per CTA
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { mn[c] = min(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o)); mx[c] = max(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o)); }
+        if ((tid & 31) == 0) { atomicMin(&s_mm[2 * c], mn[c]); atomicMax(&s_mm[2 * c + 1], mx[c]); }
+    }
+    __syncthreads();
+    if (tid < 6 && cnt > 0) { if (tid & 1) atomicMax(L.minmax + tid, s_mm[tid]); else atomicMin(L.minmax + tid, s_mm[tid]); }
+    uint8_t* g = L.out + (dst0 - phase);
+    const int b0 = phase, b1 = phase + cnt * kLasRec;
+    int a0 = (b0 + 15) & ~15; if (a0 > b1) a0 = b1;
+    int a1 = b1 & ~15;        if (a1 < a0) a1 = a0;
+    for (int k = a0 / 16 + tid; k < a1 / 16; k += kLasThreads) reinterpret_cast<uint4*>(g)[k] = reinterpret_cast<const uint4*>(s_img)[k];
+    for (int k = b0 + tid; k < a0; k += kLasThreads) g[k] = s_img[k];
+    for (int k = a1 + tid; k < b1; k += kLasThreads) g[k] = s_img[k];
+    if (fl != 0 && L.status != nullptr) atomicOr(L.status, fl);
+}
+
+// LAS 1.2 public header block (227 bytes), written after the records so the extremes are final
+__global__ void k_las_header(const __grid_constant__ LasParams L) {
+    __shared__ uint8_t h[kLasHeader];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kLasHeader; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        h[0] = 'L'; h[1] = 'A'; h[2] = 'S'; h[3] = 'F';
+        h[24] = 1; h[25] = 2;                                                       // version 1.2
+        const char sys[] = "OTHER"; for (int i = 0; i < 5; ++i) h[26 + i] = (uint8_t)sys[i];
+        const char gen[] = "livox_mc_b200"; for (int i = 0; i < 13; ++i) h[58 + i] = (uint8_t)gen[i];
+        put_le(h + 90, L.day, 2); put_le(h + 92, L.year, 2);
+        put_le(h + 94, kLasHeader, 2);                                              // header size
+        put_le(h + 96, kLasHeader, 4);                                              // offset to point data
+        h[104] = 3;                                                                 // point data format
+        put_le(h + 105, kLasRec, 2);
+        put_le(h + 107, (uint64_t)L.n, 4);                                          // number of point records
+        // number of points by return (5 x u32) stays 0: the reference never sets return numbers
+        for (int c = 0; c < 3; ++c) {
+            put_le(h + 131 + 8 * c, (uint64_t)__double_as_longlong(L.scale[c]), 8);
+            put_le(h + 155 + 8 * c, (uint64_t)__double_as_longlong(L.off[c]), 8);
+            const bool any = L.n > 0;
+            const double vmax = any ? __fma_rn((double)L.minmax[2 * c + 1], L.scale[c], L.off[c]) : 0.0;   // X * scale + offset
+            const double vmin = any ? __fma_rn((double)L.minmax[2 * c], L.scale[c], L.off[c]) : 0.0;
+            put_le(h + 179 + 16 * c, (uint64_t)__double_as_longlong(vmax), 8);
+            put_le(h + 187 + 16 * c, (uint64_t)__double_as_longlong(vmin), 8);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < kLasHeader; i += blockDim.x) L.out[i] = h[i];
+}
+
+__global__ void k_las_init(int32_t* mm) { if (threadIdx.x < 6) mm[threadIdx.x] = (threadIdx.x & 1) ? INT32_MIN : INT32_MAX; }
+
+cudaError_t launch_las_pf3(bool f64, const LasParams& L, cudaStream_t st) {
+    const int64_t tiles = (L.n + kLasTile - 1) / kLasTile;
+    if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+    k_las_init<<<1, 32, 0, st>>>(L.minmax);
+    if (tiles > 0) {
+        if (f64) k_las_records<true><<<(unsigned)tiles, kLasThreads, 0, st>>>(L);
+        else     k_las_records<false><<<(unsigned)tiles, kLasThreads, 0, st>>>(L);
+    }
+    k_las_header<<<1, 256, 0, st>>>(L);
+    return cudaGetLastError();
+}
+
+}  // namespace lmc

@@ -228,3 +228,20 @@ def pcd_ascii_body(pts: torch.Tensor):
     C.check((L.lmc_pcd_ascii_write_f64 if f64 else L.lmc_pcd_ascii_write_f32)(_req(pts, pts.dtype, "pts", (4,)), n, tile_off.data_ptr(),
                                                                               out.data_ptr(), status.data_ptr(), _stream_ptr()))
     return out, status
+
+
+def build_las_pf3(pts: torch.Tensor, *, scale=(0.01, 0.01, 0.01), offset=(0.0, 0.0, 0.0), intensity_mode: int = C.LAS_INTENSITY_UNIT,
+                  gps_time: Optional[torch.Tensor] = None, year: int = 2026, day_of_year: int = 1):
+    """(N2) A complete LAS 1.2 / PF3 file image on the device (parity unpinned: laspy absent; LAS 1.2 spec).
+    Returns (uint8 file tensor, status flags tensor)."""
+    f64 = _layout(pts)
+    n = pts.shape[0]
+    out = torch.empty(C.LAS_HEADER_BYTES + C.LAS_RECORD_BYTES * n, dtype=torch.uint8, device=pts.device)
+    mm = torch.empty(6, dtype=torch.int32, device=pts.device)
+    status = torch.zeros(1, dtype=torch.int32, device=pts.device)
+    sc = (C.ctypes.c_double * 3)(*[float(v) for v in scale])
+    of = (C.ctypes.c_double * 3)(*[float(v) for v in offset])
+    fn = C.lib().lmc_las_pf3_build_f64 if f64 else C.lib().lmc_las_pf3_build_f32
+    C.check(fn(_req(pts, pts.dtype, "pts", (4,)), _req(gps_time, torch.float64, "gps_time"), n, sc, of, int(intensity_mode),
+               int(year), int(day_of_year), out.data_ptr(), mm.data_ptr(), status.data_ptr(), _stream_ptr()))
+    return out, status

@@ -18,6 +18,29 @@ from . import _capi as C
 from . import ops
 
 
+def bind_host_to_gpu(device_index: int) -> Optional[list]:
+    """Pin this process to the CPUs NVML reports as local to the GPU (its NUMA node), so that pinned host
+    buffers allocated afterwards land in memory attached to the GPU's PCIe root -- on a two-socket 8-GPU
+    box un-bound ranks otherwise share one socket's memory and the host<->device copies collapse.
+    Returns the CPU list, or None if NVML / affinity calls are unavailable (nothing is changed then)."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1 and 64 * w + b < ncpu]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:                                      # noqa: BLE001
+        pass
+    return None
+
+
 @dataclass
 class HostStream:
     """Pinned host buffers of one stream (inputs + outputs)."""

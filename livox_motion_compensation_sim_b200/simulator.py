@@ -216,8 +216,7 @@ class LiDARMotionSimulator:
     def save_results(self, results, output_dir='lidar_simulation_output'):
         """Writes the reference's hot-path outputs under the reference's names:
         aligned_scans_pcd/aligned_frame_%04d.pcd, raw_scans_pcd/frame_%04d.pcd, merged_aligned.pcd,
-        merged_raw_overlapped.pcd, lidar_data.lvx, and the LAS integer buffers as
-        merged_aligned.las_ints.npz (the LAS container itself is laspy's, out of scope)."""
+        merged_raw_overlapped.pcd, merged_aligned.las, lidar_data.lvx."""
         os.makedirs(output_dir, exist_ok=True)
         print(f"Saving results to {output_dir}...")
         pcd_dir = os.path.join(output_dir, 'raw_scans_pcd'); os.makedirs(pcd_dir, exist_ok=True)
@@ -234,10 +233,8 @@ class LiDARMotionSimulator:
         try:
             if merged['merged_aligned'] is None:
                 raise UnboundLocalError("merged_aligned")           # what LMC:903 hits when the merge was skipped
-            X, Y, Z, I = self.quantize_las(merged['merged_aligned'])
-            np.savez(os.path.join(output_dir, 'merged_aligned.las_ints.npz'), X=X, Y=Y, Z=Z, intensity=I,
-                     scale=np.asarray(self.config['las_scale']), offset=np.asarray(self.config['las_offset']))
-            print("LAS integer buffers saved successfully")
+            self.save_las(merged['merged_aligned'], os.path.join(output_dir, 'merged_aligned.las'))
+            print("LAS format saved successfully")
         except Exception as e:                                       # LMC:905-906 swallows and prints
             print(f"Could not save LAS format: {e}")
         try:
@@ -262,6 +259,20 @@ class LiDARMotionSimulator:
                 if int(status.item()):
                     raise OverflowError("save_pcd: |value| >= 9.2e12 is outside the device formatter's range")
                 f.write(body.cpu().numpy().tobytes())
+
+    def save_las(self, points, filename):
+        """merged_aligned.las (LMC:950-963): LAS 1.2 / point format 3 with the laspy header defaults the
+        reference relies on (scale 0.01, offset 0; config 'las_scale' / 'las_offset'), intensity scaled to
+        16 bits.  The whole file image -- header extremes included -- is built on the device.  Parity
+        with laspy's bytes is unpinned (laspy is not available); the file follows the LAS 1.2 spec."""
+        import datetime
+        today = datetime.date.today()
+        data, status = ops.build_las_pf3(self._to_dev(np.asarray(points, np.float64)), scale=self.config['las_scale'],
+                                         offset=self.config['las_offset'], intensity_mode=C.LAS_INTENSITY_UNIT,
+                                         year=today.year, day_of_year=today.timetuple().tm_yday)
+        ops.ExportBuffers(status=status).raise_for_flags()
+        with open(filename, 'wb') as f:
+            f.write(data.cpu().numpy().tobytes())
 
     def save_lvx(self, results, base_filename):
         """lidar_data.lvx with the LVX v1.1 container of LMC:58-250 around device-quantised records."""

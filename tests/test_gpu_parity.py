@@ -377,7 +377,7 @@ def test_simulator_batched_alignment_and_outputs(golden, tmp_path):
     rec, _ = sim.quantize_lvx(results)
     assert np.array_equal(rec, orc.C.quantize_lvx_type2(g['raw'])[0])
     d = sim.save_results(results, str(tmp_path / "out"))
-    for f in ["merged_aligned.pcd", "merged_raw_overlapped.pcd", "lidar_data.lvx", "merged_aligned.las_ints.npz",
+    for f in ["merged_aligned.pcd", "merged_raw_overlapped.pcd", "lidar_data.lvx", "merged_aligned.las",
               "aligned_scans_pcd/aligned_frame_0000.pcd", "raw_scans_pcd/frame_0000.pcd"]:
         assert os.path.exists(os.path.join(d, f)), f
     first = open(os.path.join(d, "aligned_scans_pcd/aligned_frame_0000.pcd")).read().splitlines()
@@ -476,6 +476,38 @@ def test_pcd_ascii_large_random(f64):
     big = np.array([[1e13, 0, 0, 0]] * 3)
     _, status = ops.pcd_ascii_body(dev(big))
     assert int(status.item()) & C.FLAG_OVERFLOW
+
+
+def test_las_pf3_file_image():
+    """(N2) LAS 1.2 / PF3 file built on the device -- parity unpinned (laspy absent): checked against the LAS
+    1.2 layout, the oracle's X/Y/Z/intensity restatement and its own header extremes."""
+    import struct
+    rng = np.random.default_rng(8)
+    n = 100_003
+    pts = np.column_stack([rng.uniform(-500, 500, (n, 3)), rng.uniform(0, 1, n)])
+    gps = np.sort(rng.uniform(0, 3600, n))
+    for scale, off, mode, g in [((0.01,) * 3, (0.0,) * 3, 0, None), ((0.001, 0.001, 0.002), (10.0, -5.0, 0.25), 0, gps)]:
+        data, status = ops.build_las_pf3(dev(pts), scale=scale, offset=off, intensity_mode=mode,
+                                         gps_time=None if g is None else dev(g), year=2026, day_of_year=291)
+        assert int(status.item()) == 0
+        b = data.cpu().numpy().tobytes()
+        assert len(b) == 227 + 34 * n and b[:4] == b"LASF" and b[24:26] == bytes([1, 2])
+        hsize, offset_pts, nvlr, fmt, reclen, npts = struct.unpack_from("<HIIBHI", b, 94)
+        assert (hsize, offset_pts, nvlr, fmt, reclen, npts) == (227, 227, 0, 3, 34, n)
+        assert struct.unpack_from("<HH", b, 90) == (291, 2026)
+        assert struct.unpack_from("<3d", b, 131) == tuple(scale) and struct.unpack_from("<3d", b, 155) == tuple(off)
+        rec = np.frombuffer(b, dtype=np.dtype([("X", "<i4"), ("Y", "<i4"), ("Z", "<i4"), ("I", "<u2"), ("flags", "u1"), ("cls", "u1"),
+                                                ("ang", "i1"), ("user", "u1"), ("src", "<u2"), ("gps", "<f8"), ("rgb", "<u2", 3)]),
+                            offset=227)
+        X, Y, Z, I, _ = orc.C.quantize_las(pts, scale, off, mode)
+        assert np.array_equal(rec["X"], X) and np.array_equal(rec["Y"], Y) and np.array_equal(rec["Z"], Z) and np.array_equal(rec["I"], I)
+        assert not rec["flags"].any() and not rec["cls"].any() and not rec["rgb"].any() and not rec["src"].any()
+        assert np.array_equal(rec["gps"], np.zeros(n) if g is None else g)
+        mxx, mnx, mxy, mny, mxz, mnz = struct.unpack_from("<6d", b, 179)
+        for mx, mn, q, s, o in [(mxx, mnx, X, scale[0], off[0]), (mxy, mny, Y, scale[1], off[1]), (mxz, mnz, Z, scale[2], off[2])]:
+            assert abs(mx - (q.max() * s + o)) <= 1e-9 and abs(mn - (q.min() * s + o)) <= 1e-9
+    data, _ = ops.build_las_pf3(torch.zeros((0, 4), dtype=torch.float64, device=DEV))
+    assert data.numel() == 227
 
 
 def test_coordinate_transformer_mirror_vs_reference(golden):
