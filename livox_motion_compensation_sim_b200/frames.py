@@ -18,6 +18,20 @@ from scipy.spatial.transform import Rotation
 SEG_STRIDE = 22        # doubles per Mode C sample row (include/lmc_b200.h)
 
 
+def frame_offsets(frames: Sequence[np.ndarray]) -> np.ndarray:
+    """int64 CSR offsets[F+1] of a list of per-frame arrays."""
+    counts = np.fromiter((len(f) for f in frames), dtype=np.int64, count=len(frames))
+    off = np.zeros(len(frames) + 1, np.int64)
+    np.cumsum(counts, out=off[1:])
+    return off
+
+
+def flatten_frames_into(frames: Sequence[np.ndarray], flat: np.ndarray) -> None:
+    """Frame-major concatenation into a caller-provided (N,4) buffer (e.g. a pinned staging array)."""
+    if len(flat):
+        np.concatenate([np.asarray(f).reshape(-1, 4) for f in frames], axis=0, out=flat, casting='unsafe')
+
+
 def flatten_frames(frames: Sequence[np.ndarray], dtype=np.float64) -> Tuple[np.ndarray, np.ndarray]:
     """list of (n_f,4) arrays -> ((N,4) frame-major array, int64 CSR offsets[F+1]).
 
@@ -27,9 +41,8 @@ def flatten_frames(frames: Sequence[np.ndarray], dtype=np.float64) -> Tuple[np.n
     off = np.zeros(len(frames) + 1, np.int64)
     np.cumsum(counts, out=off[1:])
     flat = np.empty((int(off[-1]), 4), dtype)
-    for f, b in zip(frames, off[:-1]):
-        if len(f):
-            flat[b:b + len(f)] = f
+    if off[-1]:
+        np.concatenate([np.asarray(f).reshape(-1, 4) for f in frames], axis=0, out=flat, casting='unsafe')   # one C-level pass
     return flat, off
 
 
