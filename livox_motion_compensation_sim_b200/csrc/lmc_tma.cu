@@ -393,11 +393,12 @@ static cudaError_t launch_stream(const Params& P, cudaStream_t st, bool force, b
     *handled = true;
     const int grid = (int)(n_tiles < sms ? n_tiles : sms);
     // lean (compile-time export configuration) variants for the common cases of Mode A / Mode C
-    if constexpr (MODE == kRigid || MODE == kSlerp) {
+    if constexpr (MODE == kRigid || MODE == kSlerp || MODE == kGyro) {
         const int mask = (P.out ? kExOut : 0) | (P.lvx14 ? kExLvx : 0) | ((P.las_x || P.las_int) ? kExLas : 0);
         bool lean = P.n_peers == 0 && (!P.lvx14 || (P.lvx_mode == LMC_LVX_TYPE2_OF_INPUT)) && (!(mask & kExLas) || (P.las_x && P.las_int));
         if (MODE == kSlerp) lean = lean && P.hold_idx == nullptr && P.ts != nullptr && P.n_samp >= 2 && P.n_samp < 0x7fffffffLL &&
                                    (F64 || P.frame_start != nullptr);
+        if (MODE == kGyro)  lean = lean && P.ts != nullptr && P.frame_start != nullptr && P.n_samp >= 2 && P.n_samp < 0x7fffffffLL;
         if (lean) {
             if (mask == kExOut)            return launch_stream_ex<F64, MODE, kExOut>(P, st, grid, tile0, n_tiles);
             if (mask == (kExOut | kExLvx)) return launch_stream_ex<F64, MODE, kExOut | kExLvx>(P, st, grid, tile0, n_tiles);
