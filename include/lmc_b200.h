@@ -219,6 +219,28 @@ int lmc_las_pf3_build_f32(const float* pts_n4, const double* gps_time, int64_t n
                           int32_t year, int32_t day_of_year, uint8_t* file_out, int32_t* minmax_scratch,
                           uint32_t* status, void* stream);
 
+/*
+ *  LiDARMotionSimulator.scan_environment, replaces LMC:701-770 for every frame of a run at
+ * once: range cull (d2 <= range_max^2), world->sensor rotation R_f^T (env - pos_f), FOV cull, order-
+ * preserving compaction, systematic subsample to max_points.  Two calls, because the reference draws its
+ * noise from the seeded global NumPy RNG sized by each frame's point count (LMC:765-768):
+ *   lmc_scan_mark  -> flags (n_frames x n_env bytes), tile_off (n_frames x (ceil(n_env/LMC_SCAN_TILE)+1)
+ *                     int32 scratch) and n_visible[f];
+ *   (host: kept[f] = n_visible[f] if <= max_points else min(ceil(n / (n // max_points)), max_points);
+ *          frame_off = cumsum(kept); noise = np.random.normal(0, std, (sum kept, 3)) or NULL)
+ *   lmc_scan_emit  -> raw_out (sum kept, 4): rotated xyz (+ noise) and the environment intensity,
+ *                     frame-major, ready for lmc_align_rigid_f64.
+ * pos_f3 / R_f9: per-frame sensor position and SciPy rotation matrix (row-major) of the sensor pose.
+ */
+#define LMC_SCAN_TILE 256
+int lmc_scan_mark(const double* env_m4, int64_t n_env, const double* pos_f3, const double* R_f9, int32_t n_frames,
+                  double range_max_sq, double fov_h_half_deg, double fov_v_half_deg, double range_min,
+                  uint8_t* flags, int32_t* tile_off, int32_t* n_visible, void* stream);
+int lmc_scan_emit(const double* env_m4, int64_t n_env, const double* pos_f3, const double* R_f9, int32_t n_frames,
+                  double range_max_sq, const uint8_t* flags, const int32_t* tile_off, const int32_t* n_visible,
+                  const int64_t* frame_off, int32_t max_points, const double* noise_n3, double* raw_out_n4,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,8 +15,9 @@ PATH_DIRECT, PATH_AUTO, PATH_TMA = 0, 1, 2
 PCD_TILE = 256
 MAX_PEERS = 7
 LAS_HEADER_BYTES, LAS_RECORD_BYTES = 227, 34
+SCAN_TILE = 256
 
-vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+vp, i64, i32, f64 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_double
 
 
 class LmcExport(ctypes.Structure):
@@ -60,6 +61,8 @@ _SIGNATURES = {
     "lmc_pcd_ascii_write_f32": ([vp, i64, vp, vp, vp, vp], ctypes.c_int),
     "lmc_las_pf3_build_f64": ([vp, vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, vp], ctypes.c_int),
     "lmc_las_pf3_build_f32": ([vp, vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, vp], ctypes.c_int),
+    "lmc_scan_mark": ([vp, i64, vp, vp, i32, f64, f64, f64, f64, vp, vp, vp, vp], ctypes.c_int),
+    "lmc_scan_emit": ([vp, i64, vp, vp, i32, f64, vp, vp, vp, vp, i32, vp, vp, vp], ctypes.c_int),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

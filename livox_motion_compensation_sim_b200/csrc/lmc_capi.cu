@@ -12,6 +12,11 @@ cudaError_t launch_tma(bool f64, int mode, const Params& P, cudaStream_t st, boo
 cudaError_t launch_pose_lookup(const double*, int64_t, const double*, const double*, int32_t, double*, int32_t*, cudaStream_t);
 cudaError_t launch_pcd_size(bool f64, const void* pts, int64_t n, int64_t* tile_off, cudaStream_t st);
 cudaError_t launch_pcd_write(bool f64, const void* pts, int64_t n, const int64_t* tile_off, uint8_t* out, uint32_t* status, cudaStream_t st);
+cudaError_t launch_scan_mark(const double* env, int64_t M, const double* pos, const double* R, int32_t F, double rmax2, double fh, double fv,
+                             double rmin, uint8_t* flags, int32_t* tile_off, int32_t* n_visible, cudaStream_t st);
+cudaError_t launch_scan_emit(const double* env, int64_t M, const double* pos, const double* R, int32_t F, double rmax2, const uint8_t* flags,
+                             const int32_t* tile_off, const int32_t* n_visible, const int64_t* frame_off, int32_t max_points,
+                             const double* noise, double* out, cudaStream_t st);
 cudaError_t launch_las_pf3(bool f64, const LasParams& L, cudaStream_t st);
 cudaError_t launch_lvx_v11(bool f64, const void* pts, const int64_t* frame_off, const int64_t* frame_pos, const double* frame_time,
                            const int64_t* frame_id, uint8_t* out, int32_t n_frames, int64_t max_frame_points, uint32_t* status, cudaStream_t st);
@@ -292,6 +297,33 @@ int lmc_las_pf3_build_f32(const float* pts_n4, const double* gps_time, int64_t n
                           int32_t las_intensity_mode, int32_t year, int32_t day_of_year, uint8_t* file_out, int32_t* minmax_scratch,
                           uint32_t* status, void* stream) {
     return las_build(false, pts_n4, gps_time, n_points, scale, offset, las_intensity_mode, year, day_of_year, file_out, minmax_scratch, status, stream);
+}
+
+int lmc_scan_mark(const double* env_m4, int64_t n_env, const double* pos_f3, const double* R_f9, int32_t n_frames,
+                  double range_max_sq, double fov_h_half_deg, double fov_v_half_deg, double range_min,
+                  uint8_t* flags, int32_t* tile_off, int32_t* n_visible, void* stream) {
+    int rc = check_device();
+    if (rc != LMC_OK) return rc;
+    if (n_env < 0 || n_frames < 0) return fail(LMC_ERR_INVALID, "negative size");
+    if (n_frames == 0) return LMC_OK;
+    if (!pos_f3 || !R_f9 || !tile_off || !n_visible || (n_env > 0 && (!env_m4 || !flags))) return fail(LMC_ERR_INVALID, "NULL argument");
+    if (!aligned32(env_m4)) return fail(LMC_ERR_ALIGN, "environment must be 32-byte aligned");
+    cudaError_t e = lmc::launch_scan_mark(env_m4, n_env, pos_f3, R_f9, n_frames, range_max_sq, fov_h_half_deg, fov_v_half_deg, range_min,
+                                          flags, tile_off, n_visible, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_scan_mark / k_scan_offsets");
+}
+int lmc_scan_emit(const double* env_m4, int64_t n_env, const double* pos_f3, const double* R_f9, int32_t n_frames,
+                  double range_max_sq, const uint8_t* flags, const int32_t* tile_off, const int32_t* n_visible,
+                  const int64_t* frame_off, int32_t max_points, const double* noise_n3, double* raw_out_n4, void* stream) {
+    int rc = check_device();
+    if (rc != LMC_OK) return rc;
+    if (n_env < 0 || n_frames < 0 || max_points < 1) return fail(LMC_ERR_INVALID, "bad size / max_points");
+    if (n_frames == 0 || n_env == 0) return LMC_OK;
+    if (!env_m4 || !pos_f3 || !R_f9 || !flags || !tile_off || !n_visible || !frame_off || !raw_out_n4) return fail(LMC_ERR_INVALID, "NULL argument");
+    if (!aligned32(env_m4) || !aligned32(raw_out_n4)) return fail(LMC_ERR_ALIGN, "environment / output must be 32-byte aligned");
+    cudaError_t e = lmc::launch_scan_emit(env_m4, n_env, pos_f3, R_f9, n_frames, range_max_sq, flags, tile_off, n_visible, frame_off, max_points,
+                                          noise_n3, raw_out_n4, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_scan_emit");
 }
 
 }  // extern "C"

@@ -111,6 +111,26 @@ class LiDARMotionSimulator:
         out, _ = ops.align_rigid(self._to_dev(points), off, self._to_dev(pose))
         return out.cpu().numpy()
 
+    # ------------------------------------------------------------------ (N4) LMC:701-770
+    def scan_all(self, environment, positions, eulers) -> List[np.ndarray]:
+        """scan_environment for every frame in ONE device pass (range / FOV cull, compaction, subsample);
+        the noise is drawn on the host from the global NumPy RNG exactly as LMC:767 does, so a seeded
+        run reproduces the reference's raw scans.  Returns the per-frame (n_f,4) arrays."""
+        from scipy.spatial.transform import Rotation
+        positions = np.asarray(positions, np.float64).reshape(-1, 3)
+        Rm = Rotation.from_euler('xyz', np.asarray(eulers, np.float64).reshape(-1, 3)).as_matrix().reshape(-1, 9)   # LMC:726
+        c = self.config
+        raw, off = ops.scan_frames(self._to_dev(np.asarray(environment, np.float64)), self._to_dev(positions), self._to_dev(Rm),
+                                   range_max=c['range_max'], range_min=c['range_min'], fov_horizontal=c['fov_horizontal'],
+                                   fov_vertical=c['fov_vertical'], points_per_frame=c['points_per_frame'],
+                                   noise_std=c['lidar_range_noise'])
+        host = raw.cpu().numpy()
+        return [host[off[i]:off[i + 1]] if off[i + 1] > off[i] else np.array([]).reshape(0, 4) for i in range(len(off) - 1)]
+
+    def scan_environment(self, environment, sensor_pose):
+        """Same contract as LMC:701-770 for one pose (one-frame device batch)."""
+        return self.scan_all(environment, [sensor_pose['position']], [sensor_pose['orientation']])[0]
+
     # ------------------------------------------------------------------ (a2)+(a3) batched
     def align_frames(self, frames: Sequence[np.ndarray], positions: np.ndarray, eulers: np.ndarray,
                      export: Optional[ops.ExportSpec] = None):
@@ -140,8 +160,9 @@ class LiDARMotionSimulator:
         ``frame_source`` supplies what the (out-of-scope) generators produce:
           .trajectory                -> dict with 'time','position','velocity','orientation',
                                         'position_gps','orientation_imu'  (LMC:396-428)
-          .scan(i, t, sensor_pose)   -> (n,4) f64 raw sensor-frame points   (LMC:701-770)
-          .environment (optional)
+          .scan(i, t, sensor_pose)   -> (n,4) f64 raw sensor-frame points   (LMC:701-770); if absent,
+                                        .environment is scanned on the device for all frames at once (N4)
+          .environment               -> (M,4) f64 world cloud (needed when .scan is absent)
         Returns the reference's results dict (LMC:852-858)."""
         if frame_source is None:
             raise NotImplementedError(
@@ -153,12 +174,16 @@ class LiDARMotionSimulator:
         _, pose_idx = self.lookup_frame_poses(trajectory, lidar_times)
 
         all_scans, motion_data = [], []
+        device_scans = None
+        if not hasattr(frame_source, 'scan'):           # no host scanner supplied: scan every frame on the device (N4)
+            device_scans = self.scan_all(frame_source.environment, trajectory['position_gps'][pose_idx],
+                                         trajectory['orientation_imu'][pose_idx])
         for i, t in enumerate(lidar_times):
             k = int(pose_idx[i])
             sensor_pose = {'position': trajectory['position_gps'][k],
                            'orientation': trajectory['orientation_imu'][k],
                            'velocity': trajectory['velocity'][k]}
-            scan = frame_source.scan(i, t, sensor_pose)
+            scan = device_scans[i] if device_scans is not None else frame_source.scan(i, t, sensor_pose)
             all_scans.append({'frame_id': i, 'timestamp': t, 'points_local': scan, 'sensor_pose': sensor_pose})
             motion_data.append(self._motion_row(i, t, sensor_pose))
         aligned = self.align_scans(all_scans)

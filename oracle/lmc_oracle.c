@@ -329,4 +329,45 @@ void orc_deskew_slerp_f64(const double* pts, const int64_t* ts, const int64_t* f
     }
 }
 
+/* ------------------------------------------------------------------------------------
+ * (N4) scan_environment without the noise -- LMC:701-770
+ *   d2 = sum((env - pos)**2, axis=1) ; range mask d2 <= range_max**2
+ *   rotated = (R.T @ (env - pos).T).T            (dgemm, k = 0,1,2 FMA chain, also for one column)
+ *   az = arctan2(y, x) * 180 / pi ; el = arcsin(clip(z / max(sqrt(d2), 1e-6), -1, 1)) * 180 / pi
+ *   visible = |az| <= fov_h/2 & |el| <= fov_v/2 & range >= range_min   (env order kept)
+ *   n_visible > max_points: step = n_visible // max_points; keep indices arange(0, n, step)[:max]
+ * Writes the kept points (rotated xyz + intensity) to out (capacity >= M rows) and returns their
+ * count; the caller adds np.random.normal noise exactly as LMC:765-768 does.
+ * ---------------------------------------------------------------------------------- */
+int64_t orc_scan_frame(const double* env, int64_t M, const double* pos, const double* R,
+                       double rmax2, double fov_h_half, double fov_v_half, double range_min,
+                       int64_t max_points, double* out)
+{
+    const double pi = 3.141592653589793;
+    int64_t nvis = 0;
+    for (int64_t i = 0; i < M; ++i) {
+        double dx = env[4 * i] - pos[0], dy = env[4 * i + 1] - pos[1], dz = env[4 * i + 2] - pos[2];
+        double d2 = (dx * dx + dy * dy) + dz * dz;
+        if (!(d2 <= rmax2)) continue;
+        double x = fma(R[6 + 0], dz, fma(R[3 + 0], dy, R[0] * dx));
+        double y = fma(R[6 + 1], dz, fma(R[3 + 1], dy, R[1] * dx));
+        double z = fma(R[6 + 2], dz, fma(R[3 + 2], dy, R[2] * dx));
+        double rng = sqrt(d2);
+        double az = atan2(y, x) * 180.0 / pi;
+        double sr = rng > 1e-6 ? rng : 1e-6;
+        double q = z / sr; q = q < -1.0 ? -1.0 : (q > 1.0 ? 1.0 : q);
+        double el = asin(q) * 180.0 / pi;
+        if (!(fabs(az) <= fov_h_half && fabs(el) <= fov_v_half && rng >= range_min)) continue;
+        out[4 * nvis] = x; out[4 * nvis + 1] = y; out[4 * nvis + 2] = z; out[4 * nvis + 3] = env[4 * i + 3];
+        ++nvis;
+    }
+    if (nvis > max_points) {
+        int64_t step = nvis / max_points, kept = 0;
+        for (int64_t j = 0; j < nvis && kept < max_points; j += step, ++kept)
+            memmove(out + 4 * kept, out + 4 * j, 32);
+        nvis = kept;
+    }
+    return nvis;
+}
+
 int orc_version(void) { return 1; }

@@ -213,6 +213,32 @@ def pcd_fixture(LMC, manifest):
     manifest['pcd_ascii'] = dict(points=len(pts), bytes=int(len(data)), sha256=sha(data))
 
 
+def scan_fixture(LMC, name, manifest):
+    """(N4) inputs of the reference's frame loop for config `name`: environment, noisy trajectory, the
+    frame grid, the effective config and the GLOBAL NumPy RNG state right before the loop (LMC:802), so
+    the scanner + its noise stream can be replayed without the reference.  Expected output = the raw
+    sha256 anchor of the same config in MANIFEST['lmc']."""
+    sim = LMC.LiDARMotionSimulator(dict(CONFIGS[name]))
+    traj = sim.add_sensor_noise(sim.generate_trajectory())
+    with contextlib.redirect_stdout(io.StringIO()):
+        env = sim.generate_environment_pointcloud()
+    state = np.random.get_state()
+    # replay the loop with the reference's own scan_environment from this state: must hit the anchor
+    lidar_times = np.linspace(0, sim.config['duration'], int(sim.config['duration'] * sim.config['lidar_fps']))
+    raws = []
+    for t in lidar_times:
+        k = max(min(int(np.searchsorted(traj['time'], t)), len(traj['time']) - 1), 0)
+        raws.append(sim.scan_environment(env, {'position': traj['position_gps'][k], 'orientation': traj['orientation_imu'][k]}))
+    assert sha(np.vstack(raws)) == manifest['lmc'][name]['raw_sha256'], name
+    cfg = {k: sim.config[k] for k in ['range_max', 'range_min', 'fov_horizontal', 'fov_vertical', 'points_per_frame',
+                                      'lidar_range_noise', 'duration', 'lidar_fps']}
+    np.savez_compressed(os.path.join(HERE, f'scan_{name}.npz'), environment=env, traj_time=traj['time'],
+                        traj_position_gps=traj['position_gps'], traj_orientation_imu=traj['orientation_imu'],
+                        rng_keys=state[1], rng_pos=np.int64(state[2]), rng_has_gauss=np.int64(state[3]),
+                        rng_cached=np.float64(state[4]), config_json=np.frombuffer(json.dumps(cfg).encode(), np.uint8))
+    manifest.setdefault('scan', {})[name] = dict(env_points=int(len(env)), fixture=f'scan_{name}.npz')
+
+
 def modeb_fixture(CS, manifest):
     """Reference MotionCompensator.compensate_point_cloud (CS:1435-1536) + LVX2 packer
     (CS:365-374) on synthetic Mid-70-shaped frames against the reference's own 200 Hz
@@ -271,6 +297,8 @@ def main():
         lmc_fixture(LMC, name, manifest)
         print(name, manifest['lmc'][name]['total_points'], manifest['lmc'][name]['raw_sha256'][:16],
               manifest['lmc'][name]['aligned_sha256'][:16])
+    for name in ['C1a', 'C2a', 'C3']:
+        scan_fixture(LMC, name, manifest)
     lmc_edge_fixture(LMC, manifest)
     lvx_type2_fixture(LMC, manifest)
     lvx_file_fixture(LMC, manifest)
