@@ -313,6 +313,39 @@ def main_b200(args):
                                                "b200_api_ms": t_api * 1e3, "numpy_port_ms": t_np * 1e3,
                                                "bit_exact": bool(merged_p.tobytes() == want_p.tobytes()),
                                                "what": "LiDARMotionSimulator.align_frames(list of f64 (n,4)) incl. flatten, pose table, H2D, kernel, D2H vs the reference's per-frame loop + vstack"}}
+            # the reference's WHOLE frame loop for configs[1] wording (figure-eight, complex, 60 s, 10 fps): pose
+            # lookup + scan of every frame + noise replay + alignment, from the golden inputs of that run
+            gp = os.path.join(ROOT, "tests", "golden", "scan_C2a.npz")
+            if os.path.exists(gp):
+                import hashlib
+                g = dict(np.load(gp))
+                cfgp = json.loads(g['config_json'].tobytes().decode())
+
+                class _Src:
+                    trajectory = {'time': g['traj_time'], 'position_gps': g['traj_position_gps'], 'orientation_imu': g['traj_orientation_imu'],
+                                  'velocity': np.zeros_like(g['traj_position_gps'])}
+                    environment = g['environment']
+                simr = LiDARMotionSimulator(dict(cfgp, device=f'cuda:{local}'))
+                best = 1e9
+                for _ in range(3):
+                    np.random.set_state(('MT19937', g['rng_keys'], int(g['rng_pos']), int(g['rng_has_gauss']), float(g['rng_cached'])))
+                    t0 = time.perf_counter()
+                    resr = simr.run_simulation(_Src)
+                    best = min(best, time.perf_counter() - t0)
+                al = np.vstack(resr['aligned_pointclouds'])
+                np.random.set_state(('MT19937', g['rng_keys'], int(g['rng_pos']), int(g['rng_has_gauss']), float(g['rng_cached'])))
+                t0 = time.perf_counter()
+                tms = np.linspace(0, cfgp['duration'], int(cfgp['duration'] * cfgp['lidar_fps']))
+                ix = _orc.pose_lookup_hold_next_np(g['traj_time'], tms)
+                fr_c = _orc.scan_frames(g['environment'], g['traj_position_gps'][ix], g['traj_orientation_imu'][ix], cfgp)
+                _orc.align_frames_np(fr_c, g['traj_position_gps'][ix], g['traj_orientation_imu'][ix], merge=False)
+                cpu_loop_ms = (time.perf_counter() - t0) * 1e3
+                man = json.load(open(os.path.join(ROOT, "tests", "golden", "MANIFEST.json")))['lmc']['C2a']
+                presets["urban_complex_60s_whole_loop"] = {
+                    "frames": len(resr['raw_scans']), "points": int(len(al)), "b200_run_simulation_ms": best * 1e3,
+                    "aligned_sha256_matches_reference": hashlib.sha256(al.tobytes()).hexdigest() == man['aligned_sha256'],
+                    "cpu_port_ms": cpu_loop_ms,
+                    "what": "LiDARMotionSimulator.run_simulation with the device scanner (LMC:778-858 loop: lookup + scan_environment + transform), host noise replay, results as host arrays; cpu_port_ms = the oracle's C scanner + NumPy transform port of the same loop, 1 thread"}
         except Exception as e:                    # noqa: BLE001
             presets = {"error": repr(e)}
 
