@@ -289,6 +289,41 @@ def main_b200(args):
     pts64 = None
     torch.cuda.empty_cache()
 
+    # ---- M-SWEEP (BASELINE configs[4]): fused transform + LVX / LAS int32 quantise, 10 k .. 1 M points per frame,
+    #      1e8 points each (same resident points, re-framed) -----------------------------------------------------
+    m_sweep = None
+    if rank == 0 and not args.no_sweep:
+        try:
+            m_sweep = {}
+            n2 = min(N, 100_000_000)
+            lvx_b = torch.empty((n2, 14), dtype=torch.uint8, device=dev)
+            las_b = [torch.empty(n2, dtype=torch.int32, device=dev) for _ in range(3)] + [torch.empty(n2, dtype=torch.uint16, device=dev)]
+            out_b = torch.empty((n2, 4), dtype=torch.float32, device=dev)
+            for ppf in (10_000, 31_600, 96_000, 100_000, 316_000, 1_000_000):
+                Fs = (n2 + ppf - 1) // ppf
+                offs = np.minimum(np.arange(Fs + 1, dtype=np.int64) * ppf, n2)
+                offs_d, pose_s = d(offs), pose_d[:Fs].contiguous()
+                res = {}
+                for tag, spec in (("lvx", ops.ExportSpec(lvx=True, into=ops.ExportBuffers(lvx14=lvx_b))),
+                                  ("las", ops.ExportSpec(las=True, las_scale=(0.001,) * 3,
+                                                         into=ops.ExportBuffers(las_x=las_b[0], las_y=las_b[1], las_z=las_b[2], las_intensity=las_b[3])))):
+                    fn_s = lambda: ops.align_rigid(st.pts[:n2], offs_d, pose_s, out=out_b, export=spec)      # noqa: E731
+                    for _ in range(3):
+                        fn_s()
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(10):
+                        fn_s()
+                    e1.record(); torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1) / 10
+                    res[tag] = {"points_per_s": n2 / (ms * 1e-3), "frac": n2 * 46 / (ms * 1e-3) / 1e9 / peak}
+                m_sweep[str(ppf)] = res
+            del lvx_b, las_b, out_b
+        except Exception as e:                    # noqa: BLE001
+            m_sweep = {"error": repr(e)}
+        torch.cuda.empty_cache()
+
     # ---- the reference's own preset shape (BASELINE configs[1]: urban_complex, 1200 frames x ~1.6 k pts,
     #      f64 (n,4) host arrays) through the drop-in API: host list in -> host arrays out ------------------
     presets = None
@@ -523,6 +558,8 @@ def main_b200(args):
             line["writers"] = writers
         if presets:
             line["presets"] = presets
+        if m_sweep:
+            line["m_sweep"] = m_sweep
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
