@@ -248,39 +248,54 @@ def build_las_pf3(pts: torch.Tensor, *, scale=(0.01, 0.01, 0.01), offset=(0.0, 0
 
 
 def scan_frames(env: torch.Tensor, pos: torch.Tensor, Rm: torch.Tensor, *, range_max: float, range_min: float,
-                fov_horizontal: float, fov_vertical: float, points_per_frame: int, noise_std: float, noise_fn=None):
+                fov_horizontal: float, fov_vertical: float, points_per_frame: int, noise_std: float, noise_fn=None,
+                max_flag_bytes: int = 1 << 30):
     """(N4) LMC:701-770 for every frame at once.  env (M,4) f64, pos (F,3), Rm (F,9) row-major SciPy matrices.
     Returns (raw (N,4) f64 device tensor, frame_off np.int64[F+1]).
 
     noise_fn(n) must return the (n,3) host array the reference would draw -- by default
     ``np.random.normal(0, noise_std, (n, 3))`` from the GLOBAL legacy NumPy RNG, exactly the stream LMC:767
-    consumes frame after frame (one big draw == the per-frame draws, the legacy generator is a stream)."""
+    consumes frame after frame (the legacy generator is a stream: one draw per chunk of frames == the
+    reference's per-frame draws).  Frames are processed in chunks so the F x M visibility scratch stays
+    below max_flag_bytes; chunks run in frame order, so the noise stream keeps the reference's order."""
     import numpy as np
     M, F = env.shape[0], pos.shape[0]
     tiles = (M + C.SCAN_TILE - 1) // C.SCAN_TILE
     dev = env.device
-    flags = torch.empty((F, max(M, 1)), dtype=torch.uint8, device=dev)
-    tile_off = torch.empty((F, tiles + 1), dtype=torch.int32, device=dev)
-    n_vis = torch.empty(F, dtype=torch.int32, device=dev)
     rmax2 = float(range_max ** 2)                                   # LMC:714
-    L = C.lib()
-    C.check(L.lmc_scan_mark(_req(env, torch.float64, "env", (4,)), M, _req(pos, torch.float64, "pos", (3,)), _req(Rm, torch.float64, "Rm", (9,)),
-                            F, rmax2, float(fov_horizontal / 2), float(fov_vertical / 2), float(range_min),
-                            flags.data_ptr(), tile_off.data_ptr(), n_vis.data_ptr(), _stream_ptr()))
-    nv = n_vis.cpu().numpy().astype(np.int64)                       # the one sync: the noise draw is sized by these counts
     maxp = int(points_per_frame)
-    step = np.maximum(nv // maxp, 1)
-    kept = np.where(nv > maxp, np.minimum((nv + step - 1) // step, maxp), nv)
+    L = C.lib()
+    _req(env, torch.float64, "env", (4,)); _req(pos, torch.float64, "pos", (3,)); _req(Rm, torch.float64, "Rm", (9,))
+    chunk = max(1, min(F, max_flag_bytes // max(M, 1)))
+    outs, kept_all = [], []
+    for f0 in range(0, F, chunk):
+        f1 = min(F, f0 + chunk)
+        nf = f1 - f0
+        p_c, r_c = pos[f0:f1], Rm[f0:f1]
+        flags = torch.empty((nf, max(M, 1)), dtype=torch.uint8, device=dev)
+        tile_off = torch.empty((nf, tiles + 1), dtype=torch.int32, device=dev)
+        n_vis = torch.empty(nf, dtype=torch.int32, device=dev)
+        C.check(L.lmc_scan_mark(env.data_ptr(), M, p_c.data_ptr(), r_c.data_ptr(), nf, rmax2, float(fov_horizontal / 2),
+                                float(fov_vertical / 2), float(range_min), flags.data_ptr(), tile_off.data_ptr(), n_vis.data_ptr(), _stream_ptr()))
+        nv = n_vis.cpu().numpy().astype(np.int64)                   # the one sync per chunk: the noise draw is sized by these counts
+        step = np.maximum(nv // maxp, 1)
+        kept = np.where(nv > maxp, np.minimum((nv + step - 1) // step, maxp), nv)
+        off_c = np.zeros(nf + 1, np.int64)
+        np.cumsum(kept, out=off_c[1:])
+        n_c = int(off_c[-1])
+        out = torch.empty((n_c, 4), dtype=torch.float64, device=dev)
+        if n_c > 0:
+            noise_d = None
+            if noise_std > 0:
+                noise = np.random.normal(0, noise_std, (n_c, 3)) if noise_fn is None else noise_fn(n_c)
+                noise_d = torch.from_numpy(np.ascontiguousarray(noise, dtype=np.float64)).to(dev)
+            fo = torch.from_numpy(off_c).to(dev)
+            C.check(L.lmc_scan_emit(env.data_ptr(), M, p_c.data_ptr(), r_c.data_ptr(), nf, rmax2, flags.data_ptr(), tile_off.data_ptr(),
+                                    n_vis.data_ptr(), fo.data_ptr(), maxp, _req(noise_d, torch.float64, "noise", (3,)), out.data_ptr(), _stream_ptr()))
+        outs.append(out)
+        kept_all.append(kept)
+    kept_all = np.concatenate(kept_all) if kept_all else np.zeros(0, np.int64)
     frame_off = np.zeros(F + 1, np.int64)
-    np.cumsum(kept, out=frame_off[1:])
-    N = int(frame_off[-1])
-    out = torch.empty((N, 4), dtype=torch.float64, device=dev)
-    noise_d = None
-    if noise_std > 0 and N > 0:
-        noise = np.random.normal(0, noise_std, (N, 3)) if noise_fn is None else noise_fn(N)
-        noise_d = torch.from_numpy(np.ascontiguousarray(noise, dtype=np.float64)).to(dev)
-    if N > 0:
-        fo = torch.from_numpy(frame_off).to(dev)
-        C.check(L.lmc_scan_emit(env.data_ptr(), M, pos.data_ptr(), Rm.data_ptr(), F, rmax2, flags.data_ptr(), tile_off.data_ptr(),
-                                n_vis.data_ptr(), fo.data_ptr(), maxp, _req(noise_d, torch.float64, "noise", (3,)), out.data_ptr(), _stream_ptr()))
-    return out, frame_off
+    np.cumsum(kept_all, out=frame_off[1:])
+    raw = outs[0] if len(outs) == 1 else (torch.cat(outs, dim=0) if outs else torch.empty((0, 4), dtype=torch.float64, device=dev))
+    return raw, frame_off

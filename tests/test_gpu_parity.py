@@ -517,6 +517,12 @@ def test_scanner_subsample_and_single_pose():
         assert a.tobytes() == b.tobytes()
     one = sim.scan_environment(env, {'position': pos[1], 'orientation': eul[1]})
     assert one.tobytes() == want[1].tobytes()
+    # frame-chunked execution (small visibility scratch) gives the same scans and the same noise order
+    env_d, Rm = dev(env), FR.pose_table(pos, eul)[:, :9]
+    kw = dict(range_max=90.0, range_min=0.05, fov_horizontal=70.0, fov_vertical=77.2, points_per_frame=1500, noise_std=0.02)
+    np.random.seed(9); r1, o1 = ops.scan_frames(env_d, dev(pos), dev(np.ascontiguousarray(Rm)), **kw)
+    np.random.seed(9); r2, o2 = ops.scan_frames(env_d, dev(pos), dev(np.ascontiguousarray(Rm)), max_flag_bytes=2 * len(env), **kw)
+    assert np.array_equal(o1, o2) and torch.equal(r1, r2)
     # with noise: the device path consumes the global RNG exactly like the reference does
     sim2 = LiDARMotionSimulator(dict(cfg, lidar_range_noise=0.02))
     np.random.seed(123); a = sim2.scan_all(env, pos, eul)
