@@ -183,6 +183,36 @@ int lmc_lvx_v11_build_f32(const float* pts_n4, const int64_t* frame_off, const i
                           uint32_t* status, void* stream);
 
 /*
+ * (second half) the containers of the complete simulator's LivoxLVXWriter.write_lvx_file
+ * (CS:245-374), built on the device from COMPENSATED points [x y z intensity] + optional tag bytes:
+ *   LMC_LVXCS_LVX2    _write_lvx2 / _write_lvx3 (CS:269-293): per frame a 24-byte header {u32 index,
+ *                     u64 timestamp, u32 count, 8 x 0}, one 21-byte package header (CS:354-363) and the
+ *                     unpadded 14-byte records of CS:365-374 (int(v*1000) without clip, u8, u8)
+ *   LMC_LVXCS_LEGACY  _write_lvx_legacy (CS:256-267, 308-321): per frame {u64 timestamp, u32 count} and
+ *                     14-byte records {f32 x y z, u8 intensity, u8 tag}
+ * prefix = the file's leading bytes, a HOST pointer (<= LMC_LVXCS_PREFIX_MAX bytes): file header +
+ * private header / device block, which depend only on DeviceInfo and the frame count (CS:272-283,
+ * 295-306, 323-341).  File size = prefix_len + H * n_frames + 14 * n_points with H =
+ * LMC_LVXCS_LVX2_FRAME_BYTES | LMC_LVXCS_LEGACY_FRAME_BYTES.  frame_ts = the frames' 'timestamp' (ns).
+ * Errors the reference raises from struct.pack become status bits: |int(v*1000)| beyond int32 or a
+ * finite value beyond f32 range or an intensity outside 0..255 -> LMC_FLAG_OVERFLOW, NaN through
+ * int() -> LMC_FLAG_NAN.
+ */
+#define LMC_LVXCS_LVX2   0
+#define LMC_LVXCS_LEGACY 1
+#define LMC_LVXCS_PREFIX_MAX 96
+#define LMC_LVXCS_LVX2_FRAME_BYTES   45
+#define LMC_LVXCS_LEGACY_FRAME_BYTES 12
+int lmc_lvx_cs_build_f64(const double* pts_n4, const uint8_t* tag, const int64_t* frame_off,
+                         const uint64_t* frame_ts, const uint8_t* prefix_host, int32_t prefix_len,
+                         int32_t format, uint8_t* file_out, int64_t n_points, int32_t n_frames,
+                         int64_t max_frame_points, uint32_t* status, void* stream);
+int lmc_lvx_cs_build_f32(const float* pts_n4, const uint8_t* tag, const int64_t* frame_off,
+                         const uint64_t* frame_ts, const uint8_t* prefix_host, int32_t prefix_len,
+                         int32_t format, uint8_t* file_out, int64_t n_points, int32_t n_frames,
+                         int64_t max_frame_points, uint32_t* status, void* stream);
+
+/*
  *  ASCII PCD point data, replaces the per-point Python loop of
  * LiDARMotionSimulator.save_pcd (LMC:946-947): for every row of the (n,4) array the line
  *     "%.6f %.6f %.6f %.6f\n"        (x y z intensity)

@@ -10,6 +10,9 @@ from ._build import LIB_PATH
 OK, ERR_INVALID, ERR_ALIGN, ERR_CUDA = 0, -1, -2, -3
 FLAG_NAN, FLAG_OVERFLOW = 1, 2
 LVX_TYPE2_OF_INPUT, LVX2_OF_OUTPUT = 0, 1
+LVXCS_LVX2, LVXCS_LEGACY = 0, 1
+LVXCS_PREFIX_MAX = 96
+LVXCS_FRAME_BYTES = {0: 45, 1: 12}
 LAS_INTENSITY_UNIT, LAS_INTENSITY_RAW = 0, 1
 PATH_DIRECT, PATH_AUTO, PATH_TMA = 0, 1, 2
 PCD_TILE = 256
@@ -55,6 +58,8 @@ _SIGNATURES = {
     "lmc_quantize_f32": ([vp, i64, vp, vp], ctypes.c_int),
     "lmc_lvx_v11_build_f64": ([vp, vp, vp, vp, vp, vp, i64, i32, i64, vp, vp], ctypes.c_int),
     "lmc_lvx_v11_build_f32": ([vp, vp, vp, vp, vp, vp, i64, i32, i64, vp, vp], ctypes.c_int),
+    "lmc_lvx_cs_build_f64": ([vp, vp, vp, vp, vp, i32, i32, vp, i64, i32, i64, vp, vp], ctypes.c_int),
+    "lmc_lvx_cs_build_f32": ([vp, vp, vp, vp, vp, i32, i32, vp, i64, i32, i64, vp, vp], ctypes.c_int),
     "lmc_pcd_ascii_size_f64": ([vp, i64, vp, vp], ctypes.c_int),
     "lmc_pcd_ascii_size_f32": ([vp, i64, vp, vp], ctypes.c_int),
     "lmc_pcd_ascii_write_f64": ([vp, i64, vp, vp, vp, vp], ctypes.c_int),

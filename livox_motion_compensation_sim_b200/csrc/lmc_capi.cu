@@ -20,6 +20,9 @@ cudaError_t launch_scan_emit(const double* env, int64_t M, const double* pos, co
 cudaError_t launch_las_pf3(bool f64, const LasParams& L, cudaStream_t st);
 cudaError_t launch_lvx_v11(bool f64, const void* pts, const int64_t* frame_off, const int64_t* frame_pos, const double* frame_time,
                            const int64_t* frame_id, uint8_t* out, int32_t n_frames, int64_t max_frame_points, uint32_t* status, cudaStream_t st);
+cudaError_t launch_lvx_cs(bool f64, const void* pts, const uint8_t* tag, const int64_t* frame_off, const uint64_t* frame_ts,
+                          const uint8_t* prefix_host, int32_t prefix_len, int32_t format, uint8_t* out, int32_t n_frames,
+                          int64_t max_frame_points, uint32_t* status, cudaStream_t st);
 }
 
 namespace {
@@ -242,6 +245,31 @@ int lmc_lvx_v11_build_f32(const float* pts_n4, const int64_t* frame_off, const i
                           const int64_t* frame_id, uint8_t* file_out, int64_t n_points, int32_t n_frames, int64_t max_frame_points,
                           uint32_t* status, void* stream) {
     return lvx_build(false, pts_n4, frame_off, frame_pos, frame_time, frame_id, file_out, n_points, n_frames, max_frame_points, status, stream);
+}
+
+static int lvx_cs_build(bool f64, const void* pts, const uint8_t* tag, const int64_t* frame_off, const uint64_t* frame_ts,
+                        const uint8_t* prefix, int32_t prefix_len, int32_t format, uint8_t* file_out, int64_t n_points, int32_t n_frames,
+                        int64_t max_frame_points, uint32_t* status, void* stream) {
+    int rc = check_device();
+    if (rc != LMC_OK) return rc;
+    if (format != LMC_LVXCS_LVX2 && format != LMC_LVXCS_LEGACY) return fail(LMC_ERR_INVALID, "format must be LMC_LVXCS_LVX2 or LMC_LVXCS_LEGACY");
+    if (n_frames < 0 || n_points < 0 || max_frame_points < 0) return fail(LMC_ERR_INVALID, "negative count");
+    if (prefix_len < 0 || prefix_len > LMC_LVXCS_PREFIX_MAX || (prefix_len > 0 && !prefix)) return fail(LMC_ERR_INVALID, "prefix: 0..%d bytes", LMC_LVXCS_PREFIX_MAX);
+    if (!file_out || (n_frames > 0 && (!frame_off || !frame_ts)) || (n_points > 0 && !pts)) return fail(LMC_ERR_INVALID, "NULL argument");
+    if (!aligned32(pts) || !aligned32(file_out)) return fail(LMC_ERR_ALIGN, "points and file buffer must be 32-byte aligned");
+    cudaError_t e = lmc::launch_lvx_cs(f64, pts, tag, frame_off, frame_ts, prefix, prefix_len, format, file_out, n_frames, max_frame_points, status,
+                                       static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_lvx_cs");
+}
+int lmc_lvx_cs_build_f64(const double* pts_n4, const uint8_t* tag, const int64_t* frame_off, const uint64_t* frame_ts, const uint8_t* prefix_host,
+                         int32_t prefix_len, int32_t format, uint8_t* file_out, int64_t n_points, int32_t n_frames, int64_t max_frame_points,
+                         uint32_t* status, void* stream) {
+    return lvx_cs_build(true, pts_n4, tag, frame_off, frame_ts, prefix_host, prefix_len, format, file_out, n_points, n_frames, max_frame_points, status, stream);
+}
+int lmc_lvx_cs_build_f32(const float* pts_n4, const uint8_t* tag, const int64_t* frame_off, const uint64_t* frame_ts, const uint8_t* prefix_host,
+                         int32_t prefix_len, int32_t format, uint8_t* file_out, int64_t n_points, int32_t n_frames, int64_t max_frame_points,
+                         uint32_t* status, void* stream) {
+    return lvx_cs_build(false, pts_n4, tag, frame_off, frame_ts, prefix_host, prefix_len, format, file_out, n_points, n_frames, max_frame_points, status, stream);
 }
 
 static int pcd_size(bool f64, const void* pts, int64_t n, int64_t* tile_off, void* stream) {

@@ -11,6 +11,9 @@ LMC = /root/reference/lidar_motion_compensation.py
 """
 from __future__ import annotations
 
+import struct
+from dataclasses import dataclass
+
 import numpy as np
 
 POINTS_PER_PACKAGE = 96          # LMC:48
@@ -84,3 +87,104 @@ def build_lvx_v11_file(records: np.ndarray, frame_off: np.ndarray, timestamps: n
             dst = fpos[pfp] + FRAME_HEADER + (j // POINTS_PER_PACKAGE) * PKG_BYTES + PKG_HEADER + (j % POINTS_PER_PACKAGE) * RECORD
             out[dst[:, None] + np.arange(RECORD)] = records
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# The complete simulator's LivoxLVXWriter (CS = /root/reference/livox_mid70_complete_simulator.py,
+# lines 235-374): LVX2 / LVX3 / legacy containers.  The host only builds the few leading bytes that
+# depend on DeviceInfo; frames, package headers and records are laid out by the device
+# (csrc/lmc_lvx2.cu).
+# ---------------------------------------------------------------------------------------------------
+
+@dataclass
+class DeviceInfo:                    # CS:131-143
+    lidar_sn: str
+    device_type: int
+    firmware_version: str
+    extrinsic_enable: bool
+    roll: float
+    pitch: float
+    yaw: float
+    x: float
+    y: float
+    z: float
+
+
+def lvx_cs_prefix(format_version: str, device_info, n_frames: int) -> bytes:
+    """Leading bytes of the file: lvx2 / lvx3 = 24-B file header + 64-B private header (CS:272-283,
+    323-341); lvx = 28-B header + 32-B device block (CS:295-306)."""
+    sn = device_info.lidar_sn.encode('ascii').ljust(16, b'\x00')
+    if len(sn) != 16:
+        raise ValueError("lidar_sn longer than 16 bytes")
+    if format_version in ("lvx2", "lvx3"):
+        head = b"livox_tech".ljust(10, b'\x00') + b"2.0.0".ljust(6, b'\x00') + struct.pack('<I', 0xAC0EA767) + b'\x00' * 4
+        priv = (struct.pack('<II', 50, 1) + sn + struct.pack('<BB', device_info.device_type, 1 if device_info.extrinsic_enable else 0)
+                + struct.pack('<ffffff', device_info.roll, device_info.pitch, device_info.yaw, device_info.x, device_info.y, device_info.z)
+                + b'\x00' * 14)
+        return head + priv
+    if format_version == "lvx":
+        return b"livox_file" + struct.pack('<II', 1, n_frames) + b'\x00' * 10 + sn + struct.pack('<B', device_info.device_type) + b'\x00' * 15
+    raise ValueError(f"Unsupported format version: {format_version}")      # CS:242-243
+
+
+def frames_to_arrays(frames_data):
+    """frames_data (CS:2195: list of {'points': List[LiDARPoint] | (n,4+) ndarray [x y z intensity (tag)], 'timestamp': ns})
+    -> (pts (N,4) f64, tag u8[N], frame_off int64[F+1], frame_ts int64[F])."""
+    counts = np.array([len(f['points']) for f in frames_data], np.int64)
+    off = np.zeros(len(frames_data) + 1, np.int64)
+    np.cumsum(counts, out=off[1:])
+    pts = np.zeros((int(off[-1]), 4), np.float64)
+    tag = np.zeros(int(off[-1]), np.uint8)
+    for i, f in enumerate(frames_data):
+        p = f['points']
+        if len(p) == 0:
+            continue
+        if isinstance(p, np.ndarray):
+            pts[off[i]:off[i + 1]] = p[:, :4]
+            if p.shape[1] > 4:
+                tag[off[i]:off[i + 1]] = p[:, 4].astype(np.uint8)
+        else:
+            for q in p:
+                if not 0 <= q.tag <= 255:
+                    raise struct.error("ubyte format requires 0 <= number <= 255")       # what CS:374 raises
+            pts[off[i]:off[i + 1]] = [(q.x, q.y, q.z, q.intensity) for q in p]
+            tag[off[i]:off[i + 1]] = [q.tag for q in p]
+    ts = np.array([int(f['timestamp']) for f in frames_data], np.int64)
+    if (ts < 0).any():
+        raise struct.error("argument out of range")                                      # '<Q' of a negative timestamp, CS:350
+    return pts, tag, off, ts
+
+
+class LivoxLVXWriter:
+    """CS:235-374 -- same constructor and ``write_lvx_file(filename, frames_data, device_info)``; the bytes are
+    produced by one device launch (``build_bytes``) and written with one write().  No CPU fallback."""
+
+    supported_versions = ["lvx", "lvx2", "lvx3"]
+
+    def __init__(self, format_version: str = "lvx2", device: str = "cuda:0"):
+        if format_version not in self.supported_versions:
+            raise ValueError(f"Unsupported format version: {format_version}")          # CS:242-243
+        self.format_version = format_version
+        self.device = device
+
+    def build_bytes(self, frames_data, device_info) -> np.ndarray:
+        import torch
+        from . import _capi as C
+        from . import ops
+        pts, tag, off, ts = frames_to_arrays(frames_data)
+        prefix = lvx_cs_prefix(self.format_version, device_info, len(frames_data))
+        fmt = C.LVXCS_LEGACY if self.format_version == "lvx" else C.LVXCS_LVX2
+        dev = torch.device(self.device)
+        d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        data, status = ops.build_lvx_cs(d(pts), d(tag), d(off), d(ts), prefix, fmt, int(np.diff(off).max()) if len(off) > 1 else 0)
+        fl = int(status.item())
+        if fl & C.FLAG_NAN:
+            raise ValueError("cannot convert float NaN to integer")                     # int(nan), CS:368
+        if fl & C.FLAG_OVERFLOW:
+            raise struct.error("argument out of range")                                 # struct.pack beyond the field, CS:372-373 / 319-320
+        return data.cpu().numpy()
+
+    def write_lvx_file(self, filename: str, frames_data, device_info) -> None:
+        data = self.build_bytes(frames_data, device_info)
+        with open(filename, 'wb') as f:
+            f.write(data.tobytes())

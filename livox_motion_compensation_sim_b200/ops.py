@@ -213,6 +213,26 @@ def build_lvx_v11(pts: torch.Tensor, frame_off: torch.Tensor, frame_pos: torch.T
     return out, status
 
 
+def build_lvx_cs(pts: torch.Tensor, tag: Optional[torch.Tensor], frame_off: torch.Tensor, frame_ts: torch.Tensor,
+                 prefix: bytes, fmt: int, max_frame_points: int):
+    """(N1) CS:245-374 on the device: COMPENSATED points [x y z intensity] (+ tag bytes) -> the complete LVX2 / LVX3
+    (fmt = _capi.LVXCS_LVX2) or legacy LVX (LVXCS_LEGACY) file image.  prefix = the file's leading bytes
+    (lvx.lvx_cs_prefix); frame_ts int64 ns >= 0.  Returns (file bytes tensor, status flags tensor)."""
+    f64 = _layout(pts)
+    n, F = pts.shape[0], frame_off.shape[0] - 1
+    if len(prefix) > C.LVXCS_PREFIX_MAX:
+        raise ValueError("prefix too long")
+    size = len(prefix) + C.LVXCS_FRAME_BYTES[int(fmt)] * F + 14 * n
+    out = torch.empty(size, dtype=torch.uint8, device=pts.device)
+    status = torch.zeros(1, dtype=torch.int32, device=pts.device)
+    pre = (C.ctypes.c_uint8 * max(len(prefix), 1)).from_buffer_copy(bytes(prefix) or b"\0")
+    fn = C.lib().lmc_lvx_cs_build_f64 if f64 else C.lib().lmc_lvx_cs_build_f32
+    C.check(fn(_req(pts, pts.dtype, "pts", (4,)), _req(tag, torch.uint8, "tag"), _req(frame_off, torch.int64, "frame_off"),
+               _req(frame_ts, torch.int64, "frame_ts"), pre, len(prefix), int(fmt), out.data_ptr(), n, F, int(max_frame_points),
+               status.data_ptr(), _stream_ptr()))
+    return out, status
+
+
 def pcd_ascii_body(pts: torch.Tensor):
     """(N2) LMC:946-947 on the device: one '%.6f %.6f %.6f %.6f\\n' line per row, byte-identical to the
     reference's f-string formatting.  Returns (uint8 text tensor, status flags tensor)."""

@@ -289,8 +289,51 @@ def modeb_fixture(CS, manifest):
                              lvx2_sha256=sha(rec))
 
 
+def lvx_cs_fixture(CS, manifest):
+    """Reference LivoxLVXWriter.write_lvx_file (CS:245-374) for 'lvx2', 'lvx3' and 'lvx' on ragged synthetic
+    frames (one empty, one of a single point, one above 1024 points) with a non-trivial DeviceInfo."""
+    import tempfile
+    rng = np.random.default_rng(2024)
+    counts = [5, 0, 1, 1500, 96, 1024, 1025, 0]
+    stamps = [0, 100_000_000, 200_000_003, 1_700_000_000_123_456_789, 400_000_000, 500_000_000, 600_000_000, 700_000_000]
+    di = CS.DeviceInfo(lidar_sn="3GGDJ6K00200101", device_type=1, firmware_version="03.08.0000", extrinsic_enable=True,
+                       roll=0.01, pitch=-0.02, yaw=1.5, x=0.1, y=-0.2, z=1.25)
+    frames, all_pts, all_tag = [], [], []
+    for n, t in zip(counts, stamps):
+        xyz = rng.uniform(-120, 120, (n, 3))
+        if n >= 5:
+            xyz[0] = [0.0, -0.0004, 0.0009999]; xyz[1] = [-0.0015, 2147483.647, -2147483.648]
+            xyz[2] = [1e-320, -1e-320, 0.9999999999999999]
+        inten = rng.integers(0, 256, n); tag = rng.integers(0, 256, n)
+        frames.append({'points': [CS.LiDARPoint(x=float(a[0]), y=float(a[1]), z=float(a[2]), intensity=int(i), timestamp=int(t) + k,
+                                                ring=k % 16, tag=int(g)) for k, (a, i, g) in enumerate(zip(xyz, inten, tag))],
+                       'timestamp': int(t)})
+        all_pts.append(np.column_stack([xyz, inten.astype(np.float64)]).reshape(n, 4)); all_tag.append(tag.astype(np.uint8))
+    off = np.zeros(len(counts) + 1, np.int64); np.cumsum(counts, out=off[1:])
+    files = {}
+    with tempfile.TemporaryDirectory() as d:
+        for ver in ['lvx2', 'lvx3', 'lvx']:
+            fn = os.path.join(d, 'x.' + ver)
+            CS.LivoxLVXWriter(ver).write_lvx_file(fn, frames, di)
+            files[ver] = np.frombuffer(open(fn, 'rb').read(), np.uint8)
+    assert np.array_equal(files['lvx2'], files['lvx3'])
+    np.savez_compressed(os.path.join(HERE, 'lvx_cs.npz'), pts=np.vstack(all_pts), tag=np.concatenate(all_tag), frame_off=off,
+                        frame_ts=np.array(stamps, np.int64), file_lvx2=files['lvx2'], file_legacy=files['lvx'],
+                        device_info_json=np.frombuffer(json.dumps(di.__dict__).encode(), np.uint8))
+    manifest['lvx_cs'] = dict(frames=len(counts), points=int(off[-1]), lvx2_bytes=int(len(files['lvx2'])), lvx2_sha256=sha(files['lvx2']),
+                              legacy_bytes=int(len(files['lvx'])), legacy_sha256=sha(files['lvx']))
+
+
 def main():
     LMC, CS = import_reference()
+    if len(sys.argv) > 2 and sys.argv[1] == '--only':          # add / refresh single fixtures, keep the rest of the manifest
+        with open(os.path.join(HERE, 'MANIFEST.json')) as f:
+            manifest = json.load(f)
+        for name in sys.argv[2:]:
+            {'lvx_cs': lambda: lvx_cs_fixture(CS, manifest), 'text_rows': lambda: text_rows_fixture(CS, manifest)}[name]()
+        with open(os.path.join(HERE, 'MANIFEST.json'), 'w') as f:
+            json.dump(manifest, f, indent=1, sort_keys=True)
+        return
     manifest = {'generator': 'tests/golden/make_golden.py', 'numpy': np.__version__,
                 'scipy': __import__('scipy').__version__, 'lmc': {}}
     for name in CONFIGS:
@@ -305,6 +348,7 @@ def main():
     modeb_fixture(CS, manifest)
     coord_chain_fixture(CS, manifest)
     pcd_fixture(LMC, manifest)
+    lvx_cs_fixture(CS, manifest)
     with open(os.path.join(HERE, 'MANIFEST.json'), 'w') as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     print('wrote', sorted(os.listdir(HERE)))

@@ -421,6 +421,61 @@ def test_lvx_file_device_builder_ragged(f64):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("ver,key", [("lvx2", "file_lvx2"), ("lvx3", "file_lvx2"), ("lvx", "file_legacy")])
+def test_lvx_cs_file_bytes_vs_reference(golden, ver, key):
+    """(N1) CS:245-374: LVX2 / LVX3 / legacy file built on the device == the reference writer's file, byte for
+    byte, through the mirrored LivoxLVXWriter(list of LiDARPoint frames) API."""
+    import json
+    from livox_motion_compensation_sim_b200 import LiDARPoint
+    from livox_motion_compensation_sim_b200.lvx import LivoxLVXWriter, DeviceInfo
+    g = golden("lvx_cs.npz")
+    off = g['frame_off']
+    di = DeviceInfo(**json.loads(bytes(g['device_info_json']).decode()))
+    frames = [{'points': [LiDARPoint(float(p[0]), float(p[1]), float(p[2]), int(p[3]), 0, 0, int(t))
+                          for p, t in zip(g['pts'][off[i]:off[i + 1]], g['tag'][off[i]:off[i + 1]])],
+               'timestamp': int(g['frame_ts'][i])} for i in range(len(off) - 1)]
+    data = LivoxLVXWriter(ver).build_bytes(frames, di)
+    assert np.array_equal(data, g[key])
+    with pytest.raises(ValueError):
+        LivoxLVXWriter("lvx4")
+
+
+@pytest.mark.parametrize("fmt", [0, 1], ids=["lvx2", "legacy"])
+@pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
+def test_lvx_cs_device_builder_ragged(f64, fmt):
+    """Device-built LVX2 / legacy image vs the restatement on a ragged stream with multi-chunk frames, empty
+    frames (also first and last) and epoch-sized timestamps; then the struct.pack error flags."""
+    rng = np.random.default_rng(23)
+    F = 61
+    counts = rng.integers(0, 3000, F); counts[0] = 0; counts[5] = 0; counts[6] = 1024; counts[7] = 1025; counts[20] = 20_000; counts[-1] = 0
+    st = synth.make_stream(F, counts, 23, device=DEV, dtype=torch.float64 if f64 else torch.float32)
+    pts = st.pts.clone()
+    pts[:, 3] = torch.floor(pts[:, 3] * 255.999)
+    N = pts.shape[0]
+    tag = rng.integers(0, 256, N).astype(np.uint8)
+    ts = np.sort(rng.integers(0, 2 ** 62, F)).astype(np.int64)
+    prefix = bytes(rng.integers(0, 256, 88 if fmt == 0 else 60).astype(np.uint8))
+    data, status = ops.build_lvx_cs(pts, dev(tag), dev(st.frame_off), dev(ts), prefix, fmt, int(counts.max()))
+    assert int(status.item()) == 0
+    want = orc.lvx_cs_file_np(pts.cpu().numpy().astype(np.float64), tag, st.frame_off, ts, prefix, fmt)
+    got = data.cpu().numpy()
+    assert got.shape == want.shape and np.array_equal(got, want)
+    # no tag array -> tag bytes 0
+    data0, _ = ops.build_lvx_cs(pts, None, dev(st.frame_off), dev(ts), prefix, fmt, int(counts.max()))
+    assert np.array_equal(data0.cpu().numpy(), orc.lvx_cs_file_np(pts.cpu().numpy().astype(np.float64), None, st.frame_off, ts, prefix, fmt))
+    # what struct.pack refuses becomes a status bit
+    bad = pts.clone(); bad[7, 3] = 256.0
+    assert int(ops.build_lvx_cs(bad, None, dev(st.frame_off), dev(ts), prefix, fmt, int(counts.max()))[1].item()) == C.FLAG_OVERFLOW
+    bad = pts.clone(); bad[7, 1] = float('nan')
+    assert int(ops.build_lvx_cs(bad, None, dev(st.frame_off), dev(ts), prefix, fmt, int(counts.max()))[1].item()) == (C.FLAG_NAN if fmt == 0 else 0)
+    if f64:
+        bad = pts.clone(); bad[7, 2] = 2147483.648 if fmt == 0 else 3.5e38
+        assert int(ops.build_lvx_cs(bad, None, dev(st.frame_off), dev(ts), prefix, fmt, int(counts.max()))[1].item()) == C.FLAG_OVERFLOW
+    # frame list without frames: header-only file
+    e, _ = ops.build_lvx_cs(pts[:0], None, dev(np.zeros(1, np.int64)), dev(np.zeros(0, np.int64)), prefix, fmt, 0)
+    assert bytes(e.cpu().numpy()) == prefix
+
+
 def test_motion_compensator_list_api(golden):
     from livox_motion_compensation_sim_b200 import MotionCompensator, LiDARPoint, IMUData
     g = golden("modeb.npz")
