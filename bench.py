@@ -407,7 +407,18 @@ def main_b200(args):
             lvx_bytes = int(fpos[-1])
             pcd_ms = t_ms(lambda: ops.pcd_ascii_body(raw))
             pcd_bytes = int(ops.pcd_ascii_body(raw)[0].numel())
+            from livox_motion_compensation_sim_b200 import _capi as _C
+            tsw = d((st.frame_t[:fw] * 1e9).astype(np.int64))
+            pre2 = bytes(88)
+            cs_ms = t_ms(lambda: ops.build_lvx_cs(raw, None, offw, tsw, pre2, _C.LVXCS_LVX2, P))
+            cs_bytes = 88 + 45 * fw + 14 * nw
+            las_ms = t_ms(lambda: ops.build_las_pf3(raw, scale=(0.001,) * 3, offset=(0.0,) * 3))
+            las_bytes = _C.LAS_HEADER_BYTES + _C.LAS_RECORD_BYTES * nw
             writers = {"sample_points": nw,
+                       "lvx2_file": {"points_per_s": nw / (cs_ms * 1e-3), "GBps": (nw * 16 + cs_bytes) / (cs_ms * 1e-3) / 1e9,
+                                     "file_bytes": cs_bytes, "what": "float4 [x y z intensity] -> complete LVX2 file image (CS:269-374) on the device"},
+                       "las_pf3_file": {"points_per_s": nw / (las_ms * 1e-3), "GBps": (nw * 16 + las_bytes) / (las_ms * 1e-3) / 1e9,
+                                        "file_bytes": las_bytes, "what": "float4 -> LAS 1.2 PF3 file image with header min/max (LMC:950-963), parity unpinned"},
                        "lvx_v11_file": {"points_per_s": nw / (lvx_ms * 1e-3), "GBps": (nw * 16 + lvx_bytes) / (lvx_ms * 1e-3) / 1e9,
                                         "file_bytes": lvx_bytes, "what": "raw float4 -> complete LVX v1.1 file image (LMC:58-272) on the device"},
                        "pcd_ascii": {"points_per_s": nw / (pcd_ms * 1e-3), "GBps": (2 * nw * 16 + pcd_bytes) / (pcd_ms * 1e-3) / 1e9,

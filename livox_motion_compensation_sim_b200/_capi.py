@@ -12,6 +12,7 @@ FLAG_NAN, FLAG_OVERFLOW = 1, 2
 LVX_TYPE2_OF_INPUT, LVX2_OF_OUTPUT = 0, 1
 LVXCS_LVX2, LVXCS_LEGACY = 0, 1
 LVXCS_PREFIX_MAX = 96
+TEXT_MAX_COLS = 6
 LVXCS_FRAME_BYTES = {0: 45, 1: 12}
 LAS_INTENSITY_UNIT, LAS_INTENSITY_RAW = 0, 1
 PATH_DIRECT, PATH_AUTO, PATH_TMA = 0, 1, 2
@@ -64,6 +65,10 @@ _SIGNATURES = {
     "lmc_pcd_ascii_size_f32": ([vp, i64, vp, vp], ctypes.c_int),
     "lmc_pcd_ascii_write_f64": ([vp, i64, vp, vp, vp, vp], ctypes.c_int),
     "lmc_pcd_ascii_write_f32": ([vp, i64, vp, vp, vp, vp], ctypes.c_int),
+    "lmc_text_rows_size_f64": ([vp, i64, i32, i32, vp, vp, i32, vp, vp], ctypes.c_int),
+    "lmc_text_rows_size_f32": ([vp, i64, i32, i32, vp, vp, i32, vp, vp], ctypes.c_int),
+    "lmc_text_rows_write_f64": ([vp, i64, i32, i32, vp, vp, i32, vp, vp, vp, vp], ctypes.c_int),
+    "lmc_text_rows_write_f32": ([vp, i64, i32, i32, vp, vp, i32, vp, vp, vp, vp], ctypes.c_int),
     "lmc_las_pf3_build_f64": ([vp, vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, vp], ctypes.c_int),
     "lmc_las_pf3_build_f32": ([vp, vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, vp], ctypes.c_int),
     "lmc_scan_mark": ([vp, i64, vp, vp, i32, f64, f64, f64, f64, vp, vp, vp, vp], ctypes.c_int),

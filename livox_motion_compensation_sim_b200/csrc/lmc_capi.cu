@@ -20,6 +20,10 @@ cudaError_t launch_scan_emit(const double* env, int64_t M, const double* pos, co
 cudaError_t launch_las_pf3(bool f64, const LasParams& L, cudaStream_t st);
 cudaError_t launch_lvx_v11(bool f64, const void* pts, const int64_t* frame_off, const int64_t* frame_pos, const double* frame_time,
                            const int64_t* frame_id, uint8_t* out, int32_t n_frames, int64_t max_frame_points, uint32_t* status, cudaStream_t st);
+cudaError_t launch_text_size(bool f64, const void* rows, int64_t n, int32_t n_cols, int32_t row_stride, const int32_t* col, const int32_t* dec,
+                             uint8_t sep, int64_t* tile_off, cudaStream_t st);
+cudaError_t launch_text_write(bool f64, const void* rows, int64_t n, int32_t n_cols, int32_t row_stride, const int32_t* col, const int32_t* dec,
+                              uint8_t sep, const int64_t* tile_off, uint8_t* out, uint32_t* status, cudaStream_t st);
 cudaError_t launch_lvx_cs(bool f64, const void* pts, const uint8_t* tag, const int64_t* frame_off, const uint64_t* frame_ts,
                           const uint8_t* prefix_host, int32_t prefix_len, int32_t format, uint8_t* out, int32_t n_frames,
                           int64_t max_frame_points, uint32_t* status, cudaStream_t st);
@@ -287,6 +291,45 @@ static int pcd_write(bool f64, const void* pts, int64_t n, const int64_t* tile_o
     if (!aligned32(pts) || !aligned32(out)) return fail(LMC_ERR_ALIGN, "points and text buffer must be 32-byte aligned");
     cudaError_t e = lmc::launch_pcd_write(f64, pts, n, tile_off, out, status, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_pcd_write");
+}
+static int text_check(const void* rows, int64_t n, int32_t row_stride, int32_t n_cols, const int32_t* col, const int32_t* dec, int32_t sep) {
+    int rc = check_device();
+    if (rc != LMC_OK) return rc;
+    if (n < 0 || (n > 0 && !rows) || !col || !dec) return fail(LMC_ERR_INVALID, "bad argument");
+    if (n_cols < 1 || n_cols > LMC_TEXT_MAX_COLS || row_stride < 1) return fail(LMC_ERR_INVALID, "n_cols must be 1..%d, row_stride >= 1", LMC_TEXT_MAX_COLS);
+    if (sep < 1 || sep > 255) return fail(LMC_ERR_INVALID, "separator must be one byte");
+    for (int c = 0; c < n_cols; ++c)
+        if (col[c] < 0 || col[c] >= row_stride || dec[c] < 0 || dec[c] > 9) return fail(LMC_ERR_INVALID, "column %d: source index must be < row_stride, decimals 0..9", c);
+    return LMC_OK;
+}
+static int text_size(bool f64, const void* rows, int64_t n, int32_t row_stride, int32_t n_cols, const int32_t* col, const int32_t* dec, int32_t sep,
+                     int64_t* tile_off, void* stream) {
+    int rc = text_check(rows, n, row_stride, n_cols, col, dec, sep);
+    if (rc != LMC_OK) return rc;
+    if (!tile_off) return fail(LMC_ERR_INVALID, "NULL tile_off");
+    cudaError_t e = lmc::launch_text_size(f64, rows, n, n_cols, row_stride, col, dec, (uint8_t)sep, tile_off, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_text_len / k_pcd_scan");
+}
+static int text_write(bool f64, const void* rows, int64_t n, int32_t row_stride, int32_t n_cols, const int32_t* col, const int32_t* dec, int32_t sep,
+                      const int64_t* tile_off, uint8_t* out, uint32_t* status, void* stream) {
+    int rc = text_check(rows, n, row_stride, n_cols, col, dec, sep);
+    if (rc != LMC_OK) return rc;
+    if (!tile_off || (n > 0 && !out)) return fail(LMC_ERR_INVALID, "NULL argument");
+    if (!aligned32(out)) return fail(LMC_ERR_ALIGN, "text buffer must be 32-byte aligned");
+    cudaError_t e = lmc::launch_text_write(f64, rows, n, n_cols, row_stride, col, dec, (uint8_t)sep, tile_off, out, status, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_text_write");
+}
+int lmc_text_rows_size_f64(const double* rows, int64_t n_rows, int32_t row_stride, int32_t n_cols, const int32_t* col, const int32_t* decimals, int32_t sep,
+                           int64_t* tile_off, void* stream) { return text_size(true, rows, n_rows, row_stride, n_cols, col, decimals, sep, tile_off, stream); }
+int lmc_text_rows_size_f32(const float* rows, int64_t n_rows, int32_t row_stride, int32_t n_cols, const int32_t* col, const int32_t* decimals, int32_t sep,
+                           int64_t* tile_off, void* stream) { return text_size(false, rows, n_rows, row_stride, n_cols, col, decimals, sep, tile_off, stream); }
+int lmc_text_rows_write_f64(const double* rows, int64_t n_rows, int32_t row_stride, int32_t n_cols, const int32_t* col, const int32_t* decimals, int32_t sep,
+                            const int64_t* tile_off, uint8_t* text_out, uint32_t* status, void* stream) {
+    return text_write(true, rows, n_rows, row_stride, n_cols, col, decimals, sep, tile_off, text_out, status, stream);
+}
+int lmc_text_rows_write_f32(const float* rows, int64_t n_rows, int32_t row_stride, int32_t n_cols, const int32_t* col, const int32_t* decimals, int32_t sep,
+                            const int64_t* tile_off, uint8_t* text_out, uint32_t* status, void* stream) {
+    return text_write(false, rows, n_rows, row_stride, n_cols, col, decimals, sep, tile_off, text_out, status, stream);
 }
 int lmc_pcd_ascii_size_f64(const double* pts_n4, int64_t n_points, int64_t* tile_off, void* stream) { return pcd_size(true, pts_n4, n_points, tile_off, stream); }
 int lmc_pcd_ascii_size_f32(const float* pts_n4, int64_t n_points, int64_t* tile_off, void* stream) { return pcd_size(false, pts_n4, n_points, tile_off, stream); }

@@ -8,6 +8,8 @@
 // with the 73-bit product m * 10^6 held in unsigned __int128; then Q / 10^6 and Q % 10^6 are the
 // integer and fractional digits.  Values with |v| >= 9.2e12 (Q would not fit 64 bits) are printed as
 // "inf"-free saturated text and flagged LMC_FLAG_OVERFLOW -- no point cloud coordinate gets there.
+// (The generic row writer below -- k_text_*, the complete simulator's exports CS:1643-1716 -- splits
+// integer and fraction instead and covers |v| < 2^64 with 0..9 decimals per column.)
 //
 // Lines have variable length, so the text is produced in three launches:
 //   k_pcd_len    per tile of 256 points: total text bytes of the tile
@@ -164,6 +166,172 @@ __global__ void __launch_bounds__(kPcdTile) k_pcd_write(const void* __restrict__
     for (int k = b0 + tid; k < a0; k += kPcdTile) g[k] = s_img[k];
     for (int k = a1 + tid; k < b1; k += kPcdTile) g[k] = s_img[k];
     if (fl != 0 && status != nullptr) atomicOr(status, fl);
+}
+
+// ---- generic delimited text rows: CS:1643-1716 (_export_pcd '%.6f %.6f %.6f %.0f %.0f', _export_xyz, _export_csv) ----
+// "%.{d}f" with d = 0..9 per column and the full integer range a timestamp column needs (ns since the
+// epoch ~ 1.7e18): the value is split exactly into its integer part I (< 2^64) and the fraction
+// Q = round_half_even(frac * 10^d) (carry into I when Q reaches 10^d).
+constexpr int kTextCols   = 6;                      // LMC_TEXT_MAX_COLS
+constexpr int kTextNumMax = 1 + 20 + 1 + 9;         // sign, <= 20 integer digits, '.', <= 9 decimals
+
+struct TextFmt { int32_t n_cols, row_stride; int32_t col[kTextCols]; int32_t dec[kTextCols]; uint8_t sep; };
+
+__device__ __constant__ uint32_t kPow10[10] = { 1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u };
+
+struct TextNum { uint64_t ip; uint32_t fq; uint32_t len; uint8_t kind; bool neg; };   // kind 0 finite, 1 nan, 2 inf
+
+__device__ __forceinline__ TextNum fmtg_prepare(double v, int d, uint32_t& fl) {
+    TextNum t;
+    const uint64_t bits = (uint64_t)__double_as_longlong(v);
+    t.neg = bits >> 63;
+    const uint32_t ex = (uint32_t)(bits >> 52) & 0x7ffu;
+    const uint64_t frac = bits & 0xfffffffffffffull;
+    t.ip = 0; t.fq = 0;
+    if (ex == 0x7ff) { t.kind = frac ? 1 : 2; t.len = frac ? 3u : (t.neg ? 4u : 3u); return t; }
+    t.kind = 0;
+    const uint64_t m = ex ? (frac | (1ull << 52)) : frac;
+    const int e = (ex ? (int)ex : 1) - 1075;
+    const uint32_t p10 = kPow10[d];
+    if (e >= 0) {
+        if (e > 11) { fl |= LMC_FLAG_OVERFLOW; t.ip = 0xffffffffffffffffull; }     // >= 2^64
+        else t.ip = m << e;
+    } else {
+        const int s = -e;
+        uint64_t fm = m;
+        if (s < 64) { t.ip = m >> s; fm = m - (t.ip << s); }
+        if (s < 127) {
+            const unsigned __int128 P = (unsigned __int128)fm * p10;             // < 2^83
+            const unsigned __int128 Qw = P >> s;                                 // < 10^d
+            uint32_t q = (uint32_t)Qw;
+            const unsigned __int128 rem = P - (Qw << s), half = (unsigned __int128)1 << (s - 1);
+            if (rem > half || (rem == half && (d ? (q & 1u) : (uint32_t)(t.ip & 1ull)))) q += 1;   // ties to even (the last printed digit)
+            if (q >= p10) { q -= p10; t.ip += 1; }
+            t.fq = q;
+        }
+    }
+    uint32_t nd = 1;
+    for (uint64_t x = t.ip; x >= 10; x /= 10) ++nd;
+    t.len = (t.neg ? 1u : 0u) + nd + (d ? 1u + (uint32_t)d : 0u);
+    return t;
+}
+
+__device__ __forceinline__ int fmtg_write(uint8_t* dst, int d, const TextNum& t) {
+    if (t.kind) {
+        int o = 0;
+        if (t.kind == 2 && t.neg) dst[o++] = '-';
+        if (t.kind == 1) { dst[o] = 'n'; dst[o + 1] = 'a'; dst[o + 2] = 'n'; }
+        else             { dst[o] = 'i'; dst[o + 1] = 'n'; dst[o + 2] = 'f'; }
+        return o + 3;
+    }
+    int o = (int)t.len;
+    if (d) {
+        uint32_t fp = t.fq;
+        for (int k = 0; k < d; ++k) { dst[--o] = (uint8_t)('0' + fp % 10u); fp /= 10u; }
+        dst[--o] = '.';
+    }
+    uint64_t ip = t.ip;
+    do { dst[--o] = (uint8_t)('0' + (uint32_t)(ip % 10ull)); ip /= 10ull; } while (ip);
+    if (t.neg) dst[--o] = '-';
+    return (int)t.len;
+}
+
+template <bool F64>
+__device__ __forceinline__ double load_cell(const void* rows, int64_t idx) {
+    if constexpr (F64) return __ldg(reinterpret_cast<const double*>(rows) + idx);
+    else return (double)__ldg(reinterpret_cast<const float*>(rows) + idx);
+}
+
+template <bool F64>
+__global__ void __launch_bounds__(kPcdTile) k_text_len(const void* __restrict__ rows, int64_t n, const __grid_constant__ TextFmt F, int64_t* __restrict__ tile_off) {
+    __shared__ uint32_t s_warp[kPcdTile / 32];
+    const int64_t i = (int64_t)blockIdx.x * kPcdTile + threadIdx.x;
+    uint32_t len = 0, fl = 0;
+    if (i < n) {
+        len = (uint32_t)F.n_cols;                                    // separators + newline
+#pragma unroll
+        for (int c = 0; c < kTextCols; ++c) if (c < F.n_cols) len += fmtg_prepare(load_cell<F64>(rows, i * F.row_stride + F.col[c]), F.dec[c], fl).len;
+    }
+    uint32_t total;
+    block_scan_excl(len, s_warp, total);
+    if (threadIdx.x == 0) tile_off[blockIdx.x + 1] = total;
+}
+
+template <bool F64>
+__global__ void __launch_bounds__(kPcdTile) k_text_write(const void* __restrict__ rows, int64_t n, const __grid_constant__ TextFmt F,
+                                                         const int64_t* __restrict__ tile_off, uint8_t* __restrict__ out, uint32_t* __restrict__ status) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];                 // the tile's text image, sized by the host from the format
+    __shared__ uint32_t s_warp[kPcdTile / 32];
+    uint8_t* s_img = s_dyn;
+    const int tid = threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * kPcdTile + tid;
+    const int64_t dst0 = tile_off[blockIdx.x];
+    const int phase = (int)(dst0 & 15);
+    TextNum t[kTextCols];
+    uint32_t len = 0, fl = 0;
+    if (i < n) {
+        len = (uint32_t)F.n_cols;
+#pragma unroll
+        for (int c = 0; c < kTextCols; ++c) if (c < F.n_cols) {
+            t[c] = fmtg_prepare(load_cell<F64>(rows, i * F.row_stride + F.col[c]), F.dec[c], fl);
+            len += t[c].len;
+        }
+    }
+    uint32_t total;
+    const uint32_t off = block_scan_excl(len, s_warp, total);
+    if (i < n) {
+        uint8_t* d = s_img + phase + off;
+#pragma unroll
+        for (int c = 0; c < kTextCols; ++c) if (c < F.n_cols) { d += fmtg_write(d, F.dec[c], t[c]); *d++ = c == F.n_cols - 1 ? (uint8_t)'\n' : F.sep; }
+    }
+    __syncthreads();
+    uint8_t* g = out + (dst0 - phase);
+    const int b0 = phase, b1 = phase + (int)total;
+    int a0 = (b0 + 15) & ~15; if (a0 > b1) a0 = b1;
+    int a1 = b1 & ~15;        if (a1 < a0) a1 = a0;
+    for (int k = a0 / 16 + tid; k < a1 / 16; k += kPcdTile) reinterpret_cast<uint4*>(g)[k] = reinterpret_cast<const uint4*>(s_img)[k];
+    for (int k = b0 + tid; k < a0; k += kPcdTile) g[k] = s_img[k];
+    for (int k = a1 + tid; k < b1; k += kPcdTile) g[k] = s_img[k];
+    if (fl != 0 && status != nullptr) atomicOr(status, fl);
+}
+
+static TextFmt make_fmt(int32_t n_cols, int32_t row_stride, const int32_t* col, const int32_t* dec, uint8_t sep, int& img_bytes) {
+    TextFmt F{};
+    F.n_cols = n_cols; F.row_stride = row_stride; F.sep = sep;
+    int row = n_cols;
+    for (int c = 0; c < n_cols; ++c) { F.col[c] = col[c]; F.dec[c] = dec[c]; row += 1 + 20 + (dec[c] ? 1 + dec[c] : 0); }
+    img_bytes = ((kPcdTile * row + 32 + 15) / 16) * 16;
+    return F;
+}
+
+cudaError_t launch_text_size(bool f64, const void* rows, int64_t n, int32_t n_cols, int32_t row_stride, const int32_t* col, const int32_t* dec,
+                             uint8_t sep, int64_t* tile_off, cudaStream_t st) {
+    const int64_t tiles = (n + kPcdTile - 1) / kPcdTile;
+    if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+    int img;
+    const TextFmt F = make_fmt(n_cols, row_stride, col, dec, sep, img);
+    if (tiles > 0) {
+        if (f64) k_text_len<true><<<(unsigned)tiles, kPcdTile, 0, st>>>(rows, n, F, tile_off);
+        else     k_text_len<false><<<(unsigned)tiles, kPcdTile, 0, st>>>(rows, n, F, tile_off);
+    }
+    k_pcd_scan<<<1, 1024, 0, st>>>(tile_off, tiles);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_text_write(bool f64, const void* rows, int64_t n, int32_t n_cols, int32_t row_stride, const int32_t* col, const int32_t* dec,
+                              uint8_t sep, const int64_t* tile_off, uint8_t* out, uint32_t* status, cudaStream_t st) {
+    const int64_t tiles = (n + kPcdTile - 1) / kPcdTile;
+    if (tiles == 0) return cudaSuccess;
+    int img;
+    const TextFmt F = make_fmt(n_cols, row_stride, col, dec, sep, img);
+    cudaError_t e = cudaSuccess;
+    if (img > 48 * 1024)                                             // widest formats only (6 columns x 9 decimals = 49 KB)
+        e = f64 ? cudaFuncSetAttribute(k_text_write<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, img)
+                : cudaFuncSetAttribute(k_text_write<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, img);
+    if (e != cudaSuccess) return e;
+    if (f64) k_text_write<true><<<(unsigned)tiles, kPcdTile, img, st>>>(rows, n, F, tile_off, out, status);
+    else     k_text_write<false><<<(unsigned)tiles, kPcdTile, img, st>>>(rows, n, F, tile_off, out, status);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_pcd_size(bool f64, const void* pts, int64_t n, int64_t* tile_off, cudaStream_t st) {

@@ -250,6 +250,32 @@ def pcd_ascii_body(pts: torch.Tensor):
     return out, status
 
 
+def text_rows(rows: torch.Tensor, cols, decimals, sep: str = " "):
+    """(N2) CS:1643-1716 on the device: one line per row of a 2-D f64 / f32 tensor, column cols[k] printed as
+    '%.{decimals[k]}f', joined by sep, '\\n' terminated -- byte-identical to the reference's f-strings /
+    np.savetxt / pandas float_format.  Returns (uint8 text tensor, status flags tensor)."""
+    if rows.dim() != 2 or rows.dtype not in (torch.float64, torch.float32):
+        raise TypeError("rows: expected a 2-D float64 / float32 CUDA tensor")
+    f64 = rows.dtype == torch.float64
+    n, stride = rows.shape
+    k = len(cols)
+    if k != len(decimals) or not 1 <= k <= C.TEXT_MAX_COLS:
+        raise ValueError(f"1..{C.TEXT_MAX_COLS} columns, one decimals entry each")
+    ca = (C.ctypes.c_int32 * k)(*[int(c) for c in cols])
+    da = (C.ctypes.c_int32 * k)(*[int(v) for v in decimals])
+    tiles = (n + C.PCD_TILE - 1) // C.PCD_TILE
+    tile_off = torch.empty(tiles + 1, dtype=torch.int64, device=rows.device)
+    L = C.lib()
+    fs, fw = (L.lmc_text_rows_size_f64, L.lmc_text_rows_write_f64) if f64 else (L.lmc_text_rows_size_f32, L.lmc_text_rows_write_f32)
+    ptr = _req(rows, rows.dtype, "rows")
+    C.check(fs(ptr, n, stride, k, ca, da, ord(sep), tile_off.data_ptr(), _stream_ptr()))
+    size = int(tile_off[-1].item())
+    out = torch.empty(size, dtype=torch.uint8, device=rows.device)
+    status = torch.zeros(1, dtype=torch.int32, device=rows.device)
+    C.check(fw(ptr, n, stride, k, ca, da, ord(sep), tile_off.data_ptr(), out.data_ptr(), status.data_ptr(), _stream_ptr()))
+    return out, status
+
+
 def build_las_pf3(pts: torch.Tensor, *, scale=(0.01, 0.01, 0.01), offset=(0.0, 0.0, 0.0), intensity_mode: int = C.LAS_INTENSITY_UNIT,
                   gps_time: Optional[torch.Tensor] = None, year: int = 2026, day_of_year: int = 1):
     """(N2) A complete LAS 1.2 / PF3 file image on the device (parity unpinned: laspy absent; LAS 1.2 spec).

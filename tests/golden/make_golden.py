@@ -324,6 +324,30 @@ def lvx_cs_fixture(CS, manifest):
                               legacy_bytes=int(len(files['lvx'])), legacy_sha256=sha(files['lvx']))
 
 
+def text_rows_fixture(CS, manifest):
+    """Reference DataExporter._export_pcd / _export_xyz / _export_csv (CS:1643-1716) on an (N,5) array
+    [x y z intensity timestamp] with rounding ties, negative zeros, sub-ulp values and ns timestamps."""
+    import tempfile
+    rng = np.random.default_rng(31337)
+    n = 1500
+    a = np.column_stack([rng.uniform(-150, 150, (n, 3)), rng.integers(0, 256, n).astype(np.float64),
+                         (rng.integers(0, 3_600_000_000_000, n)).astype(np.float64)])
+    a[0] = [0.0, -0.0, 1e-7, 0.0, 0.0]
+    a[1] = [0.0000005, -0.0000005, 0.0000015, 0.5, 1.5]                 # ties after binary rounding
+    a[2] = [2.5e-7 * 2, 123456.7890125, -999999.9999995, 2.5, 1_700_000_000_123_456_789.0]
+    a[3] = [1e-320, -1e-320, 4.9e-324, 254.5, 255.5]
+    a[4] = [9.9999995, 99.9999995, -0.9999995, 255.0, 9_007_199_254_740_993.0]
+    a[5] = [1234567.0000005, -7654321.1234565, 0.1234565, 17.49999999, 3_599_999_999_999.5]
+    ex = CS.DataExporter({})
+    with tempfile.TemporaryDirectory() as d:
+        ex._export_pcd(a, os.path.join(d, 'a.pcd')); ex._export_xyz(a, os.path.join(d, 'a.xyz')); ex._export_csv(a, os.path.join(d, 'a.csv'))
+        pcd = open(os.path.join(d, 'a.pcd'), 'rb').read(); xyz = open(os.path.join(d, 'a.xyz'), 'rb').read(); csv = open(os.path.join(d, 'a.csv'), 'rb').read()
+    np.savez_compressed(os.path.join(HERE, 'text_rows.npz'), points=a, pcd=np.frombuffer(pcd, np.uint8), xyz=np.frombuffer(xyz, np.uint8),
+                        csv=np.frombuffer(csv, np.uint8))
+    manifest['text_rows'] = dict(points=n, pcd_sha256=sha(np.frombuffer(pcd, np.uint8)), xyz_sha256=sha(np.frombuffer(xyz, np.uint8)),
+                                 csv_sha256=sha(np.frombuffer(csv, np.uint8)))
+
+
 def main():
     LMC, CS = import_reference()
     if len(sys.argv) > 2 and sys.argv[1] == '--only':          # add / refresh single fixtures, keep the rest of the manifest
@@ -349,6 +373,7 @@ def main():
     coord_chain_fixture(CS, manifest)
     pcd_fixture(LMC, manifest)
     lvx_cs_fixture(CS, manifest)
+    text_rows_fixture(CS, manifest)
     with open(os.path.join(HERE, 'MANIFEST.json'), 'w') as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     print('wrote', sorted(os.listdir(HERE)))

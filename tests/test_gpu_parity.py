@@ -476,6 +476,54 @@ def test_lvx_cs_device_builder_ragged(f64, fmt):
     assert bytes(e.cpu().numpy()) == prefix
 
 
+def test_data_exporter_text_files_vs_reference(golden):
+    """(N2) CS:1643-1716: the PCD / XYZ / CSV files of the reference DataExporter, byte for byte, from the device
+    row formatter (ties, negative zeros, denormals, epoch-sized timestamps in the '%.0f' and '%.6f' columns)."""
+    from livox_motion_compensation_sim_b200 import DataExporter
+    g = golden("text_rows.npz")
+    ex = DataExporter({})
+    assert ex.pcd_bytes(g['points']) == bytes(g['pcd'])
+    assert ex.xyz_bytes(g['points']) == bytes(g['xyz'])
+    assert ex.csv_bytes(g['points']) == bytes(g['csv'])
+    pts = g['points'][6:106]
+    las = np.frombuffer(ex.las_bytes(pts), np.uint8)
+    assert len(las) == C.LAS_HEADER_BYTES + 100 * C.LAS_RECORD_BYTES
+    rec = las[C.LAS_HEADER_BYTES:].reshape(100, C.LAS_RECORD_BYTES)
+    X, Y, Z, I = orc.quantize_las_np(pts[:, :4], [0.001] * 3, [0.0] * 3, 1)        # CS:1679-1687 restated (parity unpinned)
+    assert np.array_equal(rec[:, 0:4].copy().view('<i4').ravel(), X) and np.array_equal(rec[:, 12:14].copy().view('<u2').ravel(), I)
+    assert np.array_equal(rec[:, 20:28].copy().view('<f8').ravel(), pts[:, 4] * 1e-9)   # CS:1690
+    with pytest.raises(OverflowError):
+        ex.las_bytes(g['points'][:6])                       # -7654321.123 m at 1 mm does not fit int32
+
+
+@pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
+def test_text_rows_random_formats(f64):
+    """Device row formatter vs CPython '%.{d}f' for every decimals value 0..9, strided column picks, all
+    magnitudes (denormal .. 1.8e19), specials, and a multi-tile ragged row count."""
+    rng = np.random.default_rng(77)
+    n, stride = 3 * 256 + 17, 7
+    mag = 10.0 ** rng.uniform(-12, 19.2, (n, stride))
+    a = np.where(rng.random((n, stride)) < 0.5, -mag, mag)
+    a[rng.random((n, stride)) < 0.05] = 0.0
+    k = rng.integers(0, 10 ** 6, (n, stride))
+    tie = rng.random((n, stride)) < 0.2
+    a[tie] = (k[tie] + 0.5) / 2.0 ** rng.integers(0, 12, tie.sum())          # exact binary ties at several scales
+    a[5, 0] = np.nan; a[6, 1] = np.inf; a[7, 2] = -np.inf; a[8, 3] = -0.0; a[9, 4] = 5e-324; a[10, 5] = 18446744073709549568.0
+    if not f64:
+        a[10, 5] = 2.0 ** 63
+        a = a.astype(np.float32).astype(np.float64)
+    t = dev(a if f64 else a.astype(np.float32))
+    for cols, decs, sep in [((0, 1, 2, 3, 4, 5), (0, 1, 2, 3, 4, 5), " "), ((6, 5, 4, 3), (9, 8, 7, 6), ","), ((2,), (0,), ";"),
+                            ((0, 0, 1, 1, 2, 2), (9, 9, 9, 9, 9, 9), "\t")]:
+        text, status = ops.text_rows(t, cols, decs, sep)
+        assert int(status.item()) == 0
+        assert text.cpu().numpy().tobytes() == orc.text_rows_np(a, cols, decs, sep)
+    big = dev(np.array([[2.0 ** 64, 1.0]]))
+    assert int(ops.text_rows(big, (0,), (0,), " ")[1].item()) == C.FLAG_OVERFLOW
+    e, _ = ops.text_rows(t[:0], (0,), (6,), " ")
+    assert e.numel() == 0
+
+
 def test_motion_compensator_list_api(golden):
     from livox_motion_compensation_sim_b200 import MotionCompensator, LiDARPoint, IMUData
     g = golden("modeb.npz")
