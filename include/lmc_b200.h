@@ -165,6 +165,22 @@ int lmc_quantize_f64(const double* pts_n4, int64_t n_points, const lmc_export* e
 int lmc_quantize_f32(const float* pts_n4, int64_t n_points, const lmc_export* ex, void* stream);
 
 /*
+ *  CoordinateTransformer.transform_points (CS:214-233): one 4x4 homogeneous matrix
+ * (T_host: HOST pointer, 16 doubles row-major; the last row is not read) applied to every point,
+ * the 4th column passing through.  `order` selects which of the reference's two summation orders is
+ * reproduced bit for bit:
+ *   LMC_HOMOG_BATCH   the call on an (n >= 2, 3) array: dgemm, fma(T3,1, fma(T2,z, fma(T1,y, T0*x)))
+ *   LMC_HOMOG_SINGLE  the call on ONE point, which is how _transform_coordinates (CS:2107-2163) calls
+ *                     it for every point of every frame: 4-term gemv, (T0*x + T2*z) + (T1*y + T3)
+ */
+#define LMC_HOMOG_BATCH  0
+#define LMC_HOMOG_SINGLE 1
+int lmc_transform_homog_f64(const double* pts_n4, const double* T_host, int32_t order,
+                            double* out_n4, int64_t n_points, void* stream);
+int lmc_transform_homog_f32(const float* pts_n4, const double* T_host, int32_t order,
+                            float* out_n4, int64_t n_points, void* stream);
+
+/*
  *  LivoxLVXWriter.write_compatible_lvx, replaces LMC:58-250: the complete LVX v1.1 file
  * image -- 88-byte preamble, per frame a 24-byte header and ceil(n/96) packages of 22-byte header +
  * 96 x 14-byte records (tail zero-padded) -- built on the device from the RAW points (LMC:977), with

@@ -13,6 +13,7 @@ LVX_TYPE2_OF_INPUT, LVX2_OF_OUTPUT = 0, 1
 LVXCS_LVX2, LVXCS_LEGACY = 0, 1
 LVXCS_PREFIX_MAX = 96
 TEXT_MAX_COLS = 6
+HOMOG_BATCH, HOMOG_SINGLE = 0, 1
 LVXCS_FRAME_BYTES = {0: 45, 1: 12}
 LAS_INTENSITY_UNIT, LAS_INTENSITY_RAW = 0, 1
 PATH_DIRECT, PATH_AUTO, PATH_TMA = 0, 1, 2
@@ -59,6 +60,8 @@ _SIGNATURES = {
     "lmc_quantize_f32": ([vp, i64, vp, vp], ctypes.c_int),
     "lmc_lvx_v11_build_f64": ([vp, vp, vp, vp, vp, vp, i64, i32, i64, vp, vp], ctypes.c_int),
     "lmc_lvx_v11_build_f32": ([vp, vp, vp, vp, vp, vp, i64, i32, i64, vp, vp], ctypes.c_int),
+    "lmc_transform_homog_f64": ([vp, vp, i32, vp, i64, vp], ctypes.c_int),
+    "lmc_transform_homog_f32": ([vp, vp, i32, vp, i64, vp], ctypes.c_int),
     "lmc_lvx_cs_build_f64": ([vp, vp, vp, vp, vp, i32, i32, vp, i64, i32, i64, vp, vp], ctypes.c_int),
     "lmc_lvx_cs_build_f32": ([vp, vp, vp, vp, vp, i32, i32, vp, i64, i32, i64, vp, vp], ctypes.c_int),
     "lmc_pcd_ascii_size_f64": ([vp, i64, vp, vp], ctypes.c_int),

@@ -6,16 +6,19 @@ A 4x4 homogeneous transform applied to (n,3) points is the Mode A kernel with th
 [T[:3,:3] row-major | T[:3,3]]: the reference's ``(T @ homog.T).T`` runs through dgemm as
 fma(T3,1, fma(T2,z, fma(T1,y, T0*x))) and fma(t,1,acc) == acc + t, so the result is bit-identical
 (golden ``coord_chain.npz``) for n >= 2 points; a single point goes through a 4-term gemv in the
-reference whose summation order differs, so that one case agrees to 1 ulp instead.  The 4x4 matrices themselves are tiny host-side bookkeeping built
-with the same NumPy calls as CS:176-212.
+reference, (T0*x + T2*z) + (T1*y + T3) with unfused products -- ``lmc_transform_homog_*`` implements
+both orders, so the per-point calls of ``_transform_coordinates`` (CS:2107-2163) are reproduced bit
+for bit as well (``transform_frames``).  The 4x4 matrices themselves are tiny host-side bookkeeping
+built with the same NumPy calls as CS:176-212.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
 
+from . import _capi as C
 from . import ops
 
 
@@ -75,7 +78,8 @@ class CoordinateTransformer:
         return T
 
     def transform_points(self, points: np.ndarray, from_frame: str, to_frame: str) -> np.ndarray:
-        """CS:214-233: (n,3) -> (n,3) in the target frame; unknown pair -> points returned unchanged."""
+        """CS:214-233: (n,3) -> (n,3) in the target frame; unknown pair -> points returned unchanged.
+        n == 1 reproduces the reference's single-point (gemv) summation order, n >= 2 the dgemm order."""
         if (from_frame, to_frame) not in self.transformations:
             return points
         points = np.asarray(points, np.float64)
@@ -83,7 +87,45 @@ class CoordinateTransformer:
         if n == 0:
             return points[:, :3].copy()
         p4 = np.zeros((n, 4)); p4[:, :3] = points[:, :3]
-        pose = pose_rows_from_matrices(self.transformations[(from_frame, to_frame)])
-        d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)   # noqa: E731
-        out, _ = ops.align_rigid(d(p4), torch.tensor([0, n], dtype=torch.int64, device=self.device), d(pose))
+        d = torch.from_numpy(p4).to(self.device)
+        out = ops.transform_homog(d, self.transformations[(from_frame, to_frame)], C.HOMOG_SINGLE if n == 1 else C.HOMOG_BATCH)
         return out.cpu().numpy()[:, :3]
+
+    # -- batched CS:2107-2163 (_transform_coordinates) ---------------------------------------------
+    def transform_frames(self, frames_data: List[Dict], target_system: str, utm_offsets: Optional[np.ndarray] = None) -> List[Dict]:
+        """All frames in one device call.  The reference transforms ONE point per ``transform_points`` call
+        (CS:2117-2138), so the single-point summation order applies to every point.  For the UTM target
+        the reference adds a per-frame ``[utm_x, utm_y, 0]`` taken from the ``utm`` package (CS:2122-2131);
+        that package is not a dependency here, so the caller passes the (F,2) easting / northing per frame
+        (``utm_offsets``; None = what the reference does when ``utm`` is missing: points unchanged).
+        Frames hold ``List[LiDARPoint]``; returns new frame dicts with ``'coordinate_system'`` set."""
+        from .compensator import LiDARPoint
+        counts = np.array([len(f['points']) for f in frames_data], np.int64)
+        off = np.zeros(len(frames_data) + 1, np.int64)
+        np.cumsum(counts, out=off[1:])
+        allp = [p for f in frames_data for p in f['points']]
+        xyz = np.zeros((len(allp), 4), np.float64)
+        if allp:
+            xyz[:, :3] = [(p.x, p.y, p.z) for p in allp]
+        if target_system == CoordinateSystem.UTM:
+            if utm_offsets is not None and len(allp):
+                o = np.asarray(utm_offsets, np.float64).reshape(len(frames_data), 2)
+                fr = np.repeat(np.arange(len(frames_data)), counts)
+                pose = np.zeros((len(frames_data), 12)); pose[:, [0, 4, 8]] = 1.0; pose[:, 9:11] = o
+                dd = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)   # noqa: E731
+                out, _ = ops.align_rigid(dd(xyz), dd(off), dd(pose))       # 1*x (+0*y +0*z) + utm: exactly point + offset
+                xyz = out.cpu().numpy()
+                del fr
+        elif len(allp):
+            key = (CoordinateSystem.SENSOR, target_system)
+            if key in self.transformations:                               # unknown pair: unchanged (CS:216-218)
+                xyz = ops.transform_homog(torch.from_numpy(xyz).to(self.device), self.transformations[key], C.HOMOG_SINGLE).cpu().numpy()
+        res = []
+        for i, f in enumerate(frames_data):
+            o = xyz[off[i]:off[i + 1]]
+            g = f.copy()
+            g['points'] = [LiDARPoint(x=r[0], y=r[1], z=r[2], intensity=p.intensity, timestamp=p.timestamp, ring=p.ring, tag=p.tag)
+                           for r, p in zip(o, f['points'])]
+            g['coordinate_system'] = target_system
+            res.append(g)
+        return res

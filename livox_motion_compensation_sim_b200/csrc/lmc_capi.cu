@@ -20,6 +20,7 @@ cudaError_t launch_scan_emit(const double* env, int64_t M, const double* pos, co
 cudaError_t launch_las_pf3(bool f64, const LasParams& L, cudaStream_t st);
 cudaError_t launch_lvx_v11(bool f64, const void* pts, const int64_t* frame_off, const int64_t* frame_pos, const double* frame_time,
                            const int64_t* frame_id, uint8_t* out, int32_t n_frames, int64_t max_frame_points, uint32_t* status, cudaStream_t st);
+cudaError_t launch_homog(bool f64, const void* in, const double* T_host, int32_t order, void* out, int64_t n, cudaStream_t st);
 cudaError_t launch_text_size(bool f64, const void* rows, int64_t n, int32_t n_cols, int32_t row_stride, const int32_t* col, const int32_t* dec,
                              uint8_t sep, int64_t* tile_off, cudaStream_t st);
 cudaError_t launch_text_write(bool f64, const void* rows, int64_t n, int32_t n_cols, int32_t row_stride, const int32_t* col, const int32_t* dec,
@@ -249,6 +250,22 @@ int lmc_lvx_v11_build_f32(const float* pts_n4, const int64_t* frame_off, const i
                           const int64_t* frame_id, uint8_t* file_out, int64_t n_points, int32_t n_frames, int64_t max_frame_points,
                           uint32_t* status, void* stream) {
     return lvx_build(false, pts_n4, frame_off, frame_pos, frame_time, frame_id, file_out, n_points, n_frames, max_frame_points, status, stream);
+}
+
+static int homog(bool f64, const void* pts, const double* T, int32_t order, void* out, int64_t n, void* stream) {
+    int rc = check_device();
+    if (rc != LMC_OK) return rc;
+    if (order != LMC_HOMOG_BATCH && order != LMC_HOMOG_SINGLE) return fail(LMC_ERR_INVALID, "order must be LMC_HOMOG_BATCH or LMC_HOMOG_SINGLE");
+    if (n < 0 || !T || (n > 0 && (!pts || !out))) return fail(LMC_ERR_INVALID, "bad argument");
+    if (!aligned32(pts) || !aligned32(out)) return fail(LMC_ERR_ALIGN, "point buffers must be 32-byte aligned");
+    cudaError_t e = lmc::launch_homog(f64, pts, T, order, out, n, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_homog");
+}
+int lmc_transform_homog_f64(const double* pts_n4, const double* T_host, int32_t order, double* out_n4, int64_t n_points, void* stream) {
+    return homog(true, pts_n4, T_host, order, out_n4, n_points, stream);
+}
+int lmc_transform_homog_f32(const float* pts_n4, const double* T_host, int32_t order, float* out_n4, int64_t n_points, void* stream) {
+    return homog(false, pts_n4, T_host, order, out_n4, n_points, stream);
 }
 
 static int lvx_cs_build(bool f64, const void* pts, const uint8_t* tag, const int64_t* frame_off, const uint64_t* frame_ts,

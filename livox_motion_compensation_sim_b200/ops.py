@@ -196,6 +196,19 @@ def quantize(pts: torch.Tensor, export: ExportSpec) -> ExportBuffers:
     return bufs
 
 
+def transform_homog(pts: torch.Tensor, T, order: int = C.HOMOG_BATCH, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(N3) CS:214-233: one 4x4 homogeneous matrix T (host array) over (n,4) points; order = _capi.HOMOG_BATCH
+    (the reference call on n >= 2 points) or HOMOG_SINGLE (the call on one point, CS:2136-2138)."""
+    import numpy as np
+    f64 = _layout(pts)
+    Th = np.ascontiguousarray(np.asarray(T, np.float64).reshape(4, 4))
+    if out is None:
+        out = torch.empty_like(pts)
+    fn = C.lib().lmc_transform_homog_f64 if f64 else C.lib().lmc_transform_homog_f32
+    C.check(fn(_req(pts, pts.dtype, "pts", (4,)), Th.ctypes.data, int(order), _req(out, pts.dtype, "out", (4,)), pts.shape[0], _stream_ptr()))
+    return out
+
+
 def build_lvx_v11(pts: torch.Tensor, frame_off: torch.Tensor, frame_pos: torch.Tensor, frame_time: torch.Tensor,
                   frame_id: torch.Tensor, max_frame_points: int):
     """(N1) LMC:58-250 on the device: RAW points -> the complete LVX v1.1 file image (uint8 tensor).

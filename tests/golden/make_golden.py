@@ -348,13 +348,41 @@ def text_rows_fixture(CS, manifest):
                                  csv_sha256=sha(np.frombuffer(csv, np.uint8)))
 
 
+def coord_frames_fixture(CS, manifest):
+    """(N3) Reference LiDARMotionSimulator._transform_coordinates (CS:2107-2163): every point goes through
+    transform_points as a (1,3) array.  Called unbound with a stub self (the method only touches
+    self.coordinate_transformer); targets 'vehicle' (default) and 'local' (user-set), ragged frames."""
+    rng = np.random.default_rng(2718)
+    ct = CS.CoordinateTransformer()
+    ct.set_transformation(CS.CoordinateSystem.SENSOR, CS.CoordinateSystem.LOCAL, [105.25, -37.5, 2.125], [0.013, -0.021, 2.3])
+    stub = types.SimpleNamespace(coordinate_transformer=ct)
+    counts = [40, 0, 1, 300]
+    frames, pts = [], []
+    for i, n in enumerate(counts):
+        xyz = rng.uniform(-90, 90, (n, 3))
+        frames.append({'points': [CS.LiDARPoint(x=float(a[0]), y=float(a[1]), z=float(a[2]), intensity=k % 256, timestamp=i * 10 ** 8 + k,
+                                                ring=k % 16, tag=k % 3) for k, a in enumerate(xyz)], 'timestamp': i * 10 ** 8})
+        pts.append(xyz)
+    out = {}
+    for target in [CS.CoordinateSystem.VEHICLE, CS.CoordinateSystem.LOCAL]:
+        res = CS.LiDARMotionSimulator._transform_coordinates(stub, frames, target, [])
+        assert all(r['coordinate_system'] == target for r in res)
+        out[target] = np.array([[p.x, p.y, p.z] for r in res for p in r['points']], np.float64)
+    off = np.zeros(len(counts) + 1, np.int64); np.cumsum(counts, out=off[1:])
+    np.savez_compressed(os.path.join(HERE, 'coord_frames.npz'), pts=np.vstack(pts), frame_off=off, out_vehicle=out['vehicle'], out_local=out['local'],
+                        T_local=ct.transformations[(CS.CoordinateSystem.SENSOR, CS.CoordinateSystem.LOCAL)],
+                        T_vehicle=ct.transformations[(CS.CoordinateSystem.SENSOR, CS.CoordinateSystem.VEHICLE)])
+    manifest['coord_frames'] = dict(points=int(off[-1]), vehicle_sha256=sha(out['vehicle']), local_sha256=sha(out['local']))
+
+
 def main():
     LMC, CS = import_reference()
     if len(sys.argv) > 2 and sys.argv[1] == '--only':          # add / refresh single fixtures, keep the rest of the manifest
         with open(os.path.join(HERE, 'MANIFEST.json')) as f:
             manifest = json.load(f)
         for name in sys.argv[2:]:
-            {'lvx_cs': lambda: lvx_cs_fixture(CS, manifest), 'text_rows': lambda: text_rows_fixture(CS, manifest)}[name]()
+            {'lvx_cs': lambda: lvx_cs_fixture(CS, manifest), 'text_rows': lambda: text_rows_fixture(CS, manifest),
+             'coord_frames': lambda: coord_frames_fixture(CS, manifest)}[name]()
         with open(os.path.join(HERE, 'MANIFEST.json'), 'w') as f:
             json.dump(manifest, f, indent=1, sort_keys=True)
         return
@@ -374,6 +402,7 @@ def main():
     pcd_fixture(LMC, manifest)
     lvx_cs_fixture(CS, manifest)
     text_rows_fixture(CS, manifest)
+    coord_frames_fixture(CS, manifest)
     with open(os.path.join(HERE, 'MANIFEST.json'), 'w') as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     print('wrote', sorted(os.listdir(HERE)))

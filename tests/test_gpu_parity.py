@@ -524,6 +524,54 @@ def test_text_rows_random_formats(f64):
     assert e.numel() == 0
 
 
+def test_transform_frames_vs_reference(golden):
+    """(N3) batched _transform_coordinates (CS:2107-2163) == the reference's per-point calls, bit for bit; UTM
+    target = per-frame offset add; unknown target = unchanged."""
+    from livox_motion_compensation_sim_b200 import LiDARPoint
+    from livox_motion_compensation_sim_b200.coords import CoordinateTransformer, CoordinateSystem
+    g = golden("coord_frames.npz")
+    off = g['frame_off']
+    frames = [{'points': [LiDARPoint(float(p[0]), float(p[1]), float(p[2]), k % 256, k, k % 16, k % 3) for k, p in enumerate(g['pts'][off[i]:off[i + 1]])],
+               'timestamp': i * 10 ** 8} for i in range(len(off) - 1)]
+    ct = CoordinateTransformer()
+    ct.set_transformation(CoordinateSystem.SENSOR, CoordinateSystem.LOCAL, [105.25, -37.5, 2.125], [0.013, -0.021, 2.3])
+    assert np.array_equal(ct.transformations[(CoordinateSystem.SENSOR, CoordinateSystem.LOCAL)], g['T_local'])
+    xyz = lambda res: np.array([[p.x, p.y, p.z] for r in res for p in r['points']], np.float64).reshape(-1, 3)   # noqa: E731
+    for k in ("vehicle", "local"):
+        res = ct.transform_frames(frames, k)
+        assert [len(r['points']) for r in res] == list(np.diff(off)) and all(r['coordinate_system'] == k for r in res)
+        assert np.array_equal(xyz(res), g['out_' + k])
+        assert res[0]['points'][3].intensity == 3 and res[0]['points'][3].tag == 0
+    # one point through transform_points: same single-point order
+    assert np.array_equal(ct.transform_points(g['pts'][7:8], "sensor", "local"), g['out_local'][7:8])
+    # UTM: offsets per frame, or untouched without them (utm package absent, CS:2133-2134)
+    assert np.array_equal(xyz(ct.transform_frames(frames, "utm")), g['pts'])
+    o = np.array([[500000.25, 4649776.5], [1.0, 2.0], [-3.5, 7.25], [448251.125, 5411932.75]])
+    want = g['pts'] + np.column_stack([np.repeat(o, np.diff(off), axis=0), np.zeros(off[-1])])
+    assert np.array_equal(xyz(ct.transform_frames(frames, "utm", utm_offsets=o)), want)
+    assert np.array_equal(xyz(ct.transform_frames(frames, "wgs84")), g['pts'])
+
+
+@pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
+def test_transform_homog_orders(f64):
+    rng = np.random.default_rng(5)
+    n = 100_001
+    p = rng.uniform(-90, 90, (n, 4))
+    if not f64:
+        p = p.astype(np.float32).astype(np.float64)
+    T = np.eye(4); T[:3, :4] = rng.normal(size=(3, 4))
+    t = dev(p if f64 else p.astype(np.float32))
+    for order, single in [(C.HOMOG_BATCH, False), (C.HOMOG_SINGLE, True)]:
+        got = ops.transform_homog(t, T, order).cpu().numpy()
+        want = orc.transform_points_np(T, p, single=single)
+        if f64:
+            assert np.array_equal(got[:, :3], want) and np.array_equal(got[:, 3], p[:, 3])
+        else:
+            assert np.array_equal(got[:, :3], want.astype(np.float32)) and np.array_equal(got[:, 3], p[:, 3].astype(np.float32))
+    with pytest.raises(C.LmcError):
+        ops.transform_homog(t, T, 7)
+
+
 def test_motion_compensator_list_api(golden):
     from livox_motion_compensation_sim_b200 import MotionCompensator, LiDARPoint, IMUData
     g = golden("modeb.npz")
