@@ -255,9 +255,13 @@ class LiDARMotionSimulator:
     def save_results(self, results, output_dir='lidar_simulation_output'):
         """Writes the reference's hot-path outputs under the reference's names:
         aligned_scans_pcd/aligned_frame_%04d.pcd, raw_scans_pcd/frame_%04d.pcd, merged_aligned.pcd,
-        merged_raw_overlapped.pcd, merged_aligned.las, lidar_data.lvx."""
+        merged_raw_overlapped.pcd, merged_aligned.las, lidar_data.lvx -- plus the two small tables
+        motion_data.csv / trajectory.csv (LMC:866-868, 916-927; plain pandas, as in the reference)."""
         os.makedirs(output_dir, exist_ok=True)
         print(f"Saving results to {output_dir}...")
+        import pandas as pd
+        if results.get('motion_data') is not None:
+            pd.DataFrame(results['motion_data']).to_csv(os.path.join(output_dir, 'motion_data.csv'), index=False)
         pcd_dir = os.path.join(output_dir, 'raw_scans_pcd'); os.makedirs(pcd_dir, exist_ok=True)
         for scan in results['raw_scans']:
             self.save_pcd(scan['points_local'], os.path.join(pcd_dir, f'frame_{scan["frame_id"]:04d}.pcd'))
@@ -281,6 +285,11 @@ class LiDARMotionSimulator:
             print("LVX formats saved successfully")
         except Exception as e:                                       # LMC:913-914
             print(f"Could not save LVX formats: {e}")
+        traj = results.get('trajectory')
+        if traj is not None and all(k in traj for k in ('time', 'position', 'position_gps')):
+            pd.DataFrame({'time': traj['time'], 'x': traj['position'][:, 0], 'y': traj['position'][:, 1], 'z': traj['position'][:, 2],
+                          'x_gps': traj['position_gps'][:, 0], 'y_gps': traj['position_gps'][:, 1],
+                          'z_gps': traj['position_gps'][:, 2]}).to_csv(os.path.join(output_dir, 'trajectory.csv'), index=False)
         print("Results saved successfully!")
         return output_dir
 

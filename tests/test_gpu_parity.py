@@ -377,7 +377,7 @@ def test_simulator_batched_alignment_and_outputs(golden, tmp_path):
     rec, _ = sim.quantize_lvx(results)
     assert np.array_equal(rec, orc.C.quantize_lvx_type2(g['raw'])[0])
     d = sim.save_results(results, str(tmp_path / "out"))
-    for f in ["merged_aligned.pcd", "merged_raw_overlapped.pcd", "lidar_data.lvx", "merged_aligned.las",
+    for f in ["merged_aligned.pcd", "merged_raw_overlapped.pcd", "lidar_data.lvx", "merged_aligned.las", "motion_data.csv",
               "aligned_scans_pcd/aligned_frame_0000.pcd", "raw_scans_pcd/frame_0000.pcd"]:
         assert os.path.exists(os.path.join(d, f)), f
     first = open(os.path.join(d, "aligned_scans_pcd/aligned_frame_0000.pcd")).read().splitlines()
