@@ -375,6 +375,40 @@ def coord_frames_fixture(CS, manifest):
     manifest['coord_frames'] = dict(points=int(off[-1]), vehicle_sha256=sha(out['vehicle']), local_sha256=sha(out['local']))
 
 
+def config2_fixture(CS, manifest):
+    """BASELINE configs[2] -- parking_detailed frames, per-point timestamps, deskew against a 200 Hz IMU stream:
+    raw C3 frames (already the LMC reference's output, lmc_C3.npz) subsampled to 600 points each, timestamps
+    frame_ns + i * (frame_period / n_f), the reference's own IMUSimulator on a 30 s circular
+    trajectory (6000 samples), pushed through the reference MotionCompensator.compensate_point_cloud."""
+    g = np.load(os.path.join(HERE, 'lmc_C3.npz'))
+    off = g['frame_off']
+    cfg = {'random_seed': 42, 'duration': 30.0, 'trajectory_type': 'circular', 'max_speed': 5.0}
+    tg = CS.TrajectoryGenerator('circular', seed=42)
+    traj = tg.generate_trajectory(30.0, dt=0.1, max_speed=5.0)
+    imu = CS.IMUSimulator(cfg).simulate_imu_data(traj, 30.0)
+    imu_ts = np.array([s.timestamp for s in imu], np.int64)
+    imu_gyro = np.array([[s.gyro_x, s.gyro_y, s.gyro_z] for s in imu], np.float64)
+    mc = CS.MotionCompensator({'enable_motion_compensation': True})
+    period = 50_000_000                                     # 20 fps
+    pts_all, ts_all, out_all, starts, counts = [], [], [], [], []
+    for i in [0, 3, 7]:
+        raw = g['raw'][off[i]:off[i + 1]]
+        raw = raw[::max(1, len(raw) // 600)][:600]
+        n = len(raw)
+        fs = int(float(g['frame_t_all'][g['frame_ids'][i]]) * 1e9)
+        ts = fs + np.arange(n, dtype=np.int64) * (period // n)
+        pts = [CS.LiDARPoint(x=float(p[0]), y=float(p[1]), z=float(p[2]), intensity=float(p[3]), timestamp=int(t), ring=k % 16, tag=0)
+               for k, (p, t) in enumerate(zip(raw, ts))]
+        comp = mc.compensate_point_cloud(pts, imu, fs, period)
+        pts_all.append(raw); ts_all.append(ts); starts.append(fs); counts.append(n)
+        out_all.append(np.array([[p.x, p.y, p.z, p.intensity] for p in comp], np.float64))
+    o = np.zeros(len(counts) + 1, np.int64); np.cumsum(counts, out=o[1:])
+    np.savez_compressed(os.path.join(HERE, 'config2.npz'), pts=np.vstack(pts_all), ts=np.concatenate(ts_all), frame_off=o,
+                        frame_start=np.array(starts, np.int64), imu_ts=imu_ts, imu_gyro=imu_gyro, compensated=np.vstack(out_all),
+                        traj_time=g['traj_time'], traj_position_gps=g['traj_position_gps'], traj_orientation_imu=g['traj_orientation_imu'])
+    manifest['config2'] = dict(points=int(o[-1]), imu_samples=len(imu), compensated_sha256=sha(np.vstack(out_all)))
+
+
 def main():
     LMC, CS = import_reference()
     if len(sys.argv) > 2 and sys.argv[1] == '--only':          # add / refresh single fixtures, keep the rest of the manifest
@@ -382,7 +416,8 @@ def main():
             manifest = json.load(f)
         for name in sys.argv[2:]:
             {'lvx_cs': lambda: lvx_cs_fixture(CS, manifest), 'text_rows': lambda: text_rows_fixture(CS, manifest),
-             'coord_frames': lambda: coord_frames_fixture(CS, manifest)}[name]()
+             'coord_frames': lambda: coord_frames_fixture(CS, manifest),
+             'config2': lambda: config2_fixture(CS, manifest)}[name]()
         with open(os.path.join(HERE, 'MANIFEST.json'), 'w') as f:
             json.dump(manifest, f, indent=1, sort_keys=True)
         return
@@ -403,6 +438,7 @@ def main():
     lvx_cs_fixture(CS, manifest)
     text_rows_fixture(CS, manifest)
     coord_frames_fixture(CS, manifest)
+    config2_fixture(CS, manifest)
     with open(os.path.join(HERE, 'MANIFEST.json'), 'w') as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     print('wrote', sorted(os.listdir(HERE)))

@@ -295,6 +295,38 @@ def test_mode_b_synthetic_vs_oracle(f64, path):
     assert np.array_equal(b.las_intensity.cpu().numpy().view(np.uint16), I)
 
 
+def test_config2_parking_detailed_per_point_deskew(golden, path):
+    """BASELINE configs[2]: parking_detailed (C3) frames with per-point timestamps against 200 Hz streams.
+    Mode B: the reference MotionCompensator on its own 200 Hz IMU stream (golden config2.npz).
+    Mode C: the 5 Hz GPS/IMU trajectory of the same run resampled to 200 Hz (SciPy Slerp + lerp on the host),
+    per-point bracket search + SLERP + lerp on the device vs the independent SciPy oracle; LVX / LAS exact."""
+    from scipy.spatial.transform import Rotation, Slerp
+    g = golden("config2.npz")
+    out, _ = ops.deskew_gyro(dev(g['pts']), dev(g['ts']), dev(g['frame_off']), dev(g['frame_start']), dev(g['imu_ts']), dev(g['imu_gyro']))
+    err = np.abs(out.cpu().numpy() - g['compensated']).max()
+    print(f"config2 mode B: max |d| = {err:.3e} m")
+    assert err <= 1e-11
+    # 200 Hz pose samples from the run's trajectory (LMC:363-426 samples it at 5 Hz)
+    tt = g['traj_time']
+    s_t = np.arange(0.0, tt[-1], 0.005)
+    s_ts = np.round(s_t * 1e9).astype(np.int64)
+    quat = Slerp(tt, Rotation.from_euler('xyz', g['traj_orientation_imu']))(s_t).as_quat()
+    pos = np.stack([np.interp(s_t, tt, g['traj_position_gps'][:, c]) for c in range(3)], axis=1)
+    seg = FR.slerp_segment_table(quat, pos, s_ts)
+    assert np.array_equal(seg, orc.slerp_segment_table(quat, pos, s_ts))
+    spec = ops.ExportSpec(lvx=True, lvx_mode=C.LVX_TYPE2_OF_INPUT, las=True, las_scale=(0.01,) * 3)
+    outc, b = ops.deskew_slerp(dev(g['pts']), dev(g['ts']), dev(g['frame_off']), dev(g['frame_start']), dev(s_ts), dev(seg), export=spec)
+    got = outc.cpu().numpy()
+    want = orc.C.deskew_slerp_f64(g['pts'], g['ts'], g['frame_off'], s_ts, seg)
+    ref2 = orc.slerp_deskew_scipy(g['pts'], g['ts'], s_ts, quat, pos)
+    print(f"config2 mode C: vs C oracle {np.abs(got - want).max():.3e} m, vs SciPy {np.abs(got - ref2).max():.3e} m")
+    assert np.abs(got - want).max() <= 1e-10 and np.abs(got - ref2).max() <= 1e-9
+    assert np.array_equal(b.lvx14.cpu().numpy(), orc.C.quantize_lvx_type2(g['pts'])[0])
+    X, Y, Z, I, _ = orc.C.quantize_las(want, [0.01] * 3, [0.0] * 3, 0)
+    assert np.array_equal(b.las_x.cpu().numpy(), X) and np.array_equal(b.las_y.cpu().numpy(), Y) and np.array_equal(b.las_z.cpu().numpy(), Z)
+    assert np.array_equal(b.las_intensity.cpu().numpy().view(np.uint16), I)
+
+
 # ------------------------------------------------------------------------------------------
 # Mode C (parity unpinned by the reference): C oracle, scipy Slerp oracle, hold-next identity
 # ------------------------------------------------------------------------------------------
