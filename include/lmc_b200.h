@@ -294,8 +294,13 @@ int lmc_las_pf3_build_f32(const float* pts_n4, const double* gps_time, int64_t n
  * once: range cull (d2 <= range_max^2), world->sensor rotation R_f^T (env - pos_f), FOV cull, order-
  * preserving compaction, systematic subsample to max_points.  Two calls, because the reference draws its
  * noise from the seeded global NumPy RNG sized by each frame's point count (LMC:765-768):
- *   lmc_scan_mark  -> flags (n_frames x n_env bytes), tile_off (n_frames x (ceil(n_env/LMC_SCAN_TILE)+1)
- *                     int32 scratch) and n_visible[f];
+ *   lmc_scan_mark  -> flags (n_frames x n_env bytes: bit 0 visible, bit 1 UNCERTAIN), tile_off
+ *                     (n_frames x (ceil(n_env/LMC_SCAN_TILE)+1) int32 scratch), n_visible[f] and
+ *                     *n_uncertain.  A point is uncertain when its |azimuth| or |elevation| lies within
+ *                     edge_eps_deg of the FOV limit: device atan2 / asin may differ from the host libm
+ *                     by a few ulp there.  When *n_uncertain > 0 the caller re-decides those points with
+ *                     the reference's NumPy expression (LMC:735-745), writes 0 / 1 into their flags and
+ *                     calls lmc_scan_recount, so every decision is the reference's;
  *   (host: kept[f] = n_visible[f] if <= max_points else min(ceil(n / (n // max_points)), max_points);
  *          frame_off = cumsum(kept); noise = np.random.normal(0, std, (sum kept, 3)) or NULL)
  *   lmc_scan_emit  -> raw_out (sum kept, 4): rotated xyz (+ noise) and the environment intensity,
@@ -305,7 +310,10 @@ int lmc_las_pf3_build_f32(const float* pts_n4, const double* gps_time, int64_t n
 #define LMC_SCAN_TILE 256
 int lmc_scan_mark(const double* env_m4, int64_t n_env, const double* pos_f3, const double* R_f9, int32_t n_frames,
                   double range_max_sq, double fov_h_half_deg, double fov_v_half_deg, double range_min,
-                  uint8_t* flags, int32_t* tile_off, int32_t* n_visible, void* stream);
+                  double edge_eps_deg, uint8_t* flags, int32_t* tile_off, int32_t* n_visible,
+                  int32_t* n_uncertain, void* stream);
+int lmc_scan_recount(const uint8_t* flags, int64_t n_env, int32_t n_frames, int32_t* tile_off,
+                     int32_t* n_visible, void* stream);
 int lmc_scan_emit(const double* env_m4, int64_t n_env, const double* pos_f3, const double* R_f9, int32_t n_frames,
                   double range_max_sq, const uint8_t* flags, const int32_t* tile_off, const int32_t* n_visible,
                   const int64_t* frame_off, int32_t max_points, const double* noise_n3, double* raw_out_n4,

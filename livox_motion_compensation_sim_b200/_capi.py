@@ -74,7 +74,8 @@ _SIGNATURES = {
     "lmc_text_rows_write_f32": ([vp, i64, i32, i32, vp, vp, i32, vp, vp, vp, vp], ctypes.c_int),
     "lmc_las_pf3_build_f64": ([vp, vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, vp], ctypes.c_int),
     "lmc_las_pf3_build_f32": ([vp, vp, i64, vp, vp, i32, i32, i32, vp, vp, vp, vp], ctypes.c_int),
-    "lmc_scan_mark": ([vp, i64, vp, vp, i32, f64, f64, f64, f64, vp, vp, vp, vp], ctypes.c_int),
+    "lmc_scan_mark": ([vp, i64, vp, vp, i32, f64, f64, f64, f64, f64, vp, vp, vp, vp, vp], ctypes.c_int),
+    "lmc_scan_recount": ([vp, i64, i32, vp, vp, vp], ctypes.c_int),
     "lmc_scan_emit": ([vp, i64, vp, vp, i32, f64, vp, vp, vp, vp, i32, vp, vp, vp], ctypes.c_int),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

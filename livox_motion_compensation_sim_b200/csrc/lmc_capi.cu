@@ -13,7 +13,8 @@ cudaError_t launch_pose_lookup(const double*, int64_t, const double*, const doub
 cudaError_t launch_pcd_size(bool f64, const void* pts, int64_t n, int64_t* tile_off, cudaStream_t st);
 cudaError_t launch_pcd_write(bool f64, const void* pts, int64_t n, const int64_t* tile_off, uint8_t* out, uint32_t* status, cudaStream_t st);
 cudaError_t launch_scan_mark(const double* env, int64_t M, const double* pos, const double* R, int32_t F, double rmax2, double fh, double fv,
-                             double rmin, uint8_t* flags, int32_t* tile_off, int32_t* n_visible, cudaStream_t st);
+                             double rmin, double edge_eps, uint8_t* flags, int32_t* tile_off, int32_t* n_visible, int32_t* n_uncertain, cudaStream_t st);
+cudaError_t launch_scan_recount(const uint8_t* flags, int64_t M, int32_t F, int32_t* tile_off, int32_t* n_visible, cudaStream_t st);
 cudaError_t launch_scan_emit(const double* env, int64_t M, const double* pos, const double* R, int32_t F, double rmax2, const uint8_t* flags,
                              const int32_t* tile_off, const int32_t* n_visible, const int64_t* frame_off, int32_t max_points,
                              const double* noise, double* out, cudaStream_t st);
@@ -388,17 +389,26 @@ int lmc_las_pf3_build_f32(const float* pts_n4, const double* gps_time, int64_t n
 }
 
 int lmc_scan_mark(const double* env_m4, int64_t n_env, const double* pos_f3, const double* R_f9, int32_t n_frames,
-                  double range_max_sq, double fov_h_half_deg, double fov_v_half_deg, double range_min,
-                  uint8_t* flags, int32_t* tile_off, int32_t* n_visible, void* stream) {
+                  double range_max_sq, double fov_h_half_deg, double fov_v_half_deg, double range_min, double edge_eps_deg,
+                  uint8_t* flags, int32_t* tile_off, int32_t* n_visible, int32_t* n_uncertain, void* stream) {
     int rc = check_device();
     if (rc != LMC_OK) return rc;
-    if (n_env < 0 || n_frames < 0) return fail(LMC_ERR_INVALID, "negative size");
+    if (n_env < 0 || n_frames < 0 || !(edge_eps_deg >= 0.0)) return fail(LMC_ERR_INVALID, "negative size / edge_eps");
     if (n_frames == 0) return LMC_OK;
     if (!pos_f3 || !R_f9 || !tile_off || !n_visible || (n_env > 0 && (!env_m4 || !flags))) return fail(LMC_ERR_INVALID, "NULL argument");
     if (!aligned32(env_m4)) return fail(LMC_ERR_ALIGN, "environment must be 32-byte aligned");
     cudaError_t e = lmc::launch_scan_mark(env_m4, n_env, pos_f3, R_f9, n_frames, range_max_sq, fov_h_half_deg, fov_v_half_deg, range_min,
-                                          flags, tile_off, n_visible, static_cast<cudaStream_t>(stream));
+                                          edge_eps_deg, flags, tile_off, n_visible, n_uncertain, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_scan_mark / k_scan_offsets");
+}
+int lmc_scan_recount(const uint8_t* flags, int64_t n_env, int32_t n_frames, int32_t* tile_off, int32_t* n_visible, void* stream) {
+    int rc = check_device();
+    if (rc != LMC_OK) return rc;
+    if (n_env < 0 || n_frames < 0) return fail(LMC_ERR_INVALID, "negative size");
+    if (n_frames == 0) return LMC_OK;
+    if (!tile_off || !n_visible || (n_env > 0 && !flags)) return fail(LMC_ERR_INVALID, "NULL argument");
+    cudaError_t e = lmc::launch_scan_recount(flags, n_env, n_frames, tile_off, n_visible, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_scan_count / k_scan_offsets");
 }
 int lmc_scan_emit(const double* env_m4, int64_t n_env, const double* pos_f3, const double* R_f9, int32_t n_frames,
                   double range_max_sq, const uint8_t* flags, const int32_t* tile_off, const int32_t* n_visible,

@@ -306,9 +306,30 @@ def build_las_pf3(pts: torch.Tensor, *, scale=(0.01, 0.01, 0.01), offset=(0.0, 0
     return out, status
 
 
+def _redecide_uncertain(env, pos, Rm, flags, fov_h, fov_v, range_min) -> int:
+    """Host re-decision of the points k_scan_mark flagged uncertain (bit 1), with the NumPy calls of LMC:726-745."""
+    import numpy as np
+    fi, pi = torch.nonzero(flags & 2, as_tuple=True)
+    if fi.numel() == 0:
+        return 0
+    e = env[pi][:, :3].cpu().numpy()
+    p = pos[fi].cpu().numpy()
+    R = Rm[fi].cpu().numpy().reshape(-1, 3, 3)
+    rel = e - p
+    d2 = np.sum(rel ** 2, axis=1)
+    rot = np.stack([(R[k].T @ rel[k:k + 1].T).T[0] for k in range(len(rel))])
+    x, y, z = rot[:, 0], rot[:, 1], rot[:, 2]
+    ranges = np.sqrt(d2)
+    azimuth = np.arctan2(y, x) * 180 / np.pi
+    elevation = np.arcsin(np.clip(z / np.maximum(ranges, 1e-6), -1, 1)) * 180 / np.pi
+    vis = (np.abs(azimuth) <= fov_h) & (np.abs(elevation) <= fov_v) & (ranges >= range_min)
+    flags[fi, pi] = torch.from_numpy(vis.astype(np.uint8)).to(flags.device)
+    return int(fi.numel())
+
+
 def scan_frames(env: torch.Tensor, pos: torch.Tensor, Rm: torch.Tensor, *, range_max: float, range_min: float,
                 fov_horizontal: float, fov_vertical: float, points_per_frame: int, noise_std: float, noise_fn=None,
-                max_flag_bytes: int = 1 << 30):
+                max_flag_bytes: int = 1 << 30, edge_eps_deg: float = 1e-9):
     """(N4) LMC:701-770 for every frame at once.  env (M,4) f64, pos (F,3), Rm (F,9) row-major SciPy matrices.
     Returns (raw (N,4) f64 device tensor, frame_off np.int64[F+1]).
 
@@ -316,7 +337,11 @@ def scan_frames(env: torch.Tensor, pos: torch.Tensor, Rm: torch.Tensor, *, range
     ``np.random.normal(0, noise_std, (n, 3))`` from the GLOBAL legacy NumPy RNG, exactly the stream LMC:767
     consumes frame after frame (the legacy generator is a stream: one draw per chunk of frames == the
     reference's per-frame draws).  Frames are processed in chunks so the F x M visibility scratch stays
-    below max_flag_bytes; chunks run in frame order, so the noise stream keeps the reference's order."""
+    below max_flag_bytes; chunks run in frame order, so the noise stream keeps the reference's order.
+
+    Points whose |azimuth| / |elevation| lies within edge_eps_deg of the FOV limit (where a few ulp of device
+    atan2 / asin could decide differently from the host libm) are re-decided on the host with the reference's
+    own NumPy expression (LMC:726-745), so every visibility decision is the reference's."""
     import numpy as np
     M, F = env.shape[0], pos.shape[0]
     tiles = (M + C.SCAN_TILE - 1) // C.SCAN_TILE
@@ -333,10 +358,17 @@ def scan_frames(env: torch.Tensor, pos: torch.Tensor, Rm: torch.Tensor, *, range
         p_c, r_c = pos[f0:f1], Rm[f0:f1]
         flags = torch.empty((nf, max(M, 1)), dtype=torch.uint8, device=dev)
         tile_off = torch.empty((nf, tiles + 1), dtype=torch.int32, device=dev)
-        n_vis = torch.empty(nf, dtype=torch.int32, device=dev)
+        cnt = torch.empty(nf + 1, dtype=torch.int32, device=dev)    # n_visible[nf] | n_uncertain
+        n_vis = cnt[:nf]
         C.check(L.lmc_scan_mark(env.data_ptr(), M, p_c.data_ptr(), r_c.data_ptr(), nf, rmax2, float(fov_horizontal / 2),
-                                float(fov_vertical / 2), float(range_min), flags.data_ptr(), tile_off.data_ptr(), n_vis.data_ptr(), _stream_ptr()))
-        nv = n_vis.cpu().numpy().astype(np.int64)                   # the one sync per chunk: the noise draw is sized by these counts
+                                float(fov_vertical / 2), float(range_min), float(edge_eps_deg), flags.data_ptr(), tile_off.data_ptr(),
+                                n_vis.data_ptr(), cnt[nf:].data_ptr(), _stream_ptr()))
+        cnt_h = cnt.cpu().numpy()                                   # the one sync per chunk: the noise draw is sized by these counts
+        if cnt_h[nf] > 0:                                           # FOV-edge points: the reference's own arithmetic decides
+            _redecide_uncertain(env, p_c, r_c, flags, fov_horizontal / 2, fov_vertical / 2, range_min)
+            C.check(L.lmc_scan_recount(flags.data_ptr(), M, nf, tile_off.data_ptr(), n_vis.data_ptr(), _stream_ptr()))
+            cnt_h = cnt.cpu().numpy()
+        nv = cnt_h[:nf].astype(np.int64)
         step = np.maximum(nv // maxp, 1)
         kept = np.where(nv > maxp, np.minimum((nv + step - 1) // step, maxp), nv)
         off_c = np.zeros(nf + 1, np.int64)

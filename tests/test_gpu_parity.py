@@ -706,6 +706,15 @@ def test_scanner_subsample_and_single_pose():
     np.random.seed(9); r1, o1 = ops.scan_frames(env_d, dev(pos), dev(np.ascontiguousarray(Rm)), **kw)
     np.random.seed(9); r2, o2 = ops.scan_frames(env_d, dev(pos), dev(np.ascontiguousarray(Rm)), max_flag_bytes=2 * len(env), **kw)
     assert np.array_equal(o1, o2) and torch.equal(r1, r2)
+    # a wide uncertainty band sends thousands of points through the host re-decision: same scans
+    seen, orig = [], ops._redecide_uncertain
+    ops._redecide_uncertain = lambda *a: seen.append(orig(*a))
+    try:
+        np.random.seed(9); r3, o3 = ops.scan_frames(env_d, dev(pos), dev(np.ascontiguousarray(Rm)), edge_eps_deg=2.0, **kw)
+    finally:
+        ops._redecide_uncertain = orig
+    assert seen and seen[0] > 1000, seen
+    assert np.array_equal(o1, o3) and torch.equal(r1, r3)
     # with noise: the device path consumes the global RNG exactly like the reference does
     sim2 = LiDARMotionSimulator(dict(cfg, lidar_range_noise=0.02))
     np.random.seed(123); a = sim2.scan_all(env, pos, eul)
