@@ -25,24 +25,18 @@ constexpr int kNumMax     = 1 + 13 + 1 + 6;         // sign + 13 integer digits 
 constexpr int kLineMax    = 4 * kNumMax + 4;        // 3 spaces + newline
 constexpr int kPcdImg     = ((kPcdTile * kLineMax + 32 + 15) / 16) * 16;
 
-struct Num { uint64_t q; uint32_t len; uint32_t kind; };   // kind 0 finite, 1 nan, 2 inf; bit 31 of len-free sign in `neg`
+// One formatted number: integer part, 6 fractional digits as an integer, text length, special-value kind
+struct Num { uint64_t ip; uint32_t fq; uint32_t len; uint32_t kind; bool neg; };   // kind 0 finite, 1 nan, 2 inf
 
-// Q = round_half_even(|v| * 1e6), text length, special-value kind
-__device__ __forceinline__ uint32_t fmt_prepare(double v, uint64_t& q, bool& neg, uint32_t& kind, uint32_t& fl) {
-    const uint64_t bits = (uint64_t)__double_as_longlong(v);
-    neg = bits >> 63;
-    const uint32_t ex = (uint32_t)(bits >> 52) & 0x7ffu;
-    const uint64_t frac = bits & 0xfffffffffffffull;
-    if (ex == 0x7ff) { kind = frac ? 1u : 2u; q = 0; return frac ? 3u : (neg ? 4u : 3u); }   // "nan" | "inf" / "-inf"
-    kind = 0;
-    const uint64_t m = ex ? (frac | (1ull << 52)) : frac;
-    const int e = (ex ? (int)ex : 1) - 1075;
+// Exact Q = round_half_even(|v| * 1e6) through the 73-bit integer product (any magnitude below 9.2e12)
+__device__ __noinline__ uint64_t fmt_q_wide(uint64_t m, int e, uint32_t& fl) {
+    uint64_t q;
     if (e >= 0) {                                    // integer-valued, >= 2^52: beyond the supported magnitude
         fl |= LMC_FLAG_OVERFLOW; q = 9199999999999999999ull;
     } else {
         const int s = -e;
         const unsigned __int128 P = (unsigned __int128)m * 1000000u;
-        if (s >= 127) q = 0;                         // < 2^-54 * 2^73-ish: far below half of the last place
+        if (s >= 127) q = 0;                         // far below half of the last place
         else {
             const unsigned __int128 Qw = P >> s;
             if (Qw > (unsigned __int128)9199999999999999999ull) { fl |= LMC_FLAG_OVERFLOW; q = 9199999999999999999ull; }
@@ -53,30 +47,70 @@ __device__ __forceinline__ uint32_t fmt_prepare(double v, uint64_t& q, bool& neg
             }
         }
     }
-    // digits of the integer part
-    const uint64_t ip = q / 1000000ull;
-    uint32_t nd = 1;
-    for (uint64_t t = ip; t >= 10; t /= 10) ++nd;
-    return (neg ? 1u : 0u) + nd + 7u;
+    return q;
 }
 
-__device__ __forceinline__ int fmt_write(uint8_t* dst, uint64_t q, bool neg, uint32_t kind, uint32_t len) {
-    if (kind) {
+// "%.6f" of v.  Fast path for |v| < 2^43 (every coordinate a LiDAR produces), all in exact FP64 steps:
+//   ip = trunc(|v|), fr = |v| - ip (exact), hi + lo = fr * 1e6 exactly (FMA error term),
+//   q = floor(hi); the tie test t = (hi - q) - 0.5 is exact whenever |t| is small, and |lo| <= ulp(hi)/2
+//   can only decide when t == 0  ->  round-half-even on the exact binary value, as printf does.
+__device__ __forceinline__ Num fmt_prepare(double v, uint32_t& fl) {
+    Num t;
+    const uint64_t bits = (uint64_t)__double_as_longlong(v);
+    t.neg = bits >> 63;
+    t.kind = 0;
+    const double a = fabs(v);
+    if (a < 8796093022208.0) {                       // 2^43
+        uint64_t ip = __double2ull_rz(a);
+        const double fr = __dsub_rn(a, __ull2double_rn(ip));
+        const double hi = __dmul_rn(fr, 1.0e6), lo = __fma_rn(fr, 1.0e6, -hi);
+        uint32_t q = __double2uint_rz(hi);
+        const double d = __dsub_rn(__dsub_rn(hi, __uint2double_rn(q)), 0.5);
+        if (d > 0.0 || (d == 0.0 && (lo > 0.0 || (lo == 0.0 && (q & 1u))))) q += 1;
+        if (q == 1000000u) { q = 0; ip += 1; }
+        t.ip = ip; t.fq = q;
+    } else {
+        const uint32_t ex = (uint32_t)(bits >> 52) & 0x7ffu;
+        const uint64_t frac = bits & 0xfffffffffffffull;
+        t.ip = 0; t.fq = 0;
+        if (ex == 0x7ff) { t.kind = frac ? 1u : 2u; t.len = frac ? 3u : (t.neg ? 4u : 3u); return t; }   // "nan" | "inf" / "-inf"
+        const uint64_t Q = fmt_q_wide(frac | (1ull << 52), (int)ex - 1075, fl);
+        t.ip = Q / 1000000ull; t.fq = (uint32_t)(Q - t.ip * 1000000ull);
+    }
+    uint32_t nd;
+    if (t.ip < 1000000ull) {
+        const uint32_t x = (uint32_t)t.ip;
+        nd = 1u + (x >= 10u) + (x >= 100u) + (x >= 1000u) + (x >= 10000u) + (x >= 100000u);
+    } else {
+        nd = 7;
+        for (uint64_t x = t.ip / 1000000ull; x >= 10; x /= 10) ++nd;
+    }
+    t.len = (t.neg ? 1u : 0u) + nd + 7u;
+    return t;
+}
+
+__device__ __forceinline__ int fmt_write(uint8_t* dst, const Num& t) {
+    if (t.kind) {
         int o = 0;
-        if (kind == 2 && neg) dst[o++] = '-';
-        if (kind == 1) { dst[o] = 'n'; dst[o + 1] = 'a'; dst[o + 2] = 'n'; }
-        else           { dst[o] = 'i'; dst[o + 1] = 'n'; dst[o + 2] = 'f'; }
+        if (t.kind == 2 && t.neg) dst[o++] = '-';
+        if (t.kind == 1) { dst[o] = 'n'; dst[o + 1] = 'a'; dst[o + 2] = 'n'; }
+        else             { dst[o] = 'i'; dst[o + 1] = 'n'; dst[o + 2] = 'f'; }
         return o + 3;
     }
-    uint64_t ip = q / 1000000ull;
-    uint32_t fp = (uint32_t)(q - ip * 1000000ull);
-    int o = (int)len;
+    int o = (int)t.len;
+    uint32_t fp = t.fq;
 #pragma unroll
     for (int k = 0; k < 6; ++k) { dst[--o] = (uint8_t)('0' + fp % 10u); fp /= 10u; }
     dst[--o] = '.';
-    do { dst[--o] = (uint8_t)('0' + (uint32_t)(ip % 10ull)); ip /= 10ull; } while (ip);
-    if (neg) dst[--o] = '-';
-    return (int)len;
+    if (t.ip < 1000000000ull) {                      // 32-bit digit loop
+        uint32_t x = (uint32_t)t.ip;
+        do { dst[--o] = (uint8_t)('0' + x % 10u); x /= 10u; } while (x);
+    } else {
+        uint64_t x = t.ip;
+        do { dst[--o] = (uint8_t)('0' + (uint32_t)(x % 10ull)); x /= 10ull; } while (x);
+    }
+    if (t.neg) dst[--o] = '-';
+    return (int)t.len;
 }
 
 template <bool F64>
@@ -109,7 +143,7 @@ __global__ void __launch_bounds__(kPcdTile) k_pcd_len(const void* __restrict__ p
         load_row<F64>(pts, i, v);
         len = 4;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { uint64_t q; bool neg; uint32_t kind; len += fmt_prepare(v[c], q, neg, kind, fl); }
+        for (int c = 0; c < 4; ++c) len += fmt_prepare(v[c], fl).len;
     }
     uint32_t total;
     block_scan_excl(len, s_warp, total);
@@ -141,21 +175,21 @@ __global__ void __launch_bounds__(kPcdTile) k_pcd_write(const void* __restrict__
     const int64_t i = (int64_t)blockIdx.x * kPcdTile + tid;
     const int64_t dst0 = tile_off[blockIdx.x];
     const int phase = (int)(dst0 & 15);
-    uint64_t q[4]; bool neg[4]; uint32_t kind[4], ln[4];
+    Num t[4];
     uint32_t len = 0, fl = 0;
     if (i < n) {
         double v[4];
         load_row<F64>(pts, i, v);
         len = 4;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { ln[c] = fmt_prepare(v[c], q[c], neg[c], kind[c], fl); len += ln[c]; }
+        for (int c = 0; c < 4; ++c) { t[c] = fmt_prepare(v[c], fl); len += t[c].len; }
     }
     uint32_t total;
     const uint32_t off = block_scan_excl(len, s_warp, total);
     if (i < n) {
         uint8_t* d = s_img + phase + off;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { d += fmt_write(d, q[c], neg[c], kind[c], ln[c]); *d++ = c == 3 ? '\n' : ' '; }
+        for (int c = 0; c < 4; ++c) { d += fmt_write(d, t[c]); *d++ = c == 3 ? '\n' : ' '; }
     }
     __syncthreads();
     uint8_t* g = out + (dst0 - phase);                              // 16-byte aligned
