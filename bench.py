@@ -414,7 +414,14 @@ def main_b200(args):
             cs_bytes = 88 + 45 * fw + 14 * nw
             las_ms = t_ms(lambda: ops.build_las_pf3(raw, scale=(0.001,) * 3, offset=(0.0,) * 3))
             las_bytes = _C.LAS_HEADER_BYTES + _C.LAS_RECORD_BYTES * nw
+            rows5 = torch.cat([raw.double(), torch.arange(nw, device=raw.device, dtype=torch.float64).unsqueeze(1) * 1000.0], dim=1).contiguous()
+            rows5[:, 3] = torch.floor(rows5[:, 3] * 255.0)
+            txt_ms = t_ms(lambda: ops.text_rows(rows5, (0, 1, 2, 3, 4), (6, 6, 6, 0, 0), " "), reps=3)
+            txt_bytes = int(ops.text_rows(rows5, (0, 1, 2, 3, 4), (6, 6, 6, 0, 0), " ")[0].numel())
+            del rows5
             writers = {"sample_points": nw,
+                       "cs_pcd_text": {"points_per_s": nw / (txt_ms * 1e-3), "GBps": (2 * nw * 40 + txt_bytes) / (txt_ms * 1e-3) / 1e9, "text_bytes": txt_bytes,
+                                       "what": "'%.6f %.6f %.6f %.0f %.0f\\n' rows of the (N,5) f64 export array (CS:1663-1664), size + write passes"},
                        "lvx2_file": {"points_per_s": nw / (cs_ms * 1e-3), "GBps": (nw * 16 + cs_bytes) / (cs_ms * 1e-3) / 1e9,
                                      "file_bytes": cs_bytes, "what": "float4 [x y z intensity] -> complete LVX2 file image (CS:269-374) on the device"},
                        "las_pf3_file": {"points_per_s": nw / (las_ms * 1e-3), "GBps": (nw * 16 + las_bytes) / (las_ms * 1e-3) / 1e9,

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kPcdTile) k_pcd_write(const void* __restrict__
 // ---- generic delimited text rows: CS:1643-1716 (_export_pcd '%.6f %.6f %.6f %.0f %.0f', _export_xyz, _export_csv) ----
 // "%.{d}f" with d = 0..9 per column and the full integer range a timestamp column needs (ns since the
 // epoch ~ 1.7e18): the value is split exactly into its integer part I (< 2^64) and the fraction
-// Q = round_half_even(frac * 10^d) (carry into I when Q reaches 10^d).
+// Q = round_half_even(frac * 10^d) (carry into I when Q reaches 10^d), all in exact FP64 steps.
 constexpr int kTextCols   = 6;                      // LMC_TEXT_MAX_COLS
 constexpr int kTextNumMax = 1 + 20 + 1 + 9;         // sign, <= 20 integer digits, '.', <= 9 decimals
 
@@ -215,37 +215,43 @@ __device__ __constant__ uint32_t kPow10[10] = { 1u, 10u, 100u, 1000u, 10000u, 10
 
 struct TextNum { uint64_t ip; uint32_t fq; uint32_t len; uint8_t kind; bool neg; };   // kind 0 finite, 1 nan, 2 inf
 
+__device__ __constant__ double kPow10d[10] = { 1.0, 10.0, 100.0, 1.0e3, 1.0e4, 1.0e5, 1.0e6, 1.0e7, 1.0e8, 1.0e9 };
+
+// Same exact-FP64 scheme as fmt_prepare: ip = trunc(|v|) (exact below 2^64), fr = |v| - ip (exact),
+// hi + lo = fr * 10^d exactly (10^d has <= 21 significant bits), q = floor(hi), tie test on (hi - q) - 0.5
+// with lo as the tie breaker; ties go to the even last printed digit (ip's when d == 0).
 __device__ __forceinline__ TextNum fmtg_prepare(double v, int d, uint32_t& fl) {
     TextNum t;
     const uint64_t bits = (uint64_t)__double_as_longlong(v);
     t.neg = bits >> 63;
-    const uint32_t ex = (uint32_t)(bits >> 52) & 0x7ffu;
-    const uint64_t frac = bits & 0xfffffffffffffull;
-    t.ip = 0; t.fq = 0;
-    if (ex == 0x7ff) { t.kind = frac ? 1 : 2; t.len = frac ? 3u : (t.neg ? 4u : 3u); return t; }
-    t.kind = 0;
-    const uint64_t m = ex ? (frac | (1ull << 52)) : frac;
-    const int e = (ex ? (int)ex : 1) - 1075;
-    const uint32_t p10 = kPow10[d];
-    if (e >= 0) {
-        if (e > 11) { fl |= LMC_FLAG_OVERFLOW; t.ip = 0xffffffffffffffffull; }     // >= 2^64
-        else t.ip = m << e;
+    t.ip = 0; t.fq = 0; t.kind = 0;
+    const double a = fabs(v);
+    if (a < 18446744073709551616.0) {                // 2^64
+        uint64_t ip = __double2ull_rz(a);
+        const double fr = __dsub_rn(a, __ull2double_rn(ip));
+        const double p10 = kPow10d[d];
+        const double hi = __dmul_rn(fr, p10), lo = __fma_rn(fr, p10, -hi);
+        uint32_t q = __double2uint_rz(hi);
+        const double dd = __dsub_rn(__dsub_rn(hi, __uint2double_rn(q)), 0.5);
+        const bool odd = d ? (q & 1u) : (uint32_t)(ip & 1ull);
+        if (dd > 0.0 || (dd == 0.0 && (lo > 0.0 || (lo == 0.0 && odd)))) q += 1;
+        if (q >= kPow10[d]) { q -= kPow10[d]; ip += 1; }
+        t.ip = ip; t.fq = q;
+    } else if (a != a) {
+        t.kind = 1; t.len = 3u; return t;
+    } else if (isinf(a)) {
+        t.kind = 2; t.len = t.neg ? 4u : 3u; return t;
     } else {
-        const int s = -e;
-        uint64_t fm = m;
-        if (s < 64) { t.ip = m >> s; fm = m - (t.ip << s); }
-        if (s < 127) {
-            const unsigned __int128 P = (unsigned __int128)fm * p10;             // < 2^83
-            const unsigned __int128 Qw = P >> s;                                 // < 10^d
-            uint32_t q = (uint32_t)Qw;
-            const unsigned __int128 rem = P - (Qw << s), half = (unsigned __int128)1 << (s - 1);
-            if (rem > half || (rem == half && (d ? (q & 1u) : (uint32_t)(t.ip & 1ull)))) q += 1;   // ties to even (the last printed digit)
-            if (q >= p10) { q -= p10; t.ip += 1; }
-            t.fq = q;
-        }
+        fl |= LMC_FLAG_OVERFLOW; t.ip = 0xffffffffffffffffull;
     }
-    uint32_t nd = 1;
-    for (uint64_t x = t.ip; x >= 10; x /= 10) ++nd;
+    uint32_t nd;
+    if (t.ip < 1000000ull) {
+        const uint32_t x = (uint32_t)t.ip;
+        nd = 1u + (x >= 10u) + (x >= 100u) + (x >= 1000u) + (x >= 10000u) + (x >= 100000u);
+    } else {
+        nd = 7;
+        for (uint64_t x = t.ip / 1000000ull; x >= 10; x /= 10) ++nd;
+    }
     t.len = (t.neg ? 1u : 0u) + nd + (d ? 1u + (uint32_t)d : 0u);
     return t;
 }
@@ -264,8 +270,13 @@ __device__ __forceinline__ int fmtg_write(uint8_t* dst, int d, const TextNum& t)
         for (int k = 0; k < d; ++k) { dst[--o] = (uint8_t)('0' + fp % 10u); fp /= 10u; }
         dst[--o] = '.';
     }
-    uint64_t ip = t.ip;
-    do { dst[--o] = (uint8_t)('0' + (uint32_t)(ip % 10ull)); ip /= 10ull; } while (ip);
+    if (t.ip < 1000000000ull) {
+        uint32_t x = (uint32_t)t.ip;
+        do { dst[--o] = (uint8_t)('0' + x % 10u); x /= 10u; } while (x);
+    } else {
+        uint64_t ip = t.ip;
+        do { dst[--o] = (uint8_t)('0' + (uint32_t)(ip % 10ull)); ip /= 10ull; } while (ip);
+    }
     if (t.neg) dst[--o] = '-';
     return (int)t.len;
 }
