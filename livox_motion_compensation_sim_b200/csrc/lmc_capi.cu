@@ -1,6 +1,7 @@
 // lmc_capi.cu -- the extern "C" boundary declared in include/lmc_b200.h.
 // Plain pointers and sizes in, int status out; no exceptions, no allocation of caller-visible
 // memory, no CPU fallback (every call needs an sm_100 device).
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -34,7 +35,7 @@ cudaError_t launch_lvx_cs(bool f64, const void* pts, const uint8_t* tag, const i
 namespace {
 
 thread_local char g_err[512] = "";
-int g_path = 1;                                    // 0 = direct, 1 = auto (TMA pipeline on large inputs), 2 = TMA always
+std::atomic<int> g_path{1};                        // 0 = direct, 1 = auto (TMA pipeline on large inputs), 2 = TMA always
 
 int fail(int code, const char* fmt, ...) {
     va_list ap; va_start(ap, fmt);
@@ -108,8 +109,9 @@ int run(bool f64, int mode, lmc::Params& P, const lmc_export* ex, void* stream) 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
     bool handled = false;
-    if (g_path >= 1 || P.n_peers > 0) {
-        e = lmc::launch_tma(f64, mode, P, st, g_path == 2 || P.n_peers > 0, &handled);
+    const int path = g_path.load(std::memory_order_relaxed);
+    if (path >= 1 || P.n_peers > 0) {
+        e = lmc::launch_tma(f64, mode, P, st, path == 2 || P.n_peers > 0, &handled);
         if (handled) return e == cudaSuccess ? LMC_OK : cuda_fail(e, "launch (tma path)");
     }
     if (P.n_peers > 0) return fail(LMC_ERR_INVALID, "peer stores need the streaming kernels (16-byte aligned timestamp / tag arrays)");
@@ -146,7 +148,7 @@ int lmc_set_path(int32_t path) {
     g_path = path;
     return LMC_OK;
 }
-int lmc_get_path(void) { return g_path; }
+int lmc_get_path(void) { return g_path.load(std::memory_order_relaxed); }
 
 int lmc_pose_lookup_hold_next(const double* traj_t, int64_t n_t, const double* traj_Rt, const double* frame_t,
                               int32_t n_frames, double* pose_Rt, int32_t* pose_idx, void* stream) {

@@ -53,13 +53,20 @@ __global__ void __launch_bounds__(kLasThreads) k_las_records(const __grid_consta
         const int32_t Z = q_las(p.z, L.scale[2], L.rcp[2], L.off[2], fl);
         const uint32_t I = q_las_intensity(p.w, L.intensity_mode, fl);
         mn[0] = min(mn[0], X); mx[0] = max(mx[0], X); mn[1] = min(mn[1], Y); mx[1] = max(mx[1], Y); mn[2] = min(mn[2], Z); mx[2] = max(mx[2], Z);
+        // the record starts at an odd address (227 + 34 j): one byte, sixteen aligned halfwords, one byte
         uint8_t* r = img + j * kLasRec;
-        put_le(r, (uint32_t)X, 4); put_le(r + 4, (uint32_t)Y, 4); put_le(r + 8, (uint32_t)Z, 4);
-        put_le(r + 12, I, 2);
-        put_le(r + 14, 0, 6);                                   // return byte, classification, scan angle, user data, point source id
-        const double g = L.gps_time ? __ldg(L.gps_time + i) : 0.0;
-        put_le(r + 20, (uint64_t)__double_as_longlong(g), 8);
-        put_le(r + 28, 0, 6);                                   // R G B
+        const uint64_t gb = (uint64_t)__double_as_longlong(L.gps_time ? __ldg(L.gps_time + i) : 0.0);
+        // bytes 0-11 X Y Z | 12-13 intensity | 14-19 return byte, classification, scan angle, user data, point source id = 0
+        // | 20-27 gps_time | 28-33 R G B = 0
+        const uint32_t W[9] = { (uint32_t)X, (uint32_t)Y, (uint32_t)Z, I & 0xffffu, 0u, (uint32_t)gb, (uint32_t)(gb >> 32), 0u, 0u };
+        r[0] = (uint8_t)W[0];
+        uint16_t* h = reinterpret_cast<uint16_t*>(r + 1);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int b = 1 + 2 * k;                                  // first byte of this halfword
+            h[k] = (b & 3) == 1 ? (uint16_t)(W[b >> 2] >> 8) : (uint16_t)((W[b >> 2] >> 24) | (W[(b >> 2) + 1] << 8));
+        }
+        r[33] = 0;
     }
     // block min / max -> one atomic per value per CTA
 #pragma unroll
@@ -69,7 +76,11 @@ __global__ void __launch_bounds__(kLasThreads) k_las_records(const __grid_consta
         if ((tid & 31) == 0) { atomicMin(&s_mm[2 * c], mn[c]); atomicMax(&s_mm[2 * c + 1], mx[c]); }
     }
     __syncthreads();
-    if (tid < 6 && cnt > 0) { if (tid & 1) atomicMax(L.minmax + tid, s_mm[tid]); else atomicMin(L.minmax + tid, s_mm[tid]); }
+    if (tid < 6 && cnt > 0) {
+        // same-address atomics serialise in L2: peek first, only CTAs that actually move an extreme issue one
+        const int32_t cur = *reinterpret_cast<volatile int32_t*>(L.minmax + tid), mine = s_mm[tid];
+        if (tid & 1) { if (mine > cur) atomicMax(L.minmax + tid, mine); } else { if (mine < cur) atomicMin(L.minmax + tid, mine); }
+    }
     uint8_t* g = L.out + (dst0 - phase);
     const int b0 = phase, b1 = phase + cnt * kLasRec;
     int a0 = (b0 + 15) & ~15; if (a0 > b1) a0 = b1;
