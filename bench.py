@@ -44,6 +44,8 @@ VARIANTS = {
     "V5": ("slerp", False, "u32", True, False, 50),
     "V5las": ("slerp", False, "u32", False, True, 50),
     "V4b": ("gyro", False, "u32", False, False, 36),
+    # the reference-native types end to end: f64 (N,4) rows, int64 ns timestamps (CS:125), f64 rows out + LVX records
+    "V6": ("slerp", True, "i64", True, False, 86),
 }
 
 
@@ -218,6 +220,9 @@ def main_b200(args):
             if pts64 is None:
                 pts64 = st.pts.to(torch.float64)
             pts = pts64
+        ts_d = st.ts_off
+        if ts == "i64":                               # absolute int64 ns per point
+            ts_d = fs_d.repeat_interleave(off_d[1:] - off_d[:-1]) + st.ts_off.to(torch.int64)
         out = torch.empty_like(pts)
         into = ops.ExportBuffers(status=torch.zeros(1, dtype=torch.int32, device=dev))
         if lvx:
@@ -229,9 +234,9 @@ def main_b200(args):
         if mode == "rigid":
             fn = lambda: ops.align_rigid(pts, off_d, pose_d, out=out, export=spec)                       # noqa: E731
         elif mode == "slerp":
-            fn = lambda: ops.deskew_slerp(pts, st.ts_off, off_d, fs_d, sts_d, seg_d, out=out, export=spec)  # noqa: E731
+            fn = lambda: ops.deskew_slerp(pts, ts_d, off_d, fs_d, sts_d, seg_d, out=out, export=spec)  # noqa: E731
         else:
-            fn = lambda: ops.deskew_gyro(pts, st.ts_off, off_d, fs_d, sts_d, gyro_d, out=out, export=spec)  # noqa: E731
+            fn = lambda: ops.deskew_gyro(pts, ts_d, off_d, fs_d, sts_d, gyro_d, out=out, export=spec)  # noqa: E731
         return fn, bpp, (out, into)
 
     def timed(fn, steps, warmup, sampler=None):
