@@ -184,3 +184,42 @@ def test_frame_sharded_merge_gloo_world2(tmp_path):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("OK") == 2
+
+
+def test_lvx_cs_host_layout_and_errors():
+    """Host side of the complete simulator's LVX writer mirror (CS:235-374): prefixes, frame flattening, the
+    struct.pack errors the reference raises before any byte is written."""
+    import struct
+    from livox_motion_compensation_sim_b200 import lvx
+    from livox_motion_compensation_sim_b200.compensator import LiDARPoint
+    di = lvx.DeviceInfo("SN123", 1, "fw", True, 0.1, 0.2, 0.3, 1.0, 2.0, 3.0)
+    p2 = lvx.lvx_cs_prefix("lvx2", di, 7)
+    assert len(p2) == 88 and p2[:10] == b"livox_tech" and p2[10:15] == b"2.0.0" and struct.unpack_from('<I', p2, 16)[0] == 0xAC0EA767
+    assert struct.unpack_from('<II', p2, 24) == (50, 1) and p2[32:37] == b"SN123" and p2[48] == 1 and p2[49] == 1
+    assert struct.unpack_from('<6f', p2, 50) == struct.unpack('<6f', struct.pack('<6f', 0.1, 0.2, 0.3, 1.0, 2.0, 3.0))
+    assert lvx.lvx_cs_prefix("lvx3", di, 7) == p2
+    p1 = lvx.lvx_cs_prefix("lvx", di, 7)
+    assert len(p1) == 60 and p1[:10] == b"livox_file" and struct.unpack_from('<II', p1, 10) == (1, 7) and p1[44] == 1
+    with pytest.raises(ValueError):
+        lvx.lvx_cs_prefix("lvx9", di, 1)
+    with pytest.raises(ValueError):
+        lvx.LivoxLVXWriter("lvx9")
+    frames = [{'points': [LiDARPoint(1.0, 2.0, 3.0, 7, 0, 0, 2)], 'timestamp': 5}, {'points': [], 'timestamp': 6},
+              {'points': np.array([[4.0, 5.0, 6.0, 9.0, 1.0]]), 'timestamp': 7}]
+    pts, tag, off, ts = lvx.frames_to_arrays(frames)
+    assert off.tolist() == [0, 1, 1, 2] and ts.tolist() == [5, 6, 7] and tag.tolist() == [2, 1]
+    assert np.array_equal(pts, [[1, 2, 3, 7], [4, 5, 6, 9]])
+    with pytest.raises(struct.error):
+        lvx.frames_to_arrays([{'points': [LiDARPoint(0.0, 0.0, 0.0, 1, 0, 0, 256)], 'timestamp': 0}])
+    with pytest.raises(struct.error):
+        lvx.frames_to_arrays([{'points': [], 'timestamp': -1}])
+
+
+def test_exporter_merge_frames():
+    from livox_motion_compensation_sim_b200 import exporter
+    from livox_motion_compensation_sim_b200.compensator import LiDARPoint
+    frames = [{'points': [LiDARPoint(1.0, 2.0, 3.0, 7, 11, 0, 2)]}, {'points': []}, {'points': np.arange(10.0).reshape(2, 5)}]
+    m = exporter.merge_frames(frames)
+    assert m.shape == (3, 5) and m[0].tolist() == [1.0, 2.0, 3.0, 7.0, 11.0] and m[2, 4] == 9.0
+    assert exporter.merge_frames([]).shape == (0, 5)
+    assert exporter.PCD_HEADER.format(n=3).count("3") == 2 and exporter.CSV_HEADER == "x,y,z,intensity,timestamp\n"
