@@ -459,7 +459,9 @@ def main_b200(args):
                         frame_off=st.frame_off[:fe + 1], frame_start=st.frame_start[:fe])
         hs.pts.copy_(st.pts[:ne]); hs.ts_off.copy_(st.ts_off[:ne])
         torch.cuda.synchronize()
-        sa = StreamingAligner(dev, hs.frame_off, hs.frame_start, mode="slerp", sample_ts=sts_d, seg=seg_d, lvx=True)
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()   # noqa: E731
+        pose_h = (pin(st.sample_quat), pin(st.sample_pos), pin(st.sample_ts))       # the pose stream travels with the points
+        sa = StreamingAligner(dev, hs.frame_off, hs.frame_start, mode="slerp", lvx=True, pose_samples=pose_h)
         sa.run(hs); torch.cuda.synchronize()          # warm-up
         if world > 1:
             dist.barrier()
@@ -476,11 +478,11 @@ def main_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
         # spot check: the pipelined host result equals the resident-data result
-        chk = ops.deskew_slerp(st.pts[:P], st.ts_off[:P], d(st.frame_off[:2]), fs_d[:1].contiguous(), sts_d, seg_d)[0]
+        chk = ops.deskew_slerp(st.pts[:P], st.ts_off[:P], d(st.frame_off[:2]), fs_d[:1].contiguous(), sa.sample_ts, sa.seg)[0]
         assert torch.equal(chk.cpu(), hs.out[:P]), "e2e pipeline result differs from the resident-data result"
         e2e = {"value": world * ne / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": sa.h2d_bytes, "d2h_bytes_per_step": sa.d2h_bytes,
                "ms_per_step": ems, "wall_ms_per_step": wall * 1e3, "points_per_step_per_gpu": ne, "kernel_launches_per_step": sa.launches,
-               "what": "StreamingAligner.run: pinned host float4+u32 ts -> chunked H2D / fused Mode C + LVX kernel / D2H of float4 + 14-B records, 3 streams",
+               "what": "StreamingAligner.run: pinned host float4 + u32 ts + the 200 Hz pose samples (quat, pos, ts) -> H2D, pose-segment table built on the device, chunked fused Mode C + LVX kernel, D2H of float4 + 14-B records, 3 streams",
                "h2d_GBps": sa.h2d_bytes / (ems * 1e-3) / 1e9, "d2h_GBps": sa.d2h_bytes / (ems * 1e-3) / 1e9,
                "host_cpus_bound": None if numa_cpus is None else len(numa_cpus)}
         del hs, sa

@@ -131,6 +131,18 @@ int lmc_deskew_gyro_f32(const float* pts_n4, const uint32_t* ts_off, const int64
                         int64_t p_begin, int64_t p_end, const lmc_export* ex, void* stream);
 
 /*
+ * (north_star subsystem 1) the pose-segment table lmc_deskew_slerp_* consume, built on the device from
+ * the GPS/IMU pose samples: unit quaternions (x y z w, normalised here), positions and int64 ns times.
+ * Row k (22 doubles) = [R_k (9) | pos_k (3) | unit axis of R_k^-1 R_{k+1} (3) | angle |
+ * pos_{k+1} - pos_k (3) | 1/(t_{k+1} - t_k) | t_k bits | (t_{k+1} - t_k) bits]; the last row has angle 0.
+ * Same definition as the host builder frames.slerp_segment_table (SciPy), which it replaces when the
+ * pose stream arrives with the points (1.7 s on the host for a 1 h / 200 Hz stream, microseconds here);
+ * the two agree to rounding (tests: table columns and the Mode C output built from either).
+ */
+int lmc_build_slerp_table(const double* sample_quat_xyzw, const double* sample_pos,
+                          const int64_t* sample_ts, int64_t n_samples, double* seg_out, void* stream);
+
+/*
  * Mode C: per-point pose-interp deskew (north_star; sketched without a body at
  * docs/Master Guide.md:339-367; no reference implementation -> parity unpinned).
  *   k = bracket(sample_ts, ts) ; alpha = (ts - t_k) * inv_dt_k      (inv_dt_k = 1/(t_{k+1} - t_k) from seg)

@@ -22,6 +22,7 @@ cudaError_t launch_scan_emit(const double* env, int64_t M, const double* pos, co
 cudaError_t launch_las_pf3(bool f64, const LasParams& L, cudaStream_t st);
 cudaError_t launch_lvx_v11(bool f64, const void* pts, const int64_t* frame_off, const int64_t* frame_pos, const double* frame_time,
                            const int64_t* frame_id, uint8_t* out, int32_t n_frames, int64_t max_frame_points, uint32_t* status, cudaStream_t st);
+cudaError_t launch_slerp_table(const double* quat, const double* pos, const int64_t* ts, int64_t S, double* seg, cudaStream_t st);
 cudaError_t launch_homog(bool f64, const void* in, const double* T_host, int32_t order, void* out, int64_t n, cudaStream_t st);
 cudaError_t launch_text_size(bool f64, const void* rows, int64_t n, int32_t n_cols, int32_t row_stride, const int32_t* col, const int32_t* dec,
                              uint8_t sep, int64_t* tile_off, cudaStream_t st);
@@ -159,6 +160,18 @@ int lmc_pose_lookup_hold_next(const double* traj_t, int64_t n_t, const double* t
     if ((reinterpret_cast<uintptr_t>(traj_Rt) | reinterpret_cast<uintptr_t>(pose_Rt)) & 15u) return fail(LMC_ERR_ALIGN, "pose tables must be 16-byte aligned");
     cudaError_t e = lmc::launch_pose_lookup(traj_t, n_t, traj_Rt, frame_t, n_frames, pose_Rt, pose_idx, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_pose_lookup");
+}
+
+int lmc_build_slerp_table(const double* sample_quat_xyzw, const double* sample_pos, const int64_t* sample_ts, int64_t n_samples,
+                          double* seg_out, void* stream) {
+    int rc = check_device();
+    if (rc != LMC_OK) return rc;
+    if (n_samples < 0) return fail(LMC_ERR_INVALID, "negative n_samples");
+    if (n_samples == 0) return LMC_OK;
+    if (!sample_quat_xyzw || !sample_pos || !sample_ts || !seg_out) return fail(LMC_ERR_INVALID, "NULL argument");
+    if ((reinterpret_cast<uintptr_t>(sample_quat_xyzw) | reinterpret_cast<uintptr_t>(seg_out)) & 15u) return fail(LMC_ERR_ALIGN, "quaternions and table must be 16-byte aligned");
+    cudaError_t e = lmc::launch_slerp_table(sample_quat_xyzw, sample_pos, sample_ts, n_samples, seg_out, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_slerp_table");
 }
 
 #define LMC_RIGID_BODY(F64)                                                                              \

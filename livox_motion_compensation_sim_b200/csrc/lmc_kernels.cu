@@ -160,6 +160,62 @@ __global__ void k_pose_lookup(const double* __restrict__ traj_t, int64_t n_t, co
     if (pose_idx) pose_idx[f] = (int32_t)lo;
 }
 
+// (north_star subsystem 1) the pose-segment table of Mode C, one thread per sample: what
+// frames.slerp_segment_table builds on the host with SciPy (1.7 s for a 1 h / 200 Hz stream), as a kernel.
+//   row k = [R_k (9) | pos_k (3) | unit axis of R_k^-1 R_{k+1} (3) | angle | pos_{k+1} - pos_k (3) | 1/dt_k | t_k bits | dt_k bits]
+// R_k from the normalised quaternion with SciPy's as_matrix formula; the relative rotation
+// q_k^-1 (x) q_{k+1} gives axis = v/|v| and angle = 2 atan2(|v|, w) (w >= 0), i.e. as_rotvec's angle.
+__global__ void k_slerp_table(const double* __restrict__ quat, const double* __restrict__ pos, const int64_t* __restrict__ ts,
+                              int64_t S, double* __restrict__ seg)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= S) return;
+    double q[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int64_t i = k + j < S ? k + j : k;
+        const double2 a = __ldg(reinterpret_cast<const double2*>(quat + 4 * i)), b = __ldg(reinterpret_cast<const double2*>(quat + 4 * i) + 1);
+        const double n = sqrt(a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y);
+        q[j][0] = a.x / n; q[j][1] = a.y / n; q[j][2] = b.x / n; q[j][3] = b.y / n;
+    }
+    double row[kSegStride];
+    {
+        const double x = q[0][0], y = q[0][1], z = q[0][2], w = q[0][3];
+        const double x2 = x * x, y2 = y * y, z2 = z * z, w2 = w * w, xy = x * y, zw = z * w, xz = x * z, yw = y * w, yz = y * z, xw = x * w;
+        row[0] = x2 - y2 - z2 + w2; row[1] = 2.0 * (xy - zw);      row[2] = 2.0 * (xz + yw);
+        row[3] = 2.0 * (xy + zw);    row[4] = -x2 + y2 - z2 + w2;  row[5] = 2.0 * (yz - xw);
+        row[6] = 2.0 * (xz - yw);    row[7] = 2.0 * (yz + xw);     row[8] = -x2 - y2 + z2 + w2;
+    }
+    const double p0 = pos[3 * k], p1 = pos[3 * k + 1], p2 = pos[3 * k + 2];
+    row[9] = p0; row[10] = p1; row[11] = p2;
+    row[12] = 1.0; row[13] = 0.0; row[14] = 0.0; row[15] = 0.0; row[16] = 0.0; row[17] = 0.0; row[18] = 0.0; row[19] = 0.0;
+    const int64_t tk = ts[k];
+    int64_t dt = 0;
+    if (k + 1 < S) {
+        // q_rel = conj(q_k) (x) q_{k+1}
+        const double ax = -q[0][0], ay = -q[0][1], az = -q[0][2], aw = q[0][3];
+        const double bx = q[1][0], by = q[1][1], bz = q[1][2], bw = q[1][3];
+        // separately rounded products (no FMA contraction): identical samples cancel to an exact zero rotation
+        double vx = __dadd_rn(__dadd_rn(__dmul_rn(aw, bx), __dmul_rn(ax, bw)), __dsub_rn(__dmul_rn(ay, bz), __dmul_rn(az, by)));
+        double vy = __dadd_rn(__dadd_rn(__dmul_rn(aw, by), __dmul_rn(ay, bw)), __dsub_rn(__dmul_rn(az, bx), __dmul_rn(ax, bz)));
+        double vz = __dadd_rn(__dadd_rn(__dmul_rn(aw, bz), __dmul_rn(az, bw)), __dsub_rn(__dmul_rn(ax, by), __dmul_rn(ay, bx)));
+        double w  = __dsub_rn(__dsub_rn(__dmul_rn(aw, bw), __dmul_rn(ax, bx)), __dadd_rn(__dmul_rn(ay, by), __dmul_rn(az, bz)));
+        if (w < 0.0) { vx = -vx; vy = -vy; vz = -vz; w = -w; }
+        const double vn = sqrt(vx * vx + vy * vy + vz * vz);
+        const double th = 2.0 * atan2(vn, w);
+        if (th > 0.0 && vn > 0.0) { row[12] = vx / vn; row[13] = vy / vn; row[14] = vz / vn; }
+        row[15] = th;
+        row[16] = pos[3 * k + 3] - p0; row[17] = pos[3 * k + 4] - p1; row[18] = pos[3 * k + 5] - p2;
+        dt = ts[k + 1] - tk;
+        row[19] = dt > 0 ? 1.0 / (double)dt : 0.0;
+    }
+    row[20] = __longlong_as_double(tk);
+    row[21] = __longlong_as_double(dt);
+    double2* dst = reinterpret_cast<double2*>(seg + kSegStride * k);
+#pragma unroll
+    for (int j = 0; j < kSegStride / 2; ++j) dst[j] = make_double2(row[2 * j], row[2 * j + 1]);
+}
+
 // ---- launchers -------------------------------------------------------------------------------
 template <bool F64, int MODE>
 static cudaError_t launch_fused(const Params& P, cudaStream_t st) {
@@ -185,6 +241,14 @@ cudaError_t launch_pose_lookup(const double* traj_t, int64_t n_t, const double* 
                                int32_t n_frames, double* pose_Rt, int32_t* pose_idx, cudaStream_t st) {
     if (n_frames <= 0) return cudaSuccess;
     k_pose_lookup<<<(n_frames + 127) / 128, 128, 0, st>>>(traj_t, n_t, traj_Rt, frame_t, n_frames, pose_Rt, pose_idx);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_slerp_table(const double* quat, const double* pos, const int64_t* ts, int64_t S, double* seg, cudaStream_t st) {
+    if (S <= 0) return cudaSuccess;
+    const int64_t blocks = (S + 127) / 128;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    k_slerp_table<<<(unsigned)blocks, 128, 0, st>>>(quat, pos, ts, S, seg);
     return cudaGetLastError();
 }
 

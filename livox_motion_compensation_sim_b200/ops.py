@@ -196,6 +196,18 @@ def quantize(pts: torch.Tensor, export: ExportSpec) -> ExportBuffers:
     return bufs
 
 
+def build_slerp_table(sample_quat_xyzw: torch.Tensor, sample_pos: torch.Tensor, sample_ts: torch.Tensor,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The (S,22) pose-segment table of deskew_slerp built on the device from (S,4) quaternions (x y z w),
+    (S,3) positions and int64 ns sample times -- the device twin of frames.slerp_segment_table."""
+    S = sample_quat_xyzw.shape[0]
+    if out is None:
+        out = torch.empty((S, 22), dtype=torch.float64, device=sample_quat_xyzw.device)
+    C.check(C.lib().lmc_build_slerp_table(_req(sample_quat_xyzw, torch.float64, "sample_quat", (4,)), _req(sample_pos, torch.float64, "sample_pos", (3,)),
+                                          _req(sample_ts, torch.int64, "sample_ts"), S, _req(out, torch.float64, "seg", (22,)), _stream_ptr()))
+    return out
+
+
 def transform_homog(pts: torch.Tensor, T, order: int = C.HOMOG_BATCH, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(N3) CS:214-233: one 4x4 homogeneous matrix T (host array) over (n,4) points; order = _capi.HOMOG_BATCH
     (the reference call on n >= 2 points) or HOMOG_SINGLE (the call on one point, CS:2136-2138)."""

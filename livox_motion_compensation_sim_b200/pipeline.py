@@ -57,12 +57,23 @@ class StreamingAligner:
 
     def __init__(self, device, frame_off: np.ndarray, frame_start: np.ndarray, *, mode: str = "slerp",
                  sample_ts: Optional[torch.Tensor] = None, seg: Optional[torch.Tensor] = None,
-                 pose_Rt: Optional[torch.Tensor] = None, chunk_points: int = 1 << 24, lvx: bool = True):
+                 pose_Rt: Optional[torch.Tensor] = None, chunk_points: int = 1 << 24, lvx: bool = True,
+                 pose_samples: Optional[tuple] = None):
+        """pose_samples = (quat_xyzw (S,4) f64, pos (S,3) f64, ts (S) int64) as pinned HOST tensors: the pose stream then
+        travels with the points -- every run() uploads it and builds the segment table on the device
+        (lmc_build_slerp_table) instead of taking a host-built ``seg``."""
         self.device = torch.device(device)
         self.mode, self.lvx = mode, lvx
         self.frame_off = np.asarray(frame_off, np.int64)
         self.frame_start = np.asarray(frame_start, np.int64)
         self.sample_ts, self.seg, self.pose_Rt = sample_ts, seg, pose_Rt
+        self.pose_samples = pose_samples
+        if pose_samples is not None:
+            S = pose_samples[0].shape[0]
+            self.d_quat = torch.empty((S, 4), dtype=torch.float64, device=self.device)
+            self.d_pos = torch.empty((S, 3), dtype=torch.float64, device=self.device)
+            self.sample_ts = torch.empty(S, dtype=torch.int64, device=self.device)
+            self.seg = torch.empty((S, 22), dtype=torch.float64, device=self.device)
         F = len(self.frame_off) - 1
         # chunk boundaries at whole frames, ~chunk_points each, point-aligned to 8 so every
         # chunk's slice of the 14-byte record array starts 16-byte aligned on the host side
@@ -104,6 +115,16 @@ class StreamingAligner:
         cur = torch.cuda.current_stream(self.device)
         for s in (self.s_in, self.s_k, self.s_out):
             s.wait_stream(cur)
+        if self.pose_samples is not None:                           # pose stream: H2D + segment table on the device
+            hq, hp, ht = self.pose_samples
+            with torch.cuda.stream(self.s_in):
+                self.d_quat.copy_(hq, non_blocking=True); self.d_pos.copy_(hp, non_blocking=True); self.sample_ts.copy_(ht, non_blocking=True)
+                self.h2d_bytes += hq.numel() * 8 + hp.numel() * 8 + ht.numel() * 8
+                ev_pose = torch.cuda.Event(); ev_pose.record(self.s_in)
+            with torch.cuda.stream(self.s_k):
+                self.s_k.wait_event(ev_pose)
+                ops.build_slerp_table(self.d_quat, self.d_pos, self.sample_ts, out=self.seg)
+                self.launches += 1
         for ci, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
             sl = ci % self.nbuf
             p0, p1 = int(off[a]), int(off[b])

@@ -361,6 +361,41 @@ def test_mode_c_vs_oracles(f64, path):
     assert np.array_equal(b.las_intensity.cpu().numpy().view(np.uint16), I)
 
 
+def test_slerp_table_device_builder():
+    """Pose-segment table built on the device vs the host (SciPy) builder: columns to rounding, Mode C output
+    from either table within 1e-10 m; unnormalised / sign-flipped quaternions, repeated samples (zero
+    angle), a single-sample table and ragged sample spacing."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(41)
+    st = synth.make_stream(12, 5000, 41, device=DEV, dtype=torch.float64)
+    q, pos, ts = st.sample_quat.copy(), st.sample_pos, st.sample_ts
+    q[5] = q[4]; q[9] = -q[9]; q[11] *= 3.5                               # zero-angle segment, -q == q, unnormalised
+    want = FR.slerp_segment_table(q, pos, ts)
+    got = ops.build_slerp_table(dev(q), dev(pos), dev(ts)).cpu().numpy()
+    assert np.array_equal(got[:, 20:22].view(np.int64), want[:, 20:22].view(np.int64))   # t_k, dt_k bits
+    assert np.array_equal(got[:, 9:12], want[:, 9:12]) and np.array_equal(got[:, 16:20], want[:, 16:20])
+    assert np.abs(got[:, :9] - want[:, :9]).max() <= 1.5e-15      # a few ulp: FMA contraction vs NumPy
+    rv_g, rv_w = got[:, 12:15] * got[:, 15:16], want[:, 12:15] * want[:, 15:16]
+    assert np.abs(rv_g - rv_w).max() <= 1e-15
+    assert got[4, 15] == 0.0 and got[4, 12:15].tolist() == [1.0, 0.0, 0.0] and got[-1, 15] == 0.0      # q[5] == q[4]: segment 4 does not rotate
+    ts64 = st.frame_start[np.repeat(np.arange(12), 5000)] + st.ts_off.cpu().numpy().astype(np.int64)
+    a, _ = ops.deskew_slerp(st.pts, dev(ts64), dev(st.frame_off), dev(st.frame_start), dev(ts), dev(want))
+    b, _ = ops.deskew_slerp(st.pts, dev(ts64), dev(st.frame_off), dev(st.frame_start), dev(ts), dev(got))
+    assert (a - b).abs().max().item() <= 1e-10
+    # large random rotations between samples, jittered spacing
+    S = 1000
+    q2 = Rotation.random(S, random_state=3).as_quat()
+    ts2 = np.cumsum(rng.integers(1, 9_000_000, S)).astype(np.int64)
+    p2 = rng.normal(0, 50, (S, 3))
+    w2 = FR.slerp_segment_table(q2, p2, ts2)
+    g2 = ops.build_slerp_table(dev(q2), dev(p2), dev(ts2)).cpu().numpy()
+    assert np.abs(g2[:, :9] - w2[:, :9]).max() <= 1.5e-15 and np.abs(g2[:, 15] - w2[:, 15]).max() <= 1e-14
+    near_pi = w2[:, 15] > 3.1                                              # the axis sign is arbitrary at angle == pi exactly; none here
+    assert np.abs(g2[~near_pi, 12:15] - w2[~near_pi, 12:15]).max() <= 1e-13
+    one = ops.build_slerp_table(dev(q2[:1]), dev(p2[:1]), dev(ts2[:1])).cpu().numpy()
+    assert one.shape == (1, 22) and one[0, 15] == 0.0 and np.abs(one[0, :9] - w2[0, :9]).max() <= 1.5e-15
+
+
 def test_mode_c_hold_next_is_mode_a():
     """Mode A == Mode C with the interpolation weight forced to hold-next: bit-identical."""
     F = 25
@@ -890,6 +925,17 @@ def test_host_buffer_pipeline_equals_resident(mode):
         torch.cuda.synchronize()
     assert torch.equal(hs.out, want.cpu()) and torch.equal(hs.lvx14, wb.lvx14.cpu())
     assert sa.h2d_bytes == N * (16 + (4 if mode == "slerp" else 0)) and sa.d2h_bytes == N * 30
+    if mode == "slerp":                                     # pose stream from the host: table built on the device inside run()
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()   # noqa: E731
+        sb = StreamingAligner(DEV, st.frame_off, st.frame_start, mode="slerp", chunk_points=30_000, lvx=True,
+                              pose_samples=(pin(st.sample_quat), pin(st.sample_pos), pin(st.sample_ts)))
+        hs.out.zero_()
+        sb.run(hs); torch.cuda.synchronize()
+        S = len(st.sample_ts)
+        assert sb.h2d_bytes == N * 20 + S * 64 and sb.launches == len([1 for a, b in zip(sb.cuts[:-1], sb.cuts[1:]) if st.frame_off[b] > st.frame_off[a]]) + 1
+        want2, _ = ops.deskew_slerp(st.pts, st.ts_off, off_d, fs_d, sb.sample_ts, sb.seg)
+        assert torch.equal(hs.out, want2.cpu())
+        assert (hs.out - want.cpu()).abs().max().item() <= 1e-5       # device-built vs host-built table: same to f32 rounding
 
 
 def test_fused_merge_multi_gpu():
