@@ -55,6 +55,9 @@ class LiDARMotionSimulator:
             'strict_reference_merge': True,      # LMC:887-891: no merged_aligned if any frame is empty
             'las_scale': (0.01, 0.01, 0.01),     # laspy header default used by LMC:953
             'las_offset': (0.0, 0.0, 0.0),
+            # 'hold_next' = the reference's per-frame pose (LMC:802-812); 'slerp' = per-point deskew: every point's
+            # timestamp is bracketed in the trajectory samples, orientation SLERPed, position lerped (north_star Mode C)
+            'pose_interpolation': 'hold_next',
         }
 
     def _validate_config(self, config: Dict) -> None:
@@ -186,7 +189,10 @@ class LiDARMotionSimulator:
             scan = device_scans[i] if device_scans is not None else frame_source.scan(i, t, sensor_pose)
             all_scans.append({'frame_id': i, 'timestamp': t, 'points_local': scan, 'sensor_pose': sensor_pose})
             motion_data.append(self._motion_row(i, t, sensor_pose))
-        aligned = self.align_scans(all_scans)
+        if self.config.get('pose_interpolation', 'hold_next') == 'slerp':
+            aligned = self.deskew_scans(all_scans, trajectory)
+        else:
+            aligned = self.align_scans(all_scans)
         return {'raw_scans': all_scans, 'aligned_pointclouds': aligned, 'motion_data': motion_data,
                 'trajectory': trajectory, 'environment': getattr(frame_source, 'environment', None)}
 
@@ -209,6 +215,35 @@ class LiDARMotionSimulator:
         merged, off, bufs = self.align_frames(frames, pos, eul, export=export)
         self.last_merged, self.last_frame_off, self.last_export = merged, off, bufs
         return FR.split_frames(merged, off)
+
+    def deskew_scans(self, raw_scans: List[dict], trajectory: Dict, export: Optional[ops.ExportSpec] = None) -> List[np.ndarray]:
+        """Per-point deskew + alignment (north_star Mode C; the reference has no such step -- parity is against the
+        builder's SciPy Slerp + lerp oracle).  Pose samples = the trajectory's GPS positions / IMU orientations at
+        their own times (LMC:396-428); a point's time is ``scan['point_times']`` (int64 ns) when the scan dict has
+        it, else frame time + i * (frame period / n_f).  Points outside the sample span hold the
+        end pose.  Returns the per-frame world clouds; merged buffer kept as in align_scans."""
+        from scipy.spatial.transform import Rotation
+        frames = [s['points_local'] for s in raw_scans]
+        flat, off = FR.flatten_frames(frames, np.float64)
+        n = int(off[-1])
+        if n == 0:
+            self.last_merged, self.last_frame_off, self.last_export = np.zeros((0, 4)), off, None
+            return FR.split_frames(self.last_merged, off)
+        period_ns = int(round(1e9 / float(self.config['lidar_fps'])))
+        fstart = np.array([int(s['timestamp'] * 1e9) for s in raw_scans], np.int64)
+        ts = np.empty(n, np.int64)
+        for i, s in enumerate(raw_scans):
+            m = int(off[i + 1] - off[i])
+            if m:
+                pt = s.get('point_times')
+                ts[off[i]:off[i + 1]] = pt if pt is not None else fstart[i] + np.arange(m, dtype=np.int64) * (period_ns // m)
+        s_ts = np.round(np.asarray(trajectory['time'], np.float64) * 1e9).astype(np.int64)
+        quat = Rotation.from_euler('xyz', np.asarray(trajectory['orientation_imu'], np.float64)).as_quat()
+        seg = ops.build_slerp_table(self._to_dev(quat), self._to_dev(np.asarray(trajectory['position_gps'], np.float64)), self._to_dev(s_ts))
+        out, bufs = ops.deskew_slerp(self._to_dev(flat), self._to_dev(ts), self._to_dev(off), self._to_dev(fstart), self._to_dev(s_ts), seg,
+                                     export=export)
+        self.last_merged, self.last_frame_off, self.last_export = out.cpu().numpy(), off, bufs
+        return FR.split_frames(self.last_merged, off)
 
     # ------------------------------------------------------------------ (a3) LMC:886-899
     def merge_results(self, results) -> Dict[str, Optional[np.ndarray]]:
