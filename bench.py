@@ -386,6 +386,28 @@ def main_b200(args):
                     "aligned_sha256_matches_reference": hashlib.sha256(al.tobytes()).hexdigest() == man['aligned_sha256'],
                     "cpu_port_ms": cpu_loop_ms,
                     "what": "LiDARMotionSimulator.run_simulation with the device scanner (LMC:778-858 loop: lookup + scan_environment + transform), host noise replay, results as host arrays; cpu_port_ms = the oracle's C scanner + NumPy transform port of the same loop, 1 thread"}
+            # configs[2] wording: parking_detailed (circular, medium, 30 s at 20 fps) with the per-point deskew
+            # (pose_interpolation='slerp'): lookup + scan of every frame + per-point SLERP alignment
+            gp3 = os.path.join(ROOT, "tests", "golden", "scan_C3.npz")
+            if os.path.exists(gp3):
+                g3 = dict(np.load(gp3))
+                cfg3 = json.loads(g3['config_json'].tobytes().decode())
+
+                class _Src3:
+                    trajectory = {'time': g3['traj_time'], 'position_gps': g3['traj_position_gps'], 'orientation_imu': g3['traj_orientation_imu'],
+                                  'velocity': np.zeros_like(g3['traj_position_gps'])}
+                    environment = g3['environment']
+                sim3 = LiDARMotionSimulator(dict(cfg3, device=f'cuda:{local}', pose_interpolation='slerp'))
+                best3 = 1e9
+                for _ in range(3):
+                    np.random.set_state(('MT19937', g3['rng_keys'], int(g3['rng_pos']), int(g3['rng_has_gauss']), float(g3['rng_cached'])))
+                    t0 = time.perf_counter()
+                    res3 = sim3.run_simulation(_Src3)
+                    best3 = min(best3, time.perf_counter() - t0)
+                presets["parking_detailed_30s_per_point_deskew"] = {
+                    "frames": len(res3['raw_scans']), "points": int(sum(len(a) for a in res3['aligned_pointclouds'])),
+                    "b200_run_simulation_ms": best3 * 1e3,
+                    "what": "LiDARMotionSimulator({'pose_interpolation': 'slerp'}).run_simulation: device scanner + per-point bracket search / SLERP / lerp over the trajectory samples (parity vs the SciPy oracle in tests)"}
         except Exception as e:                    # noqa: BLE001
             presets = {"error": repr(e)}
 
