@@ -207,7 +207,6 @@ __global__ void __launch_bounds__(kPcdTile) k_pcd_write(const void* __restrict__
 // epoch ~ 1.7e18): the value is split exactly into its integer part I (< 2^64) and the fraction
 // Q = round_half_even(frac * 10^d) (carry into I when Q reaches 10^d), all in exact FP64 steps.
 constexpr int kTextCols   = 6;                      // LMC_TEXT_MAX_COLS
-constexpr int kTextNumMax = 1 + 20 + 1 + 9;         // sign, <= 20 integer digits, '.', <= 9 decimals
 
 struct TextFmt { int32_t n_cols, row_stride; int32_t col[kTextCols]; int32_t dec[kTextCols]; uint8_t sep; };
 
