@@ -263,23 +263,23 @@ int lmc_pcd_ascii_write_f32(const float* pts_n4, int64_t n_points, const int64_t
  * DataExporter._export_pcd (CS:1663-1664, '%.6f %.6f %.6f %.0f %.0f\n' over [x y z intensity timestamp]),
  * _export_xyz (CS:1703, np.savetxt '%.6f' x 3) and the body of _export_csv (CS:1711-1712, pandas
  * float_format '%.6f', ',' separated): every row of a (n_rows, row_stride) array becomes
- *     "%.{decimals[0]}f" sep "%.{decimals[1]}f" sep ... "\n"     over the columns col[0..n_cols)
+ *     "%.{decimals[0]}f" sep "%.{decimals[1]}f" sep ... "\n"     over the columns col_host[0..n_cols)
  * byte-identical to C printf / CPython (correctly rounded, half-even on the exact binary value).
- * col / decimals are HOST arrays of n_cols <= LMC_TEXT_MAX_COLS entries, decimals 0..9.  Same two-call
+ * col_host / decimals_host are HOST arrays of n_cols <= LMC_TEXT_MAX_COLS entries, decimals 0..9.  Same two-call
  * protocol and tile size as the PCD writer.  |v| >= 2^64 sets LMC_FLAG_OVERFLOW.
  */
 #define LMC_TEXT_MAX_COLS 6
 int lmc_text_rows_size_f64(const double* rows, int64_t n_rows, int32_t row_stride, int32_t n_cols,
-                           const int32_t* col, const int32_t* decimals, int32_t sep,
+                           const int32_t* col_host, const int32_t* decimals_host, int32_t sep,
                            int64_t* tile_off, void* stream);
 int lmc_text_rows_size_f32(const float* rows, int64_t n_rows, int32_t row_stride, int32_t n_cols,
-                           const int32_t* col, const int32_t* decimals, int32_t sep,
+                           const int32_t* col_host, const int32_t* decimals_host, int32_t sep,
                            int64_t* tile_off, void* stream);
 int lmc_text_rows_write_f64(const double* rows, int64_t n_rows, int32_t row_stride, int32_t n_cols,
-                            const int32_t* col, const int32_t* decimals, int32_t sep,
+                            const int32_t* col_host, const int32_t* decimals_host, int32_t sep,
                             const int64_t* tile_off, uint8_t* text_out, uint32_t* status, void* stream);
 int lmc_text_rows_write_f32(const float* rows, int64_t n_rows, int32_t row_stride, int32_t n_cols,
-                            const int32_t* col, const int32_t* decimals, int32_t sep,
+                            const int32_t* col_host, const int32_t* decimals_host, int32_t sep,
                             const int64_t* tile_off, uint8_t* text_out, uint32_t* status, void* stream);
 
 /*
