@@ -115,7 +115,7 @@ class LiDARMotionSimulator:
         return out.cpu().numpy()
 
     # ------------------------------------------------------------------ (N4) LMC:701-770
-    def scan_all(self, environment, positions, eulers) -> List[np.ndarray]:
+    def scan_all(self, environment, positions, eulers, keep_device: bool = False) -> List[np.ndarray]:
         """scan_environment for every frame in ONE device pass (range / FOV cull, compaction, subsample);
         the noise is drawn on the host from the global NumPy RNG exactly as LMC:767 does, so a seeded
         run reproduces the reference's raw scans.  Returns the per-frame (n_f,4) arrays."""
@@ -127,6 +127,7 @@ class LiDARMotionSimulator:
                                    range_max=c['range_max'], range_min=c['range_min'], fov_horizontal=c['fov_horizontal'],
                                    fov_vertical=c['fov_vertical'], points_per_frame=c['points_per_frame'],
                                    noise_std=c['lidar_range_noise'])
+        self._dev_scan = (raw, off) if keep_device else None      # run_simulation aligns the device copy directly
         host = raw.cpu().numpy()
         return [host[off[i]:off[i + 1]] if off[i + 1] > off[i] else np.array([]).reshape(0, 4) for i in range(len(off) - 1)]
 
@@ -180,7 +181,7 @@ class LiDARMotionSimulator:
         device_scans = None
         if not hasattr(frame_source, 'scan'):           # no host scanner supplied: scan every frame on the device (N4)
             device_scans = self.scan_all(frame_source.environment, trajectory['position_gps'][pose_idx],
-                                         trajectory['orientation_imu'][pose_idx])
+                                         trajectory['orientation_imu'][pose_idx], keep_device=True)
         for i, t in enumerate(lidar_times):
             k = int(pose_idx[i])
             sensor_pose = {'position': trajectory['position_gps'][k],
@@ -189,8 +190,18 @@ class LiDARMotionSimulator:
             scan = device_scans[i] if device_scans is not None else frame_source.scan(i, t, sensor_pose)
             all_scans.append({'frame_id': i, 'timestamp': t, 'points_local': scan, 'sensor_pose': sensor_pose})
             motion_data.append(self._motion_row(i, t, sensor_pose))
+        dev_scan = getattr(self, '_dev_scan', None) if device_scans is not None else None
+        self._dev_scan = None
         if self.config.get('pose_interpolation', 'hold_next') == 'slerp':
-            aligned = self.deskew_scans(all_scans, trajectory)
+            aligned = self.deskew_scans(all_scans, trajectory, _device_raw=dev_scan)
+        elif dev_scan is not None and self._np_dtype() == np.float64 and dev_scan[0].shape[0] > 0:
+            # the scans are still resident: align them where they are (no flatten, no second upload)
+            raw_d, off = dev_scan
+            pose = FR.pose_table(trajectory['position_gps'][pose_idx], trajectory['orientation_imu'][pose_idx])
+            out, _ = ops.align_rigid(raw_d, self._to_dev(off), self._to_dev(pose))
+            self.last_merged, self.last_frame_off, self.last_export = out.cpu().numpy(), off, None
+            self._performance_stats['total_points_processed'] += int(off[-1])
+            aligned = FR.split_frames(self.last_merged, off)
         else:
             aligned = self.align_scans(all_scans)
         return {'raw_scans': all_scans, 'aligned_pointclouds': aligned, 'motion_data': motion_data,
@@ -216,19 +227,25 @@ class LiDARMotionSimulator:
         self.last_merged, self.last_frame_off, self.last_export = merged, off, bufs
         return FR.split_frames(merged, off)
 
-    def deskew_scans(self, raw_scans: List[dict], trajectory: Dict, export: Optional[ops.ExportSpec] = None) -> List[np.ndarray]:
+    def deskew_scans(self, raw_scans: List[dict], trajectory: Dict, export: Optional[ops.ExportSpec] = None,
+                     _device_raw=None) -> List[np.ndarray]:
         """Per-point deskew + alignment (north_star Mode C; the reference has no such step -- parity is against the
         builder's SciPy Slerp + lerp oracle).  Pose samples = the trajectory's GPS positions / IMU orientations at
         their own times (LMC:396-428); a point's time is ``scan['point_times']`` (int64 ns) when the scan dict has
         it, else frame time + i * (frame period / n_f).  Points outside the sample span hold the
         end pose.  Returns the per-frame world clouds; merged buffer kept as in align_scans."""
         from scipy.spatial.transform import Rotation
-        frames = [s['points_local'] for s in raw_scans]
-        flat, off = FR.flatten_frames(frames, np.float64)
+        if _device_raw is not None:                                 # scans still resident on the device (run_simulation)
+            flat_d, off = _device_raw
+        else:
+            flat, off = FR.flatten_frames([s['points_local'] for s in raw_scans], np.float64)
+            flat_d = None
         n = int(off[-1])
         if n == 0:
             self.last_merged, self.last_frame_off, self.last_export = np.zeros((0, 4)), off, None
             return FR.split_frames(self.last_merged, off)
+        if flat_d is None:
+            flat_d = self._to_dev(flat)
         period_ns = int(round(1e9 / float(self.config['lidar_fps'])))
         fstart = np.array([int(s['timestamp'] * 1e9) for s in raw_scans], np.int64)
         ts = np.empty(n, np.int64)
@@ -240,7 +257,7 @@ class LiDARMotionSimulator:
         s_ts = np.round(np.asarray(trajectory['time'], np.float64) * 1e9).astype(np.int64)
         quat = Rotation.from_euler('xyz', np.asarray(trajectory['orientation_imu'], np.float64)).as_quat()
         seg = ops.build_slerp_table(self._to_dev(quat), self._to_dev(np.asarray(trajectory['position_gps'], np.float64)), self._to_dev(s_ts))
-        out, bufs = ops.deskew_slerp(self._to_dev(flat), self._to_dev(ts), self._to_dev(off), self._to_dev(fstart), self._to_dev(s_ts), seg,
+        out, bufs = ops.deskew_slerp(flat_d, self._to_dev(ts), self._to_dev(off), self._to_dev(fstart), self._to_dev(s_ts), seg,
                                      export=export)
         self.last_merged, self.last_frame_off, self.last_export = out.cpu().numpy(), off, bufs
         return FR.split_frames(self.last_merged, off)
