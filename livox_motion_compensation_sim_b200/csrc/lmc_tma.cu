@@ -71,9 +71,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra D;\n\tbra W;\n\tD:\n\t}"
-        :: "r"(bar), "r"(parity) : "memory");
+        :: "r"(bar), "r"(parity), "r"(0x100000u) : "memory");
 }
 // global -> shared bulk copy (TMA, 1-D): 16-byte aligned addresses, size multiple of 16
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint32_t bar) {
