@@ -518,9 +518,12 @@ struct PointCtx {
     }
 
     // LEAN: the launcher has checked hold_idx == NULL, 2 <= n_samp < 2^31 (Mode C) -- no runtime tests here
-    template <bool LEAN = false>
+    // CACHE: the producer of the streaming kernel may have staged the pose rows [k_base, k_base + n_rows) of this tile in
+    // shared memory (rows_s = their address, info_s + 56 = {k_base, n_rows}); rows found there are read from it.
+    template <bool LEAN = false, bool CACHE = false>
     __device__ __forceinline__ void pair(const Params& P, const int32_t (&f)[2], const bool (&single)[2], const int64_t (&fs)[2],
-                                         const int64_t (&tsraw)[2], const Pt (&in)[2], Pt (&out)[2]) {
+                                         const int64_t (&tsraw)[2], const Pt (&in)[2], Pt (&out)[2],
+                                         uint32_t info_s = 0, uint32_t rows_s = 0) {
         if constexpr (MODE == kRigid) {
             if (f[0] == f[1] && !single[0]) {
                 if (f[0] != (int32_t)key) {
@@ -543,13 +546,19 @@ struct PointCtx {
                 int32_t k = __double2int_rz(__dmul_rn((double)(ta - t0), rate));
                 k = max(0, min(k, (int32_t)S - 2));
                 const double2* sr = reinterpret_cast<const double2*>(P.samp_tab + (int64_t)kSegStride * k);
+                if constexpr (CACHE) {
+                    uint32_t kb, nr;
+                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(kb), "=r"(nr) : "r"(info_s + 56u));
+                    const uint32_t r = (uint32_t)k - kb;
+                    if (r < nr) sr = reinterpret_cast<const double2*>(__cvta_shared_to_generic(rows_s + r * (uint32_t)(kSegStride * 8)));
+                }
                 // Only the "front" of the row (axis, theta, dpos, 1/dt, t_k, dt_k = columns 12..21) is kept in
                 // registers across pairs; R_k and pos_k (columns 0..11) are re-read per pair from L1, where the
                 // row stays hot -- holding all 22 doubles plus two points in flight overflows 128 registers
                 // and the spills cost more LSU traffic than six broadcast loads.
                 if (k != key) {
 #pragma unroll
-                    for (int q = 6; q < kSegStride / 2; ++q) { const double2 v = __ldg(sr + q); tab[2 * q] = v.x; tab[2 * q + 1] = v.y; }
+                    for (int q = 6; q < kSegStride / 2; ++q) { const double2 v = CACHE ? sr[q] : __ldg(sr + q); tab[2 * q] = v.x; tab[2 * q + 1] = v.y; }
                     key = k;
                 }
                 const int64_t tk = __double_as_longlong(tab[20]);
@@ -559,7 +568,7 @@ struct PointCtx {
                 if ((uint64_t)da < dtk && (uint64_t)db < dtk && tab[15] <= kSmallAngle) {
                     double row[kSegStride];
 #pragma unroll
-                    for (int q = 0; q < 6; ++q) { const double2 v = __ldg(sr + q); row[2 * q] = v.x; row[2 * q + 1] = v.y; }
+                    for (int q = 0; q < 6; ++q) { const double2 v = CACHE ? sr[q] : __ldg(sr + q); row[2 * q] = v.x; row[2 * q + 1] = v.y; }
 #pragma unroll
                     for (int q = 12; q < kSegStride; ++q) row[q] = tab[q];
                     const double a0 = __dmul_rn((double)da, row[19]);

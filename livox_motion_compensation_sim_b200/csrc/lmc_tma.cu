@@ -41,7 +41,9 @@ template <bool F64, int MODE> struct StreamCfg {
     static constexpr int TAG_STAGE = TP;
     static constexpr int STAGE     = PTS_STAGE + TS_STAGE + TAG_STAGE;
     static constexpr int LVX_SLAB  = PPT * 64 * 14;              // bytes per consumer warp
-    static constexpr int SMEM      = STAGES * STAGE + kCW * LVX_SLAB + STAGES * (int)sizeof(TileMeta) + STAGES * 64 + 2 * STAGES * 8 + 128;
+    static constexpr int ROWS      = (MODE == kSlerp && !F64) ? 12 : 0;   // pose rows staged per tile (Mode C, float4 layout): a 2880-point tile of a 10 us / 200 Hz stream touches 7
+    static constexpr int ROW_STAGE = ROWS * kSegStride * 8;
+    static constexpr int SMEM      = STAGES * (STAGE + ROW_STAGE) + kCW * LVX_SLAB + STAGES * (int)sizeof(TileMeta) + STAGES * 64 + 2 * STAGES * 8 + 128;
 };
 
 // Everything a consumer needs to know about a tile, prepared once by the producer (64 bytes = four
@@ -54,7 +56,7 @@ struct TileInfo {
     int32_t rel_e1;               // tile-local index of the first point of frame f_lo + 1 (INT_MAX: none)
     int32_t flags;                // bit 0 simple, bit 1 / 2: frame f_lo / f_lo + 1 holds exactly one point
     int64_t fs0, fs1;             // frame_start of f_lo and f_lo + 1 (Mode B/C)
-    int64_t pad;
+    int32_t k_base, n_rows;       // Mode C: pose rows [k_base, k_base + n_rows) are staged in shared memory with the tile
 };
 
 // ---- mbarrier / bulk-copy PTX ---------------------------------------------------------------
@@ -92,7 +94,7 @@ template <bool F64, int MODE, int EX, bool FULL>
 __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti, const TileMeta& tm,
                                              const uint8_t* s_pts, const uint8_t* s_ts, const uint8_t* s_tag,
                                              uint8_t* slab, uint32_t empty_bar, PointCtx<F64, MODE>& ctx,
-                                             uint32_t& fl, int cw, int lane)
+                                             uint32_t& fl, int cw, int lane, uint32_t info_s = 0, uint32_t rows_s = 0)
 {
     using Cfg = StreamCfg<F64, MODE>;
     constexpr int PPT = Cfg::PPT;
@@ -168,7 +170,9 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
                     }
             }
         }
-        if (j == PPT - 1) {                                  // everything this warp needs from the stage is in registers
+        // with staged pose rows the stage is still being read by ctx.pair() below: release it after the last pair's math
+        constexpr bool ROWS_STAGED = FULL && !GEN && MODE == kSlerp && !F64;   // (f64 tiles are one pair per thread: holding the stage through the math costs more than the row reads)
+        if (j == PPT - 1 && !ROWS_STAGED) {                  // everything this warp needs from the stage is in registers
             __syncwarp();
             if (lane == 0) mbar_arrive(empty_bar);
         }
@@ -188,10 +192,14 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
             }
         }
         Pt o[2] = { in[0], in[1] };
-        if (FULL || (va && vb)) ctx.template pair<!GEN>(P, fr, single, fsv, tsv, in, o);
+        if (FULL || (va && vb)) ctx.template pair<!GEN, ROWS_STAGED>(P, fr, single, fsv, tsv, in, o, info_s, rows_s);
         else {
             if (va) o[0] = ctx.one(P, fr[0], single[0], fsv[0], tsv[0], in[0]);
             if (vb) o[1] = ctx.one(P, fr[1], single[1], fsv[1], tsv[1], in[1]);
+        }
+        if (j == PPT - 1 && ROWS_STAGED) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar);
         }
         if (do_out) {
             if constexpr (F64) store_pair<true, FULL>(P.out, p, va, vb, o[0], o[1]);
@@ -271,6 +279,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
     TileInfo* s_info  = reinterpret_cast<TileInfo*>(s_meta + Cfg::STAGES);
     uint64_t* s_full  = reinterpret_cast<uint64_t*>(s_info + Cfg::STAGES);
     uint64_t* s_empty = s_full + Cfg::STAGES;
+    uint8_t*  s_rows  = reinterpret_cast<uint8_t*>(s_empty + Cfg::STAGES);        // Cfg::STAGES x ROW_STAGE (16-byte aligned)
 
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     asm volatile("" : "+r"(warp), "+r"(lane));                                  // keep them in registers (no S2R re-reads in the loop)
@@ -292,6 +301,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
         int s = 0; uint32_t ph = 0;
         int64_t hint = -1;
         int64_t base = tile0 + t_begin * Cfg::TP;
+        [[maybe_unused]] int64_t p_t0 = 0; [[maybe_unused]] double p_rate = 0.0;   // same bracket guess as PointCtx::init
+        if constexpr (MODE == kSlerp && !GEN && !F64) {
+            p_t0 = __ldg(P.samp_ts);
+            const int64_t span = __ldg(P.samp_ts + P.n_samp - 1) - p_t0;
+            p_rate = span > 0 ? (double)(P.n_samp - 1) / (double)span : 0.0;
+        }
         for (int32_t it = 0; it < my_tiles; ++it, base += Cfg::TP) {
             mbar_wait(empty0 + 8 * s, ph ^ 1);                                   // slot free (first lap passes)
             const int64_t lim_lo = base > P.p_begin ? base : P.p_begin;
@@ -303,7 +318,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
                 hint = (int64_t)s_meta[s].f_lo + (s_meta[s].overflow ? 0 : s_meta[s].nb);   // frame of the tile's last point
             }
             if (lane == 0) {
-                TileInfo inf{ base, lim_lo, lim_hi, full ? 1 : 0, 0, 0x7fffffff, 1, 0, 0, 0 };
+                TileInfo inf{ base, lim_lo, lim_hi, full ? 1 : 0, 0, 0x7fffffff, 1, 0, 0, 0, 0 };
                 if constexpr (MODE != kQuantOnly) {
                     const TileMeta& tm = s_meta[s];
                     const int32_t nb = tm.nb;
@@ -318,11 +333,35 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
                         if (P.frame_start != nullptr) { inf.fs0 = tm.fstart[0]; inf.fs1 = tm.fstart[nb]; }
                     }
                 }
+                uint32_t row_bytes = 0;
+                const double* row_src = nullptr;
+                if constexpr (MODE == kSlerp && !GEN && !F64) {
+                    // the pose rows this tile reads, from the times of its first and last point (exact for time-ordered
+                    // points; anything outside the staged window is simply read from global memory by the consumer)
+                    if (full && !s_meta[s].overflow && (reinterpret_cast<uintptr_t>(P.samp_tab) & 15u) == 0) {
+                        int64_t ta, tb;
+                        if constexpr (F64) {
+                            ta = __ldg(reinterpret_cast<const int64_t*>(P.ts) + lim_lo); tb = __ldg(reinterpret_cast<const int64_t*>(P.ts) + lim_hi - 1);
+                        } else {
+                            ta = (int64_t)__ldg(reinterpret_cast<const uint32_t*>(P.ts) + lim_lo) + s_meta[s].fstart[0];
+                            tb = (int64_t)__ldg(reinterpret_cast<const uint32_t*>(P.ts) + lim_hi - 1) + s_meta[s].fstart[s_meta[s].nb];
+                        }
+                        int64_t ka = (int64_t)__double2ll_rz((double)(ta - p_t0) * p_rate) - 1, kb = (int64_t)__double2ll_rz((double)(tb - p_t0) * p_rate) + 2;
+                        ka = ka < 0 ? 0 : ka; kb = kb > P.n_samp ? P.n_samp : kb;
+                        if (kb > ka) {
+                            if (kb - ka > Cfg::ROWS) kb = ka + Cfg::ROWS;
+                            inf.k_base = (int32_t)ka; inf.n_rows = (int32_t)(kb - ka);
+                            row_bytes = (uint32_t)(kb - ka) * (uint32_t)(kSegStride * 8);
+                            row_src = P.samp_tab + kSegStride * ka;
+                        }
+                    }
+                }
                 s_info[s] = inf;
                 uint8_t* st = s_stage + s * Cfg::STAGE;
                 if (full) {
-                    const uint32_t bytes = Cfg::PTS_STAGE + (has_ts ? Cfg::TS_STAGE : 0) + (has_tag ? Cfg::TAG_STAGE : 0);
+                    const uint32_t bytes = Cfg::PTS_STAGE + (has_ts ? Cfg::TS_STAGE : 0) + (has_tag ? Cfg::TAG_STAGE : 0) + row_bytes;
                     mbar_arrive_expect_tx(full0 + 8 * s, bytes);
+                    if (row_bytes) bulk_g2s(s_rows + s * Cfg::ROW_STAGE, row_src, row_bytes, full0 + 8 * s);
                     bulk_g2s(st, reinterpret_cast<const uint8_t*>(P.pts) + base * Cfg::PT_BYTES, Cfg::PTS_STAGE, full0 + 8 * s);
                     if (has_ts)  bulk_g2s(st + Cfg::PTS_STAGE, reinterpret_cast<const uint8_t*>(P.ts) + base * Cfg::TS_BYTES, Cfg::TS_STAGE, full0 + 8 * s);
                     if (has_tag) bulk_g2s(st + Cfg::PTS_STAGE + Cfg::TS_STAGE, P.tag + base, Cfg::TAG_STAGE, full0 + 8 * s);
@@ -344,7 +383,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
             mbar_wait(full0 + 8 * s, ph);
             const TileInfo ti = s_info[s];
             const uint8_t* st = s_stage + s * Cfg::STAGE;
-            if (ti.full) consume_tile<F64, MODE, EX, true>(P, ti, s_meta[s], st, st + Cfg::PTS_STAGE, st + Cfg::PTS_STAGE + Cfg::TS_STAGE, slab, empty0 + 8 * s, ctx, fl, warp, lane);
+            if (ti.full) consume_tile<F64, MODE, EX, true>(P, ti, s_meta[s], st, st + Cfg::PTS_STAGE, st + Cfg::PTS_STAGE + Cfg::TS_STAGE, slab, empty0 + 8 * s, ctx, fl, warp, lane,
+                                                           smem_u32(s_info + s), smem_u32(s_rows + s * Cfg::ROW_STAGE));
             else         consume_tile<F64, MODE, EX, false>(P, ti, s_meta[s], st, st + Cfg::PTS_STAGE, st + Cfg::PTS_STAGE + Cfg::TS_STAGE, slab, empty0 + 8 * s, ctx, fl, warp, lane);
             if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
