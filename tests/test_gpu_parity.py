@@ -396,6 +396,45 @@ def test_slerp_table_device_builder():
     assert one.shape == (1, 22) and one[0, 15] == 0.0 and np.abs(one[0, :9] - w2[0, :9]).max() <= 1.5e-15
 
 
+@pytest.mark.parametrize("case", ["dense_table", "reversed_frames", "shuffled_times"])
+def test_mode_c_staged_rows_fallbacks(case):
+    """The streaming Mode C kernel stages each tile's pose rows in shared memory from the times of the tile's first and
+    last point.  Whatever is not in that window must come from global memory with identical results: a table so dense
+    that a tile spans more rows than the stage holds, frames stored in reverse time order (empty window), and
+    per-point times shuffled inside each frame (rows outside the window)."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(77)
+    F, Pn = 96, 10_000
+    st = synth.make_stream(F, Pn, 77, device=DEV, dtype=torch.float32)
+    fstart = st.frame_start.copy()
+    ts_off = st.ts_off.cpu().numpy().astype(np.int64)
+    s_ts, quat, pos = st.sample_ts, st.sample_quat, st.sample_pos
+    if case == "dense_table":                              # 4 kHz pose samples: ~115 rows per 2880-point tile
+        s_ts = np.arange(0, int(F * 0.1 * 4000) + 1, dtype=np.int64) * 250_000
+        eul = np.column_stack([0.05 * np.sin(s_ts * 1e-9 * 3.0), 0.03 * np.cos(s_ts * 1e-9 * 2.0), s_ts * 1e-9 * 0.4])
+        quat = Rotation.from_euler('xyz', eul).as_quat()
+        pos = np.column_stack([10 * np.sin(s_ts * 1e-9), 5 * np.cos(s_ts * 1e-9 * 0.7), np.full(len(s_ts), 1.5)])
+    elif case == "reversed_frames":
+        fstart = fstart[::-1].copy()
+    else:
+        ts_off = ts_off.reshape(F, Pn)
+        ts_off = np.stack([rng.permutation(r) for r in ts_off]).reshape(-1)
+    seg = FR.slerp_segment_table(quat, pos, s_ts)
+    ts64 = fstart[np.repeat(np.arange(F), Pn)] + ts_off
+    pts64 = st.pts.cpu().numpy().astype(np.float64)
+    want = orc.C.deskew_slerp_f64(pts64, ts64, st.frame_off, s_ts, seg)
+    C.set_path(C.PATH_TMA)
+    try:
+        out, b = ops.deskew_slerp(st.pts, dev(ts_off.astype(np.uint32)), dev(st.frame_off), dev(fstart), dev(s_ts), dev(seg),
+                                  export=ops.ExportSpec(lvx=True))
+    finally:
+        C.set_path(C.PATH_AUTO)
+    got = out.cpu().numpy().astype(np.float64)
+    assert np.abs(got - want).max() <= TOL_M
+    assert (got.astype(np.float32) != want.astype(np.float32)).sum() <= 4
+    assert np.array_equal(b.lvx14.cpu().numpy(), orc.C.quantize_lvx_type2(pts64)[0])
+
+
 def test_mode_c_hold_next_is_mode_a():
     """Mode A == Mode C with the interpolation weight forced to hold-next: bit-identical."""
     F = 25
