@@ -98,6 +98,10 @@ __device__ __forceinline__ void stg256(float* p, const float (&v)[8]) {
                  : "memory");
 }
 
+__device__ __forceinline__ void lds_f64x2(uint32_t addr, double& a, double& b) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+
 // ------------------------------------------------------------------------------------------
 // Reference operation orders
 // ------------------------------------------------------------------------------------------
@@ -148,6 +152,19 @@ __device__ __forceinline__ void sin_vercos_small(double x, double& s, double& v)
     s = fma(x * u, ps, x);
     v = u * pc;
 }
+// Gyro deskew angles are rate * (<= 0.1 s): below 2^-4 rad for anything a vehicle does (0.6 rad/s).  Degree 9 / 8
+// is then exact to half an ulp (next terms 2e-20 / 3e-19), and cos comes out of one FMA instead of 1 - v:
+// 8 FP64 operations per angle instead of 13.  Mode B picks this tier per POINT (all three angles below
+// kTinyAngle), in the fast and the general path alike, so a point's result does not depend on which path
+// evaluated it.
+constexpr double kTinyAngle = 0.0625;
+__device__ __forceinline__ void sin_cos_tiny(double x, double& s, double& c) {          // |x| < kTinyAngle
+    const double u = x * x;
+    const double ps = fma(fma(fma(kSinC[3], u, kSinC[4]), u, kSinC[5]), u, kSinC[6]);
+    const double pc = fma(fma(fma(-kCosC[4], u, -kCosC[5]), u, -kCosC[6]), u, -kCosC[7]);
+    s = fma(x * u, ps, x);
+    c = fma(u, pc, 1.0);
+}
 __device__ __forceinline__ void sin_vercos_mid(double x, double& s, double& v) {        // |x| <= 0.5
     const double u = x * x;
     double ps = kSinC[0], pc = kCosC[0];
@@ -174,11 +191,18 @@ __device__ __forceinline__ void sin_vercos(double x, double& s, double& v) {
 // (CS:1465) M @ p in gemv order.  The structural zeros/ones of the factors are kept as literal
 // operands so signed zeros and non-finite inputs behave exactly like the reference's dgemm.
 __device__ __forceinline__ void gyro_rotate(double ax, double ay, double az, const Pt& p, Pt& o) {
-    double sa, va, sb, vb, sc, vc;
-    sin_vercos(-ax, sa, va);
-    sin_vercos(-ay, sb, vb);
-    sin_vercos(-az, sc, vc);
-    const double ca = 1.0 - va, cb = 1.0 - vb, cc = 1.0 - vc;
+    double sa, ca, sb, cb, sc, cc;
+    if (fmax(fmax(fabs(ax), fabs(ay)), fabs(az)) < kTinyAngle) {
+        sin_cos_tiny(-ax, sa, ca);
+        sin_cos_tiny(-ay, sb, cb);
+        sin_cos_tiny(-az, sc, cc);
+    } else {
+        double va, vb, vc;
+        sin_vercos(-ax, sa, va);
+        sin_vercos(-ay, sb, vb);
+        sin_vercos(-az, sc, vc);
+        ca = 1.0 - va; cb = 1.0 - vb; cc = 1.0 - vc;
+    }
     const double Rx[9] = { 1.0, 0.0, 0.0,   0.0, ca, -sa,   0.0, sa, ca };
     const double Ry[9] = { cb, 0.0, sb,   0.0, 1.0, 0.0,   -sb, 0.0, cb };
     const double Rz[9] = { cc, -sc, 0.0,   sc, cc, 0.0,   0.0, 0.0, 1.0 };
@@ -203,12 +227,20 @@ __device__ __forceinline__ void gyro_rotate(double ax, double ay, double az, con
 // away: every surviving operation is the one the dgemm chain of gyro_rotate() performs on non-zero
 // operands (x*0 terms and "+0" additions dropped), so results agree bit-for-bit except possibly in the
 // sign of an exact zero.  14 FP64 ops for the matrix instead of 54, branch-free.
+template <bool TINY>
 __device__ __forceinline__ void gyro_rotate_small(double ax, double ay, double az, const Pt& p, Pt& o) {
-    double sa, va, sb, vb, sc, vc;
-    sin_vercos_small(-ax, sa, va);
-    sin_vercos_small(-ay, sb, vb);
-    sin_vercos_small(-az, sc, vc);
-    const double ca = 1.0 - va, cb = 1.0 - vb, cc = 1.0 - vc;
+    double sa, ca, sb, cb, sc, cc;
+    if constexpr (TINY) {                                                // every |angle| < kTinyAngle
+        sin_cos_tiny(-ax, sa, ca);
+        sin_cos_tiny(-ay, sb, cb);
+        sin_cos_tiny(-az, sc, cc);
+    } else {
+        double va, vb, vc;
+        sin_vercos_small(-ax, sa, va);
+        sin_vercos_small(-ay, sb, vb);
+        sin_vercos_small(-az, sc, vc);
+        ca = 1.0 - va; cb = 1.0 - vb; cc = 1.0 - vc;
+    }
     const double t10 = __dmul_rn(sa, sb), t20 = -__dmul_rn(ca, sb);         // (Rx Ry)[1][0], [2][0]
     const double m00 = __dmul_rn(cb, cc), m01 = -__dmul_rn(cb, sc), m02 = sb;
     const double m10 = __fma_rn(ca, sc, __dmul_rn(t10, cc)), m11 = __fma_rn(ca, cc, -__dmul_rn(t10, sc)), m12 = -__dmul_rn(sa, cb);
@@ -546,19 +578,25 @@ struct PointCtx {
                 int32_t k = __double2int_rz(__dmul_rn((double)(ta - t0), rate));
                 k = max(0, min(k, (int32_t)S - 2));
                 const double2* sr = reinterpret_cast<const double2*>(P.samp_tab + (int64_t)kSegStride * k);
+                [[maybe_unused]] bool in_s = false; [[maybe_unused]] uint32_t row_s = 0;
                 if constexpr (CACHE) {
                     uint32_t kb, nr;
                     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(kb), "=r"(nr) : "r"(info_s + 56u));
                     const uint32_t r = (uint32_t)k - kb;
-                    if (r < nr) sr = reinterpret_cast<const double2*>(__cvta_shared_to_generic(rows_s + r * (uint32_t)(kSegStride * 8)));
+                    in_s = r < nr; row_s = rows_s + r * (uint32_t)(kSegStride * 8);      // explicit LDS below: a generic pointer costs V4 2.5 %
                 }
                 // Only the "front" of the row (axis, theta, dpos, 1/dt, t_k, dt_k = columns 12..21) is kept in
                 // registers across pairs; R_k and pos_k (columns 0..11) are re-read per pair from L1, where the
                 // row stays hot -- holding all 22 doubles plus two points in flight overflows 128 registers
                 // and the spills cost more LSU traffic than six broadcast loads.
                 if (k != key) {
+                    if (CACHE && in_s) {
 #pragma unroll
-                    for (int q = 6; q < kSegStride / 2; ++q) { const double2 v = CACHE ? sr[q] : __ldg(sr + q); tab[2 * q] = v.x; tab[2 * q + 1] = v.y; }
+                        for (int q = 6; q < kSegStride / 2; ++q) lds_f64x2(row_s + 16 * q, tab[2 * q], tab[2 * q + 1]);
+                    } else {
+#pragma unroll
+                        for (int q = 6; q < kSegStride / 2; ++q) { const double2 v = __ldg(sr + q); tab[2 * q] = v.x; tab[2 * q + 1] = v.y; }
+                    }
                     key = k;
                 }
                 const int64_t tk = __double_as_longlong(tab[20]);
@@ -567,8 +605,13 @@ struct PointCtx {
                 // the row's own [t_k, t_k + dt_k) verifies the guess for both points at once
                 if ((uint64_t)da < dtk && (uint64_t)db < dtk && tab[15] <= kSmallAngle) {
                     double row[kSegStride];
+                    if (CACHE && in_s) {
 #pragma unroll
-                    for (int q = 0; q < 6; ++q) { const double2 v = CACHE ? sr[q] : __ldg(sr + q); row[2 * q] = v.x; row[2 * q + 1] = v.y; }
+                        for (int q = 0; q < 6; ++q) lds_f64x2(row_s + 16 * q, row[2 * q], row[2 * q + 1]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) { const double2 v = __ldg(sr + q); row[2 * q] = v.x; row[2 * q + 1] = v.y; }
+                    }
 #pragma unroll
                     for (int q = 12; q < kSegStride; ++q) row[q] = tab[q];
                     const double a0 = __dmul_rn((double)da, row[19]);
@@ -607,7 +650,7 @@ struct PointCtx {
                 const int64_t dd[2] = { ta - tk, tb - tk };
                 if ((uint64_t)dd[0] < dtk && (uint64_t)dd[1] < dtk) {
                     double ang[2][3];
-                    double amax = 0.0;
+                    double am[2] = {0.0, 0.0};
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         // alpha = (t - t_before) / (t_after - t_before) (CS:1503): reciprocal + two Markstein
@@ -621,12 +664,21 @@ struct PointCtx {
                         for (int c = 0; c < 3; ++c) {
                             const double gc = __dadd_rn(tab[c], __dmul_rn(q, tab[3 + c]));             // CS:1507-1509
                             ang[h][c] = __dmul_rn(gc, dt);                                            // CS:1457-1458
-                            amax = fmax(amax, fabs(ang[h][c]));
+                            am[h] = fmax(am[h], fabs(ang[h][c]));
                         }
                     }
-                    if (amax <= kSmallAngle) {
-                        gyro_rotate_small(ang[0][0], ang[0][1], ang[0][2], in[0], out[0]);
-                        gyro_rotate_small(ang[1][0], ang[1][1], ang[1][2], in[1], out[1]);
+                    const double amax = fmax(am[0], am[1]);
+                    if (amax < kTinyAngle) {                                  // what a vehicle-mounted IMU produces
+                        gyro_rotate_small<true>(ang[0][0], ang[0][1], ang[0][2], in[0], out[0]);
+                        gyro_rotate_small<true>(ang[1][0], ang[1][1], ang[1][2], in[1], out[1]);
+                        return;
+                    }
+                    if (amax <= kSmallAngle) {                                // polynomial tier per point, as gyro_rotate() picks it
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (am[h] < kTinyAngle) gyro_rotate_small<true>(ang[h][0], ang[h][1], ang[h][2], in[h], out[h]);
+                            else                    gyro_rotate_small<false>(ang[h][0], ang[h][1], ang[h][2], in[h], out[h]);
+                        }
                         return;
                     }
                 }
