@@ -259,6 +259,29 @@ int lmc_pcd_ascii_write_f32(const float* pts_n4, int64_t n_points, const int64_t
                             uint8_t* text_out, uint32_t* status, void* stream);
 
 /*
+ * Byte offsets of arbitrary rows inside the text _write produces (e.g. the frame boundaries of a frame-major
+ * buffer): byte_off[q] = offset of the first byte of row rows[q] (rows[q] = n_points gives the total size).
+ * One formatting pass then serves every per-frame file of save_results (LMC:870-884: raw_scans_pcd/frame_%04d.pcd,
+ * aligned_scans_pcd/aligned_frame_%04d.pcd) and the merged files (LMC:893-899) as slices of the same text.
+ * rows / byte_off are device arrays of n_rows entries; tile_off as filled by _size.
+ */
+int lmc_pcd_ascii_row_offsets_f64(const double* pts_n4, int64_t n_points, const int64_t* tile_off,
+                                  const int64_t* rows, int32_t n_rows, int64_t* byte_off, void* stream);
+int lmc_pcd_ascii_row_offsets_f32(const float* pts_n4, int64_t n_points, const int64_t* tile_off,
+                                  const int64_t* rows, int32_t n_rows, int64_t* byte_off, void* stream);
+
+/*
+ * Host-side staging helpers (HOST pointers, synchronous, no device work).  The reference's interface is lists of
+ * small per-frame arrays (results['raw_scans'][i]['points_local'], LMC:818-823; np.vstack at LMC:888): packing
+ * them into one pinned frame-major buffer is memory-bound host work, split here over n_threads threads.
+ *   lmc_host_gather: source i (src[i], dst_off[i+1] - dst_off[i] bytes) is copied to dst + dst_off[i]; dst_off has
+ *                    n_src + 1 non-decreasing entries.
+ *   lmc_host_copy:   plain copy of n_bytes.
+ */
+int lmc_host_gather(const void* const* src, const int64_t* dst_off, int64_t n_src, void* dst, int32_t n_threads);
+int lmc_host_copy(void* dst, const void* src, int64_t n_bytes, int32_t n_threads);
+
+/*
  *  the complete simulator's text exports, replaces the per-row Python loops of
  * DataExporter._export_pcd (CS:1663-1664, '%.6f %.6f %.6f %.0f %.0f\n' over [x y z intensity timestamp]),
  * _export_xyz (CS:1703, np.savetxt '%.6f' x 3) and the body of _export_csv (CS:1711-1712, pandas

@@ -5,6 +5,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
+#include <thread>
+#include <vector>
 #include "lmc_device.cuh"
 
 namespace lmc {
@@ -13,6 +16,8 @@ cudaError_t launch_tma(bool f64, int mode, const Params& P, cudaStream_t st, boo
 cudaError_t launch_pose_lookup(const double*, int64_t, const double*, const double*, int32_t, double*, int32_t*, cudaStream_t);
 cudaError_t launch_pcd_size(bool f64, const void* pts, int64_t n, int64_t* tile_off, cudaStream_t st);
 cudaError_t launch_pcd_write(bool f64, const void* pts, int64_t n, const int64_t* tile_off, uint8_t* out, uint32_t* status, cudaStream_t st);
+cudaError_t launch_pcd_row_off(bool f64, const void* pts, int64_t n, const int64_t* tile_off, const int64_t* rows, int32_t n_rows,
+                               int64_t* byte_off, cudaStream_t st);
 cudaError_t launch_scan_mark(const double* env, int64_t M, const double* pos, const double* R, int32_t F, double rmax2, double fh, double fv,
                              double rmin, double edge_eps, uint8_t* flags, int32_t* tile_off, int32_t* n_visible, int32_t* n_uncertain, cudaStream_t st);
 cudaError_t launch_scan_recount(const uint8_t* flags, int64_t M, int32_t F, int32_t* tile_off, int32_t* n_visible, cudaStream_t st);
@@ -325,6 +330,14 @@ static int pcd_write(bool f64, const void* pts, int64_t n, const int64_t* tile_o
     cudaError_t e = lmc::launch_pcd_write(f64, pts, n, tile_off, out, status, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_pcd_write");
 }
+static int pcd_row_off(bool f64, const void* pts, int64_t n, const int64_t* tile_off, const int64_t* rows, int32_t n_rows, int64_t* byte_off, void* stream) {
+    int rc = check_device();
+    if (rc != LMC_OK) return rc;
+    if (n < 0 || n_rows < 0 || !tile_off || (n > 0 && !pts) || (n_rows > 0 && (!rows || !byte_off))) return fail(LMC_ERR_INVALID, "bad argument");
+    if (!aligned32(pts)) return fail(LMC_ERR_ALIGN, "points must be 32-byte aligned");
+    cudaError_t e = lmc::launch_pcd_row_off(f64, pts, n, tile_off, rows, n_rows, byte_off, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_pcd_row_off");
+}
 static int text_check(const void* rows, int64_t n, int32_t row_stride, int32_t n_cols, const int32_t* col, const int32_t* dec, int32_t sep) {
     int rc = check_device();
     if (rc != LMC_OK) return rc;
@@ -371,6 +384,58 @@ int lmc_pcd_ascii_write_f64(const double* pts_n4, int64_t n_points, const int64_
 }
 int lmc_pcd_ascii_write_f32(const float* pts_n4, int64_t n_points, const int64_t* tile_off, uint8_t* text_out, uint32_t* status, void* stream) {
     return pcd_write(false, pts_n4, n_points, tile_off, text_out, status, stream);
+}
+
+int lmc_pcd_ascii_row_offsets_f64(const double* pts_n4, int64_t n_points, const int64_t* tile_off, const int64_t* rows, int32_t n_rows,
+                                  int64_t* byte_off, void* stream) { return pcd_row_off(true, pts_n4, n_points, tile_off, rows, n_rows, byte_off, stream); }
+int lmc_pcd_ascii_row_offsets_f32(const float* pts_n4, int64_t n_points, const int64_t* tile_off, const int64_t* rows, int32_t n_rows,
+                                  int64_t* byte_off, void* stream) { return pcd_row_off(false, pts_n4, n_points, tile_off, rows, n_rows, byte_off, stream); }
+
+// ---- host-side staging helpers (no device work): the reference hands over / expects lists of small per-frame
+// arrays; packing them into the pinned staging buffer (and unpacking results) is memory-bound host work that one
+// Python thread does at 8 GB/s.  These split the byte range over n_threads std::threads.
+static void run_threads(int n_threads, int64_t total, const std::function<void(int64_t, int64_t)>& body) {
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    const int64_t min_chunk = 1 << 20;                                       // not worth a thread below 1 MiB
+    int64_t want = (total + min_chunk - 1) / min_chunk;
+    if (want < 1) want = 1;
+    if (want < n_threads) n_threads = (int)want;
+    if (n_threads == 1) { body(0, total); return; }
+    std::vector<std::thread> th;
+    th.reserve(n_threads - 1);
+    const int64_t per = ((total + n_threads - 1) / n_threads + 63) & ~int64_t(63);
+    for (int t = 1; t < n_threads; ++t) {
+        const int64_t b = per * t, e = b + per < total ? b + per : total;
+        if (b < e) th.emplace_back(body, b, e);
+    }
+    body(0, per < total ? per : total);
+    for (auto& x : th) x.join();
+}
+int lmc_host_gather(const void* const* src, const int64_t* dst_off, int64_t n_src, void* dst, int32_t n_threads) {
+    if (n_src < 0 || (n_src > 0 && (!src || !dst_off || !dst))) return fail(LMC_ERR_INVALID, "bad argument");
+    if (n_src == 0) return LMC_OK;
+    for (int64_t i = 0; i < n_src; ++i) {
+        if (dst_off[i + 1] < dst_off[i]) return fail(LMC_ERR_INVALID, "dst_off must be non-decreasing");
+        if (dst_off[i + 1] > dst_off[i] && !src[i]) return fail(LMC_ERR_INVALID, "NULL source %lld", (long long)i);
+    }
+    const int64_t base = dst_off[0], total = dst_off[n_src] - base;
+    run_threads(n_threads, total, [&](int64_t b, int64_t e) {
+        // first source whose byte range reaches past b
+        int64_t lo = 0, hi = n_src;
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (dst_off[mid + 1] - base <= b) lo = mid + 1; else hi = mid; }
+        for (int64_t i = lo; i < n_src && dst_off[i] - base < e; ++i) {
+            const int64_t s0 = dst_off[i] - base, s1 = dst_off[i + 1] - base;
+            const int64_t c0 = s0 > b ? s0 : b, c1 = s1 < e ? s1 : e;
+            if (c1 > c0) memcpy(static_cast<char*>(dst) + base + c0, static_cast<const char*>(src[i]) + (c0 - s0), (size_t)(c1 - c0));
+        }
+    });
+    return LMC_OK;
+}
+int lmc_host_copy(void* dst, const void* src, int64_t n_bytes, int32_t n_threads) {
+    if (n_bytes < 0 || (n_bytes > 0 && (!dst || !src))) return fail(LMC_ERR_INVALID, "bad argument");
+    run_threads(n_threads, n_bytes, [&](int64_t b, int64_t e) { memcpy(static_cast<char*>(dst) + b, static_cast<const char*>(src) + b, (size_t)(e - b)); });
+    return LMC_OK;
 }
 
 static int las_build(bool f64, const void* pts, const double* gps_time, int64_t n, const double* scale, const double* offset,

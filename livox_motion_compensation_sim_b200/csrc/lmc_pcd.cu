@@ -202,6 +202,31 @@ __global__ void __launch_bounds__(kPcdTile) k_pcd_write(const void* __restrict__
     if (fl != 0 && status != nullptr) atomicOr(status, fl);
 }
 
+// Byte offset of the text of arbitrary rows (frame boundaries): one warp per query sums the line lengths of
+// the rows of its tile that precede the row.  With these offsets ONE formatting pass over the frame-major
+// buffer yields every per-frame file body of save_results (LMC:870-884) as a slice of the same text.
+template <bool F64>
+__global__ void __launch_bounds__(256) k_pcd_row_off(const void* __restrict__ pts, int64_t n, const int64_t* __restrict__ tile_off,
+                                                     const int64_t* __restrict__ rows, int32_t n_rows, int64_t* __restrict__ byte_off) {
+    const int lane = threadIdx.x & 31;
+    const int64_t qi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= n_rows) return;
+    int64_t r = rows[qi];
+    r = r < 0 ? 0 : (r > n ? n : r);
+    const int64_t tile = r / kPcdTile, first = tile * kPcdTile;
+    uint32_t sum = 0, fl = 0;
+    for (int64_t i = first + lane; i < r; i += 32) {
+        double v[4];
+        load_row<F64>(pts, i, v);
+        sum += 4;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sum += fmt_prepare(v[c], fl).len;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) byte_off[qi] = tile_off[tile] + sum;
+}
+
 // ---- generic delimited text rows: CS:1643-1716 (_export_pcd '%.6f %.6f %.6f %.0f %.0f', _export_xyz, _export_csv) ----
 // "%.{d}f" with d = 0..9 per column and the full integer range a timestamp column needs (ns since the
 // epoch ~ 1.7e18): the value is split exactly into its integer part I (< 2^64) and the fraction
@@ -386,6 +411,15 @@ cudaError_t launch_pcd_size(bool f64, const void* pts, int64_t n, int64_t* tile_
         else     k_pcd_len<false><<<(unsigned)tiles, kPcdTile, 0, st>>>(pts, n, tile_off);
     }
     k_pcd_scan<<<1, 1024, 0, st>>>(tile_off, tiles);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pcd_row_off(bool f64, const void* pts, int64_t n, const int64_t* tile_off, const int64_t* rows, int32_t n_rows,
+                               int64_t* byte_off, cudaStream_t st) {
+    if (n_rows <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n_rows + 7) / 8);
+    if (f64) k_pcd_row_off<true><<<grid, 256, 0, st>>>(pts, n, tile_off, rows, n_rows, byte_off);
+    else     k_pcd_row_off<false><<<grid, 256, 0, st>>>(pts, n, tile_off, rows, n_rows, byte_off);
     return cudaGetLastError();
 }
 

@@ -10,6 +10,8 @@ LMC = lidar_motion_compensation.py        CS = livox_mid70_complete_simulator.py
 """
 from __future__ import annotations
 
+import ctypes
+import os
 from typing import List, Sequence, Tuple
 
 import numpy as np
@@ -26,10 +28,42 @@ def frame_offsets(frames: Sequence[np.ndarray]) -> np.ndarray:
     return off
 
 
+def _host_threads() -> int:
+    try:
+        return max(1, min(16, len(os.sched_getaffinity(0))))
+    except AttributeError:                                   # pragma: no cover
+        return max(1, min(16, os.cpu_count() or 1))
+
+
+def _addr(a: np.ndarray) -> int:
+    """Address of an array's first byte (the cheapest route CPython offers: ~0.8 us per array)."""
+    if a.nbytes == 0:
+        return 0
+    try:
+        return ctypes.addressof(ctypes.c_char.from_buffer(a))
+    except (TypeError, ValueError):                          # read-only buffer
+        return a.__array_interface__['data'][0]
+
+
 def flatten_frames_into(frames: Sequence[np.ndarray], flat: np.ndarray) -> None:
-    """Frame-major concatenation into a caller-provided (N,4) buffer (e.g. a pinned staging array)."""
-    if len(flat):
-        np.concatenate([np.asarray(f).reshape(-1, 4) for f in frames], axis=0, out=flat, casting='unsafe')
+    """Frame-major concatenation into a caller-provided (N,4) buffer (e.g. a pinned staging array).
+
+    Frames that already have the buffer's dtype and are C-contiguous (what the reference's scanner produces) are
+    packed by liblmc_b200's multi-threaded ``lmc_host_gather``; anything else goes through one NumPy pass."""
+    if not len(flat):
+        return
+    arrs = [np.asarray(f) for f in frames]
+    if flat.flags.c_contiguous and all(a.dtype == flat.dtype and a.flags.c_contiguous for a in arrs):
+        from . import _capi as C
+        n = len(arrs)
+        ptrs = np.fromiter((_addr(a) for a in arrs), dtype=np.uintp, count=n)
+        boff = np.zeros(n + 1, np.int64)
+        np.cumsum(np.fromiter((a.nbytes for a in arrs), dtype=np.int64, count=n), out=boff[1:])
+        if int(boff[-1]) != flat.nbytes:
+            raise ValueError(f"frames hold {int(boff[-1])} bytes, the buffer {flat.nbytes}")
+        C.check(C.lib().lmc_host_gather(ptrs.ctypes.data, boff.ctypes.data, n, flat.ctypes.data, _host_threads()))
+        return
+    np.concatenate([a.reshape(-1, 4) for a in arrs], axis=0, out=flat, casting='unsafe')
 
 
 def flatten_frames(frames: Sequence[np.ndarray], dtype=np.float64) -> Tuple[np.ndarray, np.ndarray]:

@@ -275,6 +275,30 @@ def pcd_ascii_body(pts: torch.Tensor):
     return out, status
 
 
+def pcd_ascii_frames(pts: torch.Tensor, frame_off: torch.Tensor):
+    """(N2) the '%.6f' bodies of EVERY per-frame PCD file in one formatting pass: pts is the frame-major buffer,
+    frame_off int64[F+1] its CSR offsets (device).  Returns (uint8 text tensor, int64[F+1] device byte offsets,
+    status): frame f's file body (LMC:946-947 over that frame's rows) is text[byte_off[f]:byte_off[f+1]], and the
+    whole text is the body of the merged file (np.vstack order, LMC:888 / 897)."""
+    f64 = _layout(pts)
+    n = pts.shape[0]
+    tiles = (n + C.PCD_TILE - 1) // C.PCD_TILE
+    tile_off = torch.empty(tiles + 1, dtype=torch.int64, device=pts.device)
+    status = torch.zeros(1, dtype=torch.int32, device=pts.device)
+    nq = frame_off.shape[0]
+    byte_off = torch.empty(nq, dtype=torch.int64, device=pts.device)
+    L = C.lib()
+    ptr = _req(pts, pts.dtype, "pts", (4,))
+    C.check((L.lmc_pcd_ascii_size_f64 if f64 else L.lmc_pcd_ascii_size_f32)(ptr, n, tile_off.data_ptr(), _stream_ptr()))
+    C.check((L.lmc_pcd_ascii_row_offsets_f64 if f64 else L.lmc_pcd_ascii_row_offsets_f32)(
+        ptr, n, tile_off.data_ptr(), _req(frame_off, torch.int64, "frame_off"), nq, byte_off.data_ptr(), _stream_ptr()))
+    total = int(tile_off[-1].item())                       # the one host sync: the text buffer has to be sized
+    out = torch.empty(total, dtype=torch.uint8, device=pts.device)
+    C.check((L.lmc_pcd_ascii_write_f64 if f64 else L.lmc_pcd_ascii_write_f32)(ptr, n, tile_off.data_ptr(), out.data_ptr(), status.data_ptr(),
+                                                                              _stream_ptr()))
+    return out, byte_off, status
+
+
 def text_rows(rows: torch.Tensor, cols, decimals, sep: str = " "):
     """(N2) CS:1643-1716 on the device: one line per row of a 2-D f64 / f32 tensor, column cols[k] printed as
     '%.{decimals[k]}f', joined by sep, '\\n' terminated -- byte-identical to the reference's f-strings /

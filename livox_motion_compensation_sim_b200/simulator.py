@@ -58,6 +58,10 @@ class LiDARMotionSimulator:
             # 'hold_next' = the reference's per-frame pose (LMC:802-812); 'slerp' = per-point deskew: every point's
             # timestamp is bracketed in the trajectory samples, orientation SLERPed, position lerped (north_star Mode C)
             'pose_interpolation': 'hold_next',
+            # results come back in page-locked host memory from torch's caching host allocator (a D2H copy into a fresh
+            # pageable array runs at ~2 GB/s: 30 of the 42 ms of an align_frames call on the reference's own run shapes);
+            # False = stage through the reusable pinned buffer and copy into an ordinary NumPy array
+            'pinned_results': True,
         }
 
     def _validate_config(self, config: Dict) -> None:
@@ -90,6 +94,25 @@ class LiDARMotionSimulator:
     def _to_dev(self, a: np.ndarray, dtype=None) -> torch.Tensor:
         t = torch.from_numpy(np.ascontiguousarray(a if dtype is None else a.astype(dtype, copy=False)))
         return t.to(self.device, non_blocking=False)
+
+    def _to_host(self, t: torch.Tensor) -> np.ndarray:
+        """Device result -> host array the caller owns."""
+        if t.device.type != 'cuda' or t.numel() == 0:
+            return t.cpu().numpy()
+        if self.config.get('pinned_results', True):
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)      # cached block after the first call of a size
+            h.copy_(t)
+            return h.numpy()                                              # keeps the pinned block alive while referenced
+        flat = t.reshape(-1)
+        n8 = (flat.numel() * flat.element_size() + 7) // 8
+        st = getattr(self, '_stage_out', None)
+        if st is None or st.shape[0] < n8:
+            self._stage_out = st = torch.empty(max(n8, 1 << 16), dtype=torch.int64, pin_memory=True)
+        hb = st.view(torch.uint8)[:flat.numel() * flat.element_size()]
+        hb.copy_(flat.view(torch.uint8))
+        out = np.empty(tuple(t.shape), dtype=torch.empty(0, dtype=t.dtype).numpy().dtype)
+        C.check(C.lib().lmc_host_copy(out.ctypes.data, hb.data_ptr(), out.nbytes, FR._host_threads()))
+        return out
 
     # ------------------------------------------------------------------ (a1) LMC:802-812
     def lookup_frame_poses(self, trajectory: Dict, lidar_times: np.ndarray):
@@ -128,7 +151,7 @@ class LiDARMotionSimulator:
                                    fov_vertical=c['fov_vertical'], points_per_frame=c['points_per_frame'],
                                    noise_std=c['lidar_range_noise'])
         self._dev_scan = (raw, off) if keep_device else None      # run_simulation aligns the device copy directly
-        host = raw.cpu().numpy()
+        host = self._to_host(raw)
         return [host[off[i]:off[i + 1]] if off[i + 1] > off[i] else np.array([]).reshape(0, 4) for i in range(len(off) - 1)]
 
     def scan_environment(self, environment, sensor_pose):
@@ -155,7 +178,7 @@ class LiDARMotionSimulator:
         pts_d = stage.to(self.device, non_blocking=True)
         out, bufs = ops.align_rigid(pts_d, self._to_dev(off), self._to_dev(pose), export=export)
         self._performance_stats['total_points_processed'] += n
-        return out.cpu().numpy(), off, bufs
+        return self._to_host(out), off, bufs
 
     # ------------------------------------------------------------------ LMC:778-858
     def run_simulation(self, frame_source=None):
@@ -199,7 +222,7 @@ class LiDARMotionSimulator:
             raw_d, off = dev_scan
             pose = FR.pose_table(trajectory['position_gps'][pose_idx], trajectory['orientation_imu'][pose_idx])
             out, _ = ops.align_rigid(raw_d, self._to_dev(off), self._to_dev(pose))
-            self.last_merged, self.last_frame_off, self.last_export = out.cpu().numpy(), off, None
+            self.last_merged, self.last_frame_off, self.last_export = self._to_host(out), off, None
             self._performance_stats['total_points_processed'] += int(off[-1])
             aligned = FR.split_frames(self.last_merged, off)
         else:
@@ -259,26 +282,33 @@ class LiDARMotionSimulator:
         seg = ops.build_slerp_table(self._to_dev(quat), self._to_dev(np.asarray(trajectory['position_gps'], np.float64)), self._to_dev(s_ts))
         out, bufs = ops.deskew_slerp(flat_d, self._to_dev(ts), self._to_dev(off), self._to_dev(fstart), self._to_dev(s_ts), seg,
                                      export=export)
-        self.last_merged, self.last_frame_off, self.last_export = out.cpu().numpy(), off, bufs
+        self.last_merged, self.last_frame_off, self.last_export = self._to_host(out), off, bufs
         return FR.split_frames(self.last_merged, off)
 
     # ------------------------------------------------------------------ (a3) LMC:886-899
+    def _merge_flags(self, results):
+        """The reference's two merge guards (LMC:887-899) with its warnings: (merged_aligned exists, merged_raw exists)."""
+        aligned = results['aligned_pointclouds']
+        strict = self.config.get('strict_reference_merge', True)
+        has_aligned = bool(aligned) and (all(len(pc) > 0 for pc in aligned) or not strict)
+        if not has_aligned:
+            print("Warning: No aligned point clouds to merge")
+        has_raw = any(len(s['points_local']) > 0 for s in results['raw_scans'])
+        if not has_raw:
+            print("Warning: No raw point clouds to merge")
+        return has_aligned, has_raw
+
     def merge_results(self, results) -> Dict[str, Optional[np.ndarray]]:
         """merged_aligned / merged_raw with the reference's guards."""
         aligned = results['aligned_pointclouds']
         out: Dict[str, Optional[np.ndarray]] = {'merged_aligned': None, 'merged_raw': None}
-        strict = self.config.get('strict_reference_merge', True)
-        if aligned and (all(len(pc) > 0 for pc in aligned) or not strict):
+        has_aligned, has_raw = self._merge_flags(results)
+        if has_aligned:
             base = getattr(self, 'last_merged', None)
             same = base is not None and len(aligned) and aligned[0].base is base
             out['merged_aligned'] = base if same else np.vstack(aligned)
-        else:
-            print("Warning: No aligned point clouds to merge")
-        raw = [s['points_local'] for s in results['raw_scans'] if len(s['points_local']) > 0]
-        if raw:
-            out['merged_raw'] = np.vstack(raw)
-        else:
-            print("Warning: No raw point clouds to merge")
+        if has_raw:
+            out['merged_raw'] = np.vstack([s['points_local'] for s in results['raw_scans'] if len(s['points_local']) > 0])
         return out
 
     # ------------------------------------------------------------------ (a4) LMC:252-272 / 965-990
@@ -290,7 +320,7 @@ class LiDARMotionSimulator:
             return np.zeros((0, 14), np.uint8), off
         bufs = ops.quantize(self._to_dev(flat), ops.ExportSpec(lvx=True, lvx_mode=C.LVX_TYPE2_OF_INPUT))
         bufs.raise_for_flags()
-        return bufs.lvx14.cpu().numpy(), off
+        return self._to_host(bufs.lvx14), off
 
     # ------------------------------------------------------------------ (a5) LMC:950-963
     def quantize_las(self, points: np.ndarray):
@@ -314,24 +344,26 @@ class LiDARMotionSimulator:
         import pandas as pd
         if results.get('motion_data') is not None:
             pd.DataFrame(results['motion_data']).to_csv(os.path.join(output_dir, 'motion_data.csv'), index=False)
+        # LMC:870-899: every per-frame PCD and the two merged PCDs.  One formatting pass per cloud family: the text
+        # of the frame-major buffer IS the merged file's body, and each per-frame body is a slice of it
+        has_aligned, has_raw = self._merge_flags(results)
         pcd_dir = os.path.join(output_dir, 'raw_scans_pcd'); os.makedirs(pcd_dir, exist_ok=True)
-        for scan in results['raw_scans']:
-            self.save_pcd(scan['points_local'], os.path.join(pcd_dir, f'frame_{scan["frame_id"]:04d}.pcd'))
+        self.save_pcd_frames([scan['points_local'] for scan in results['raw_scans']],
+                             [os.path.join(pcd_dir, f'frame_{scan["frame_id"]:04d}.pcd') for scan in results['raw_scans']],
+                             os.path.join(output_dir, 'merged_raw_overlapped.pcd') if has_raw else None)
         aligned_dir = os.path.join(output_dir, 'aligned_scans_pcd'); os.makedirs(aligned_dir, exist_ok=True)
-        for i, pc in enumerate(results['aligned_pointclouds']):
-            self.save_pcd(pc, os.path.join(aligned_dir, f'aligned_frame_{i:04d}.pcd'))
-        merged = self.merge_results(results)
-        if merged['merged_aligned'] is not None:
-            self.save_pcd(merged['merged_aligned'], os.path.join(output_dir, 'merged_aligned.pcd'))
-        if merged['merged_raw'] is not None:
-            self.save_pcd(merged['merged_raw'], os.path.join(output_dir, 'merged_raw_overlapped.pcd'))
+        aligned = results['aligned_pointclouds']
+        aligned_d = self.save_pcd_frames(aligned, [os.path.join(aligned_dir, f'aligned_frame_{i:04d}.pcd') for i in range(len(aligned))],
+                                         os.path.join(output_dir, 'merged_aligned.pcd') if has_aligned else None)
         try:
-            if merged['merged_aligned'] is None:
+            if not has_aligned:
                 raise UnboundLocalError("merged_aligned")           # what LMC:903 hits when the merge was skipped
-            self.save_las(merged['merged_aligned'], os.path.join(output_dir, 'merged_aligned.las'))
+            self.save_las(np.zeros((0, 4)) if aligned_d is None else None, os.path.join(output_dir, 'merged_aligned.las'),
+                          _device_pts=aligned_d)                                    # the aligned cloud is still resident
             print("LAS format saved successfully")
         except Exception as e:                                       # LMC:905-906 swallows and prints
             print(f"Could not save LAS format: {e}")
+        del aligned_d
         try:
             self.save_lvx(results, os.path.join(output_dir, 'lidar_data'))
             print("LVX formats saved successfully")
@@ -345,34 +377,72 @@ class LiDARMotionSimulator:
         print("Results saved successfully!")
         return output_dir
 
+    @staticmethod
+    def _pcd_header(n: int) -> bytes:
+        """LMC:934-945."""
+        return ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z intensity\n"
+                "SIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\n"
+                f"WIDTH {n}\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS {n}\nDATA ascii\n").encode('ascii')
+
     def save_pcd(self, points, filename):
         """ASCII PCD, byte-identical to LMC:932-948 ('%.6f' per field); the point lines are formatted on the GPU."""
         points = np.asarray(points, np.float64).reshape(-1, 4)
         n = len(points)
-        header = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z intensity\n"
-                  "SIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\n"
-                  f"WIDTH {n}\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS {n}\nDATA ascii\n")
         with open(filename, 'wb') as f:
-            f.write(header.encode('ascii'))
+            f.write(self._pcd_header(n))
             if n:
                 body, status = ops.pcd_ascii_body(self._to_dev(points))       # (N2) '%.6f' formatting on the device
                 if int(status.item()):
                     raise OverflowError("save_pcd: |value| >= 9.2e12 is outside the device formatter's range")
                 f.write(body.cpu().numpy().tobytes())
 
-    def save_las(self, points, filename):
+    def save_pcd_frames(self, frames: Sequence[np.ndarray], filenames: Sequence[str], merged_filename: Optional[str] = None):
+        """save_pcd for a whole list of frames (LMC:870-884) plus their np.vstack (LMC:893-899) with ONE upload and
+        ONE formatting pass: the frame-major buffer is formatted once, frame f's file body is the byte range between
+        the offsets of its first and one-past-last row (``lmc_pcd_ascii_row_offsets``), the merged file's body is the
+        whole text.  Every file is byte-identical to what save_pcd writes.  Returns the device copy of the
+        frame-major (N,4) f64 buffer (None when there are no points)."""
+        if len(frames) != len(filenames):
+            raise ValueError("one filename per frame")
+        off = FR.frame_offsets(frames)
+        n = int(off[-1])
+        pts_d = None
+        if n:
+            stage = self._pinned_stage(n, np.float64)
+            FR.flatten_frames_into(frames, stage.numpy())
+            pts_d = stage.to(self.device, non_blocking=True)
+            text_d, boff_d, status = ops.pcd_ascii_frames(pts_d, self._to_dev(off))   # (syncs: the staging buffer is free again)
+            if int(status.item()):
+                raise OverflowError("save_pcd: |value| >= 9.2e12 is outside the device formatter's range")
+            text = memoryview(self._to_host(text_d))
+            boff = boff_d.cpu().numpy()
+        for i, fn in enumerate(filenames):
+            m = int(off[i + 1] - off[i])
+            with open(fn, 'wb') as f:
+                f.write(self._pcd_header(m))
+                if m:
+                    f.write(text[int(boff[i]):int(boff[i + 1])])
+        if merged_filename is not None:
+            with open(merged_filename, 'wb') as f:
+                f.write(self._pcd_header(n))
+                if n:
+                    f.write(text)
+        return pts_d
+
+    def save_las(self, points, filename, _device_pts: Optional[torch.Tensor] = None):
         """merged_aligned.las (LMC:950-963): LAS 1.2 / point format 3 with the laspy header defaults the
         reference relies on (scale 0.01, offset 0; config 'las_scale' / 'las_offset'), intensity scaled to
         16 bits.  The whole file image -- header extremes included -- is built on the device.  Parity
         with laspy's bytes is unpinned (laspy is not available); the file follows the LAS 1.2 spec."""
         import datetime
         today = datetime.date.today()
-        data, status = ops.build_las_pf3(self._to_dev(np.asarray(points, np.float64)), scale=self.config['las_scale'],
+        pts_d = _device_pts if _device_pts is not None else self._to_dev(np.asarray(points, np.float64))
+        data, status = ops.build_las_pf3(pts_d, scale=self.config['las_scale'],
                                          offset=self.config['las_offset'], intensity_mode=C.LAS_INTENSITY_UNIT,
                                          year=today.year, day_of_year=today.timetuple().tm_yday)
         ops.ExportBuffers(status=status).raise_for_flags()
         with open(filename, 'wb') as f:
-            f.write(data.cpu().numpy().tobytes())
+            f.write(memoryview(self._to_host(data)))
 
     def save_lvx(self, results, base_filename):
         """lidar_data.lvx with the LVX v1.1 container of LMC:58-250 around device-quantised records."""
@@ -394,4 +464,4 @@ class LiDARMotionSimulator:
                                          self._to_dev(ids), int(np.diff(off).max()))
         bufs = ops.ExportBuffers(status=status)
         bufs.raise_for_flags()
-        return data.cpu().numpy()
+        return self._to_host(data)

@@ -735,6 +735,72 @@ def test_pcd_ascii_large_random(f64):
     assert int(status.item()) & C.FLAG_OVERFLOW
 
 
+@pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
+def test_pcd_ascii_frames_one_pass(f64):
+    """Every per-frame PCD body out of ONE formatting pass: frame f's slice of the frame-major text equals the
+    frame formatted on its own (CPython '%' formatting), for frame boundaries on / next to the 256-row tiles,
+    empty frames at both ends, and the offset of row n = total size."""
+    rng = np.random.default_rng(12)
+    cnt = [0, 1, 255, 256, 257, 0, 0, 511, 513, 1024, 3, 700, 0]
+    off = np.zeros(len(cnt) + 1, np.int64); np.cumsum(cnt, out=off[1:])
+    n = int(off[-1])
+    pts = np.column_stack([rng.uniform(-2000, 2000, (n, 3)), rng.uniform(0, 1, n)])
+    pts[::5, 2] = np.round(pts[::5, 2], 2); pts[3::17, 0] *= 1e-5; pts[40, 1] = np.nan; pts[41, 1] = -np.inf
+    if not f64:
+        pts = pts.astype(np.float32)
+    text, boff, status = ops.pcd_ascii_frames(dev(pts), dev(off))
+    assert int(status.item()) == 0
+    t, b = text.cpu().numpy().tobytes(), boff.cpu().numpy()
+    assert b[0] == 0 and b[-1] == len(t)
+    whole, _ = ops.pcd_ascii_body(dev(pts))
+    assert whole.cpu().numpy().tobytes() == t
+    p64 = pts.astype(np.float64)
+    for i in range(len(cnt)):
+        want = "".join("%.6f %.6f %.6f %.6f\n" % tuple(r) for r in p64[off[i]:off[i + 1]]).encode()
+        assert t[b[i]:b[i + 1]] == want, i
+
+
+def test_save_results_files_are_save_pcd_files(golden, tmp_path):
+    """save_results writes every per-frame / merged PCD from the batched pass: byte-identical to save_pcd frame by
+    frame (which is pinned to the reference's file bytes), with the reference's merge guards; results come back
+    the same with pinned_results on and off."""
+    from livox_motion_compensation_sim_b200 import LiDARMotionSimulator
+    g = golden("lmc_C1a.npz")
+    off = g['frame_off']
+    F = len(off) - 1
+    raw_scans = [{'frame_id': int(g['frame_ids'][i]), 'timestamp': float(g['frame_t_all'][g['frame_ids'][i]]),
+                  'points_local': g['raw'][off[i]:off[i + 1]] if off[i + 1] > off[i] else np.array([]).reshape(0, 4),
+                  'sensor_pose': {'position': g['pose_position'][i], 'orientation': g['pose_euler'][i], 'velocity': np.zeros(3)}}
+                 for i in range(F)]
+    sim = LiDARMotionSimulator()
+    aligned = sim.align_scans(raw_scans)
+    sim2 = LiDARMotionSimulator({'pinned_results': False})
+    aligned2 = sim2.align_scans(raw_scans)
+    assert all(a.tobytes() == b.tobytes() for a, b in zip(aligned, aligned2))
+    assert sim.last_merged.tobytes() == g['aligned'].tobytes() == sim2.last_merged.tobytes()
+    results = {'raw_scans': raw_scans, 'aligned_pointclouds': aligned, 'motion_data': None, 'trajectory': None, 'environment': None}
+    d = sim.save_results(results, str(tmp_path / "out"))
+    one = tmp_path / "one.pcd"
+    any_empty = False
+    for i in range(F):
+        for cloud, fn in ((raw_scans[i]['points_local'], f"raw_scans_pcd/frame_{raw_scans[i]['frame_id']:04d}.pcd"),
+                          (aligned[i], f"aligned_scans_pcd/aligned_frame_{i:04d}.pcd")):
+            sim.save_pcd(cloud, str(one))
+            assert open(os.path.join(d, fn), 'rb').read() == one.read_bytes(), fn
+        any_empty |= len(aligned[i]) == 0
+    sim.save_pcd(g['raw'], str(one))
+    assert open(os.path.join(d, "merged_raw_overlapped.pcd"), 'rb').read() == one.read_bytes()
+    # LMC:887-891: a run with an empty frame writes no merged_aligned.pcd / .las
+    assert os.path.exists(os.path.join(d, "merged_aligned.pcd")) == (not any_empty)
+    assert os.path.exists(os.path.join(d, "merged_aligned.las")) == (not any_empty)
+    sim3 = LiDARMotionSimulator({'strict_reference_merge': False})
+    d3 = sim3.save_results(results, str(tmp_path / "out3"))
+    sim.save_pcd(g['aligned'], str(one))
+    assert open(os.path.join(d3, "merged_aligned.pcd"), 'rb').read() == one.read_bytes()
+    las = open(os.path.join(d3, "merged_aligned.las"), 'rb').read()
+    assert las[:4] == b"LASF" and len(las) == C.LAS_HEADER_BYTES + C.LAS_RECORD_BYTES * len(g['aligned'])
+
+
 @pytest.mark.parametrize("name", ["C1a", "C2a", "C3"])
 def test_scanner_whole_run_vs_reference(golden, name):
     """(N4) the reference's whole frame loop on the device: scan every frame (range / FOV cull, compaction,

@@ -100,6 +100,44 @@ def test_frame_times_and_flatten():
     assert [len(b) for b in back] == [0, 3, 0, 1]
 
 
+def test_host_gather_and_copy(built_lib):
+    """lmc_host_gather / lmc_host_copy (host-only helpers of the C ABI): the threaded pack of a frame list equals
+    np.vstack for ragged, empty, read-only and mixed-dtype lists, at every thread count."""
+    rng = np.random.default_rng(5)
+    cnt = rng.integers(0, 3000, 700)
+    cnt[[0, 5, 699]] = 0
+    frames = [rng.uniform(-90, 90, (c, 4)) for c in cnt]
+    frames[7] = np.array([]).reshape(0, 4)
+    frames[9].flags.writeable = False
+    want = np.vstack(frames)
+    flat = np.full_like(want, np.nan)
+    FR.flatten_frames_into(frames, flat)
+    assert flat.tobytes() == want.tobytes()
+    mixed = list(frames)
+    mixed[3] = mixed[3].astype(np.float32)                      # NumPy route (dtype conversion)
+    mixed[4] = np.asfortranarray(mixed[4])
+    flat[:] = np.nan
+    FR.flatten_frames_into(mixed, flat)
+    assert np.allclose(flat, want, rtol=1e-6)
+    with pytest.raises(ValueError):
+        FR.flatten_frames_into(frames[:-2], flat)
+    L = _capi.lib()
+    ptrs = np.array([FR._addr(a) for a in frames], np.uintp)
+    boff = np.zeros(len(frames) + 1, np.int64)
+    np.cumsum([a.nbytes for a in frames], out=boff[1:])
+    for th in (1, 2, 3, 7, 64, 1000, 0, -3):
+        dst = np.zeros(want.nbytes + 64, np.uint8)
+        assert L.lmc_host_gather(ptrs.ctypes.data, boff.ctypes.data, len(frames), dst.ctypes.data, th) == 0
+        assert dst[:want.nbytes].tobytes() == want.tobytes() and not dst[want.nbytes:].any()
+        dst2 = np.zeros(want.nbytes + 64, np.uint8)
+        assert L.lmc_host_copy(dst2.ctypes.data, want.ctypes.data, want.nbytes, th) == 0
+        assert dst2[:want.nbytes].tobytes() == want.tobytes() and not dst2[want.nbytes:].any()
+    assert L.lmc_host_gather(None, None, 0, None, 4) == 0 and L.lmc_host_copy(None, None, 0, 4) == 0
+    bad = boff.copy(); bad[3] = bad[4] + 8
+    assert L.lmc_host_gather(ptrs.ctypes.data, bad.ctypes.data, len(frames), flat.ctypes.data, 2) == _capi.ERR_INVALID
+    assert L.lmc_host_copy(None, want.ctypes.data, 8, 1) == _capi.ERR_INVALID
+
+
 def test_pose_table_is_scipy_exact(golden):
     g = golden("lmc_edge.npz")
     assert np.array_equal(FR.pose_table(g['pose_position'], g['pose_euler']), orc.pose_table_np(g['pose_position'], g['pose_euler']))
