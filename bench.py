@@ -386,6 +386,23 @@ def main_b200(args):
                     "aligned_sha256_matches_reference": hashlib.sha256(al.tobytes()).hexdigest() == man['aligned_sha256'],
                     "cpu_port_ms": cpu_loop_ms,
                     "what": "LiDARMotionSimulator.run_simulation with the device scanner (LMC:778-858 loop: lookup + scan_environment + transform), host noise replay, results as host arrays; cpu_port_ms = the oracle's C scanner + NumPy transform port of the same loop, 1 thread"}
+                # the run's hot-path outputs (LMC:860-930): 2 x 600 per-frame PCDs + 2 merged PCDs + LAS + LVX, text formatted
+                # / quantised / laid out on the device (one formatting pass per cloud family), files written to local disk
+                import shutil
+                import tempfile
+                tmpd = tempfile.mkdtemp(prefix="lmc_save_")
+                try:
+                    t0 = time.perf_counter()
+                    simr.save_results(resr, tmpd)
+                    save_ms = (time.perf_counter() - t0) * 1e3
+                    n_files = sum(len(fs) for _, _, fs in os.walk(tmpd))
+                    n_bytes = sum(os.path.getsize(os.path.join(dp, f)) for dp, _, fs in os.walk(tmpd) for f in fs)
+                    presets["urban_complex_60s_save_results"] = {
+                        "files": n_files, "bytes": n_bytes, "b200_save_results_ms": save_ms,
+                        "what": "LiDARMotionSimulator.save_results of that run: per-frame + merged PCD ('%.6f' text of 4 x 976 720 points), "
+                                "LAS, LVX v1.1, CSVs; the reference's per-point Python writers format 0.26-0.8 Mpts/s (PCD) and 0.04 Mpts/s (LVX)"}
+                finally:
+                    shutil.rmtree(tmpd, ignore_errors=True)
             # configs[2] wording: parking_detailed (circular, medium, 30 s at 20 fps) with the per-point deskew
             # (pose_interpolation='slerp'): lookup + scan of every frame + per-point SLERP alignment
             gp3 = os.path.join(ROOT, "tests", "golden", "scan_C3.npz")

@@ -295,6 +295,34 @@ def test_mode_b_synthetic_vs_oracle(f64, path):
     assert np.array_equal(b.las_intensity.cpu().numpy().view(np.uint16), I)
 
 
+@pytest.mark.parametrize("sigma", [0.05, 0.4, 3.0], ids=["tiny", "tiny+small", "all-tiers"])
+def test_mode_b_polynomial_tiers_are_path_independent(sigma, path):
+    """Mode B picks its sin / cos polynomial per POINT (all three angles < 2^-4: degree 9 / 8; else per angle:
+    <= 0.125, <= 0.5, library), so the straight-line pair path, the general path taken by ragged shard edges and
+    both kernels give the same bytes: odd-cut shards compose to the single launch, and every tier stays within
+    1e-10 m of the libm oracle."""
+    F, P = 12, 4001
+    st = synth.make_stream(F, P, 77, device=DEV, dtype=torch.float64)
+    rng = np.random.default_rng(3)
+    imu_ts = st.sample_ts[: F * 20 + 1]
+    gyro = rng.normal(0, sigma, (len(imu_ts), 3))
+    gyro[::9] *= 0.01                                         # tiny and larger angles inside one warp / one pair
+    ts64 = st.frame_start[np.repeat(np.arange(F), P)] + st.ts_off.cpu().numpy().astype(np.int64)
+    args = (dev(ts64), dev(st.frame_off), dev(st.frame_start), dev(imu_ts), dev(gyro))
+    whole, _ = ops.deskew_gyro(st.pts, *args)
+    want = orc.C.deskew_gyro_f64(st.pts.cpu().numpy(), ts64, st.frame_off, st.frame_start, imu_ts, gyro)
+    assert np.abs(whole.cpu().numpy() - want).max() <= 1e-10
+    out = torch.zeros_like(whole)
+    cuts = [0, 1, 4001, 9999, 10002, 30007, F * P]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        ops.deskew_gyro(st.pts, *args, out=out, p_range=(a, b))
+    assert torch.equal(out, whole)
+    C.set_path(C.PATH_DIRECT if path == C.PATH_TMA else C.PATH_TMA)
+    other, _ = ops.deskew_gyro(st.pts, *args)
+    C.set_path(path)
+    assert torch.equal(other, whole)
+
+
 def test_config2_parking_detailed_per_point_deskew(golden, path):
     """BASELINE configs[2]: parking_detailed (C3) frames with per-point timestamps against 200 Hz streams.
     Mode B: the reference MotionCompensator on its own 200 Hz IMU stream (golden config2.npz).
