@@ -103,6 +103,37 @@ __device__ __forceinline__ void lds_f64x2(uint32_t addr, double& a, double& b) {
 }
 
 // ------------------------------------------------------------------------------------------
+// shared -> global TMA bulk stores (cp.async.bulk, SASS UBLKCP.G.S).  Output that is assembled in shared
+// memory (packed 14-byte records, file images, text) leaves as ONE asynchronous bulk copy per contiguous
+// run instead of an LDS.128 + STG.128 round trip through registers per 16 bytes: fewer instructions, full-line
+// writes, and the issuing thread moves on while the copy drains.  The data was written through the generic
+// proxy, so every writer executes fence.proxy.async before the barrier that precedes the copy.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {      // 16-byte aligned, size % 16 == 0
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit()      { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0()  { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0()       { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Bytes [b0, b1) of a CTA's shared-memory image -> g[b0, b1), where the image was assembled at the destination's
+// 16-byte phase (g + k and img + k are congruent mod 16): aligned body as one bulk store by thread 0, ragged ends
+// byte-wise.  Contains the CTA barrier that completes the image; returns once the copy has finished reading it.
+__device__ __forceinline__ void cta_image_out(uint8_t* g, const uint8_t* img, int b0, int b1, int tid, int n_threads) {
+    fence_async_smem();
+    __syncthreads();
+    int a0 = (b0 + 15) & ~15; if (a0 > b1) a0 = b1;
+    int a1 = b1 & ~15;        if (a1 < a0) a1 = a0;
+    const bool body = tid == 0 && a1 > a0;
+    if (body) { bulk_s2g(g + a0, img + a0, (uint32_t)(a1 - a0)); bulk_commit(); }
+    for (int k = b0 + tid; k < a0; k += n_threads) g[k] = img[k];
+    for (int k = a1 + tid; k < b1; k += n_threads) g[k] = img[k];
+    if (body) bulk_wait_read0();
+}
+
+// ------------------------------------------------------------------------------------------
 // Reference operation orders
 // ------------------------------------------------------------------------------------------
 // sum_k a_k*b_k as OpenBLAS dgemm runs it for the reference's (3x3)@(3xN), N >= 2  (LMC:775)

@@ -9,7 +9,7 @@
 //   3. per point: frame -> pose (L1 broadcast) -> f64 transform in the reference's op order
 //   4. aligned points leave as 256-bit stores; LAS ints as 64-bit SoA stores; LVX 14-byte
 //      records are assembled as 7 words per point pair in shared memory (stride 7 words is
-//      coprime with 32 banks: conflict-free) and leave as 16-byte coalesced stores
+//      coprime with 32 banks: conflict-free) and leave as one TMA bulk store per tile
 //
 //   LMC = lidar_motion_compensation.py        CS = livox_mid70_complete_simulator.py
 #include "lmc_device.cuh"
@@ -109,21 +109,8 @@ __device__ __forceinline__ void tile_body(const Params& P, int64_t base, int64_t
         }
     }
 
-    if (P.lvx14 != nullptr) {
-        __syncthreads();
-        // copy bytes [b0, b1) of the tile's record block: 16-byte body, byte-wise ragged ends
-        const int b0 = (int)(lim_lo - base) * 14, b1 = (int)(lim_hi - base) * 14;
-        uint8_t* g = P.lvx14 + 14 * base;
-        const uint8_t* s = reinterpret_cast<const uint8_t*>(s_lvx);
-        int a0 = (b0 + 15) & ~15; if (a0 > b1) a0 = b1;
-        int a1 = b1 & ~15;        if (a1 < a0) a1 = a0;
-        for (int i = a0 / 16 + tid; i < a1 / 16; i += kThreads)
-            reinterpret_cast<uint4*>(g)[i] = reinterpret_cast<const uint4*>(s)[i];
-        if (!FULL) {
-            for (int i = b0 + tid; i < a0; i += kThreads) g[i] = s[i];
-            for (int i = a1 + tid; i < b1; i += kThreads) g[i] = s[i];
-        }
-    }
+    if (P.lvx14 != nullptr)      // bytes [b0, b1) of the tile's record block: one TMA bulk store for the 16-byte body, byte-wise ragged ends
+        cta_image_out(P.lvx14 + 14 * base, reinterpret_cast<const uint8_t*>(s_lvx), (int)(lim_lo - base) * 14, (int)(lim_hi - base) * 14, tid, kThreads);
     if (fl != 0 && P.status != nullptr) atomicOr(P.status, fl);
 }
 

@@ -13,7 +13,7 @@
 //
 // Two launches: k_las_records (records + min/max reduction; the 227-byte data offset makes every
 // record start at an odd address, so each CTA assembles its contiguous byte range in shared memory at
-// the destination's 16-byte phase and copies it out with 16-byte stores), then k_las_header.
+// the destination's 16-byte phase and hands the aligned body to the TMA engine as one bulk store), then k_las_header.
 #include "lmc_device.cuh"
 
 namespace lmc {
@@ -81,13 +81,7 @@ __global__ void __launch_bounds__(kLasThreads) k_las_records(const __grid_consta
         const int32_t cur = *reinterpret_cast<volatile int32_t*>(L.minmax + tid), mine = s_mm[tid];
         if (tid & 1) { if (mine > cur) atomicMax(L.minmax + tid, mine); } else { if (mine < cur) atomicMin(L.minmax + tid, mine); }
     }
-    uint8_t* g = L.out + (dst0 - phase);
-    const int b0 = phase, b1 = phase + cnt * kLasRec;
-    int a0 = (b0 + 15) & ~15; if (a0 > b1) a0 = b1;
-    int a1 = b1 & ~15;        if (a1 < a0) a1 = a0;
-    for (int k = a0 / 16 + tid; k < a1 / 16; k += kLasThreads) reinterpret_cast<uint4*>(g)[k] = reinterpret_cast<const uint4*>(s_img)[k];
-    for (int k = b0 + tid; k < a0; k += kLasThreads) g[k] = s_img[k];
-    for (int k = a1 + tid; k < b1; k += kLasThreads) g[k] = s_img[k];
+    cta_image_out(L.out + (dst0 - phase), s_img, phase, phase + cnt * kLasRec, tid, kLasThreads);   // TMA bulk store of the aligned body
     if (fl != 0 && L.status != nullptr) atomicOr(L.status, fl);
 }
 

@@ -10,7 +10,7 @@
 //
 // One CTA = up to kPk consecutive packages of one frame (grid.x = frame, grid.y = chunk).  The CTA
 // assembles its contiguous byte range in shared memory at the destination's 16-byte phase and copies
-// it out with 16-byte stores (byte stores on the ragged ends): every output byte is written exactly
+// it out as one TMA bulk store (byte stores on the ragged ends): every output byte is written exactly
 // once, nothing outside the range is touched.
 #include "lmc_device.cuh"
 
@@ -87,16 +87,8 @@ __global__ void __launch_bounds__(kLvxThreads) k_lvx_v11(const void* __restrict_
         put16(img, off + 8, z); put16(img, off + 10, z >> 16);
         put16(img, off + 12, r);                                                      // reflectivity, tag = 0
     }
-    __syncthreads();
-
-    // copy img[0, nbytes) -> out[dst0, dst0 + nbytes): aligned 16-byte body, byte-wise ends
-    uint8_t* g = out + (dst0 - phase);                                                // 16-byte aligned
-    const int b0 = phase, b1 = phase + nbytes;
-    int a0 = (b0 + 15) & ~15; if (a0 > b1) a0 = b1;
-    int a1 = b1 & ~15;        if (a1 < a0) a1 = a0;
-    for (int i = a0 / 16 + tid; i < a1 / 16; i += kLvxThreads) reinterpret_cast<uint4*>(g)[i] = reinterpret_cast<const uint4*>(s_img)[i];
-    for (int i = b0 + tid; i < a0; i += kLvxThreads) g[i] = s_img[i];
-    for (int i = a1 + tid; i < b1; i += kLvxThreads) g[i] = s_img[i];
+    // img[0, nbytes) -> out[dst0, dst0 + nbytes): one TMA bulk store for the aligned body, byte-wise ends
+    cta_image_out(out + (dst0 - phase), s_img, phase, phase + nbytes, tid, kLvxThreads);
     if (fl != 0 && status != nullptr) atomicOr(status, fl);
 }
 

@@ -16,7 +16,7 @@
 // One CTA = up to kCsChunk consecutive points of one frame (grid.x = frame, grid.y = chunk; chunk 0 also
 // owns the frame's headers, so empty frames still get theirs).  The records start at arbitrary byte
 // parity (45*f), so the CTA assembles its contiguous byte range in shared memory at the destination's
-// 16-byte phase and copies it out with 16-byte stores (byte stores on the ragged ends): every output
+// 16-byte phase and copies it out as one TMA bulk store (byte stores on the ragged ends): every output
 // byte is written exactly once.
 #include "lmc_device.cuh"
 
@@ -113,15 +113,7 @@ __global__ void __launch_bounds__(kCsThreads) k_lvx_cs(const __grid_constant__ L
         const uint32_t t = P.tag ? (uint32_t)__ldg(P.tag + i) : 0u;
         put_record(img + hdr + 14 * j, x, y, z, q_u8_copy(p.w, fl) | (t << 8));                                                      // CS:373-374 / 320-321
     }
-    __syncthreads();
-
-    uint8_t* g = P.out + (dst0 - phase);                                              // 16-byte aligned
-    const int b0 = phase, b1 = phase + nbytes;
-    int a0 = (b0 + 15) & ~15; if (a0 > b1) a0 = b1;
-    int a1 = b1 & ~15;        if (a1 < a0) a1 = a0;
-    for (int i = a0 / 16 + tid; i < a1 / 16; i += kCsThreads) reinterpret_cast<uint4*>(g)[i] = reinterpret_cast<const uint4*>(s_img)[i];
-    for (int i = b0 + tid; i < a0; i += kCsThreads) g[i] = s_img[i];
-    for (int i = a1 + tid; i < b1; i += kCsThreads) g[i] = s_img[i];
+    cta_image_out(P.out + (dst0 - phase), s_img, phase, phase + nbytes, tid, kCsThreads);      // TMA bulk store of the aligned body
     if (fl != 0 && P.status != nullptr) atomicOr(P.status, fl);
 }
 

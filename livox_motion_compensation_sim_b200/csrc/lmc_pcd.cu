@@ -15,7 +15,7 @@
 //   k_pcd_len    per tile of 256 points: total text bytes of the tile
 //   k_pcd_scan   one CTA: exclusive prefix sum of the tile sizes -> byte offset of every tile
 //   k_pcd_write  per tile: format again, lay the lines out in shared memory (block scan of the line
-//                lengths) and copy the tile's contiguous byte range out with 16-byte stores
+//                lengths) and copy the tile's contiguous byte range out as one TMA bulk store
 #include "lmc_device.cuh"
 
 namespace lmc {
@@ -191,14 +191,7 @@ __global__ void __launch_bounds__(kPcdTile) k_pcd_write(const void* __restrict__
 #pragma unroll
         for (int c = 0; c < 4; ++c) { d += fmt_write(d, t[c]); *d++ = c == 3 ? '\n' : ' '; }
     }
-    __syncthreads();
-    uint8_t* g = out + (dst0 - phase);                              // 16-byte aligned
-    const int b0 = phase, b1 = phase + (int)total;
-    int a0 = (b0 + 15) & ~15; if (a0 > b1) a0 = b1;
-    int a1 = b1 & ~15;        if (a1 < a0) a1 = a0;
-    for (int k = a0 / 16 + tid; k < a1 / 16; k += kPcdTile) reinterpret_cast<uint4*>(g)[k] = reinterpret_cast<const uint4*>(s_img)[k];
-    for (int k = b0 + tid; k < a0; k += kPcdTile) g[k] = s_img[k];
-    for (int k = a1 + tid; k < b1; k += kPcdTile) g[k] = s_img[k];
+    cta_image_out(out + (dst0 - phase), s_img, phase, phase + (int)total, tid, kPcdTile);        // TMA bulk store of the aligned body
     if (fl != 0 && status != nullptr) atomicOr(status, fl);
 }
 
@@ -353,14 +346,7 @@ __global__ void __launch_bounds__(kPcdTile) k_text_write(const void* __restrict_
 #pragma unroll
         for (int c = 0; c < kTextCols; ++c) if (c < F.n_cols) { d += fmtg_write(d, F.dec[c], t[c]); *d++ = c == F.n_cols - 1 ? (uint8_t)'\n' : F.sep; }
     }
-    __syncthreads();
-    uint8_t* g = out + (dst0 - phase);
-    const int b0 = phase, b1 = phase + (int)total;
-    int a0 = (b0 + 15) & ~15; if (a0 > b1) a0 = b1;
-    int a1 = b1 & ~15;        if (a1 < a0) a1 = a0;
-    for (int k = a0 / 16 + tid; k < a1 / 16; k += kPcdTile) reinterpret_cast<uint4*>(g)[k] = reinterpret_cast<const uint4*>(s_img)[k];
-    for (int k = b0 + tid; k < a0; k += kPcdTile) g[k] = s_img[k];
-    for (int k = a1 + tid; k < b1; k += kPcdTile) g[k] = s_img[k];
+    cta_image_out(out + (dst0 - phase), s_img, phase, phase + (int)total, tid, kPcdTile);
     if (fl != 0 && status != nullptr) atomicOr(status, fl);
 }
 
