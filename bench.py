@@ -340,11 +340,12 @@ def main_b200(args):
             frames_h = [np.column_stack([rngp.uniform(-60, 60, (c, 3)), rngp.uniform(0.1, 0.9, c)]) for c in cnt]
             posp, eulp = rngp.uniform(-30, 30, (1200, 3)), rngp.normal(0, 0.3, (1200, 3))
             simp = LiDARMotionSimulator({'device': f'cuda:{local}'})
-            simp.align_frames(frames_h, posp, eulp)
+            for _ in range(3):                                          # steady state: pinned result blocks cached
+                simp.align_frames(frames_h, posp, eulp)
             t0 = time.perf_counter()
-            for _ in range(3):
+            for _ in range(5):
                 merged_p, _, _ = simp.align_frames(frames_h, posp, eulp)
-            t_api = (time.perf_counter() - t0) / 3
+            t_api = (time.perf_counter() - t0) / 5
             from oracle import lmc_oracle as _orc                       # CPU port of the same loop, for context only
             t0 = time.perf_counter()
             want_p = _orc.align_frames_np(frames_h, posp, eulp)
@@ -392,13 +393,16 @@ def main_b200(args):
                 import tempfile
                 tmpd = tempfile.mkdtemp(prefix="lmc_save_")
                 try:
-                    t0 = time.perf_counter()
-                    simr.save_results(resr, tmpd)
-                    save_ms = (time.perf_counter() - t0) * 1e3
-                    n_files = sum(len(fs) for _, _, fs in os.walk(tmpd))
-                    n_bytes = sum(os.path.getsize(os.path.join(dp, f)) for dp, _, fs in os.walk(tmpd) for f in fs)
+                    save_t = []
+                    for rep in range(3):                                # first call pays `import pandas` and the pinned blocks
+                        t0 = time.perf_counter()
+                        simr.save_results(resr, os.path.join(tmpd, f"r{rep}"))
+                        save_t.append((time.perf_counter() - t0) * 1e3)
+                    one = os.path.join(tmpd, "r2")
+                    n_files = sum(len(fs) for _, _, fs in os.walk(one))
+                    n_bytes = sum(os.path.getsize(os.path.join(dp, f)) for dp, _, fs in os.walk(one) for f in fs)
                     presets["urban_complex_60s_save_results"] = {
-                        "files": n_files, "bytes": n_bytes, "b200_save_results_ms": save_ms,
+                        "files": n_files, "bytes": n_bytes, "b200_save_results_ms": min(save_t[1:]), "first_call_ms": save_t[0],
                         "what": "LiDARMotionSimulator.save_results of that run: per-frame + merged PCD ('%.6f' text of 4 x 976 720 points), "
                                 "LAS, LVX v1.1, CSVs; the reference's per-point Python writers format 0.26-0.8 Mpts/s (PCD) and 0.04 Mpts/s (LVX)"}
                 finally:
