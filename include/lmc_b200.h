@@ -282,6 +282,18 @@ int lmc_host_gather(const void* const* src, const int64_t* dst_off, int64_t n_sr
 int lmc_host_copy(void* dst, const void* src, int64_t n_bytes, int32_t n_threads);
 
 /*
+ * Host-side replay of np.random.normal(loc, scale, n) on NumPy's legacy global generator (RandomState: MT19937 +
+ * polar Box-Muller) -- the stream scan_environment consumes for its range noise (LMC:767, seeded at LMC:288), which
+ * a run has to consume exactly to reproduce the reference's raw scans.  mt_key (624 words), *mt_pos (0..624),
+ * *has_gauss and *cached_gauss are the four fields of np.random.get_state() and are updated in place, so
+ * np.random.set_state() afterwards leaves the generator where NumPy itself would have left it.  The word stream and
+ * the rejection loop are sequential; the sqrt / log part is spread over n_threads.  Bit-identical to NumPy (same
+ * libm calls; tests/test_host.py).
+ */
+int lmc_host_legacy_normal(uint32_t* mt_key, int32_t* mt_pos, int32_t* has_gauss, double* cached_gauss,
+                           double loc, double scale, int64_t n, double* out, int32_t n_threads);
+
+/*
  *  the complete simulator's text exports, replaces the per-row Python loops of
  * DataExporter._export_pcd (CS:1663-1664, '%.6f %.6f %.6f %.0f %.0f\n' over [x y z intensity timestamp]),
  * _export_xyz (CS:1703, np.savetxt '%.6f' x 3) and the body of _export_csv (CS:1711-1712, pandas

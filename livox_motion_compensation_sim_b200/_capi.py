@@ -73,6 +73,7 @@ _SIGNATURES = {
     "lmc_pcd_ascii_row_offsets_f32": ([vp, i64, vp, vp, i32, vp, vp], ctypes.c_int),
     "lmc_host_gather": ([vp, vp, i64, vp, i32], ctypes.c_int),
     "lmc_host_copy": ([vp, vp, i64, i32], ctypes.c_int),
+    "lmc_host_legacy_normal": ([vp, vp, vp, vp, f64, f64, i64, vp, i32], ctypes.c_int),
     "lmc_text_rows_size_f64": ([vp, i64, i32, i32, vp, vp, i32, vp, vp], ctypes.c_int),
     "lmc_text_rows_size_f32": ([vp, i64, i32, i32, vp, vp, i32, vp, vp], ctypes.c_int),
     "lmc_text_rows_write_f64": ([vp, i64, i32, i32, vp, vp, i32, vp, vp, vp, vp], ctypes.c_int),

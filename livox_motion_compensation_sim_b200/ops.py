@@ -370,7 +370,8 @@ def scan_frames(env: torch.Tensor, pos: torch.Tensor, Rm: torch.Tensor, *, range
     Returns (raw (N,4) f64 device tensor, frame_off np.int64[F+1]).
 
     noise_fn(n) must return the (n,3) host array the reference would draw -- by default
-    ``np.random.normal(0, noise_std, (n, 3))`` from the GLOBAL legacy NumPy RNG, exactly the stream LMC:767
+    ``np.random.normal(0, noise_std, (n, 3))`` from the GLOBAL legacy NumPy RNG (replayed bit-identically by
+    ``frames.legacy_normal``, which leaves the generator where NumPy would), exactly the stream LMC:767
     consumes frame after frame (the legacy generator is a stream: one draw per chunk of frames == the
     reference's per-frame draws).  Frames are processed in chunks so the F x M visibility scratch stays
     below max_flag_bytes; chunks run in frame order, so the noise stream keeps the reference's order.
@@ -414,8 +415,15 @@ def scan_frames(env: torch.Tensor, pos: torch.Tensor, Rm: torch.Tensor, *, range
         if n_c > 0:
             noise_d = None
             if noise_std > 0:
-                noise = np.random.normal(0, noise_std, (n_c, 3)) if noise_fn is None else noise_fn(n_c)
-                noise_d = torch.from_numpy(np.ascontiguousarray(noise, dtype=np.float64)).to(dev)
+                if noise_fn is None:
+                    # the reference's own draw, np.random.normal(0, noise_std, (n_c, 3)) on the global generator, replayed
+                    # bit-identically by lmc_host_legacy_normal (threaded sqrt / log) straight into pinned memory
+                    from .frames import legacy_normal
+                    stage = torch.empty(3 * n_c, dtype=torch.float64, pin_memory=dev.type == 'cuda')
+                    legacy_normal(float(noise_std), 3 * n_c, out=stage.numpy())
+                    noise_d = stage.to(dev, non_blocking=True).view(n_c, 3)
+                else:
+                    noise_d = torch.from_numpy(np.ascontiguousarray(noise_fn(n_c), dtype=np.float64)).to(dev)
             fo = torch.from_numpy(off_c).to(dev)
             C.check(L.lmc_scan_emit(env.data_ptr(), M, p_c.data_ptr(), r_c.data_ptr(), nf, rmax2, flags.data_ptr(), tile_off.data_ptr(),
                                     n_vis.data_ptr(), fo.data_ptr(), maxp, _req(noise_d, torch.float64, "noise", (3,)), out.data_ptr(), _stream_ptr()))

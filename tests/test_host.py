@@ -138,6 +138,35 @@ def test_host_gather_and_copy(built_lib):
     assert L.lmc_host_copy(None, want.ctypes.data, 8, 1) == _capi.ERR_INVALID
 
 
+def test_legacy_normal_replays_numpy_global_stream(built_lib):
+    """lmc_host_legacy_normal == np.random.normal on the seeded global generator (the stream scan_environment
+    consumes at LMC:767): identical bits for even / odd / zero sizes, a cached second half carried across calls,
+    block boundaries of the 624-word state, NumPy draws interleaved with ours, and the generator left behind."""
+    for seed in (42, 7, 2024):
+        for sizes in ([7, 8, 1, 0, 50_001, 5, 2], [2, 2, 623, 1, 20_000], [1] * 9 + [0, 3, 1234]):
+            np.random.seed(seed); np.random.uniform(size=seed % 5)
+            want = [np.random.normal(0, 0.02, n) for n in sizes]
+            tail_w = (np.random.normal(0, 1, 5), np.random.random(3), np.random.randint(0, 1 << 30, 4))
+            np.random.seed(seed); np.random.uniform(size=seed % 5)
+            got = [FR.legacy_normal(0.02, n) for n in sizes]
+            tail_g = (np.random.normal(0, 1, 5), np.random.random(3), np.random.randint(0, 1 << 30, 4))
+            assert all(a.tobytes() == b.tobytes() for a, b in zip(want, got))
+            assert all(a.tobytes() == b.tobytes() for a, b in zip(tail_w, tail_g))
+    np.random.seed(9)
+    a = (np.random.normal(0, 0.5, 3), np.random.normal(0, 0.5, (4, 3)), np.random.normal(0, 0.5, 2))
+    np.random.seed(9)
+    b = (np.random.normal(0, 0.5, 3), FR.legacy_normal(0.5, 12).reshape(4, 3), np.random.normal(0, 0.5, 2))
+    assert all(x.tobytes() == y.tobytes() for x, y in zip(a, b))
+    out = np.empty(10)
+    assert FR.legacy_normal(1.0, 10, out=out) is out
+    with pytest.raises(ValueError):
+        FR.legacy_normal(-1.0, 4)
+    with pytest.raises(ValueError):
+        FR.legacy_normal(1.0, 4, out=np.empty(5))
+    L = _capi.lib()
+    assert L.lmc_host_legacy_normal(None, None, None, None, 0.0, 1.0, 4, out.ctypes.data, 1) == _capi.ERR_INVALID
+
+
 def test_pose_table_is_scipy_exact(golden):
     g = golden("lmc_edge.npz")
     assert np.array_equal(FR.pose_table(g['pose_position'], g['pose_euler']), orc.pose_table_np(g['pose_position'], g['pose_euler']))
