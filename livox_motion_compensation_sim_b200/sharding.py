@@ -8,7 +8,7 @@ full-size merged buffer.  The only exchange step is assembling the merged cloud 
 all-gather(v) of the disjoint slices over NCCL/NVLink (gloo on CPU for the tests)."""
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import Sequence, Tuple
 
 import numpy as np
 import torch
