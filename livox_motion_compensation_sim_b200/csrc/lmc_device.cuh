@@ -189,6 +189,7 @@ __device__ __forceinline__ void sin_vercos_small(double x, double& s, double& v)
 // kTinyAngle), in the fast and the general path alike, so a point's result does not depend on which path
 // evaluated it.
 constexpr double kTinyAngle = 0.0625;
+constexpr uint32_t kTinyHi = 0x3FB00000u, kSmallHi = 0x3FC00000u;      // high words of 2^-4 and of kSmallAngle = 2^-3
 __device__ __forceinline__ void sin_cos_tiny(double x, double& s, double& c) {          // |x| < kTinyAngle
     const double u = x * x;
     const double ps = fma(fma(fma(kSinC[3], u, kSinC[4]), u, kSinC[5]), u, kSinC[6]);
@@ -681,7 +682,9 @@ struct PointCtx {
                 const int64_t dd[2] = { ta - tk, tb - tk };
                 if ((uint64_t)dd[0] < dtk && (uint64_t)dd[1] < dtk) {
                     double ang[2][3];
-                    double am[2] = {0.0, 0.0};
+                    // max |angle| per point, compared on the high words (exact for the power-of-two tier limits; a NaN
+                    // ranks above everything and takes the general path) -- integer ALU instead of DSETP + selects
+                    uint32_t am[2] = {0u, 0u};
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         // alpha = (t - t_before) / (t_after - t_before) (CS:1503): reciprocal + two Markstein
@@ -695,19 +698,19 @@ struct PointCtx {
                         for (int c = 0; c < 3; ++c) {
                             const double gc = __dadd_rn(tab[c], __dmul_rn(q, tab[3 + c]));             // CS:1507-1509
                             ang[h][c] = __dmul_rn(gc, dt);                                            // CS:1457-1458
-                            am[h] = fmax(am[h], fabs(ang[h][c]));
+                            am[h] = max(am[h], (uint32_t)__double2hiint(ang[h][c]) & 0x7fffffffu);
                         }
                     }
-                    const double amax = fmax(am[0], am[1]);
-                    if (amax < kTinyAngle) {                                  // what a vehicle-mounted IMU produces
+                    const uint32_t amax = max(am[0], am[1]);
+                    if (amax < kTinyHi) {                                     // what a vehicle-mounted IMU produces
                         gyro_rotate_small<true>(ang[0][0], ang[0][1], ang[0][2], in[0], out[0]);
                         gyro_rotate_small<true>(ang[1][0], ang[1][1], ang[1][2], in[1], out[1]);
                         return;
                     }
-                    if (amax <= kSmallAngle) {                                // polynomial tier per point, as gyro_rotate() picks it
+                    if (amax < kSmallHi) {                                    // polynomial tier per point, as gyro_rotate() picks it
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            if (am[h] < kTinyAngle) gyro_rotate_small<true>(ang[h][0], ang[h][1], ang[h][2], in[h], out[h]);
+                            if (am[h] < kTinyHi) gyro_rotate_small<true>(ang[h][0], ang[h][1], ang[h][2], in[h], out[h]);
                             else                    gyro_rotate_small<false>(ang[h][0], ang[h][1], ang[h][2], in[h], out[h]);
                         }
                         return;
