@@ -672,7 +672,7 @@ struct PointCtx {
                         tab[3 + c] = __dsub_rn(ga, gb);                               // CS:1507 (after - before)
                     }
                     tab[6] = __longlong_as_double(tk);
-                    tab[7] = __longlong_as_double(tn - tk);
+                    tab[7] = __longlong_as_double(((tn - tk) >> 50) == 0 ? tn - tk : 0);   // >= 2^50 ns (13 days): general path
                     tab[8] = (double)(tn - tk);
                     tab[9] = tn > tk ? 1.0 / tab[8] : 0.0;                            // correctly rounded reciprocal (IEEE division)
                     key = k;
@@ -687,11 +687,13 @@ struct PointCtx {
                     uint32_t am[2] = {0u, 0u};
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        // alpha = (t - t_before) / (t_after - t_before) (CS:1503): reciprocal + two Markstein
-                        // corrections = the correctly rounded quotient
+                        // alpha = (t - t_before) / (t_after - t_before) (CS:1503): reciprocal + ONE Markstein correction
+                        // is the correctly rounded quotient here.  a < b are integers, b < 2^50 (checked where the row
+                        // is loaded): q0 = a * RN(1/b) is within 2 ulp, the remainder a - b*q0 is exact, so
+                        // q0 + rem * r = a/b (1 + 2^-104); and an integer quotient a/b stays >= 2^-51 ulp away from any
+                        // rounding boundary when b < 2^50.  (oracle/check_div.c: 4.5e8 (a, b) pairs against IEEE division, none differs.)
                         const double a = (double)dd[h];
                         double q = __dmul_rn(a, tab[9]);
-                        q = __fma_rn(__fma_rn(-tab[8], q, a), tab[9], q);
                         q = __fma_rn(__fma_rn(-tab[8], q, a), tab[9], q);
                         const double dt = __dmul_rn((double)((h == 0 ? ta : tb) - fs[h]), 1e-9);      // CS:1454
 #pragma unroll

@@ -167,6 +167,17 @@ def test_legacy_normal_replays_numpy_global_stream(built_lib):
     assert L.lmc_host_legacy_normal(None, None, None, None, 0.0, 1.0, 4, out.ctypes.data, 1) == _capi.ERR_INVALID
 
 
+def test_one_markstein_correction_is_ieee_division(tmp_path):
+    """The Mode B kernel forms alpha = a / b (CS:1503; integers a < b < 2^50) as a * RN(1/b) plus ONE Markstein
+    correction; oracle/check_div.c compares that sequence with the IEEE division (fma() is exact in libm)."""
+    exe = tmp_path / "check_div"
+    src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "check_div.c")
+    subprocess.run(["gcc", "-O2", "-o", str(exe), src, "-lm"], check=True)
+    r = subprocess.run([str(exe), "3000000"], capture_output=True, text=True, timeout=300)
+    n, bad = (int(x) for x in r.stdout.split())
+    assert r.returncode == 0 and n > 2e7 and bad == 0
+
+
 def test_pose_table_is_scipy_exact(golden):
     g = golden("lmc_edge.npz")
     assert np.array_equal(FR.pose_table(g['pose_position'], g['pose_euler']), orc.pose_table_np(g['pose_position'], g['pose_euler']))
