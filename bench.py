@@ -44,6 +44,8 @@ VARIANTS = {
     "V5": ("slerp", False, "u32", True, False, 50),
     "V5las": ("slerp", False, "u32", False, True, 50),
     "V4b": ("gyro", False, "u32", False, False, 36),
+    # the second simulator's fused product: gyro deskew + LVX2 records of the COMPENSATED points (CS:1435-1536 + 365-374)
+    "V5b": ("gyro", False, "u32", "lvx2", False, 50),
     # the reference-native types end to end: f64 (N,4) rows, int64 ns timestamps (CS:125), f64 rows out + LVX records
     "V6": ("slerp", True, "i64", True, False, 86),
 }
@@ -230,7 +232,8 @@ def main_b200(args):
         if las:
             into.las_x, into.las_y, into.las_z = (torch.empty(N, dtype=torch.int32, device=dev) for _ in range(3))
             into.las_intensity = torch.empty(N, dtype=torch.uint16, device=dev)
-        spec = ops.ExportSpec(lvx=lvx, las=las, las_scale=(0.001,) * 3, into=into) if (lvx or las) else None
+        spec = ops.ExportSpec(lvx=bool(lvx), lvx_mode=C.LVX2_OF_OUTPUT if lvx == "lvx2" else C.LVX_TYPE2_OF_INPUT, las=las,
+                              las_scale=(0.001,) * 3, into=into) if (lvx or las) else None
         if mode == "rigid":
             fn = lambda: ops.align_rigid(pts, off_d, pose_d, out=out, export=spec)                       # noqa: E731
         elif mode == "slerp":

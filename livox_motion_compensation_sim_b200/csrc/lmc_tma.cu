@@ -86,7 +86,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // Lean variants also assume what the launcher has verified: LVX records are type-2-of-input without
 // tag bytes, timestamps / frame starts are present where the mode needs them, no hold_idx,
 // 2 <= n_samp < 2^31.
-constexpr int kExOut = 1, kExLvx = 2, kExLas = 4, kExGeneric = 8;
+// kExLvx2 (with kExLvx): the records are CS:365-374 on the COMPENSATED point (+ optional tag bytes) instead of LMC:252-272 on
+// the raw one -- the second simulator's product, lean for Mode B.
+constexpr int kExOut = 1, kExLvx = 2, kExLas = 4, kExGeneric = 8, kExLvx2 = 16;
 
 // ---- one tile on the consumer side ------------------------------------------------------------
 template <bool F64, int MODE, int EX, bool FULL>
@@ -103,7 +105,8 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
     const bool do_las = GEN ? (P.las_x != nullptr || P.las_int != nullptr) : bool(EX & kExLas);
     const bool has_ts = (MODE == kGyro || MODE == kSlerp) && (GEN ? P.ts != nullptr : true);
     const bool has_fs = (MODE == kGyro || MODE == kSlerp) && (GEN ? P.frame_start != nullptr : (MODE == kGyro || !F64));
-    const bool has_tag = GEN && do_lvx && P.tag != nullptr && P.lvx_mode == LMC_LVX2_OF_OUTPUT;
+    constexpr bool LVX2 = !GEN && (EX & kExLvx2);                // lean, records of the output
+    const bool has_tag = LVX2 ? P.tag != nullptr : (GEN && do_lvx && P.tag != nullptr && P.lvx_mode == LMC_LVX2_OF_OUTPUT);
     const int64_t base = ti.base;
 
     // tile-level frame facts (prepared by the producer) in registers
@@ -184,7 +187,7 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
             if (lane == 0) mbar_arrive(empty_bar);
         }
 
-        if constexpr (!GEN) {
+        if constexpr (!GEN && !LVX2) {
             // lean: the LVX record is LMC:252-272 on the RAW input point -- independent of the transform,
             // so pack it first and let its temporaries die before the FP64-heavy part
             if (do_lvx) {
@@ -227,7 +230,7 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
                 if (P.peer_out[r] != nullptr) store_pair<F64, FULL>(P.peer_out[r], p, va, vb, o[0], o[1]);
         }
         if (do_las) store_las_pair<FULL>(P, p, va, vb, o[0], o[1], fl);
-        if constexpr (GEN) {
+        if constexpr (GEN || LVX2) {
             if (do_lvx) {
                 uint32_t x[2] = {0, 0}, y[2] = {0, 0}, z[2] = {0, 0}, rt[2] = {0, 0};
                 if (FULL || va) lvx_words<MODE>(P, in[0], o[0], tagv & 0xffu, x[0], y[0], z[0], rt[0], fl);
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
     const uint32_t full0 = smem_u32(s_full), empty0 = smem_u32(s_empty);       // barrier s lives at +8*s
 
     const bool has_ts = (MODE == kGyro || MODE == kSlerp) && (GEN ? P.ts != nullptr : true);
-    const bool has_tag = GEN && P.lvx14 != nullptr && P.tag != nullptr && P.lvx_mode == LMC_LVX2_OF_OUTPUT;
+    const bool has_tag = (GEN || (EX & kExLvx2)) && P.lvx14 != nullptr && P.tag != nullptr && P.lvx_mode == LMC_LVX2_OF_OUTPUT;
 
     if (warp == kCW) {
         // ================================ producer warp ==========================================
@@ -444,13 +447,17 @@ static cudaError_t launch_stream(const Params& P, cudaStream_t st, bool force, b
     // lean (compile-time export configuration) variants for the common cases of Mode A / Mode C
     if constexpr (MODE == kRigid || MODE == kSlerp || MODE == kGyro) {
         const int mask = (P.out ? kExOut : 0) | (P.lvx14 ? kExLvx : 0) | ((P.las_x || P.las_int) ? kExLas : 0);
-        bool lean = P.n_peers == 0 && (!P.lvx14 || (P.lvx_mode == LMC_LVX_TYPE2_OF_INPUT)) && (!(mask & kExLas) || (P.las_x && P.las_int));
+        const bool lvx2 = P.lvx14 && P.lvx_mode == LMC_LVX2_OF_OUTPUT;
+        bool lean = P.n_peers == 0 && (!lvx2 || MODE == kGyro) && (!(mask & kExLas) || (P.las_x && P.las_int));
         if (MODE == kSlerp) lean = lean && P.hold_idx == nullptr && P.ts != nullptr && P.n_samp >= 2 && P.n_samp < 0x7fffffffLL &&
                                    (F64 || P.frame_start != nullptr);
         if (MODE == kGyro)  lean = lean && P.ts != nullptr && P.frame_start != nullptr && P.n_samp >= 2 && P.n_samp < 0x7fffffffLL;
         if (lean) {
             if (mask == kExOut)            return launch_stream_ex<F64, MODE, kExOut>(P, st, grid, tile0, n_tiles);
-            if (mask == (kExOut | kExLvx)) return launch_stream_ex<F64, MODE, kExOut | kExLvx>(P, st, grid, tile0, n_tiles);
+            if constexpr (MODE == kGyro) {
+                if (mask == (kExOut | kExLvx) && lvx2) return launch_stream_ex<F64, MODE, kExOut | kExLvx | kExLvx2>(P, st, grid, tile0, n_tiles);
+            }
+            if (mask == (kExOut | kExLvx) && !lvx2) return launch_stream_ex<F64, MODE, kExOut | kExLvx>(P, st, grid, tile0, n_tiles);
             if (mask == (kExOut | kExLas)) return launch_stream_ex<F64, MODE, kExOut | kExLas>(P, st, grid, tile0, n_tiles);
         }
     }

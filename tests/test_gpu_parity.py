@@ -1010,6 +1010,53 @@ def test_no_write_outside_buffers(f64, path):
     assert bool((li_f.view(torch.int16)[:G + b] == 0x5A5A).all()) and bool((li_f.view(torch.int16)[G + e:] == 0x5A5A).all())
 
 
+@pytest.mark.parametrize("mode", ["rigid", "slerp"])
+@pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
+def test_lean_lvx_bulk_store_epilogue_with_ragged_shards(mode, f64):
+    """The lean (aligned cloud + LVX records) kernels hand each warp's records to a TMA bulk store out of a
+    warp-private slab.  Several tiles per CTA with ragged shard edges (edge tile -> full tiles -> edge tile, i.e.
+    register stores and bulk stores alternating on the same slab): odd-cut shards must compose to the single launch,
+    which must equal the direct kernel, and nothing may be written outside [b, e) -- guard bands around the records."""
+    rng = np.random.default_rng(21)
+    F = 160
+    counts = rng.integers(9_000, 11_000, F); counts[[3, 77]] = 0; counts[[4, 90]] = 1
+    st = synth.make_stream(F, counts, 21, device=DEV, dtype=torch.float64 if f64 else torch.float32)
+    N = st.n_points                                            # ~1.6 M points: 3-11 tiles for each of the 148 CTAs
+    off, fs = dev(st.frame_off), dev(st.frame_start)
+    pose = dev(st.gps_Rt[orc.pose_lookup_hold_next_np(st.gps_t, st.frame_t)])
+    fidx = np.repeat(np.arange(F), counts)
+    ts = dev(st.frame_start[fidx] + st.ts_off.cpu().numpy().astype(np.int64)) if f64 else st.ts_off
+    sts, seg = dev(st.sample_ts), dev(st.seg)
+
+    def run(out, lvx, p_range=None):
+        spec = ops.ExportSpec(lvx=True, into=ops.ExportBuffers(lvx14=lvx))
+        if mode == "rigid":
+            ops.align_rigid(st.pts, off, pose, out=out, export=spec, p_range=p_range)
+        else:
+            ops.deskew_slerp(st.pts, ts, off, fs, sts, seg, out=out, export=spec, p_range=p_range)
+    try:
+        C.set_path(C.PATH_DIRECT)
+        ref_out, ref_lvx = torch.empty_like(st.pts), torch.empty((N, 14), dtype=torch.uint8, device=DEV)
+        run(ref_out, ref_lvx)
+        C.set_path(C.PATH_TMA)
+        out, lvx = torch.empty_like(st.pts), torch.empty((N, 14), dtype=torch.uint8, device=DEV)
+        run(out, lvx)
+        assert torch.equal(out, ref_out) and torch.equal(lvx, ref_lvx)
+        G = 4096
+        lvx_f = torch.full((N + 2 * G, 14), 0xAB, dtype=torch.uint8, device=DEV)
+        out2 = torch.full_like(st.pts, -7.0)
+        cuts = [1237, 2881, 500_003, 500_004, 1_000_001, N - 911]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            run(out2, lvx_f[G:G + N], (a, b))
+        torch.cuda.synchronize()
+        b0, e0 = cuts[0], cuts[-1]
+        assert torch.equal(out2[b0:e0], ref_out[b0:e0]) and torch.equal(lvx_f[G + b0:G + e0], ref_lvx[b0:e0])
+        assert bool((lvx_f[:G + b0] == 0xAB).all()) and bool((lvx_f[G + e0:] == 0xAB).all())
+        assert bool((out2[:b0] == -7.0).all()) and bool((out2[e0:] == -7.0).all())
+    finally:
+        C.set_path(C.PATH_AUTO)
+
+
 # ------------------------------------------------------------------------------------------
 # full-size stream: size-independent properties + spot checks against the oracle
 # ------------------------------------------------------------------------------------------
