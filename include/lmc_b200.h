@@ -11,7 +11,9 @@
  *
  * Conventions
  *   - every data pointer is a caller-owned DEVICE pointer (e.g. torch.Tensor.data_ptr()) unless
- *     the parameter name ends in _host; the library never allocates or frees caller-visible memory
+ *     the parameter name ends in _host; the library never allocates or frees caller-visible memory.
+ *     The lmc_host_* functions are the exception: HOST pointers only, no device work, synchronous
+ *     (the host side of the boundary: frame-list packing and the scanner's NumPy noise stream)
  *   - point arrays, record arrays and LAS arrays must be 32-byte aligned at index 0
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all calls are
  *     asynchronous and stream-ordered, re-entrant across streams and devices
