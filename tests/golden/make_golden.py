@@ -239,6 +239,35 @@ def scan_fixture(LMC, name, manifest):
     manifest.setdefault('scan', {})[name] = dict(env_points=int(len(env)), fixture=f'scan_{name}.npz')
 
 
+def outputs_fixture(LMC, name, manifest):
+    """The reference's whole output directory for config `name` (run_simulation + save_results, LMC:860-930): sha256 and
+    size of every hot-path file -- raw_scans_pcd/frame_%04d.pcd, aligned_scans_pcd/aligned_frame_%04d.pcd,
+    merged_aligned.pcd (absent when a frame is empty, LMC:887-891), merged_raw_overlapped.pcd, lidar_data.lvx.
+    (merged_aligned.las needs laspy; the two CSVs carry generator columns the scan fixtures do not store.)"""
+    import tempfile
+    import shutil
+    sim, res = run_lmc(LMC, CONFIGS[name])
+    tmp = tempfile.mkdtemp(prefix='lmc_ref_out_')
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            sim.save_results(res, tmp)
+        names, digests, sizes = [], [], []
+        for dp, _, fs in os.walk(tmp):
+            for f in fs:
+                rel = os.path.relpath(os.path.join(dp, f), tmp).replace(os.sep, '/')
+                if not (rel.endswith('.pcd') or rel.endswith('.lvx')):
+                    continue
+                data = open(os.path.join(dp, f), 'rb').read()
+                names.append(rel); digests.append(hashlib.sha256(data).hexdigest()); sizes.append(len(data))
+        order = np.argsort(names)
+        np.savez_compressed(os.path.join(HERE, f'outputs_{name}.npz'), names=np.array(names)[order],
+                            sha256=np.array(digests)[order], sizes=np.array(sizes, np.int64)[order])
+        manifest.setdefault('outputs', {})[name] = dict(files=len(names), bytes=int(np.sum(sizes)), fixture=f'outputs_{name}.npz',
+                                                        merged_aligned='merged_aligned.pcd' in names)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def modeb_fixture(CS, manifest):
     """Reference MotionCompensator.compensate_point_cloud (CS:1435-1536) + LVX2 packer
     (CS:365-374) on synthetic Mid-70-shaped frames against the reference's own 200 Hz
@@ -417,7 +446,8 @@ def main():
         for name in sys.argv[2:]:
             {'lvx_cs': lambda: lvx_cs_fixture(CS, manifest), 'text_rows': lambda: text_rows_fixture(CS, manifest),
              'coord_frames': lambda: coord_frames_fixture(CS, manifest),
-             'config2': lambda: config2_fixture(CS, manifest)}[name]()
+             'config2': lambda: config2_fixture(CS, manifest),
+             'outputs': lambda: [outputs_fixture(LMC, n, manifest) for n in ['C1a', 'C2a', 'C3']]}[name]()
         with open(os.path.join(HERE, 'MANIFEST.json'), 'w') as f:
             json.dump(manifest, f, indent=1, sort_keys=True)
         return
@@ -439,6 +469,8 @@ def main():
     text_rows_fixture(CS, manifest)
     coord_frames_fixture(CS, manifest)
     config2_fixture(CS, manifest)
+    for name in ['C1a', 'C2a', 'C3']:
+        outputs_fixture(LMC, name, manifest)
     with open(os.path.join(HERE, 'MANIFEST.json'), 'w') as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     print('wrote', sorted(os.listdir(HERE)))

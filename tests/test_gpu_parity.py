@@ -830,10 +830,13 @@ def test_save_results_files_are_save_pcd_files(golden, tmp_path):
 
 
 @pytest.mark.parametrize("name", ["C1a", "C2a", "C3"])
-def test_scanner_whole_run_vs_reference(golden, name):
+def test_scanner_whole_run_vs_reference(golden, name, tmp_path):
     """(N4) the reference's whole frame loop on the device: scan every frame (range / FOV cull, compaction,
     subsample) + the reference's own noise stream replayed from the saved global-RNG state + alignment.
-    sha256 of all raw scans and of all aligned clouds == the reference run's anchors."""
+    sha256 of all raw scans and of all aligned clouds == the reference run's anchors.
+    Then save_results: the run's whole output directory -- every raw_scans_pcd / aligned_scans_pcd file, the
+    merged PCDs (merged_aligned.pcd only when the reference writes one, LMC:887-891) and lidar_data.lvx -- has the
+    sha256 of the file the reference itself wrote for this config (golden outputs_<name>.npz: 1202-1203 files)."""
     from livox_motion_compensation_sim_b200 import LiDARMotionSimulator
     g = golden(f"scan_{name}.npz")
     cfg = json.loads(g['config_json'].tobytes().decode())
@@ -851,6 +854,20 @@ def test_scanner_whole_run_vs_reference(golden, name):
     raw = np.vstack([s['points_local'] for s in res['raw_scans']])
     assert sha(raw) == e['raw_sha256']
     assert sha(np.vstack(res['aligned_pointclouds'])) == e['aligned_sha256']
+    import contextlib, hashlib, io
+    ref = golden(f"outputs_{name}.npz")
+    want = dict(zip((str(n) for n in ref['names']), (str(d) for d in ref['sha256'])))
+    with contextlib.redirect_stdout(io.StringIO()):
+        d = sim.save_results(res, str(tmp_path / "out"))
+    got = {}
+    for dp, _, fs in os.walk(d):
+        for f in fs:
+            rel = os.path.relpath(os.path.join(dp, f), d).replace(os.sep, '/')
+            if rel.endswith('.pcd') or rel.endswith('.lvx'):
+                got[rel] = hashlib.sha256(open(os.path.join(dp, f), 'rb').read()).hexdigest()
+    assert sorted(got) == sorted(want)
+    bad = [k for k in want if got[k] != want[k]]
+    assert not bad, bad[:5]
 
 
 def test_run_simulation_slerp_pose_interpolation(golden):
