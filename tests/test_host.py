@@ -157,6 +157,12 @@ def test_legacy_normal_replays_numpy_global_stream(built_lib):
     np.random.seed(9)
     b = (np.random.normal(0, 0.5, 3), FR.legacy_normal(0.5, 12).reshape(4, 3), np.random.normal(0, 0.5, 2))
     assert all(x.tobytes() == y.tobytes() for x, y in zip(a, b))
+    # from the generator state the reference run itself was in right before its frame loop (golden scan_C3.npz)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scan_C3.npz"))
+    state = ('MT19937', g['rng_keys'], int(g['rng_pos']), int(g['rng_has_gauss']), float(g['rng_cached']))
+    np.random.set_state(state); w = np.random.normal(0, 0.02, (100_003, 3)); w2 = np.random.normal(0, 0.02, 7)
+    np.random.set_state(state); v = FR.legacy_normal(0.02, 300_009).reshape(-1, 3); v2 = np.random.normal(0, 0.02, 7)
+    assert w.tobytes() == v.tobytes() and w2.tobytes() == v2.tobytes()
     out = np.empty(10)
     assert FR.legacy_normal(1.0, 10, out=out) is out
     with pytest.raises(ValueError):
