@@ -138,6 +138,30 @@ def test_host_gather_and_copy(built_lib):
     assert L.lmc_host_copy(None, want.ctypes.data, 8, 1) == _capi.ERR_INVALID
 
 
+def test_host_gather_property(built_lib):
+    """Property test of lmc_host_gather: any list of byte runs (empty ones included), any thread count, any destination
+    offset -> the concatenation, and not one byte outside it."""
+    from hypothesis import given, settings, strategies as st
+    L = _capi.lib()
+
+    @settings(max_examples=60, deadline=None)
+    @given(sizes=st.lists(st.integers(0, 3_000_000), min_size=0, max_size=40), threads=st.integers(-2, 70),
+           lead=st.integers(0, 100), seed=st.integers(0, 2 ** 31))
+    def check(sizes, threads, lead, seed):
+        rng = np.random.default_rng(seed)
+        srcs = [rng.integers(0, 256, n, dtype=np.uint8) for n in sizes]
+        want = np.concatenate(srcs) if srcs else np.zeros(0, np.uint8)
+        ptrs = np.array([FR._addr(a) for a in srcs], np.uintp)
+        boff = np.full(len(srcs) + 1, lead, np.int64)
+        if srcs:
+            boff[1:] += np.cumsum(sizes)
+        dst = np.full(lead + len(want) + 64, 0xEE, np.uint8)
+        assert L.lmc_host_gather(ptrs.ctypes.data, boff.ctypes.data, len(srcs), dst.ctypes.data, threads) == 0
+        assert dst[lead:lead + len(want)].tobytes() == want.tobytes()
+        assert (dst[:lead] == 0xEE).all() and (dst[lead + len(want):] == 0xEE).all()
+    check()
+
+
 def test_legacy_normal_replays_numpy_global_stream(built_lib):
     """lmc_host_legacy_normal == np.random.normal on the seeded global generator (the stream scan_environment
     consumes at LMC:767): identical bits for even / odd / zero sizes, a cached second half carried across calls,
