@@ -138,33 +138,66 @@ def measured_peak():
 
 
 # ----------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU path (NumPy port) on this box's host cores
+# reference arm: the reference's own CPU path on this box's host cores
+#   kind "reference": the UNMODIFIED reference staged under oracle/_ref (oracle/make_ref.py), stock code path,
+#                     one forked worker per host core (oracle/ref_arm.py)
+#   kind "port":      the vectorised NumPy/SciPy port on a thread pool (oracle/cpu_baseline.py) -- reported beside it as the
+#                     "fair CPU" figure, and the fallback when oracle/_ref was never staged
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, frames, ppf):
+def workload_name(F, P):
+    return f"M-1H synthetic 1 h Mid-70 stream: {F} frames x {P} pts = {F * P} points, 200 Hz pose samples ({F * 20 + 1}), seed {SEED}"
+
+
+def cpu_port_run(steps, warmup, frames, ppf):
     from oracle import cpu_baseline as cb
     threads = cb.default_threads()
     sample = cb.make_sample(frames, ppf)
-    for _ in range(min(warmup, 1)):
+    for _ in range(warmup):
         cb.run_port(sample, threads)
     times = [cb.run_port(sample, threads) for _ in range(steps)]
     t = float(np.mean(times))
-    return dict(value=sample['n_points'] / t, seconds_per_step=t, cores=threads, n_points=sample['n_points'],
-                sample=f"{frames} frames x {ppf} pts of the M-1H stream per step (f64 (n,4), NumPy/SciPy port of LMC:802-832 + vstack + LVX mm quantise)")
+    return dict(value=sample['n_points'] / t, seconds_per_step=t, cores=threads, n_points=sample['n_points'], kind="port",
+                sample=f"{frames} frames x {ppf} pts of the M-1H stream per step (f64 (n,4), NumPy/SciPy port of LMC:802-832 + vstack + LVX mm quantise, {threads} threads)")
+
+
+def cpu_reference_run(steps, warmup, frames, ppf):
+    """The stock reference when oracle/_ref is staged, else the port.  Always returns the port's rate too."""
+    from oracle import make_ref
+    if make_ref.available():
+        from oracle import ref_arm
+        r = ref_arm.run(steps, warmup, frames, ppf)
+        r["kind"] = "reference"
+        port = cpu_port_run(min(steps, 3), 1, frames, ppf)
+        r["fair_port"] = {"points_per_s": port["value"], "cores": port["cores"], "what": port["sample"]}
+        return r
+    r = cpu_port_run(steps, warmup, frames, ppf)
+    r["note"] = "oracle/_ref is not staged on this box (python oracle/make_ref.py in the build container): the port stands in"
+    return r
+
+
+def cpu_baseline_block(r):
+    b = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+    for k in ("stage_a_points_per_s", "stage_b_points_per_s", "fair_port", "note"):
+        if k in r:
+            b[k] = r[k]
+    return b
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 20))
-    r = cpu_reference_run(steps, args.warmup, args.cpu_frames, args.ppf)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    r = cpu_reference_run(steps, warmup, args.cpu_frames, args.ppf)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["seconds_per_step"] * 1e3,
+        "steps": steps, "warmup": warmup, "ms_per_step": r["seconds_per_step"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "M-1H synthetic 1 h Mid-70 stream (36000 frames x 10000 pts), bounded sample per step",
-                   "variant": "reference CPU path: hold-next pose per frame + transform_pointcloud + vstack + LVX int32-mm"},
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "config": {"workload": workload_name(args.frames, args.ppf),
+                   "variant": "the reference's CPU path for the hot path: hold-next pose per frame + transform_pointcloud + vstack + LVX int32-mm records "
+                              "(Mode A + LVX = the GPU arm's config.like_for_like variant V2; the reference has no per-point pose interpolation)",
+                   "sample_per_step": r["sample"]},
+        "cpu_baseline": cpu_baseline_block(r),
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -488,6 +521,7 @@ def main_b200(args):
 
     # ---- end to end: pinned host buffers in, pinned host buffers out ---------------------------------
     e2e = None
+    e2e_mode_a = None
     if not args.no_e2e:
         try:
             import psutil
@@ -531,79 +565,180 @@ def main_b200(args):
                "what": "StreamingAligner.run: pinned host float4 + u32 ts + the 200 Hz pose samples (quat, pos, ts) -> H2D, pose-segment table built on the device, chunked fused Mode C + LVX kernel, D2H of float4 + 14-B records, 3 streams",
                "h2d_GBps": sa.h2d_bytes / (ems * 1e-3) / 1e9, "d2h_GBps": sa.d2h_bytes / (ems * 1e-3) / 1e9,
                "host_cpus_bound": None if numa_cpus is None else len(numa_cpus)}
+        # the same host buffers through the reference's own transform (Mode A + LVX records = variant V2): the like-for-like
+        # partner of the reference arm, which has no per-point pose interpolation
+        try:
+            sa2 = StreamingAligner(dev, hs.frame_off, hs.frame_start, mode="rigid", lvx=True, pose_Rt=pose_d[:fe].contiguous())
+            sa2.run(hs); torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0.record()
+            for _ in range(args.e2e_steps):
+                sa2.run(hs)
+            e1.record(); torch.cuda.synchronize()
+            ems2 = e0.elapsed_time(e1) / args.e2e_steps
+            if world > 1:
+                t = torch.tensor([ems2], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ems2 = float(t.item())
+            e2e_mode_a = {"value": world * ne / (ems2 * 1e-3), "ms_per_step": ems2, "h2d_bytes_per_step": sa2.h2d_bytes, "d2h_bytes_per_step": sa2.d2h_bytes}
+            del sa2
+        except Exception as e:                     # noqa: BLE001
+            e2e_mode_a = {"error": repr(e)}
         del hs, sa
-    # ---- merged cloud (BASELINE configs[3] literally): ONE 1 h stream, frame-sharded over the N ranks, the
-    #      merged aligned cloud + LVX records assembled on every rank.  Strong scaling, reported under "merge":
-    #      (a) shard kernel + NCCL all-gather(v), (b) merged-cloud assembly fused into the kernel epilogue
-    #      (peer stores over NVLink into every rank's symmetric-memory copy).
+        torch.cuda.empty_cache()
+        # raw copy ceiling of this box for the step's byte mix (profiles/pcie_ceiling.py: cudaMemcpyAsync only, every rank at once)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "profiles"))
+            import pcie_ceiling
+            ceil = pcie_ceiling.measure(dev, world, total=1 << 30, reps=2)
+            e2e["copy_ceiling_points_per_s"] = ceil["e2e_points_per_s_ceiling_per_gpu"] * world
+            e2e["frac_of_copy_ceiling"] = e2e["value"] / e2e["copy_ceiling_points_per_s"]
+            e2e["copy_ceiling"] = {"duplex_h2d_GBps_per_gpu": ceil["duplex_h2d_GBps_per_gpu"], "duplex_d2h_GBps_per_gpu": ceil["duplex_d2h_GBps_per_gpu"],
+                                   "h2d_alone_GBps_per_gpu": ceil["h2d_GBps_per_gpu"], "d2h_alone_GBps_per_gpu": ceil["d2h_GBps_per_gpu"],
+                                   "what": "pinned cudaMemcpyAsync H2D || D2H in the step's 20:30 byte ratio, all ranks concurrently, no kernels (max over ranks)"}
+        except Exception as e:                     # noqa: BLE001
+            e2e["copy_ceiling_error"] = repr(e)
+    # ---- merged cloud (BASELINE configs[3] literally): ONE 1 h stream, frame-sharded over the N ranks, the merged aligned
+    #      cloud + LVX records assembled on every rank (np.vstack of LMC:886-899, as an all-gather).  Strong scaling.  Every
+    #      method's merged buffers are compared byte for byte, on every rank, with the single-launch result of the whole
+    #      stream computed on that rank; any difference fails the run.
     merge = None
     if world > 1:
-        try:
-            from livox_motion_compensation_sim_b200 import sharding
-            del st
-            torch.cuda.empty_cache()
-            sm_st = synth.make_stream(F, P, SEED, device=dev, dtype=torch.float32)          # the SAME stream on every rank
-            Nm = sm_st.n_points
-            offm, fsm = d(sm_st.frame_off), d(sm_st.frame_start)
-            fcuts, pcuts = sharding.shard_ranges(sm_st.frame_off, world)
-            pb, pe = int(pcuts[rank]), int(pcuts[rank + 1])
-            symm = sharding.SymmetricMerged(Nm, dev, lvx=True)
-            po, pl = symm.peer_ptrs()
+        from livox_motion_compensation_sim_b200 import sharding
+        del st
+        torch.cuda.empty_cache()
+        sm_st = synth.make_stream(F, P, SEED, device=dev, dtype=torch.float32)          # the SAME stream on every rank
+        Nm = sm_st.n_points
+        offm, fsm = d(sm_st.frame_off), d(sm_st.frame_start)
+        fcuts, pcuts = sharding.shard_ranges(sm_st.frame_off, world)
+        pb, pe = int(pcuts[rank]), int(pcuts[rank + 1])
+        symm = sharding.SymmetricMerged(Nm, dev, lvx=True)
+        po, pl = symm.peer_ptrs()
+        mo, ml = symm.mc_ptrs()
+        whole, wbuf = ops.deskew_slerp(sm_st.pts, sm_st.ts_off, offm, fsm, sts_d, seg_d, export=ops.ExportSpec(lvx=True))   # 1-GPU result
+        own = lambda: ops.ExportBuffers(lvx14=symm.lvx14)                                # noqa: E731
 
-            def run_nccl():
-                ops.deskew_slerp(sm_st.pts, sm_st.ts_off, offm, fsm, sts_d, seg_d, out=symm.out,
-                                 export=ops.ExportSpec(lvx=True, into=ops.ExportBuffers(lvx14=symm.lvx14)), p_range=(pb, pe))
-                sharding.all_gather_merged([symm.out, symm.lvx14], pcuts)
+        def run_shard_only():
+            ops.deskew_slerp(sm_st.pts, sm_st.ts_off, offm, fsm, sts_d, seg_d, out=symm.out,
+                             export=ops.ExportSpec(lvx=True, into=own()), p_range=(pb, pe))
 
-            def run_fused():
-                ops.deskew_slerp(sm_st.pts, sm_st.ts_off, offm, fsm, sts_d, seg_d, out=symm.out,
-                                 export=ops.ExportSpec(lvx=True, into=ops.ExportBuffers(lvx14=symm.lvx14), peer_out=po, peer_lvx14=pl),
-                                 p_range=(pb, pe))
-                symm.barrier()
+        def run_nccl():
+            run_shard_only()
+            sharding.all_gather_merged([symm.out, symm.lvx14], pcuts)
 
-            def run_shard_only():
-                ops.deskew_slerp(sm_st.pts, sm_st.ts_off, offm, fsm, sts_d, seg_d, out=symm.out,
-                                 export=ops.ExportSpec(lvx=True, into=ops.ExportBuffers(lvx14=symm.lvx14)), p_range=(pb, pe))
+        def run_fused():
+            ops.deskew_slerp(sm_st.pts, sm_st.ts_off, offm, fsm, sts_d, seg_d, out=symm.out,
+                             export=ops.ExportSpec(lvx=True, into=own(), peer_out=po, peer_lvx14=pl), p_range=(pb, pe))
+            symm.barrier()
 
-            def t_max_ms(fn, reps=5):
-                for _ in range(2):
-                    fn()
-                torch.cuda.synchronize(); dist.barrier()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(reps):
-                    fn()
-                e1.record(); torch.cuda.synchronize()
-                t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                dist.barrier()
-                return float(t.item())
-            shard_ms, nccl_ms, fused_ms = t_max_ms(run_shard_only), t_max_ms(run_nccl), t_max_ms(run_fused)
-            recv = (Nm - (pe - pb)) * 30
-            merge = {"what": "ONE 1 h stream (3.6e8 pts) frame-sharded over the ranks; aligned float4 cloud + 14-B LVX records merged on every rank",
-                     "scaling": "strong", "points": Nm, "bytes_received_per_rank": recv,
-                     "shard_kernel_only": {"ms": shard_ms, "points_per_s": Nm / (shard_ms * 1e-3)},
-                     "kernel_plus_nccl_allgather": {"ms": nccl_ms, "points_per_s": Nm / (nccl_ms * 1e-3)},
-                     "fused_peer_store_epilogue": {"ms": fused_ms, "points_per_s": Nm / (fused_ms * 1e-3),
-                                                   "ingress_GBps_per_rank": recv / (fused_ms * 1e-3) / 1e9,
-                                                   "what": "same kernel, epilogue also stores into every peer's symmetric-memory copy over NVLink, then one cross-rank barrier"}}
-            del symm, sm_st
-        except Exception as e:                     # noqa: BLE001
-            merge = {"error": repr(e)}
+        def run_mc():
+            ops.deskew_slerp(sm_st.pts, sm_st.ts_off, offm, fsm, sts_d, seg_d, out=symm.out,
+                             export=ops.ExportSpec(lvx=True, into=own(), peer_out=po, peer_lvx14=pl, mc_out=mo, mc_lvx14=ml), p_range=(pb, pe))
+            symm.barrier()
+
+        def identical(fn):
+            """zero the merged buffers everywhere, run once, compare with the single-launch result on every rank"""
+            symm.out.zero_(); symm.lvx14.zero_()
+            symm.barrier()
+            fn()
+            torch.cuda.synchronize()
+            ok = torch.equal(symm.out, whole) and torch.equal(symm.lvx14, wbuf.lvx14)
+            t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return bool(t.item())
+
+        def t_max_ms(fn, reps=5):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize(); dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.barrier()
+            return float(t.item())
+
+        recv = (Nm - (pe - pb)) * 30
+        recv_t = torch.tensor([recv], dtype=torch.int64, device=dev)
+        dist.all_reduce(recv_t, op=dist.ReduceOp.MAX)
+        recv = int(recv_t.item())
+        shard_ms = t_max_ms(run_shard_only)
+        methods = {}
+        for name, fn, what in (
+                ("nccl_allgather", run_nccl, "shard kernel, then NCCL all-gather(v) of the aligned cloud + records"),
+                ("fused_peer_store", run_fused, "ONE kernel: the epilogue also stores every result into each peer's symmetric-memory copy (st.global over NVLink), then a stream-ordered cross-rank barrier"),
+                ("fused_multicast", run_mc if mo else None, "ONE kernel: every result of a full tile leaves as one multimem.st to the NVSwitch multicast mapping (replicated by the switch into all copies), then the barrier")):
+            if fn is None:
+                methods[name] = {"unavailable": "the symmetric buffers have no multicast mapping on this box"}
+                continue
+            try:
+                ok = identical(fn)
+                ms = t_max_ms(fn)
+                methods[name] = {"ms": ms, "points_per_s": Nm / (ms * 1e-3), "ingress_GBps_per_rank": recv / (ms * 1e-3) / 1e9,
+                                 "byte_identical": ok, "what": what}
+            except Exception as e:                 # noqa: BLE001
+                methods[name] = {"error": repr(e)}
+        timed_ok = {k: v for k, v in methods.items() if "ms" in v}
+        if not timed_ok:
+            raise SystemExit(f"merged-cloud assembly failed on every path: {methods}")
+        bad = [k for k, v in timed_ok.items() if not v["byte_identical"]]
+        if bad:
+            raise SystemExit(f"merged cloud differs from the single-launch result: {bad}")
+        best = min(timed_ok, key=lambda k: timed_ok[k]["ms"])
+        merge = {"what": f"ONE 1 h stream ({Nm} pts) frame-sharded over {world} ranks; aligned float4 cloud + 14-B LVX records merged on EVERY rank (np.vstack of LMC:886-899 as an all-gather); strong scaling",
+                 "points": Nm, "bytes_received_per_rank": recv,
+                 "shard_ms": shard_ms, "shard_points_per_s": Nm / (shard_ms * 1e-3),
+                 "nccl_ms": methods["nccl_allgather"].get("ms"), "fused_ms": methods["fused_peer_store"].get("ms"),
+                 "multicast_ms": methods["fused_multicast"].get("ms"),
+                 "best": best, "best_ms": timed_ok[best]["ms"], "merged_points_per_s": Nm / (timed_ok[best]["ms"] * 1e-3),
+                 "ingress_GBps": timed_ok[best]["ingress_GBps_per_rank"],
+                 "byte_identical": all(v["byte_identical"] for v in timed_ok.values()), "methods": methods}
+        del symm, sm_st, whole, wbuf
         torch.cuda.empty_cache()
 
-    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------------
+    # ---- CPU baseline (rank 0, N = 1 only): the reference's own code on the host cores + the integer parity check ----------
     cpu = None
+    int_mism = None
     if rank == 0 and world == 1 and not args.no_cpu:
         os.sched_setaffinity(0, orig_affinity)             # the CPU baseline gets every host core back
         r = cpu_reference_run(3, 1, args.cpu_frames, P)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        cpu = cpu_baseline_block(r)
         try:
             from oracle import cpu_baseline as cb
             cpu["c_port_mode_c_1thread_points_per_s"] = cb.run_c_port_mode_c()
             cpu["writers_port_points_per_s"] = cb.run_writers_port()
         except Exception as e:                     # noqa: BLE001
             cpu["c_port_error"] = repr(e)
+        # integer export buffers of the first 48 frames against the oracle (bit-exact is the bar: every count must be 0)
+        try:
+            from oracle import lmc_oracle as orc
+            fc = min(F, 48)
+            nc = int(st.frame_off[fc])
+            offc, fsc = d(st.frame_off[:fc + 1]), fs_d[:fc].contiguous()
+            p64 = st.pts[:nc].cpu().numpy().astype(np.float64)
+            ts64 = st.frame_start[np.repeat(np.arange(fc), np.diff(st.frame_off[:fc + 1]))] + st.ts_off[:nc].cpu().numpy().astype(np.int64)
+            spec = ops.ExportSpec(lvx=True, las=True, las_scale=(0.001,) * 3)
+            o_c, b_c = ops.deskew_slerp(st.pts[:nc].contiguous(), st.ts_off[:nc].contiguous(), offc, fsc, sts_d, seg_d, export=spec)
+            want = orc.C.deskew_slerp_f64(p64, ts64, st.frame_off[:fc + 1], st.sample_ts, st.seg)
+            X, Y, Z, I, _ = orc.C.quantize_las(want, [0.001] * 3, [0.0] * 3, 0)
+            int_mism = {"points": nc,
+                        "lvx_records_mode_c": int((b_c.lvx14.cpu().numpy() != orc.C.quantize_lvx_type2(p64)[0]).any(axis=1).sum()),
+                        "las_xyz_mode_c": int((b_c.las_x.cpu().numpy() != X).sum() + (b_c.las_y.cpu().numpy() != Y).sum() + (b_c.las_z.cpu().numpy() != Z).sum()),
+                        "las_intensity_mode_c": int((b_c.las_intensity.cpu().numpy() != I).sum()),
+                        "float_max_abs_err_m": float(np.abs(o_c.cpu().numpy().astype(np.float64) - want).max())}
+            pose_c = st.gps_Rt[orc.pose_lookup_hold_next_np(st.gps_t, st.frame_t[:fc])]
+            o_a, b_a = ops.align_rigid(d(p64), offc, d(pose_c), export=ops.ExportSpec(lvx=True, las=True, las_scale=(0.001,) * 3))
+            want_a = orc.C.align_rigid_f64(p64, st.frame_off[:fc + 1], pose_c)
+            Xa, Ya, Za, Ia, _ = orc.C.quantize_las(want_a, [0.001] * 3, [0.0] * 3, 0)
+            int_mism["f64_rows_mode_a"] = int((o_a.cpu().numpy() != want_a).any(axis=1).sum())
+            int_mism["lvx_records_mode_a"] = int((b_a.lvx14.cpu().numpy() != orc.C.quantize_lvx_type2(p64)[0]).any(axis=1).sum())
+            int_mism["las_xyz_mode_a"] = int((b_a.las_x.cpu().numpy() != Xa).sum() + (b_a.las_y.cpu().numpy() != Ya).sum() + (b_a.las_z.cpu().numpy() != Za).sum())
+        except Exception as e:                     # noqa: BLE001
+            int_mism = {"error": repr(e)}
 
     if rank == 0:
         mode, f64, ts, lvx, las, _ = VARIANTS[args.variant]
@@ -611,7 +746,7 @@ def main_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"M-1H synthetic 1 h Mid-70 stream: {F} frames x {P} pts = {N} points per GPU, 200 Hz pose samples ({n_samples}), seed {SEED}",
+            "config": {"workload": workload_name(F, P), "per_gpu": f"every rank owns one such stream (rank r = hour r of an N-hour recording, seed {SEED} + 17 r)",
                        "variant": f"{args.variant}: mode={mode} io={'f64' if f64 else 'f32 float4'} ts={ts} lvx={lvx} las={las}, f64 arithmetic",
                        "bytes_per_point": bpp, "kernel_path": {0: "direct", 1: "auto (persistent TMA pipeline at this size)", 2: "tma"}[C.get_path()],
                        "l2": f"inputs {N * (16 + 4) / 1e9:.1f} GB >> 126 MB L2: no flush needed", "parallelism": f"frame-sharded x{world}",
@@ -621,8 +756,17 @@ def main_b200(args):
                          "algorithmic_bytes_per_launch": N * bpp, "frac_of_nominal_8TBps": achieved / 8000.0},
             "clocks": clocks, "gpu_launches": args.steps, "e2e": e2e, "cpu_baseline": cpu,
         }
+        if int_mism is not None:
+            line["config"]["int_mismatches"] = int_mism
+        if sweep.get("V2") or e2e_mode_a:
+            line["config"]["like_for_like"] = {
+                "variant": "V2: Mode A (the reference's hold-next frame pose, LMC:802-832) + LVX records -- the transform the reference arm runs",
+                "value": (sweep.get("V2") or {}).get("points_per_s"), "roofline_frac": (sweep.get("V2") or {}).get("frac"), "e2e": e2e_mode_a}
         if merge:
-            line["merge"] = merge
+            line["config"]["merge"] = merge
+            line["roofline"]["nvlink"] = {"bound": "nvlink ingress", "bytes_received_per_rank": merge["bytes_received_per_rank"], "ms": merge["best_ms"],
+                                          "achieved": merge["ingress_GBps"], "peak": 900.0, "unit": "GB/s", "frac": merge["ingress_GBps"] / 900.0,
+                                          "method": merge["best"], "peak_source": "NVLink 5 nominal 900 GB/s per direction per GPU (B200_PROFILING.md); measured raw all-gather ceiling of this pool: profiles/r02_nvlink_ceiling_n*.json"}
         if sweep:
             line["variants"] = sweep
         if writers:

@@ -79,6 +79,13 @@ typedef struct lmc_export {
     int32_t   n_peers;            /* 0 .. LMC_MAX_PEERS                                              */
     void*     peer_out[7];        /* same layout as out_n4 (NULL entries are skipped)                 */
     uint8_t*  peer_lvx14[7];      /* same layout as lvx14                                             */
+    /* The same assembly through the NVSwitch multicast mapping of the merged buffers (torch symmetric memory
+     * `multicast_ptr`): when both are non-NULL (float4 layout, out + type-2 LVX records) every result of a full
+     * tile leaves as ONE multimem.st that the switch replicates into every rank's copy -- this rank's included --
+     * instead of a local store plus n_peers peer stores.  The peer pointers above must still be given: a
+     * shard's ragged first / last tile uses them. */
+    void*     mc_out;
+    uint8_t*  mc_lvx14;
 } lmc_export;
 #define LMC_MAX_PEERS 7
 

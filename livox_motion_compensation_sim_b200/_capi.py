@@ -34,6 +34,7 @@ class LmcExport(ctypes.Structure):
         ("las_scale", ctypes.c_double * 3), ("las_offset", ctypes.c_double * 3),
         ("status", vp),
         ("n_peers", i32), ("peer_out", vp * 7), ("peer_lvx14", vp * 7),
+        ("mc_out", vp), ("mc_lvx14", vp),
     ]
 
 

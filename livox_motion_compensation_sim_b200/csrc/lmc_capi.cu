@@ -71,7 +71,7 @@ int check_device() {
 
 int fill_export(lmc::Params& P, const lmc_export* ex) {
     P.lvx14 = nullptr; P.tag = nullptr; P.las_x = P.las_y = P.las_z = nullptr; P.las_int = nullptr; P.status = nullptr;
-    P.lvx_mode = 0; P.las_int_mode = 0; P.n_peers = 0;
+    P.lvx_mode = 0; P.las_int_mode = 0; P.n_peers = 0; P.mc_out = nullptr; P.mc_lvx = nullptr;
     for (int r = 0; r < LMC_MAX_PEERS; ++r) { P.peer_out[r] = nullptr; P.peer_lvx[r] = nullptr; }
     for (int c = 0; c < 3; ++c) { P.las_scale[c] = 0.01; P.las_rcp[c] = 1.0 / 0.01; P.las_off[c] = 0.0; }
     if (!ex) return LMC_OK;
@@ -92,6 +92,12 @@ int fill_export(lmc::Params& P, const lmc_export* ex) {
     for (int r = 0; r < ex->n_peers; ++r) {
         if (!aligned32(ex->peer_out[r]) || !aligned32(ex->peer_lvx14[r])) return fail(LMC_ERR_ALIGN, "peer buffers must be 32-byte aligned");
         P.peer_out[r] = ex->peer_out[r]; P.peer_lvx[r] = ex->peer_lvx14[r];
+    }
+    if ((ex->mc_out != nullptr) != (ex->mc_lvx14 != nullptr)) return fail(LMC_ERR_INVALID, "mc_out and mc_lvx14 must be given together");
+    if (ex->mc_out != nullptr) {
+        if (!aligned32(ex->mc_out) || !aligned32(ex->mc_lvx14)) return fail(LMC_ERR_ALIGN, "multicast buffers must be 32-byte aligned");
+        if (ex->n_peers < 1) return fail(LMC_ERR_INVALID, "multicast merge also needs the peer pointers (ragged edge tiles use them)");
+        P.mc_out = ex->mc_out; P.mc_lvx = ex->mc_lvx14;
     }
     for (int c = 0; c < 3; ++c) { P.las_scale[c] = ex->las_scale[c]; P.las_rcp[c] = 1.0 / ex->las_scale[c]; P.las_off[c] = ex->las_offset[c]; }
     return LMC_OK;

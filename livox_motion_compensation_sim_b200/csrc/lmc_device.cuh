@@ -46,6 +46,9 @@ struct Params {
     int32_t         n_peers;
     void*           peer_out[LMC_MAX_PEERS];
     uint8_t*        peer_lvx[LMC_MAX_PEERS];
+    // the same through the NVSwitch multicast mapping of the symmetric buffers (multimem.st)
+    void*           mc_out;
+    uint8_t*        mc_lvx;
 };
 
 struct Pt { double x, y, z, w; };

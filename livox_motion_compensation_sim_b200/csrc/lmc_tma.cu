@@ -88,7 +88,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // 2 <= n_samp < 2^31.
 // kExLvx2 (with kExLvx): the records are CS:365-374 on the COMPENSATED point (+ optional tag bytes) instead of LMC:252-272 on
 // the raw one -- the second simulator's product, lean for Mode B.
-constexpr int kExOut = 1, kExLvx = 2, kExLas = 4, kExGeneric = 8, kExLvx2 = 16;
+// kExMc (with kExOut | kExLvx): fused merged-cloud assembly through the NVSwitch multicast mapping of the symmetric buffers --
+// every result of a full tile leaves as ONE multimem.st (the switch replicates it into every rank's copy, this rank's
+// included) instead of a local store plus one store per peer; ragged edge tiles fall back to local + per-peer stores.
+constexpr int kExOut = 1, kExLvx = 2, kExLas = 4, kExGeneric = 8, kExLvx2 = 16, kExMc = 32;
+
+// 16 bytes to the multicast address (PTX multimem.st; the switch fans the write out to every member of the group)
+__device__ __forceinline__ void mc_st128(void* mc, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(mc), "f"(__uint_as_float(a)), "f"(__uint_as_float(b)), "f"(__uint_as_float(c)), "f"(__uint_as_float(d)) : "memory");
+}
 
 // ---- one tile on the consumer side ------------------------------------------------------------
 template <bool F64, int MODE, int EX, bool FULL>
@@ -100,6 +109,7 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
     using Cfg = StreamCfg<F64, MODE>;
     constexpr int PPT = Cfg::PPT;
     constexpr bool GEN = EX == kExGeneric;
+    constexpr bool MC = !GEN && (EX & kExMc);                    // full tiles: multimem.st only; edge tiles: local + per-peer stores
     const bool do_out = GEN ? P.out != nullptr : bool(EX & kExOut);
     const bool do_lvx = GEN ? P.lvx14 != nullptr : bool(EX & kExLvx);
     const bool do_las = GEN ? (P.las_x != nullptr || P.las_int != nullptr) : bool(EX & kExLas);
@@ -215,7 +225,11 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
             if constexpr (F64) store_pair<true, FULL>(P.out, p, va, vb, o[0], o[1]);
             else {
                 float* dst = reinterpret_cast<float*>(P.out) + 4 * p;
-                if (FULL || (va && vb)) {
+                if constexpr (MC && FULL) {
+                    float* mc = reinterpret_cast<float*>(P.mc_out) + 4 * p;
+                    mc_st128(mc, __float_as_uint((float)o[0].x), __float_as_uint((float)o[0].y), __float_as_uint((float)o[0].z), __float_as_uint(wraw[0]));
+                    mc_st128(mc + 4, __float_as_uint((float)o[1].x), __float_as_uint((float)o[1].y), __float_as_uint((float)o[1].z), __float_as_uint(wraw[1]));
+                } else if (FULL || (va && vb)) {
                     const float v[8] = { (float)o[0].x, (float)o[0].y, (float)o[0].z, wraw[0], (float)o[1].x, (float)o[1].y, (float)o[1].z, wraw[1] };
                     stg256(dst, v);
                 } else {
@@ -224,7 +238,7 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
                 }
             }
         }
-        if constexpr (GEN) {
+        if constexpr (GEN || (MC && !FULL)) {
             // fused merged-cloud assembly: the same pair goes to every peer's copy of the merged buffer
             for (int r = 0; r < P.n_peers; ++r)
                 if (P.peer_out[r] != nullptr) store_pair<F64, FULL>(P.peer_out[r], p, va, vb, o[0], o[1]);
@@ -244,7 +258,14 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
         const int64_t wfirst = base + 2 * (int64_t)(cw * PPT) * 32;          // first point of the warp's block
         uint8_t* g = P.lvx14 + 14 * wfirst;
         constexpr int NB = PPT * 64 * 14;
-        if constexpr (FULL) {
+        if constexpr (MC && FULL) {
+            __syncwarp();
+            uint8_t* mc = P.mc_lvx + 14 * wfirst;
+            for (int i = lane; i < NB / 16; i += 32) {
+                const uint4 v = reinterpret_cast<const uint4*>(slab)[i];
+                mc_st128(mc + 16 * i, v.x, v.y, v.z, v.w);
+            }
+        } else if constexpr (FULL) {
             fence_async_smem();
             __syncwarp();
             if (lane == 0) { bulk_s2g(g, slab, NB); bulk_commit(); }
@@ -261,7 +282,7 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
                 for (int i = a1 + lane; i < b1; i += 32) g[i] = slab[i];
             }
         }
-        if constexpr (GEN) {
+        if constexpr (GEN || (MC && !FULL)) {
             for (int r = 0; r < P.n_peers; ++r) {
                 uint8_t* gp = P.peer_lvx[r];
                 if (gp == nullptr) continue;
@@ -448,10 +469,16 @@ static cudaError_t launch_stream(const Params& P, cudaStream_t st, bool force, b
     if constexpr (MODE == kRigid || MODE == kSlerp || MODE == kGyro) {
         const int mask = (P.out ? kExOut : 0) | (P.lvx14 ? kExLvx : 0) | ((P.las_x || P.las_int) ? kExLas : 0);
         const bool lvx2 = P.lvx14 && P.lvx_mode == LMC_LVX2_OF_OUTPUT;
-        bool lean = P.n_peers == 0 && (!lvx2 || MODE == kGyro) && (!(mask & kExLas) || (P.las_x && P.las_int));
+        const bool mc = P.mc_out != nullptr && P.mc_lvx != nullptr;           // multicast merge: lean out + LVX kernel, float4 layout
+        if (mc && !(MODE != kGyro && !F64 && mask == (kExOut | kExLvx) && !lvx2)) return cudaErrorInvalidValue;
+        bool lean = (P.n_peers == 0 || mc) && (!lvx2 || MODE == kGyro) && (!(mask & kExLas) || (P.las_x && P.las_int));
         if (MODE == kSlerp) lean = lean && P.hold_idx == nullptr && P.ts != nullptr && P.n_samp >= 2 && P.n_samp < 0x7fffffffLL &&
                                    (F64 || P.frame_start != nullptr);
         if (MODE == kGyro)  lean = lean && P.ts != nullptr && P.frame_start != nullptr && P.n_samp >= 2 && P.n_samp < 0x7fffffffLL;
+        if (mc && !lean) return cudaErrorInvalidValue;
+        if constexpr (MODE != kGyro && !F64) {
+            if (lean && mc) return launch_stream_ex<F64, MODE, kExOut | kExLvx | kExMc>(P, st, grid, tile0, n_tiles);
+        }
         if (lean) {
             if (mask == kExOut)            return launch_stream_ex<F64, MODE, kExOut>(P, st, grid, tile0, n_tiles);
             if constexpr (MODE == kGyro) {

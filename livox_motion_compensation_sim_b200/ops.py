@@ -13,7 +13,37 @@ from . import _capi as C
 
 
 def _stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream().cuda_stream          # the CURRENT device's stream: ops run inside _on_tensor_device
+
+
+def _on_tensor_device(fn):
+    """Run the operator on the device its tensors live on, whatever the caller's current device is: the C ABI
+    launches on the calling thread's current device and stream, so the guard switches to the tensors' GPU (and
+    its current stream) for the duration of the call and refuses arguments spread over several devices."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        def visit(v):
+            nonlocal dev
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                if dev is None:
+                    dev = v.device
+                elif v.device != dev:
+                    raise ValueError(f"{fn.__name__}: tensors on different devices ({dev} and {v.device})")
+            elif isinstance(v, (ExportSpec, ExportBuffers)):
+                for x in vars(v).values():
+                    visit(x)
+        for v in args:
+            visit(v)
+        for v in kwargs.values():
+            visit(v)
+        if dev is None:
+            return fn(*args, **kwargs)                      # no CUDA tensor: the operator's own checks raise
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def _req(t: Optional[torch.Tensor], dtype, name: str, shape_tail=None) -> int:
@@ -65,6 +95,8 @@ class ExportSpec:
     into: Optional[ExportBuffers] = None                 # reuse caller buffers (merged cloud shards)
     peer_out: Sequence[int] = ()                         # peer-mapped device pointers of the other ranks' `out` copies
     peer_lvx14: Sequence[int] = ()                       # ... and of their lvx14 copies (fused merged-cloud assembly)
+    mc_out: int = 0                                      # NVSwitch multicast address of `out` (0 = per-peer stores)
+    mc_lvx14: int = 0                                    # ... and of lvx14; both or neither
 
 
 def _make_export(spec: Optional[ExportSpec], n: int, device):
@@ -101,6 +133,8 @@ def _make_export(spec: Optional[ExportSpec], n: int, device):
     for r in range(npeer):
         ex.peer_out[r] = int(spec.peer_out[r]) if r < len(spec.peer_out) else None
         ex.peer_lvx14[r] = int(spec.peer_lvx14[r]) if (spec.lvx and r < len(spec.peer_lvx14)) else None
+    ex.mc_out = int(spec.mc_out) or None
+    ex.mc_lvx14 = int(spec.mc_lvx14) or None
     return ex, b
 
 
@@ -118,6 +152,7 @@ def _range(n, p_range):
     return int(p_range[0]), int(p_range[1])
 
 
+@_on_tensor_device
 def pose_lookup_hold_next(traj_t: torch.Tensor, traj_Rt: torch.Tensor, frame_t: torch.Tensor):
     """(a1) LMC:802-812 on the device. Returns (pose_Rt (F,12) f64, pose_idx (F) int32)."""
     F = frame_t.shape[0]
@@ -129,6 +164,7 @@ def pose_lookup_hold_next(traj_t: torch.Tensor, traj_Rt: torch.Tensor, frame_t: 
     return pose, idx
 
 
+@_on_tensor_device
 def align_rigid(pts: torch.Tensor, frame_off: torch.Tensor, pose_Rt: torch.Tensor, *, out: Optional[torch.Tensor] = None,
                 export: Optional[ExportSpec] = None, p_range=None, want_out: bool = True):
     """(a2)+(a3) LMC:772-776 over all frames, frame-major (LMC:888). Returns (aligned, ExportBuffers|None)."""
@@ -147,6 +183,7 @@ def align_rigid(pts: torch.Tensor, frame_off: torch.Tensor, pose_Rt: torch.Tenso
     return out, bufs
 
 
+@_on_tensor_device
 def deskew_gyro(pts: torch.Tensor, ts: torch.Tensor, frame_off: torch.Tensor, frame_start: torch.Tensor,
                 imu_ts: torch.Tensor, imu_gyro: torch.Tensor, *, out: Optional[torch.Tensor] = None,
                 export: Optional[ExportSpec] = None, p_range=None, want_out: bool = True):
@@ -165,6 +202,7 @@ def deskew_gyro(pts: torch.Tensor, ts: torch.Tensor, frame_off: torch.Tensor, fr
     return out, bufs
 
 
+@_on_tensor_device
 def deskew_slerp(pts: torch.Tensor, ts: Optional[torch.Tensor], frame_off: torch.Tensor, frame_start: Optional[torch.Tensor],
                  sample_ts: torch.Tensor, seg: torch.Tensor, *, hold_idx: Optional[torch.Tensor] = None,
                  out: Optional[torch.Tensor] = None, export: Optional[ExportSpec] = None, p_range=None, want_out: bool = True):
@@ -184,6 +222,7 @@ def deskew_slerp(pts: torch.Tensor, ts: Optional[torch.Tensor], frame_off: torch
     return out, bufs
 
 
+@_on_tensor_device
 def quantize(pts: torch.Tensor, export: ExportSpec) -> ExportBuffers:
     """(a4)/(a5)/(a9)/(a10) stand-alone quantisers over an (N,4) point array."""
     f64 = _layout(pts)
@@ -196,6 +235,7 @@ def quantize(pts: torch.Tensor, export: ExportSpec) -> ExportBuffers:
     return bufs
 
 
+@_on_tensor_device
 def build_slerp_table(sample_quat_xyzw: torch.Tensor, sample_pos: torch.Tensor, sample_ts: torch.Tensor,
                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """The (S,22) pose-segment table of deskew_slerp built on the device from (S,4) quaternions (x y z w),
@@ -208,6 +248,7 @@ def build_slerp_table(sample_quat_xyzw: torch.Tensor, sample_pos: torch.Tensor, 
     return out
 
 
+@_on_tensor_device
 def transform_homog(pts: torch.Tensor, T, order: int = C.HOMOG_BATCH, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(N3) CS:214-233: one 4x4 homogeneous matrix T (host array) over (n,4) points; order = _capi.HOMOG_BATCH
     (the reference call on n >= 2 points) or HOMOG_SINGLE (the call on one point, CS:2136-2138)."""
@@ -221,6 +262,7 @@ def transform_homog(pts: torch.Tensor, T, order: int = C.HOMOG_BATCH, out: Optio
     return out
 
 
+@_on_tensor_device
 def build_lvx_v11(pts: torch.Tensor, frame_off: torch.Tensor, frame_pos: torch.Tensor, frame_time: torch.Tensor,
                   frame_id: torch.Tensor, max_frame_points: int):
     """(N1) LMC:58-250 on the device: RAW points -> the complete LVX v1.1 file image (uint8 tensor).
@@ -238,6 +280,7 @@ def build_lvx_v11(pts: torch.Tensor, frame_off: torch.Tensor, frame_pos: torch.T
     return out, status
 
 
+@_on_tensor_device
 def build_lvx_cs(pts: torch.Tensor, tag: Optional[torch.Tensor], frame_off: torch.Tensor, frame_ts: torch.Tensor,
                  prefix: bytes, fmt: int, max_frame_points: int):
     """(N1) CS:245-374 on the device: COMPENSATED points [x y z intensity] (+ tag bytes) -> the complete LVX2 / LVX3
@@ -258,6 +301,7 @@ def build_lvx_cs(pts: torch.Tensor, tag: Optional[torch.Tensor], frame_off: torc
     return out, status
 
 
+@_on_tensor_device
 def pcd_ascii_body(pts: torch.Tensor):
     """(N2) LMC:946-947 on the device: one '%.6f %.6f %.6f %.6f\\n' line per row, byte-identical to the
     reference's f-string formatting.  Returns (uint8 text tensor, status flags tensor)."""
@@ -275,6 +319,7 @@ def pcd_ascii_body(pts: torch.Tensor):
     return out, status
 
 
+@_on_tensor_device
 def pcd_ascii_frames(pts: torch.Tensor, frame_off: torch.Tensor):
     """(N2) the '%.6f' bodies of EVERY per-frame PCD file in one formatting pass: pts is the frame-major buffer,
     frame_off int64[F+1] its CSR offsets (device).  Returns (uint8 text tensor, int64[F+1] device byte offsets,
@@ -299,6 +344,7 @@ def pcd_ascii_frames(pts: torch.Tensor, frame_off: torch.Tensor):
     return out, byte_off, status
 
 
+@_on_tensor_device
 def text_rows(rows: torch.Tensor, cols, decimals, sep: str = " "):
     """(N2) CS:1643-1716 on the device: one line per row of a 2-D f64 / f32 tensor, column cols[k] printed as
     '%.{decimals[k]}f', joined by sep, '\\n' terminated -- byte-identical to the reference's f-strings /
@@ -325,6 +371,7 @@ def text_rows(rows: torch.Tensor, cols, decimals, sep: str = " "):
     return out, status
 
 
+@_on_tensor_device
 def build_las_pf3(pts: torch.Tensor, *, scale=(0.01, 0.01, 0.01), offset=(0.0, 0.0, 0.0), intensity_mode: int = C.LAS_INTENSITY_UNIT,
                   gps_time: Optional[torch.Tensor] = None, year: int = 2026, day_of_year: int = 1):
     """(N2) A complete LAS 1.2 / PF3 file image on the device (parity unpinned: laspy absent; LAS 1.2 spec).
@@ -363,6 +410,7 @@ def _redecide_uncertain(env, pos, Rm, flags, fov_h, fov_v, range_min) -> int:
     return int(fi.numel())
 
 
+@_on_tensor_device
 def scan_frames(env: torch.Tensor, pos: torch.Tensor, Rm: torch.Tensor, *, range_max: float, range_min: float,
                 fov_horizontal: float, fov_vertical: float, points_per_frame: int, noise_std: float, noise_fn=None,
                 max_flag_bytes: int = 1 << 30, edge_eps_deg: float = 1e-9):

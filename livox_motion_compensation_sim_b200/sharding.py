@@ -57,9 +57,10 @@ def all_gather_merged(buffers: Sequence[torch.Tensor], point_cuts: np.ndarray, g
 class SymmetricMerged:
     """Merged-cloud buffers in NVLink-symmetric memory (torch.distributed._symmetric_memory): every rank
     holds a full-size copy of the aligned cloud (and LVX records) and can address the other ranks' copies
-    directly.  Passing ``peer_spec()`` to the fused operators makes the kernel epilogue store each result
-    into every rank's copy (remote st.global over NVLink), so the all-gather overlaps the transform instead
-    of following it; ``barrier()`` after the launch makes the remote writes visible.  torch is only the
+    directly.  Passing ``peer_ptrs()`` (and, where the fabric offers it, ``mc_ptrs()``) to the fused operators
+    makes the kernel epilogue store each result into every rank's copy -- remote st.global over NVLink, or one
+    multimem.st per result that the NVSwitch replicates -- so the all-gather overlaps the transform instead of
+    following it; ``barrier()`` after the launch makes the remote writes visible.  torch is only the
     allocator / rendezvous plumbing here -- the data moves inside the sm_100a kernel."""
 
     def __init__(self, n_points: int, device, *, dtype=torch.float32, lvx: bool = True, group=None):
@@ -73,12 +74,27 @@ class SymmetricMerged:
             self.lvx14 = symm.empty((n_points, 14), dtype=torch.uint8, device=device)
             self.h_lvx = symm.rendezvous(self.lvx14, self.group)
 
+    @staticmethod
+    def _off(h) -> int:
+        """byte offset of the tensor inside its symmetric allocation (0 unless a memory pool packs several tensors into one)"""
+        o = getattr(h, "offset", 0)
+        return int(o) if isinstance(o, int) else 0
+
     def peer_ptrs(self):
         others = [r for r in range(self.world) if r != self.rank]
-        po = [int(self.h_out.buffer_ptrs[r]) for r in others]
-        pl = [int(self.h_lvx.buffer_ptrs[r]) for r in others] if self.h_lvx is not None else []
+        po = [int(self.h_out.buffer_ptrs[r]) + self._off(self.h_out) for r in others]
+        pl = [int(self.h_lvx.buffer_ptrs[r]) + self._off(self.h_lvx) for r in others] if self.h_lvx is not None else []
         return po, pl
 
+    def mc_ptrs(self):
+        """(multicast address of out, of lvx14), or (0, 0) when the buffers have no NVSwitch multicast mapping."""
+        if self.h_lvx is None:
+            return 0, 0
+        mo, ml = int(getattr(self.h_out, "multicast_ptr", 0) or 0), int(getattr(self.h_lvx, "multicast_ptr", 0) or 0)
+        return (mo + self._off(self.h_out), ml + self._off(self.h_lvx)) if (mo and ml) else (0, 0)
+
     def barrier(self):
-        torch.cuda.current_stream().synchronize()
+        """Cross-rank barrier ON THE CURRENT STREAM (a signal-pad kernel: every rank's earlier work on its stream,
+        the fused kernel's remote stores included, is complete and visible before any rank's later work starts).
+        Nothing blocks on the host."""
         self.h_out.barrier()

@@ -61,9 +61,26 @@ def main():
         t_fused = time.perf_counter() - t0
     assert torch.equal(sm.out, whole), "fused merge: aligned cloud differs"
     assert torch.equal(sm.lvx14, wb.lvx14), "fused merge: LVX records differ"
+
+    # (3) the same through the NVSwitch multicast mapping (multimem.st), where the box offers one
+    mo, ml = sm.mc_ptrs()
+    t_mc = None
+    if mo:
+        sm.out.zero_(); sm.lvx14.zero_()
+        sm.barrier()
+        spec_mc = lambda: ops.ExportSpec(lvx=True, into=ops.ExportBuffers(lvx14=sm.lvx14), peer_out=po, peer_lvx14=pl, mc_out=mo, mc_lvx14=ml)  # noqa: E731
+        for it in range(2):
+            torch.cuda.synchronize(); dist.barrier()
+            t0 = time.perf_counter()
+            ops.deskew_slerp(st.pts, st.ts_off, off_d, fs_d, sts_d, seg_d, out=sm.out, export=spec_mc(), p_range=(b, e))
+            sm.barrier()
+            torch.cuda.synchronize(); dist.barrier()
+            t_mc = time.perf_counter() - t0
+        assert torch.equal(sm.out, whole), "multicast merge: aligned cloud differs"
+        assert torch.equal(sm.lvx14, wb.lvx14), "multicast merge: LVX records differ"
     if rank == 0:
         print(f"OK world={world} points={N} shard={e - b}  kernel+NCCL all-gather {t_nccl * 1e3:.2f} ms (first call)  "
-              f"fused peer-store epilogue {t_fused * 1e3:.2f} ms")
+              f"fused peer-store epilogue {t_fused * 1e3:.2f} ms  multicast epilogue " + (f"{t_mc * 1e3:.2f} ms" if t_mc else "unavailable"))
     dist.barrier()
     dist.destroy_process_group()
 

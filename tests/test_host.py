@@ -40,7 +40,8 @@ def test_capi_struct_layout_matches_header():
     assert E.las_x.offset == 24 and E.las_intensity.offset == 48 and E.las_intensity_mode.offset == 56
     assert E.las_scale.offset == 64 and E.las_offset.offset == 88 and E.status.offset == 112
     assert E.n_peers.offset == 120 and E.peer_out.offset == 128 and E.peer_lvx14.offset == 184
-    assert ctypes.sizeof(E) == 240
+    assert E.mc_out.offset == 240 and E.mc_lvx14.offset == 248
+    assert ctypes.sizeof(E) == 256
 
 
 def test_capi_fails_loudly_without_gpu(built_lib):
