@@ -148,6 +148,11 @@ def workload_name(F, P):
     return f"M-1H synthetic 1 h Mid-70 stream: {F} frames x {P} pts = {F * P} points, 200 Hz pose samples ({F * 20 + 1}), seed {SEED}"
 
 
+def sharding_pcd_header(n):
+    from livox_motion_compensation_sim_b200.simulator import LiDARMotionSimulator
+    return LiDARMotionSimulator._pcd_header(int(n))
+
+
 def cpu_port_run(steps, warmup, frames, ppf):
     from oracle import cpu_baseline as cb
     threads = cb.default_threads()
@@ -611,16 +616,17 @@ def main_b200(args):
         sm_st = synth.make_stream(F, P, SEED, device=dev, dtype=torch.float32)          # the SAME stream on every rank
         Nm = sm_st.n_points
         offm, fsm = d(sm_st.frame_off), d(sm_st.frame_start)
+        stsm, segm = d(sm_st.sample_ts), d(sm_st.seg)                                    # ITS pose table (the ranks' own streams differ)
         fcuts, pcuts = sharding.shard_ranges(sm_st.frame_off, world)
         pb, pe = int(pcuts[rank]), int(pcuts[rank + 1])
         symm = sharding.SymmetricMerged(Nm, dev, lvx=True)
         po, pl = symm.peer_ptrs()
         mo, ml = symm.mc_ptrs()
-        whole, wbuf = ops.deskew_slerp(sm_st.pts, sm_st.ts_off, offm, fsm, sts_d, seg_d, export=ops.ExportSpec(lvx=True))   # 1-GPU result
+        whole, wbuf = ops.deskew_slerp(sm_st.pts, sm_st.ts_off, offm, fsm, stsm, segm, export=ops.ExportSpec(lvx=True))   # 1-GPU result
         own = lambda: ops.ExportBuffers(lvx14=symm.lvx14)                                # noqa: E731
 
         def run_shard_only():
-            ops.deskew_slerp(sm_st.pts, sm_st.ts_off, offm, fsm, sts_d, seg_d, out=symm.out,
+            ops.deskew_slerp(sm_st.pts, sm_st.ts_off, offm, fsm, stsm, segm, out=symm.out,
                              export=ops.ExportSpec(lvx=True, into=own()), p_range=(pb, pe))
 
         def run_nccl():
@@ -628,12 +634,12 @@ def main_b200(args):
             sharding.all_gather_merged([symm.out, symm.lvx14], pcuts)
 
         def run_fused():
-            ops.deskew_slerp(sm_st.pts, sm_st.ts_off, offm, fsm, sts_d, seg_d, out=symm.out,
+            ops.deskew_slerp(sm_st.pts, sm_st.ts_off, offm, fsm, stsm, segm, out=symm.out,
                              export=ops.ExportSpec(lvx=True, into=own(), peer_out=po, peer_lvx14=pl), p_range=(pb, pe))
             symm.barrier()
 
         def run_mc():
-            ops.deskew_slerp(sm_st.pts, sm_st.ts_off, offm, fsm, sts_d, seg_d, out=symm.out,
+            ops.deskew_slerp(sm_st.pts, sm_st.ts_off, offm, fsm, stsm, segm, out=symm.out,
                              export=ops.ExportSpec(lvx=True, into=own(), peer_out=po, peer_lvx14=pl, mc_out=mo, mc_lvx14=ml), p_range=(pb, pe))
             symm.barrier()
 
@@ -697,6 +703,52 @@ def main_b200(args):
                  "best": best, "best_ms": timed_ok[best]["ms"], "merged_points_per_s": Nm / (timed_ok[best]["ms"] * 1e-3),
                  "ingress_GBps": timed_ok[best]["ingress_GBps_per_rank"],
                  "byte_identical": all(v["byte_identical"] for v in timed_ok.values()), "methods": methods}
+        # ---- replication-free file production: every rank turns ITS frames into ITS byte range of the LVX / LAS / PCD files
+        #      (closed-form or prefix-summed offsets; only 6 + W integers cross ranks) -- the path that scales with N.
+        try:
+            from livox_motion_compensation_sim_b200.lvx import frame_layout
+            fa, fb = int(fcuts[rank]), int(fcuts[rank + 1])
+            ids_np = np.arange(F, dtype=np.int64)
+            _, fpos_np = frame_layout(sm_st.frame_off)
+            las_kw = dict(scale=(0.001,) * 3, year=2026, day_of_year=1)
+
+            def files_sharded():
+                run_shard_only()
+                a = sharding.lvx_v11_shard(sm_st.pts, sm_st.frame_off, sm_st.frame_t, ids_np, fa, fb)
+                b = sharding.las_pf3_shard(symm.out, pb, pe, rank, **las_kw)
+                c = sharding.pcd_ascii_shard(symm.out[pb:pe], Nm, rank)
+                return a, b, c
+
+            def files_one_gpu():
+                ops.deskew_slerp(sm_st.pts, sm_st.ts_off, offm, fsm, stsm, segm, out=whole, export=ops.ExportSpec(lvx=True, into=ops.ExportBuffers(lvx14=wbuf.lvx14)))
+                a = ops.build_lvx_v11(sm_st.pts, offm, d(fpos_np), d(sm_st.frame_t), d(ids_np), P)
+                b = ops.build_las_pf3(whole, **las_kw)
+                c = ops.pcd_ascii_body(whole)
+                return a, b, c
+            (lv_s, lv_pos, _), (la_s, la_pos, _), (tx_s, tx_pos, tx_hdr, _) = files_sharded()
+            (lv_w, _), (la_w, _), (tx_w, _) = files_one_gpu()
+            torch.cuda.synchronize()
+            hdr_len = len(sharding_pcd_header(Nm))
+            same = (torch.equal(lv_s, lv_w[lv_pos:lv_pos + lv_s.numel()]) and torch.equal(la_s, la_w[la_pos:la_pos + la_s.numel()])
+                    and torch.equal(tx_s, tx_w[tx_pos - hdr_len:tx_pos - hdr_len + tx_s.numel()]))
+            t = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            file_bytes = int(lv_w.numel() + la_w.numel() + tx_w.numel() + hdr_len)
+            del lv_s, la_s, tx_s, lv_w, la_w, tx_w
+            torch.cuda.empty_cache()
+            if not bool(t.item()):
+                raise SystemExit("sharded file ranges differ from the single-GPU file images")
+            one_ms = t_max_ms(lambda: (torch.cuda.synchronize(), files_one_gpu()), reps=2)
+            shard_files_ms = t_max_ms(lambda: (torch.cuda.synchronize(), files_sharded()), reps=2)
+            sharded_files = {"what": "aligned cloud + LVX v1.1 file image (raw points) + LAS 1.2 PF3 file image + ASCII PCD text of the merged cloud, every rank building only ITS byte range "
+                                     "(shard kernel + k_lvx_v11 + k_las_* + k_pcd_*; all-reduce of 6 extremes, all-gather of W text sizes); one_gpu_ms = the same kernels over the whole stream on one GPU",
+                             "file_bytes": file_bytes, "ms": shard_files_ms, "one_gpu_ms": one_ms, "speedup_vs_one_gpu": one_ms / shard_files_ms,
+                             "points_per_s": Nm / (shard_files_ms * 1e-3), "byte_identical": True}
+        except SystemExit:
+            raise
+        except Exception as e:                     # noqa: BLE001
+            sharded_files = {"error": repr(e)}
+        merge["sharded_files"] = sharded_files
         del symm, sm_st, whole, wbuf
         torch.cuda.empty_cache()
 

@@ -220,6 +220,21 @@ int lmc_lvx_v11_build_f32(const float* pts_n4, const int64_t* frame_off, const i
                           uint32_t* status, void* stream);
 
 /*
+ * The same for frames [f_begin, f_end) only -- a rank's shard of the file (every rank builds and writes its own
+ * byte range, nothing is gathered).  shard_out[0] is file byte out_file_pos: 0 for the rank that owns frame 0 (its range
+ * then starts with the 88-byte preamble), frame_pos[f_begin] otherwise; the shard holds
+ * frame_pos[f_end] - out_file_pos bytes.  All arrays are the GLOBAL ones (frame headers carry absolute file offsets).
+ */
+int lmc_lvx_v11_build_range_f64(const double* pts_n4, const int64_t* frame_off, const int64_t* frame_pos,
+                                const double* frame_time, const int64_t* frame_id, uint8_t* shard_out,
+                                int64_t out_file_pos, int64_t n_points, int32_t n_frames, int32_t f_begin,
+                                int32_t f_end, int64_t max_frame_points, uint32_t* status, void* stream);
+int lmc_lvx_v11_build_range_f32(const float* pts_n4, const int64_t* frame_off, const int64_t* frame_pos,
+                                const double* frame_time, const int64_t* frame_id, uint8_t* shard_out,
+                                int64_t out_file_pos, int64_t n_points, int32_t n_frames, int32_t f_begin,
+                                int32_t f_end, int64_t max_frame_points, uint32_t* status, void* stream);
+
+/*
  * (second half) the containers of the complete simulator's LivoxLVXWriter.write_lvx_file
  * (CS:245-374), built on the device from COMPENSATED points [x y z intensity] + optional tag bytes:
  *   LMC_LVXCS_LVX2    _write_lvx2 / _write_lvx3 (CS:269-293): per frame a 24-byte header {u32 index,
@@ -344,6 +359,22 @@ int lmc_las_pf3_build_f32(const float* pts_n4, const double* gps_time, int64_t n
                           const double scale[3], const double offset[3], int32_t las_intensity_mode,
                           int32_t year, int32_t day_of_year, uint8_t* file_out, int32_t* minmax_scratch,
                           uint32_t* status, void* stream);
+
+/*
+ * The same in two parts, for frame-sharded ranks: lmc_las_pf3_records_* writes the records of points
+ * [p_begin, p_end) into shard_out, where shard_out[0] is file byte out_file_pos (0 for the rank that also holds the
+ * header, LMC_LAS_HEADER_BYTES + LMC_LAS_RECORD_BYTES * p_begin otherwise), and leaves the shard's integer extremes
+ * {minX, maxX, minY, maxY, minZ, maxZ} in minmax (6 device int32).  After the ranks have min / max-reduced those six
+ * integers, lmc_las_pf3_header builds the 227-byte header of the n_points-record file from them.
+ */
+int lmc_las_pf3_records_f64(const double* pts_n4, const double* gps_time, int64_t n_points, int64_t p_begin, int64_t p_end,
+                            const double scale[3], const double offset[3], int32_t las_intensity_mode,
+                            uint8_t* shard_out, int64_t out_file_pos, int32_t* minmax, uint32_t* status, void* stream);
+int lmc_las_pf3_records_f32(const float* pts_n4, const double* gps_time, int64_t n_points, int64_t p_begin, int64_t p_end,
+                            const double scale[3], const double offset[3], int32_t las_intensity_mode,
+                            uint8_t* shard_out, int64_t out_file_pos, int32_t* minmax, uint32_t* status, void* stream);
+int lmc_las_pf3_header(int64_t n_points, const double scale[3], const double offset[3], int32_t year, int32_t day_of_year,
+                       const int32_t* minmax, uint8_t* header_out, void* stream);
 
 /*
  *  LiDARMotionSimulator.scan_environment, replaces LMC:701-770 for every frame of a run at

@@ -62,6 +62,11 @@ _SIGNATURES = {
     "lmc_quantize_f32": ([vp, i64, vp, vp], ctypes.c_int),
     "lmc_lvx_v11_build_f64": ([vp, vp, vp, vp, vp, vp, i64, i32, i64, vp, vp], ctypes.c_int),
     "lmc_lvx_v11_build_f32": ([vp, vp, vp, vp, vp, vp, i64, i32, i64, vp, vp], ctypes.c_int),
+    "lmc_lvx_v11_build_range_f64": ([vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, i64, vp, vp], ctypes.c_int),
+    "lmc_lvx_v11_build_range_f32": ([vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, i64, vp, vp], ctypes.c_int),
+    "lmc_las_pf3_records_f64": ([vp, vp, i64, i64, i64, vp, vp, i32, vp, i64, vp, vp, vp], ctypes.c_int),
+    "lmc_las_pf3_records_f32": ([vp, vp, i64, i64, i64, vp, vp, i32, vp, i64, vp, vp, vp], ctypes.c_int),
+    "lmc_las_pf3_header": ([i64, vp, vp, i32, i32, vp, vp, vp], ctypes.c_int),
     "lmc_transform_homog_f64": ([vp, vp, i32, vp, i64, vp], ctypes.c_int),
     "lmc_transform_homog_f32": ([vp, vp, i32, vp, i64, vp], ctypes.c_int),
     "lmc_lvx_cs_build_f64": ([vp, vp, vp, vp, vp, i32, i32, vp, i64, i32, i64, vp, vp], ctypes.c_int),

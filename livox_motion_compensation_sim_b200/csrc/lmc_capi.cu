@@ -24,9 +24,10 @@ cudaError_t launch_scan_recount(const uint8_t* flags, int64_t M, int32_t F, int3
 cudaError_t launch_scan_emit(const double* env, int64_t M, const double* pos, const double* R, int32_t F, double rmax2, const uint8_t* flags,
                              const int32_t* tile_off, const int32_t* n_visible, const int64_t* frame_off, int32_t max_points,
                              const double* noise, double* out, cudaStream_t st);
-cudaError_t launch_las_pf3(bool f64, const LasParams& L, cudaStream_t st);
+cudaError_t launch_las_pf3(bool f64, const LasParams& L, int parts, cudaStream_t st);
 cudaError_t launch_lvx_v11(bool f64, const void* pts, const int64_t* frame_off, const int64_t* frame_pos, const double* frame_time,
-                           const int64_t* frame_id, uint8_t* out, int32_t n_frames, int64_t max_frame_points, uint32_t* status, cudaStream_t st);
+                           const int64_t* frame_id, uint8_t* out, int32_t n_frames, int32_t f_begin, int32_t f_end, int64_t max_frame_points,
+                           uint32_t* status, cudaStream_t st);
 cudaError_t launch_slerp_table(const double* quat, const double* pos, const int64_t* ts, int64_t S, double* seg, cudaStream_t st);
 cudaError_t launch_homog(bool f64, const void* in, const double* T_host, int32_t order, void* out, int64_t n, cudaStream_t st);
 cudaError_t launch_text_size(bool f64, const void* rows, int64_t n, int32_t n_cols, int32_t row_stride, const int32_t* col, const int32_t* dec,
@@ -257,26 +258,38 @@ int lmc_quantize_f32(const float* pts_n4, int64_t n_points, const lmc_export* ex
 }
 
 static int lvx_build(bool f64, const void* pts, const int64_t* frame_off, const int64_t* frame_pos, const double* frame_time,
-                     const int64_t* frame_id, uint8_t* file_out, int64_t n_points, int32_t n_frames, int64_t max_frame_points,
-                     uint32_t* status, void* stream) {
+                     const int64_t* frame_id, uint8_t* file_out, int64_t out_file_pos, int64_t n_points, int32_t n_frames,
+                     int32_t f_begin, int32_t f_end, int64_t max_frame_points, uint32_t* status, void* stream) {
     int rc = check_device();
     if (rc != LMC_OK) return rc;
     if (n_frames < 1 || n_points < 0 || max_frame_points < 0) return fail(LMC_ERR_INVALID, "need n_frames >= 1 (the reference refuses an empty frame list, LMC:75-76)");
+    if (f_begin < 0 || f_end > n_frames || f_begin > f_end || out_file_pos < 0) return fail(LMC_ERR_INVALID, "bad frame range [%d, %d) of %d", f_begin, f_end, n_frames);
     if (!frame_off || !frame_pos || !frame_time || !frame_id || !file_out || (n_points > 0 && !pts)) return fail(LMC_ERR_INVALID, "NULL argument");
     if (!aligned32(pts) || !aligned32(file_out)) return fail(LMC_ERR_ALIGN, "points and file buffer must be 32-byte aligned");
-    cudaError_t e = lmc::launch_lvx_v11(f64, pts, frame_off, frame_pos, frame_time, frame_id, file_out, n_frames, max_frame_points, status,
-                                        static_cast<cudaStream_t>(stream));
+    if (out_file_pos & 1) return fail(LMC_ERR_INVALID, "out_file_pos must be even (frame positions are)");
+    cudaError_t e = lmc::launch_lvx_v11(f64, pts, frame_off, frame_pos, frame_time, frame_id, file_out - out_file_pos, n_frames, f_begin, f_end,
+                                        max_frame_points, status, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_lvx_v11");
+}
+int lmc_lvx_v11_build_range_f64(const double* pts_n4, const int64_t* frame_off, const int64_t* frame_pos, const double* frame_time,
+                                const int64_t* frame_id, uint8_t* shard_out, int64_t out_file_pos, int64_t n_points, int32_t n_frames,
+                                int32_t f_begin, int32_t f_end, int64_t max_frame_points, uint32_t* status, void* stream) {
+    return lvx_build(true, pts_n4, frame_off, frame_pos, frame_time, frame_id, shard_out, out_file_pos, n_points, n_frames, f_begin, f_end, max_frame_points, status, stream);
+}
+int lmc_lvx_v11_build_range_f32(const float* pts_n4, const int64_t* frame_off, const int64_t* frame_pos, const double* frame_time,
+                                const int64_t* frame_id, uint8_t* shard_out, int64_t out_file_pos, int64_t n_points, int32_t n_frames,
+                                int32_t f_begin, int32_t f_end, int64_t max_frame_points, uint32_t* status, void* stream) {
+    return lvx_build(false, pts_n4, frame_off, frame_pos, frame_time, frame_id, shard_out, out_file_pos, n_points, n_frames, f_begin, f_end, max_frame_points, status, stream);
 }
 int lmc_lvx_v11_build_f64(const double* pts_n4, const int64_t* frame_off, const int64_t* frame_pos, const double* frame_time,
                           const int64_t* frame_id, uint8_t* file_out, int64_t n_points, int32_t n_frames, int64_t max_frame_points,
                           uint32_t* status, void* stream) {
-    return lvx_build(true, pts_n4, frame_off, frame_pos, frame_time, frame_id, file_out, n_points, n_frames, max_frame_points, status, stream);
+    return lvx_build(true, pts_n4, frame_off, frame_pos, frame_time, frame_id, file_out, 0, n_points, n_frames, 0, n_frames, max_frame_points, status, stream);
 }
 int lmc_lvx_v11_build_f32(const float* pts_n4, const int64_t* frame_off, const int64_t* frame_pos, const double* frame_time,
                           const int64_t* frame_id, uint8_t* file_out, int64_t n_points, int32_t n_frames, int64_t max_frame_points,
                           uint32_t* status, void* stream) {
-    return lvx_build(false, pts_n4, frame_off, frame_pos, frame_time, frame_id, file_out, n_points, n_frames, max_frame_points, status, stream);
+    return lvx_build(false, pts_n4, frame_off, frame_pos, frame_time, frame_id, file_out, 0, n_points, n_frames, 0, n_frames, max_frame_points, status, stream);
 }
 
 static int homog(bool f64, const void* pts, const double* T, int32_t order, void* out, int64_t n, void* stream) {
@@ -444,24 +457,43 @@ int lmc_host_copy(void* dst, const void* src, int64_t n_bytes, int32_t n_threads
     return LMC_OK;
 }
 
+// parts: 1 records of [p_begin, p_end) into out (out[0] = file byte out_file_pos), 2 header into out[0..227), 3 both
 static int las_build(bool f64, const void* pts, const double* gps_time, int64_t n, const double* scale, const double* offset,
-                     int32_t mode, int32_t year, int32_t day, uint8_t* out, int32_t* mm, uint32_t* status, void* stream) {
+                     int32_t mode, int32_t year, int32_t day, uint8_t* out, int32_t* mm, uint32_t* status, void* stream,
+                     int parts = 3, int64_t p_begin = 0, int64_t p_end = -1, int64_t out_file_pos = 0) {
     int rc = check_device();
     if (rc != LMC_OK) return rc;
+    if (p_end < 0) p_end = n;
     if (n < 0 || n > 0xffffffffLL) return fail(LMC_ERR_INVALID, "LAS 1.2 holds at most 2^32 - 1 point records");
-    if (!out || !mm || !scale || !offset || (n > 0 && !pts)) return fail(LMC_ERR_INVALID, "NULL argument");
+    if (p_begin < 0 || p_end > n || p_begin > p_end || out_file_pos < 0) return fail(LMC_ERR_INVALID, "bad point range");
+    if (!out || !mm || !scale || !offset || ((parts & 1) && p_end > p_begin && !pts)) return fail(LMC_ERR_INVALID, "NULL argument");
     if (mode != LMC_LAS_INTENSITY_UNIT && mode != LMC_LAS_INTENSITY_RAW) return fail(LMC_ERR_INVALID, "bad las_intensity_mode");
     if (!aligned32(pts) || !aligned32(out)) return fail(LMC_ERR_ALIGN, "points and file buffer must be 32-byte aligned");
     lmc::LasParams L;
     memset(&L, 0, sizeof L);
-    L.pts = pts; L.gps_time = gps_time; L.out = out; L.minmax = mm; L.status = status; L.n = n;
+    L.pts = pts; L.gps_time = gps_time; L.out = out - out_file_pos; L.minmax = mm; L.status = status; L.n = (parts == 2) ? n : p_end; L.p_begin = p_begin;
     for (int c = 0; c < 3; ++c) {
         if (!(scale[c] > 0.0)) return fail(LMC_ERR_INVALID, "scale[%d] must be > 0", c);
         L.scale[c] = scale[c]; L.rcp[c] = 1.0 / scale[c]; L.off[c] = offset[c];
     }
     L.intensity_mode = mode; L.year = (uint16_t)year; L.day = (uint16_t)day;
-    cudaError_t e = lmc::launch_las_pf3(f64, L, static_cast<cudaStream_t>(stream));
+    cudaError_t e = lmc::launch_las_pf3(f64, L, parts, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_las_records / k_las_header");
+}
+int lmc_las_pf3_records_f64(const double* pts_n4, const double* gps_time, int64_t n_points, int64_t p_begin, int64_t p_end,
+                            const double scale[3], const double offset[3], int32_t las_intensity_mode, uint8_t* shard_out,
+                            int64_t out_file_pos, int32_t* minmax, uint32_t* status, void* stream) {
+    return las_build(true, pts_n4, gps_time, n_points, scale, offset, las_intensity_mode, 0, 0, shard_out, minmax, status, stream, 1, p_begin, p_end, out_file_pos);
+}
+int lmc_las_pf3_records_f32(const float* pts_n4, const double* gps_time, int64_t n_points, int64_t p_begin, int64_t p_end,
+                            const double scale[3], const double offset[3], int32_t las_intensity_mode, uint8_t* shard_out,
+                            int64_t out_file_pos, int32_t* minmax, uint32_t* status, void* stream) {
+    return las_build(false, pts_n4, gps_time, n_points, scale, offset, las_intensity_mode, 0, 0, shard_out, minmax, status, stream, 1, p_begin, p_end, out_file_pos);
+}
+int lmc_las_pf3_header(int64_t n_points, const double scale[3], const double offset[3], int32_t year, int32_t day_of_year,
+                       const int32_t* minmax, uint8_t* header_out, void* stream) {
+    return las_build(false, nullptr, nullptr, n_points, scale, offset, LMC_LAS_INTENSITY_UNIT, year, day_of_year, header_out,
+                     const_cast<int32_t*>(minmax), nullptr, stream, 2);
 }
 int lmc_las_pf3_build_f64(const double* pts_n4, const double* gps_time, int64_t n_points, const double scale[3], const double offset[3],
                           int32_t las_intensity_mode, int32_t year, int32_t day_of_year, uint8_t* file_out, int32_t* minmax_scratch,

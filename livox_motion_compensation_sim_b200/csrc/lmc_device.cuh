@@ -60,7 +60,8 @@ struct LasParams {
     uint8_t*      out;
     int32_t*      minmax;        // device scratch: {minX, maxX, minY, maxY, minZ, maxZ}, pre-set to {MAX, MIN, ...}
     uint32_t*     status;
-    int64_t       n;
+    int64_t       n;             // records of points [p_begin, n)
+    int64_t       p_begin;
     double        scale[3], rcp[3], off[3];
     int32_t       intensity_mode;
     uint16_t      year, day;

@@ -34,10 +34,11 @@ __global__ void __launch_bounds__(kLasThreads) k_las_records(const __grid_consta
     __shared__ __align__(16) uint8_t s_img[kLasImg];
     __shared__ int32_t s_mm[6];
     const int tid = threadIdx.x;
-    const int64_t first = (int64_t)blockIdx.x * kLasTile;
+    // points [p_begin, n) of the cloud; L.out is the (possibly virtual) address of file byte 0 (see lmc_las_pf3_records_*)
+    const int64_t first = L.p_begin + (int64_t)blockIdx.x * kLasTile;
     const int cnt = (int)min((int64_t)kLasTile, L.n - first);
     const int64_t dst0 = kLasHeader + first * kLasRec;
-    const int phase = (int)(dst0 & 15);
+    const int phase = (int)(reinterpret_cast<uintptr_t>(L.out + dst0) & 15);
     uint8_t* img = s_img + phase;
     if (tid < 6) s_mm[tid] = (tid & 1) ? INT32_MIN : INT32_MAX;
     __syncthreads();
@@ -119,15 +120,18 @@ __global__ void k_las_header(const __grid_constant__ LasParams L) {
 
 __global__ void k_las_init(int32_t* mm) { if (threadIdx.x < 6) mm[threadIdx.x] = (threadIdx.x & 1) ? INT32_MIN : INT32_MAX; }
 
-cudaError_t launch_las_pf3(bool f64, const LasParams& L, cudaStream_t st) {
-    const int64_t tiles = (L.n + kLasTile - 1) / kLasTile;
+// parts: 1 = records of points [p_begin, n) + min / max reduction into L.minmax, 2 = header from L.minmax, 3 = both
+cudaError_t launch_las_pf3(bool f64, const LasParams& L, int parts, cudaStream_t st) {
+    const int64_t tiles = (L.n - L.p_begin + kLasTile - 1) / kLasTile;
     if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
-    k_las_init<<<1, 32, 0, st>>>(L.minmax);
-    if (tiles > 0) {
-        if (f64) k_las_records<true><<<(unsigned)tiles, kLasThreads, 0, st>>>(L);
-        else     k_las_records<false><<<(unsigned)tiles, kLasThreads, 0, st>>>(L);
+    if (parts & 1) {
+        k_las_init<<<1, 32, 0, st>>>(L.minmax);
+        if (tiles > 0) {
+            if (f64) k_las_records<true><<<(unsigned)tiles, kLasThreads, 0, st>>>(L);
+            else     k_las_records<false><<<(unsigned)tiles, kLasThreads, 0, st>>>(L);
+        }
     }
-    k_las_header<<<1, 256, 0, st>>>(L);
+    if (parts & 2) k_las_header<<<1, 256, 0, st>>>(L);
     return cudaGetLastError();
 }
 

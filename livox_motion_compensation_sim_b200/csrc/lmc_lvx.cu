@@ -30,10 +30,12 @@ template <bool F64>
 __global__ void __launch_bounds__(kLvxThreads) k_lvx_v11(const void* __restrict__ pts, const int64_t* __restrict__ frame_off,
                                                          const int64_t* __restrict__ frame_pos, const double* __restrict__ frame_time,
                                                          const int64_t* __restrict__ frame_id, uint8_t* __restrict__ out,
-                                                         int32_t n_frames, uint32_t* __restrict__ status)
+                                                         int32_t n_frames, int32_t f_begin, uint32_t* __restrict__ status)
 {
+    // out is the (possibly virtual) address of file byte 0: a rank that builds only frames [f_begin, f_end) passes
+    // shard_buffer - file_position_of_its_first_byte, so every store lands inside its own buffer
     __shared__ __align__(16) uint8_t s_img[kImg];
-    const int f = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
+    const int f = f_begin + blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
     const int64_t p0 = frame_off[f], n = frame_off[f + 1] - p0;
     const int64_t pkgs = (n + kPkPoints - 1) / kPkPoints;
     const int64_t pk0 = (int64_t)chunk * kPk;
@@ -55,8 +57,8 @@ __global__ void __launch_bounds__(kLvxThreads) k_lvx_v11(const void* __restrict_
     const int hdr = chunk == 0 ? 24 : 0;
     const int64_t dst0 = frame_pos[f] + (chunk == 0 ? 0 : 24 + pk0 * kPkBytes);
     const int nbytes = hdr + npk * kPkBytes;
-    const int phase = (int)(dst0 & 15);
-    uint8_t* img = s_img + phase;                                                     // img[i] <-> out[dst0 + i]; dst0 is even
+    const int phase = (int)(reinterpret_cast<uintptr_t>(out + dst0) & 15);
+    uint8_t* img = s_img + phase;                                                     // img[i] <-> out[dst0 + i]; the address is even
 
     for (int i = tid; i < kImg / 16; i += kLvxThreads) reinterpret_cast<uint4*>(s_img)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
@@ -93,16 +95,16 @@ __global__ void __launch_bounds__(kLvxThreads) k_lvx_v11(const void* __restrict_
 }
 
 cudaError_t launch_lvx_v11(bool f64, const void* pts, const int64_t* frame_off, const int64_t* frame_pos, const double* frame_time,
-                           const int64_t* frame_id, uint8_t* out, int32_t n_frames, int64_t max_frame_points, uint32_t* status,
-                           cudaStream_t st) {
-    if (n_frames <= 0) return cudaSuccess;
+                           const int64_t* frame_id, uint8_t* out, int32_t n_frames, int32_t f_begin, int32_t f_end, int64_t max_frame_points,
+                           uint32_t* status, cudaStream_t st) {
+    if (n_frames <= 0 || f_end <= f_begin) return cudaSuccess;
     const int64_t max_pk = (max_frame_points + kPkPoints - 1) / kPkPoints;
     int64_t chunks = (max_pk + kPk - 1) / kPk;
     if (chunks < 1) chunks = 1;
     if (chunks > 65535) return cudaErrorInvalidValue;                                 // > 50 M points in one frame
-    dim3 grid((unsigned)n_frames, (unsigned)chunks);
-    if (f64) k_lvx_v11<true><<<grid, kLvxThreads, 0, st>>>(pts, frame_off, frame_pos, frame_time, frame_id, out, n_frames, status);
-    else     k_lvx_v11<false><<<grid, kLvxThreads, 0, st>>>(pts, frame_off, frame_pos, frame_time, frame_id, out, n_frames, status);
+    dim3 grid((unsigned)(f_end - f_begin), (unsigned)chunks);
+    if (f64) k_lvx_v11<true><<<grid, kLvxThreads, 0, st>>>(pts, frame_off, frame_pos, frame_time, frame_id, out, n_frames, f_begin, status);
+    else     k_lvx_v11<false><<<grid, kLvxThreads, 0, st>>>(pts, frame_off, frame_pos, frame_time, frame_id, out, n_frames, f_begin, status);
     return cudaGetLastError();
 }
 

@@ -281,6 +281,55 @@ def build_lvx_v11(pts: torch.Tensor, frame_off: torch.Tensor, frame_pos: torch.T
 
 
 @_on_tensor_device
+def build_lvx_v11_range(pts: torch.Tensor, frame_off: torch.Tensor, frame_pos: torch.Tensor, frame_time: torch.Tensor,
+                        frame_id: torch.Tensor, f_begin: int, f_end: int, file_pos0: int, n_bytes: int, max_frame_points: int):
+    """(N1) a rank's shard of the LVX v1.1 file: frames [f_begin, f_end) of the GLOBAL arrays.  The returned
+    uint8 tensor holds file bytes [file_pos0, file_pos0 + n_bytes) -- file_pos0 = 0 for the rank owning frame 0 (its range
+    starts with the 88-byte preamble), frame_pos[f_begin] otherwise; n_bytes = frame_pos[f_end] - file_pos0."""
+    f64 = _layout(pts)
+    F = frame_off.shape[0] - 1
+    out = torch.empty(max(int(n_bytes), 0), dtype=torch.uint8, device=pts.device)
+    status = torch.zeros(1, dtype=torch.int32, device=pts.device)
+    fn = C.lib().lmc_lvx_v11_build_range_f64 if f64 else C.lib().lmc_lvx_v11_build_range_f32
+    if n_bytes > 0:
+        C.check(fn(_req(pts, pts.dtype, "pts", (4,)), _req(frame_off, torch.int64, "frame_off"), _req(frame_pos, torch.int64, "frame_pos"),
+                   _req(frame_time, torch.float64, "frame_time"), _req(frame_id, torch.int64, "frame_id"), out.data_ptr(), int(file_pos0),
+                   pts.shape[0], F, int(f_begin), int(f_end), int(max_frame_points), status.data_ptr(), _stream_ptr()))
+    return out, status
+
+
+@_on_tensor_device
+def las_pf3_records(pts: torch.Tensor, p_begin: int, p_end: int, file_pos0: int, *, scale=(0.01, 0.01, 0.01), offset=(0.0, 0.0, 0.0),
+                    intensity_mode: int = C.LAS_INTENSITY_UNIT, gps_time: Optional[torch.Tensor] = None):
+    """(N2) a rank's shard of the LAS 1.2 / PF3 file: the records of points [p_begin, p_end) of the GLOBAL
+    cloud `pts`.  Returns (uint8 tensor = file bytes [file_pos0, 227 + 34 p_end), int32[6] shard extremes, status);
+    file_pos0 = 0 for the rank that also holds the header (filled in later by las_pf3_header), 227 + 34 p_begin otherwise."""
+    f64 = _layout(pts)
+    n = pts.shape[0]
+    size = C.LAS_HEADER_BYTES + C.LAS_RECORD_BYTES * int(p_end) - int(file_pos0)
+    out = torch.empty(size, dtype=torch.uint8, device=pts.device)
+    mm = torch.empty(6, dtype=torch.int32, device=pts.device)
+    status = torch.zeros(1, dtype=torch.int32, device=pts.device)
+    sc = (C.ctypes.c_double * 3)(*[float(v) for v in scale])
+    of = (C.ctypes.c_double * 3)(*[float(v) for v in offset])
+    fn = C.lib().lmc_las_pf3_records_f64 if f64 else C.lib().lmc_las_pf3_records_f32
+    C.check(fn(_req(pts, pts.dtype, "pts", (4,)), _req(gps_time, torch.float64, "gps_time"), n, int(p_begin), int(p_end), sc, of,
+               int(intensity_mode), out.data_ptr(), int(file_pos0), mm.data_ptr(), status.data_ptr(), _stream_ptr()))
+    return out, mm, status
+
+
+@_on_tensor_device
+def las_pf3_header(header_out: torch.Tensor, minmax: torch.Tensor, n_points: int, *, scale=(0.01, 0.01, 0.01), offset=(0.0, 0.0, 0.0),
+                   year: int = 2026, day_of_year: int = 1) -> None:
+    """(N2) the 227-byte LAS header of an n_points-record file from the (all-reduced) integer extremes,
+    written into header_out[:227] (the first bytes of the header-owning rank's shard)."""
+    sc = (C.ctypes.c_double * 3)(*[float(v) for v in scale])
+    of = (C.ctypes.c_double * 3)(*[float(v) for v in offset])
+    C.check(C.lib().lmc_las_pf3_header(int(n_points), sc, of, int(year), int(day_of_year), _req(minmax, torch.int32, "minmax"),
+                                       _req(header_out, torch.uint8, "header_out"), _stream_ptr()))
+
+
+@_on_tensor_device
 def build_lvx_cs(pts: torch.Tensor, tag: Optional[torch.Tensor], frame_off: torch.Tensor, frame_ts: torch.Tensor,
                  prefix: bytes, fmt: int, max_frame_points: int):
     """(N1) CS:245-374 on the device: COMPENSATED points [x y z intensity] (+ tag bytes) -> the complete LVX2 / LVX3

@@ -78,6 +78,42 @@ def main():
             t_mc = time.perf_counter() - t0
         assert torch.equal(sm.out, whole), "multicast merge: aligned cloud differs"
         assert torch.equal(sm.lvx14, wb.lvx14), "multicast merge: LVX records differ"
+    # (4) replication-free file production: every rank builds ITS byte range of each output file from ITS frames and
+    #     pwrite()s it at its offset; the file on disk equals the single-GPU image
+    import tempfile
+    from livox_motion_compensation_sim_b200.lvx import frame_layout
+    from livox_motion_compensation_sim_b200.simulator import LiDARMotionSimulator
+    fa, fb = int(fcuts[rank]), int(fcuts[rank + 1])
+    ids = np.arange(F, dtype=np.int64)
+    _, fpos = frame_layout(st.frame_off)
+    lvx_whole, _ = ops.build_lvx_v11(st.pts, off_d, d(fpos), d(st.frame_t), d(ids), int(np.diff(st.frame_off).max()))
+    las_whole, _ = ops.build_las_pf3(whole, scale=(0.001,) * 3, year=2026, day_of_year=7)
+    txt_whole, _ = ops.pcd_ascii_body(whole)
+    hdr = LiDARMotionSimulator._pcd_header(N)
+    tmp = os.path.join(tempfile.gettempdir(), "lmc_sharded_files")
+    if rank == 0:
+        os.makedirs(tmp, exist_ok=True)
+        for f in ("a.lvx", "a.las", "a.pcd"):
+            if os.path.exists(os.path.join(tmp, f)):
+                os.remove(os.path.join(tmp, f))
+    dist.barrier()
+    sh, pos0, stat = sharding.lvx_v11_shard(st.pts, st.frame_off, st.frame_t, ids, fa, fb)
+    assert torch.equal(sh, lvx_whole[pos0:pos0 + sh.numel()]), "sharded LVX range differs"
+    sharding.pwrite_range(os.path.join(tmp, "a.lvx"), pos0, sh.cpu().numpy())
+    sh, pos0, stat = sharding.las_pf3_shard(whole, b, e, rank, scale=(0.001,) * 3, year=2026, day_of_year=7)
+    assert torch.equal(sh, las_whole[pos0:pos0 + sh.numel()]), "sharded LAS range differs"
+    sharding.pwrite_range(os.path.join(tmp, "a.las"), pos0, sh.cpu().numpy())
+    sh, pos0, h0, stat = sharding.pcd_ascii_shard(whole[b:e], N, rank)
+    assert torch.equal(sh, txt_whole[pos0 - len(hdr):pos0 - len(hdr) + sh.numel()]), "sharded PCD text differs"
+    if rank == 0:
+        assert h0 == hdr
+        sharding.pwrite_range(os.path.join(tmp, "a.pcd"), 0, h0)
+    sharding.pwrite_range(os.path.join(tmp, "a.pcd"), pos0, sh.cpu().numpy())
+    dist.barrier()
+    if rank == 0:
+        assert open(os.path.join(tmp, "a.lvx"), "rb").read() == lvx_whole.cpu().numpy().tobytes()
+        assert open(os.path.join(tmp, "a.las"), "rb").read() == las_whole.cpu().numpy().tobytes()
+        assert open(os.path.join(tmp, "a.pcd"), "rb").read() == hdr + txt_whole.cpu().numpy().tobytes()
     if rank == 0:
         print(f"OK world={world} points={N} shard={e - b}  kernel+NCCL all-gather {t_nccl * 1e3:.2f} ms (first call)  "
               f"fused peer-store epilogue {t_fused * 1e3:.2f} ms  multicast epilogue " + (f"{t_mc * 1e3:.2f} ms" if t_mc else "unavailable"))

@@ -295,6 +295,72 @@ def test_frame_sharded_merge_gloo_world2(tmp_path):
     assert r.stdout.count("OK") == 2
 
 
+GLOO_FILES_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["LMC_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from livox_motion_compensation_sim_b200 import sharding
+from livox_motion_compensation_sim_b200.lvx import build_lvx_v11_file, frame_layout
+from oracle import lmc_oracle as orc
+dist.init_process_group("gloo")
+rank, W = dist.get_rank(), dist.get_world_size()
+out_dir = os.environ["LMC_OUT"]
+rng = np.random.default_rng(11)
+F = 37
+counts = rng.integers(0, 300, F); counts[5] = 0
+off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+N = int(off[-1])
+pts = np.column_stack([rng.uniform(-90, 90, (N, 3)), rng.uniform(0, 1, N)])
+ts, ids = np.arange(F) * 0.1, np.arange(F, dtype=np.int64)
+fcuts, pcuts = sharding.shard_ranges(off, W)
+a, b = int(fcuts[rank]), int(fcuts[rank + 1])
+# LVX v1.1: closed-form offsets, no exchange.  (Host-logic test: the CPU restatement stands in for the kernel; each rank cuts
+# ITS byte range out of the image and writes it at ITS offset.)
+whole = build_lvx_v11_file(orc.C.quantize_lvx_type2(pts)[0], off, ts, ids)
+_, fpos = frame_layout(off)
+pos0 = 0 if a == 0 else int(fpos[a])
+mine = whole[pos0:int(fpos[b])]
+path = os.path.join(out_dir, "sharded.lvx")
+assert sharding.pwrite_range(path, pos0, mine) == len(mine)
+# variable-length text: sizes all-gathered, offsets by prefix sum, rank 0 owns the header
+lines = ["%.6f %.6f %.6f %.6f\n" % tuple(r) for r in pts]
+text_mine = "".join(lines[int(pcuts[rank]):int(pcuts[rank + 1])]).encode()
+header = b"# header of %d points\n" % N
+sizes = sharding.all_gather_sizes(len(text_mine), torch.device("cpu"))
+offs = sharding.file_offsets(sizes, len(header))
+tpath = os.path.join(out_dir, "sharded.pcd")
+if rank == 0:
+    sharding.pwrite_range(tpath, 0, header)
+sharding.pwrite_range(tpath, int(offs[rank]) + (len(header) if rank == 0 else 0), text_mine)
+dist.barrier()
+if rank == 0:
+    assert open(path, "rb").read() == whole.tobytes()
+    assert open(tpath, "rb").read() == header + "".join(lines).encode()
+    assert int(offs[-1]) == len(header) + sum(len(l) for l in lines)
+dist.destroy_process_group()
+print("OK", rank)
+'''
+
+
+def test_sharded_file_writers_gloo_world2(tmp_path):
+    """SURVEY 8e, replication-free file production: every rank pwrite()s its own byte range (closed-form LVX offsets;
+    all-gathered text sizes) and the result is the single-writer file."""
+    script = tmp_path / "worker_files.py"
+    script.write_text(GLOO_FILES_WORKER)
+    env = dict(os.environ, LMC_ROOT=ROOT, MASTER_ADDR="127.0.0.1", LMC_OUT=str(tmp_path))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29619", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("OK") == 2
+
+
+def test_file_offsets():
+    from livox_motion_compensation_sim_b200.sharding import file_offsets
+    assert file_offsets([10, 0, 5], 7).tolist() == [0, 17, 17, 22]
+    assert file_offsets([3], 0).tolist() == [0, 3]
+
+
 def test_lvx_cs_host_layout_and_errors():
     """Host side of the complete simulator's LVX writer mirror (CS:235-374): prefixes, frame flattening, the
     struct.pack errors the reference raises before any byte is written."""
