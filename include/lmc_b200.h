@@ -224,6 +224,7 @@ int lmc_lvx_v11_build_f32(const float* pts_n4, const int64_t* frame_off, const i
  * byte range, nothing is gathered).  shard_out[0] is file byte out_file_pos: 0 for the rank that owns frame 0 (its range
  * then starts with the 88-byte preamble), frame_pos[f_begin] otherwise; the shard holds
  * frame_pos[f_end] - out_file_pos bytes.  All arrays are the GLOBAL ones (frame headers carry absolute file offsets).
+ * shard_out must be congruent to out_file_pos modulo 16 (the byte ranges are assembled at the file's 16-byte phase).
  */
 int lmc_lvx_v11_build_range_f64(const double* pts_n4, const int64_t* frame_off, const int64_t* frame_pos,
                                 const double* frame_time, const int64_t* frame_id, uint8_t* shard_out,
@@ -366,6 +367,7 @@ int lmc_las_pf3_build_f32(const float* pts_n4, const double* gps_time, int64_t n
  * header, LMC_LAS_HEADER_BYTES + LMC_LAS_RECORD_BYTES * p_begin otherwise), and leaves the shard's integer extremes
  * {minX, maxX, minY, maxY, minZ, maxZ} in minmax (6 device int32).  After the ranks have min / max-reduced those six
  * integers, lmc_las_pf3_header builds the 227-byte header of the n_points-record file from them.
+ * shard_out must be congruent to out_file_pos modulo 16.
  */
 int lmc_las_pf3_records_f64(const double* pts_n4, const double* gps_time, int64_t n_points, int64_t p_begin, int64_t p_end,
                             const double scale[3], const double offset[3], int32_t las_intensity_mode,

@@ -54,6 +54,9 @@ int cuda_fail(cudaError_t e, const char* what) {
     return fail(LMC_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
 }
 bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
+// one point row: 32 bytes (f64) or 16 bytes (float4) -- what the row-at-a-time kernels (text writers) need, so that any
+// row slice of a frame-major buffer (a rank's shard) can be passed as it is
+bool aligned_row(const void* p, bool f64) { return (reinterpret_cast<uintptr_t>(p) & (f64 ? 31u : 15u)) == 0; }
 
 // the kernels are built for sm_100a only: refuse anything else loudly (no fallback path exists)
 int check_device() {
@@ -265,8 +268,9 @@ static int lvx_build(bool f64, const void* pts, const int64_t* frame_off, const 
     if (n_frames < 1 || n_points < 0 || max_frame_points < 0) return fail(LMC_ERR_INVALID, "need n_frames >= 1 (the reference refuses an empty frame list, LMC:75-76)");
     if (f_begin < 0 || f_end > n_frames || f_begin > f_end || out_file_pos < 0) return fail(LMC_ERR_INVALID, "bad frame range [%d, %d) of %d", f_begin, f_end, n_frames);
     if (!frame_off || !frame_pos || !frame_time || !frame_id || !file_out || (n_points > 0 && !pts)) return fail(LMC_ERR_INVALID, "NULL argument");
-    if (!aligned32(pts) || !aligned32(file_out)) return fail(LMC_ERR_ALIGN, "points and file buffer must be 32-byte aligned");
-    if (out_file_pos & 1) return fail(LMC_ERR_INVALID, "out_file_pos must be even (frame positions are)");
+    // the kernels lay every byte range out at the FILE's 16-byte phase: the shard buffer must sit at the same phase
+    if (!aligned32(pts) || ((reinterpret_cast<uintptr_t>(file_out) - (uintptr_t)out_file_pos) & 15u))
+        return fail(LMC_ERR_ALIGN, "points must be 32-byte aligned and the file buffer congruent to its file position modulo 16");
     cudaError_t e = lmc::launch_lvx_v11(f64, pts, frame_off, frame_pos, frame_time, frame_id, file_out - out_file_pos, n_frames, f_begin, f_end,
                                         max_frame_points, status, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_lvx_v11");
@@ -337,7 +341,7 @@ static int pcd_size(bool f64, const void* pts, int64_t n, int64_t* tile_off, voi
     int rc = check_device();
     if (rc != LMC_OK) return rc;
     if (n < 0 || !tile_off || (n > 0 && !pts)) return fail(LMC_ERR_INVALID, "bad argument");
-    if (!aligned32(pts)) return fail(LMC_ERR_ALIGN, "points must be 32-byte aligned");
+    if (!aligned_row(pts, f64)) return fail(LMC_ERR_ALIGN, "points must be aligned to one row (32 bytes f64, 16 bytes float4)");
     cudaError_t e = lmc::launch_pcd_size(f64, pts, n, tile_off, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_pcd_len / k_pcd_scan");
 }
@@ -345,7 +349,7 @@ static int pcd_write(bool f64, const void* pts, int64_t n, const int64_t* tile_o
     int rc = check_device();
     if (rc != LMC_OK) return rc;
     if (n < 0 || !tile_off || (n > 0 && (!pts || !out))) return fail(LMC_ERR_INVALID, "bad argument");
-    if (!aligned32(pts) || !aligned32(out)) return fail(LMC_ERR_ALIGN, "points and text buffer must be 32-byte aligned");
+    if (!aligned_row(pts, f64) || !aligned32(out)) return fail(LMC_ERR_ALIGN, "points must be aligned to one row and the text buffer to 32 bytes");
     cudaError_t e = lmc::launch_pcd_write(f64, pts, n, tile_off, out, status, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_pcd_write");
 }
@@ -353,7 +357,7 @@ static int pcd_row_off(bool f64, const void* pts, int64_t n, const int64_t* tile
     int rc = check_device();
     if (rc != LMC_OK) return rc;
     if (n < 0 || n_rows < 0 || !tile_off || (n > 0 && !pts) || (n_rows > 0 && (!rows || !byte_off))) return fail(LMC_ERR_INVALID, "bad argument");
-    if (!aligned32(pts)) return fail(LMC_ERR_ALIGN, "points must be 32-byte aligned");
+    if (!aligned_row(pts, f64)) return fail(LMC_ERR_ALIGN, "points must be aligned to one row (32 bytes f64, 16 bytes float4)");
     cudaError_t e = lmc::launch_pcd_row_off(f64, pts, n, tile_off, rows, n_rows, byte_off, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? LMC_OK : cuda_fail(e, "k_pcd_row_off");
 }
@@ -468,7 +472,8 @@ static int las_build(bool f64, const void* pts, const double* gps_time, int64_t 
     if (p_begin < 0 || p_end > n || p_begin > p_end || out_file_pos < 0) return fail(LMC_ERR_INVALID, "bad point range");
     if (!out || !mm || !scale || !offset || ((parts & 1) && p_end > p_begin && !pts)) return fail(LMC_ERR_INVALID, "NULL argument");
     if (mode != LMC_LAS_INTENSITY_UNIT && mode != LMC_LAS_INTENSITY_RAW) return fail(LMC_ERR_INVALID, "bad las_intensity_mode");
-    if (!aligned32(pts) || !aligned32(out)) return fail(LMC_ERR_ALIGN, "points and file buffer must be 32-byte aligned");
+    if (!aligned32(pts) || ((reinterpret_cast<uintptr_t>(out) - (uintptr_t)out_file_pos) & 15u))
+        return fail(LMC_ERR_ALIGN, "points must be 32-byte aligned and the file buffer congruent to its file position modulo 16");
     lmc::LasParams L;
     memset(&L, 0, sizeof L);
     L.pts = pts; L.gps_time = gps_time; L.out = out - out_file_pos; L.minmax = mm; L.status = status; L.n = (parts == 2) ? n : p_end; L.p_begin = p_begin;

@@ -12,10 +12,16 @@
 // integer and fraction instead and covers |v| < 2^64 with 0..9 decimals per column.)
 //
 // Lines have variable length, so the text is produced in three launches:
-//   k_pcd_len    per tile of 256 points: total text bytes of the tile
+//   k_pcd_len    per tile of 256 points: total text bytes of the tile.  The length of "%.6f" needs no digits: it is
+//                sign + 7 + the digit count of the ROUNDED integer part, and |v| rounds up to 10^k exactly when
+//                |v| >= 10^k - 5e-7 -- a real number no double equals, so comparing with the first double above it
+//                (kDigitT) is exact.  Four compares per number; HBM-bound.
 //   k_pcd_scan   one CTA: exclusive prefix sum of the tile sizes -> byte offset of every tile
-//   k_pcd_write  per tile: format again, lay the lines out in shared memory (block scan of the line
-//                lengths) and copy the tile's contiguous byte range out as one TMA bulk store
+//   k_pcd_write  per tile: format, lay the lines out in shared memory (block scan of the line lengths) and copy the
+//                tile's contiguous byte range out as one TMA bulk store.  Numbers below 10^4 (every LiDAR coordinate)
+//                take a branch-free path: digits come in pairs from a 100-entry shared-memory table and every
+//                character is stored at a fixed offset from the END of its number, so the stores carry immediate
+//                offsets and no address arithmetic; anything else (>= 10^4, nan, inf) takes the general formatter.
 #include "lmc_device.cuh"
 
 namespace lmc {
@@ -113,6 +119,64 @@ __device__ __forceinline__ int fmt_write(uint8_t* dst, const Num& t) {
     return (int)t.len;
 }
 
+// ---- fast path: |v| < kDigitT[3] (at most 4 integer digits after rounding) ----------------------------------------
+// kDigitT[k-1] = the smallest double >= 10^k - 5e-7 (tests/test_host.py re-derives them with exact fractions)
+__device__ __constant__ double kDigitT[4] = { 0x1.3ffffef390860p+3, 0x1.8fffffde7210cp+6, 0x1.f3fffffbce422p+9, 0x1.387fffffbce43p+13 };
+
+__device__ __noinline__ uint32_t fmt_len_slow(double v, uint32_t& fl) { return fmt_prepare(v, fl).len; }
+__device__ __noinline__ int fmt_write_slow(uint8_t* dst, double v, uint32_t& fl) { const Num t = fmt_prepare(v, fl); return fmt_write(dst, t); }
+
+// text length of "%.6f" % v; bit 31 (kSlowBit) marks a value for the general formatter
+constexpr uint32_t kSlowBit = 0x80000000u;
+__device__ __forceinline__ uint32_t fmt_len_tagged(double v, uint32_t& fl) {
+    const double a = fabs(v);
+    if (!(a < kDigitT[3])) return fmt_len_slow(v, fl) | kSlowBit;   // >= 10^4, inf, nan
+    return ((uint32_t)__double2hiint(v) >> 31) + 8u + (a >= kDigitT[0]) + (a >= kDigitT[1]) + (a >= kDigitT[2]);
+}
+__device__ __forceinline__ uint32_t fmt_len(double v, uint32_t& fl) { return fmt_len_tagged(v, fl) & ~kSlowBit; }
+
+// the 100-entry digit-pair table: s_lut[n] = '0' + n / 10 | ('0' + n % 10) << 8
+__device__ __forceinline__ void lut_init(uint16_t* s_lut, int tid) {
+    if (tid < 100) s_lut[tid] = (uint16_t)(0x3030u + (uint32_t)(tid / 10) + ((uint32_t)(tid % 10) << 8));
+}
+
+// Write "%.6f" % v followed by `sep` so that the separator lands at img[end]; tagged = fmt_len_tagged(v).
+// Every store is relative to `end`: fraction and '.' at fixed offsets, integer digits predicated on the digit count.
+__device__ __forceinline__ void fmt_emit(uint8_t* img, uint32_t end, double v, uint32_t tagged, uint8_t sep, const uint16_t* s_lut, uint32_t& fl) {
+    const double a = fabs(v);
+    const uint32_t neg = (uint32_t)__double2hiint(v) >> 31;
+    uint8_t* e = img + end;
+    e[0] = sep;
+    if (tagged & kSlowBit) {                                         // general formatter (rare): it writes forwards
+        fmt_write_slow(e - (tagged & ~kSlowBit), v, fl);
+        return;
+    }
+    uint32_t ip = __double2uint_rz(a);
+    const double fr = __dsub_rn(a, __uint2double_rn(ip));
+    const double hi = __dmul_rn(fr, 1.0e6), lo = __fma_rn(fr, 1.0e6, -hi);
+    uint32_t q = __double2uint_rz(hi);
+    const double d = __dsub_rn(__dsub_rn(hi, __uint2double_rn(q)), 0.5);
+    uint32_t inc = d > 0.0 ? 1u : 0u;
+    if (d == 0.0) inc = (lo > 0.0 ? 1u : 0u) | ((lo == 0.0 ? 1u : 0u) & q);      // exact tie of hi: lo decides, then half-even
+    q += inc;
+    const uint32_t carry = q == 1000000u ? 1u : 0u;
+    q = carry ? 0u : q;
+    ip += carry;
+    const uint32_t nd = tagged - 7u - neg;
+    const uint32_t q1 = q / 10000u, r = q - q1 * 10000u, q2 = r / 100u, q3 = r - q2 * 100u;
+    const uint32_t i1 = ip / 100u, i0 = ip - i1 * 100u;
+    const uint32_t c1 = s_lut[q1], c2 = s_lut[q2], c3 = s_lut[q3], d0 = s_lut[i0], d1 = s_lut[i1];
+    e[-1] = (uint8_t)(c3 >> 8); e[-2] = (uint8_t)c3;
+    e[-3] = (uint8_t)(c2 >> 8); e[-4] = (uint8_t)c2;
+    e[-5] = (uint8_t)(c1 >> 8); e[-6] = (uint8_t)c1;
+    e[-7] = '.';
+    e[-8] = (uint8_t)(d0 >> 8);
+    if (nd >= 2) e[-9] = (uint8_t)d0;
+    if (nd >= 3) e[-10] = (uint8_t)(d1 >> 8);
+    if (nd >= 4) e[-11] = (uint8_t)d1;
+    if (neg) img[end - 8u - nd] = '-';
+}
+
 template <bool F64>
 __device__ __forceinline__ void load_row(const void* pts, int64_t i, double (&v)[4]) {
     if constexpr (F64) { const double* s = reinterpret_cast<const double*>(pts) + 4 * i; ldg256(s, v[0], v[1], v[2], v[3]); }
@@ -143,7 +207,7 @@ __global__ void __launch_bounds__(kPcdTile) k_pcd_len(const void* __restrict__ p
         load_row<F64>(pts, i, v);
         len = 4;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) len += fmt_prepare(v[c], fl).len;
+        for (int c = 0; c < 4; ++c) len += fmt_len(v[c], fl);
     }
     uint32_t total;
     block_scan_excl(len, s_warp, total);
@@ -171,25 +235,27 @@ __global__ void __launch_bounds__(kPcdTile) k_pcd_write(const void* __restrict__
                                                         uint8_t* __restrict__ out, uint32_t* __restrict__ status) {
     __shared__ __align__(16) uint8_t s_img[kPcdImg];
     __shared__ uint32_t s_warp[kPcdTile / 32];
+    __shared__ uint16_t s_lut[100];
     const int tid = threadIdx.x;
     const int64_t i = (int64_t)blockIdx.x * kPcdTile + tid;
     const int64_t dst0 = tile_off[blockIdx.x];
     const int phase = (int)(dst0 & 15);
-    Num t[4];
+    lut_init(s_lut, tid);
+    double v[4] = { 0.0, 0.0, 0.0, 0.0 };
+    uint32_t ln[4] = { 0, 0, 0, 0 };
     uint32_t len = 0, fl = 0;
     if (i < n) {
-        double v[4];
         load_row<F64>(pts, i, v);
         len = 4;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { t[c] = fmt_prepare(v[c], fl); len += t[c].len; }
+        for (int c = 0; c < 4; ++c) { ln[c] = fmt_len_tagged(v[c], fl); len += ln[c] & ~kSlowBit; }
     }
     uint32_t total;
-    const uint32_t off = block_scan_excl(len, s_warp, total);
+    const uint32_t off = block_scan_excl(len, s_warp, total);       // (its barrier also publishes s_lut)
     if (i < n) {
-        uint8_t* d = s_img + phase + off;
+        uint32_t e = (uint32_t)phase + off;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { d += fmt_write(d, t[c]); *d++ = c == 3 ? '\n' : ' '; }
+        for (int c = 0; c < 4; ++c) { e += ln[c] & ~kSlowBit; fmt_emit(s_img, e, v[c], ln[c], c == 3 ? (uint8_t)'\n' : (uint8_t)' ', s_lut, fl); e += 1; }
     }
     cta_image_out(out + (dst0 - phase), s_img, phase, phase + (int)total, tid, kPcdTile);        // TMA bulk store of the aligned body
     if (fl != 0 && status != nullptr) atomicOr(status, fl);
@@ -213,7 +279,7 @@ __global__ void __launch_bounds__(256) k_pcd_row_off(const void* __restrict__ pt
         load_row<F64>(pts, i, v);
         sum += 4;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) sum += fmt_prepare(v[c], fl).len;
+        for (int c = 0; c < 4; ++c) sum += fmt_len(v[c], fl);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);

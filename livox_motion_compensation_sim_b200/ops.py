@@ -280,6 +280,13 @@ def build_lvx_v11(pts: torch.Tensor, frame_off: torch.Tensor, frame_pos: torch.T
     return out, status
 
 
+def _file_range_buffer(n_bytes: int, file_pos0: int, device) -> torch.Tensor:
+    """uint8 buffer for file bytes [file_pos0, file_pos0 + n_bytes) whose address is congruent to file_pos0 modulo 16:
+    the writer kernels assemble every byte range at the FILE's 16-byte phase (odd record starts in the LAS file stay odd)."""
+    pad = file_pos0 % 16
+    return torch.empty(pad + n_bytes, dtype=torch.uint8, device=device)[pad:]
+
+
 @_on_tensor_device
 def build_lvx_v11_range(pts: torch.Tensor, frame_off: torch.Tensor, frame_pos: torch.Tensor, frame_time: torch.Tensor,
                         frame_id: torch.Tensor, f_begin: int, f_end: int, file_pos0: int, n_bytes: int, max_frame_points: int):
@@ -288,7 +295,7 @@ def build_lvx_v11_range(pts: torch.Tensor, frame_off: torch.Tensor, frame_pos: t
     starts with the 88-byte preamble), frame_pos[f_begin] otherwise; n_bytes = frame_pos[f_end] - file_pos0."""
     f64 = _layout(pts)
     F = frame_off.shape[0] - 1
-    out = torch.empty(max(int(n_bytes), 0), dtype=torch.uint8, device=pts.device)
+    out = _file_range_buffer(max(int(n_bytes), 0), int(file_pos0), pts.device)
     status = torch.zeros(1, dtype=torch.int32, device=pts.device)
     fn = C.lib().lmc_lvx_v11_build_range_f64 if f64 else C.lib().lmc_lvx_v11_build_range_f32
     if n_bytes > 0:
@@ -307,7 +314,7 @@ def las_pf3_records(pts: torch.Tensor, p_begin: int, p_end: int, file_pos0: int,
     f64 = _layout(pts)
     n = pts.shape[0]
     size = C.LAS_HEADER_BYTES + C.LAS_RECORD_BYTES * int(p_end) - int(file_pos0)
-    out = torch.empty(size, dtype=torch.uint8, device=pts.device)
+    out = _file_range_buffer(size, int(file_pos0), pts.device)
     mm = torch.empty(6, dtype=torch.int32, device=pts.device)
     status = torch.zeros(1, dtype=torch.int32, device=pts.device)
     sc = (C.ctypes.c_double * 3)(*[float(v) for v in scale])

@@ -398,3 +398,21 @@ def test_exporter_merge_frames():
     assert m.shape == (3, 5) and m[0].tolist() == [1.0, 2.0, 3.0, 7.0, 11.0] and m[2, 4] == 9.0
     assert exporter.merge_frames([]).shape == (0, 5)
     assert exporter.PCD_HEADER.format(n=3).count("3") == 2 and exporter.CSV_HEADER == "x,y,z,intensity,timestamp\n"
+
+
+def test_pcd_digit_count_thresholds_are_exact():
+    """csrc/lmc_pcd.cu: the length of '%.6f' is decided by comparing |v| with kDigitT[k-1] = the smallest double >= 10^k - 5e-7
+    (the real threshold is never a double, so the comparison is exact).  Re-derive the four constants with exact fractions
+    and check the boundary doubles against CPython's formatting."""
+    import math
+    from fractions import Fraction
+    src = open(os.path.join(ROOT, "livox_motion_compensation_sim_b200", "csrc", "lmc_pcd.cu")).read()
+    m = re.search(r"kDigitT\[4\]\s*=\s*\{([^}]*)\}", src)
+    consts = [float.fromhex(t.strip()) for t in m.group(1).split(",")]
+    assert len(consts) == 4
+    for k, c in enumerate(consts, start=1):
+        thr = Fraction(10) ** k - Fraction(5, 10 ** 7)
+        below = math.nextafter(c, 0.0)
+        assert Fraction(below) < thr < Fraction(c)
+        assert "%.6f" % c == "1" + "0" * k + ".000000" and "%.6f" % below == "9" * k + ".999999"
+        assert len("%.6f" % -c) == k + 9 and len("%.6f" % -below) == k + 8
