@@ -119,66 +119,104 @@ __device__ __forceinline__ int fmt_write(uint8_t* dst, const Num& t) {
     return (int)t.len;
 }
 
-// ---- fast path: |v| < kDigitT[3] (at most 4 integer digits after rounding) ----------------------------------------
-// kDigitT[k-1] = the smallest double >= 10^k - 5e-7 (tests/test_host.py re-derives them with exact fractions)
+// ---- fast path: |v| below 10^4 after rounding (at most 4 integer digits) ------------------------------------------
+// kDigitT[k-1] = the smallest double >= 10^k - 5e-7 (tests/test_host.py re-derives them with exact fractions); for a
+// float-valued |v| the same thresholds are 10, 100, 1000, 10000 (the float just below 10^k prints 9...9.99....).
 __device__ __constant__ double kDigitT[4] = { 0x1.3ffffef390860p+3, 0x1.8fffffde7210cp+6, 0x1.f3fffffbce422p+9, 0x1.387fffffbce43p+13 };
+constexpr uint32_t kSlowBit = 0x80000000u;                          // tags a length: the value needs the general formatter
 
 __device__ __noinline__ uint32_t fmt_len_slow(double v, uint32_t& fl) { return fmt_prepare(v, fl).len; }
 __device__ __noinline__ int fmt_write_slow(uint8_t* dst, double v, uint32_t& fl) { const Num t = fmt_prepare(v, fl); return fmt_write(dst, t); }
 
-// text length of "%.6f" % v; bit 31 (kSlowBit) marks a value for the general formatter
-constexpr uint32_t kSlowBit = 0x80000000u;
-__device__ __forceinline__ uint32_t fmt_len_tagged(double v, uint32_t& fl) {
+// text length of "%.6f" % v, without any digit: four compares
+__device__ __forceinline__ uint32_t fmt_len(double v, uint32_t& fl) {
     const double a = fabs(v);
-    if (!(a < kDigitT[3])) return fmt_len_slow(v, fl) | kSlowBit;   // >= 10^4, inf, nan
+    if (!(a < kDigitT[3])) return fmt_len_slow(v, fl);              // >= 10^4, inf, nan
     return ((uint32_t)__double2hiint(v) >> 31) + 8u + (a >= kDigitT[0]) + (a >= kDigitT[1]) + (a >= kDigitT[2]);
 }
-__device__ __forceinline__ uint32_t fmt_len(double v, uint32_t& fl) { return fmt_len_tagged(v, fl) & ~kSlowBit; }
+__device__ __forceinline__ uint32_t fmt_len(float v, uint32_t& fl) {
+    const float a = fabsf(v);
+    if (!(a < 10000.0f)) return fmt_len_slow((double)v, fl);
+    return (__float_as_uint(v) >> 31) + 8u + (a >= 10.0f) + (a >= 100.0f) + (a >= 1000.0f);
+}
+
+// One number ready to print: rounded integer part, the 6 fractional digits as an integer, tagged text length
+struct Prep { uint32_t ip, q, len; };
+
+__device__ __forceinline__ void prep_finish(Prep& p, uint32_t ip, uint32_t q, uint32_t neg) {
+    const uint32_t carry = q == 1000000u ? 1u : 0u;                  // 0.9999995 -> 1.000000
+    p.q = carry ? 0u : q;
+    p.ip = ip + carry;
+    p.len = neg + 8u + (p.ip >= 10u) + (p.ip >= 100u) + (p.ip >= 1000u);
+}
+// float4 layout: |v| - trunc(|v|) is exact in f32 and its product with 10^6 = 2^6 * 15625 is exact in f64 (24 + 14 bits),
+// so ONE round-to-nearest-even conversion is printf's rounding of the exact binary value -- no tie handling at all
+__device__ __forceinline__ Prep fmt_prep(float v, uint32_t& fl) {
+    Prep p;
+    const float a = fabsf(v);
+    if (!(a < 10000.0f)) { p.ip = p.q = 0; p.len = fmt_len_slow((double)v, fl) | kSlowBit; return p; }
+    const uint32_t ip = __float2uint_rz(a);
+    const float fr = __fsub_rn(a, __uint2float_rn(ip));
+    prep_finish(p, ip, __double2uint_rn(__dmul_rn((double)fr, 1.0e6)), __float_as_uint(v) >> 31);
+    return p;
+}
+// f64: hi + lo = fr * 10^6 exactly (FMA error term).  RNE(hi) is the answer unless hi sits exactly on a tie k + 0.5 (the only
+// place where the sign of lo can change the decision, since k + 0.5 is itself a double and rounding is monotonic)
+__device__ __forceinline__ Prep fmt_prep(double v, uint32_t& fl) {
+    Prep p;
+    const double a = fabs(v);
+    if (!(a < kDigitT[3])) { p.ip = p.q = 0; p.len = fmt_len_slow(v, fl) | kSlowBit; return p; }
+    const uint32_t ip = __double2uint_rz(a);
+    const double fr = __dsub_rn(a, __uint2double_rn(ip));
+    const double hi = __dmul_rn(fr, 1.0e6);
+    uint32_t q = __double2uint_rn(hi);
+    if (fabs(__dsub_rn(hi, __uint2double_rn(q))) == 0.5) {
+        const double lo = __fma_rn(fr, 1.0e6, -hi);
+        const uint32_t dn = __double2uint_rz(hi);
+        if (lo > 0.0) q = dn + 1u; else if (lo < 0.0) q = dn;
+    }
+    prep_finish(p, ip, q, (uint32_t)__double2hiint(v) >> 31);
+    return p;
+}
 
 // the 100-entry digit-pair table: s_lut[n] = '0' + n / 10 | ('0' + n % 10) << 8
 __device__ __forceinline__ void lut_init(uint16_t* s_lut, int tid) {
     if (tid < 100) s_lut[tid] = (uint16_t)(0x3030u + (uint32_t)(tid / 10) + ((uint32_t)(tid % 10) << 8));
 }
 
-// Write "%.6f" % v followed by `sep` so that the separator lands at img[end]; tagged = fmt_len_tagged(v).
-// Every store is relative to `end`: fraction and '.' at fixed offsets, integer digits predicated on the digit count.
-__device__ __forceinline__ void fmt_emit(uint8_t* img, uint32_t end, double v, uint32_t tagged, uint8_t sep, const uint16_t* s_lut, uint32_t& fl) {
-    const double a = fabs(v);
-    const uint32_t neg = (uint32_t)__double2hiint(v) >> 31;
+// Write the prepared number followed by `sep` so that the separator lands at img[end].  Every store is relative to
+// `end`: fraction and '.' at fixed offsets (immediate operands), integer digits predicated on the digit count.
+__device__ __forceinline__ void fmt_emit(uint8_t* img, uint32_t end, const Prep& p, double v, uint8_t sep, const uint16_t* s_lut, uint32_t& fl) {
     uint8_t* e = img + end;
     e[0] = sep;
-    if (tagged & kSlowBit) {                                         // general formatter (rare): it writes forwards
-        fmt_write_slow(e - (tagged & ~kSlowBit), v, fl);
+    if (p.len & kSlowBit) {                                          // general formatter (rare): it writes forwards
+        fmt_write_slow(e - (p.len & ~kSlowBit), v, fl);
         return;
     }
-    uint32_t ip = __double2uint_rz(a);
-    const double fr = __dsub_rn(a, __uint2double_rn(ip));
-    const double hi = __dmul_rn(fr, 1.0e6), lo = __fma_rn(fr, 1.0e6, -hi);
-    uint32_t q = __double2uint_rz(hi);
-    const double d = __dsub_rn(__dsub_rn(hi, __uint2double_rn(q)), 0.5);
-    uint32_t inc = d > 0.0 ? 1u : 0u;
-    if (d == 0.0) inc = (lo > 0.0 ? 1u : 0u) | ((lo == 0.0 ? 1u : 0u) & q);      // exact tie of hi: lo decides, then half-even
-    q += inc;
-    const uint32_t carry = q == 1000000u ? 1u : 0u;
-    q = carry ? 0u : q;
-    ip += carry;
-    const uint32_t nd = tagged - 7u - neg;
-    const uint32_t q1 = q / 10000u, r = q - q1 * 10000u, q2 = r / 100u, q3 = r - q2 * 100u;
-    const uint32_t i1 = ip / 100u, i0 = ip - i1 * 100u;
+    const uint32_t q1 = p.q / 10000u, r = p.q - q1 * 10000u, q2 = r / 100u, q3 = r - q2 * 100u;
+    const uint32_t i1 = p.ip / 100u, i0 = p.ip - i1 * 100u;
     const uint32_t c1 = s_lut[q1], c2 = s_lut[q2], c3 = s_lut[q3], d0 = s_lut[i0], d1 = s_lut[i1];
     e[-1] = (uint8_t)(c3 >> 8); e[-2] = (uint8_t)c3;
     e[-3] = (uint8_t)(c2 >> 8); e[-4] = (uint8_t)c2;
     e[-5] = (uint8_t)(c1 >> 8); e[-6] = (uint8_t)c1;
     e[-7] = '.';
     e[-8] = (uint8_t)(d0 >> 8);
-    if (nd >= 2) e[-9] = (uint8_t)d0;
-    if (nd >= 3) e[-10] = (uint8_t)(d1 >> 8);
-    if (nd >= 4) e[-11] = (uint8_t)d1;
-    if (neg) img[end - 8u - nd] = '-';
+    if (p.ip >= 10u) e[-9] = (uint8_t)d0;
+    if (p.ip >= 100u) e[-10] = (uint8_t)(d1 >> 8);
+    if (p.ip >= 1000u) e[-11] = (uint8_t)d1;
+    if ((uint32_t)__double2hiint(v) >> 31) img[end - p.len] = '-';    // the sign is the number's first character
 }
 
 template <bool F64>
 __device__ __forceinline__ void load_row(const void* pts, int64_t i, double (&v)[4]) {
+    if constexpr (F64) { const double* s = reinterpret_cast<const double*>(pts) + 4 * i; ldg256(s, v[0], v[1], v[2], v[3]); }
+    else { const float4 f = __ldg(reinterpret_cast<const float4*>(pts) + i); v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w; }
+}
+// the row in its own type (float4 rows are formatted from the floats: no conversion, f32 compares)
+template <bool F64> struct RowT { using T = double; };
+template <> struct RowT<false> { using T = float; };
+template <bool F64>
+__device__ __forceinline__ void load_row_native(const void* pts, int64_t i, typename RowT<F64>::T (&v)[4]) {
     if constexpr (F64) { const double* s = reinterpret_cast<const double*>(pts) + 4 * i; ldg256(s, v[0], v[1], v[2], v[3]); }
     else { const float4 f = __ldg(reinterpret_cast<const float4*>(pts) + i); v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w; }
 }
@@ -203,8 +241,8 @@ __global__ void __launch_bounds__(kPcdTile) k_pcd_len(const void* __restrict__ p
     const int64_t i = (int64_t)blockIdx.x * kPcdTile + threadIdx.x;
     uint32_t len = 0, fl = 0;
     if (i < n) {
-        double v[4];
-        load_row<F64>(pts, i, v);
+        typename RowT<F64>::T v[4];
+        load_row_native<F64>(pts, i, v);
         len = 4;
 #pragma unroll
         for (int c = 0; c < 4; ++c) len += fmt_len(v[c], fl);
@@ -241,21 +279,21 @@ __global__ void __launch_bounds__(kPcdTile) k_pcd_write(const void* __restrict__
     const int64_t dst0 = tile_off[blockIdx.x];
     const int phase = (int)(dst0 & 15);
     lut_init(s_lut, tid);
-    double v[4] = { 0.0, 0.0, 0.0, 0.0 };
-    uint32_t ln[4] = { 0, 0, 0, 0 };
+    typename RowT<F64>::T v[4] = { 0, 0, 0, 0 };
+    Prep pr[4];
     uint32_t len = 0, fl = 0;
     if (i < n) {
-        load_row<F64>(pts, i, v);
+        load_row_native<F64>(pts, i, v);
         len = 4;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { ln[c] = fmt_len_tagged(v[c], fl); len += ln[c] & ~kSlowBit; }
+        for (int c = 0; c < 4; ++c) { pr[c] = fmt_prep(v[c], fl); len += pr[c].len & ~kSlowBit; }
     }
     uint32_t total;
     const uint32_t off = block_scan_excl(len, s_warp, total);       // (its barrier also publishes s_lut)
     if (i < n) {
         uint32_t e = (uint32_t)phase + off;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { e += ln[c] & ~kSlowBit; fmt_emit(s_img, e, v[c], ln[c], c == 3 ? (uint8_t)'\n' : (uint8_t)' ', s_lut, fl); e += 1; }
+        for (int c = 0; c < 4; ++c) { e += pr[c].len & ~kSlowBit; fmt_emit(s_img, e, pr[c], (double)v[c], c == 3 ? (uint8_t)'\n' : (uint8_t)' ', s_lut, fl); e += 1; }
     }
     cta_image_out(out + (dst0 - phase), s_img, phase, phase + (int)total, tid, kPcdTile);        // TMA bulk store of the aligned body
     if (fl != 0 && status != nullptr) atomicOr(status, fl);
@@ -275,8 +313,8 @@ __global__ void __launch_bounds__(256) k_pcd_row_off(const void* __restrict__ pt
     const int64_t tile = r / kPcdTile, first = tile * kPcdTile;
     uint32_t sum = 0, fl = 0;
     for (int64_t i = first + lane; i < r; i += 32) {
-        double v[4];
-        load_row<F64>(pts, i, v);
+        typename RowT<F64>::T v[4];
+        load_row_native<F64>(pts, i, v);
         sum += 4;
 #pragma unroll
         for (int c = 0; c < 4; ++c) sum += fmt_len(v[c], fl);
