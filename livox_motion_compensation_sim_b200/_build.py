@@ -10,13 +10,13 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "liblmc_b200.so")
+LIB_PATH = os.environ.get("LMC_B200_LIB_OUT") or os.path.join(PKG_DIR, "liblmc_b200.so")   # (_LIB_OUT: experiment builds)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
 ]
-OBJ_DIR = os.path.join(PKG_DIR, "build")          # git-ignored
+OBJ_DIR = os.environ.get("LMC_B200_OBJ_DIR") or os.path.join(PKG_DIR, "build")          # git-ignored
 
 
 def sources():

@@ -30,9 +30,15 @@ constexpr int kStreamThreads = 32 * (kCW + 1);           // + producer warp
 // Tile shape per kernel family (measured on B200, see profiles/): Mode C on float4 points amortises its
 // per-tile bookkeeping best with 3 pairs per thread over a 3-stage ring; everything else runs 2 pairs
 // (f32) / 1 pair (f64) per thread over 4 stages.
+#ifndef LMC_PPT_SLERP
+#define LMC_PPT_SLERP 3
+#endif
+#ifndef LMC_STAGES
+#define LMC_STAGES 4
+#endif
 template <bool F64, int MODE> struct StreamCfg {
-    static constexpr int PPT      = F64 ? 1 : (MODE == kSlerp ? 3 : 2);   // point pairs per consumer thread per tile
-    static constexpr int STAGES   = (!F64 && MODE == kSlerp) ? 3 : 4;
+    static constexpr int PPT      = F64 ? 1 : (MODE == kSlerp ? LMC_PPT_SLERP : 2);   // point pairs per consumer thread per tile
+    static constexpr int STAGES   = (!F64 && MODE == kSlerp && LMC_PPT_SLERP == 3) ? 3 : LMC_STAGES;
     static constexpr int TP       = kCW * 32 * 2 * PPT;          // points per tile: 960 (f64) / 1920 / 2880 (f32)
     static constexpr int PT_BYTES = F64 ? 32 : 16;
     static constexpr int TS_BYTES = F64 ? 8 : 4;
@@ -44,6 +50,7 @@ template <bool F64, int MODE> struct StreamCfg {
     static constexpr int ROWS      = (MODE == kSlerp && !F64) ? 12 : 0;   // pose rows staged per tile (Mode C, float4 layout): a 2880-point tile of a 10 us / 200 Hz stream touches 7
     static constexpr int ROW_STAGE = ROWS * kSegStride * 8;
     static constexpr int SMEM      = STAGES * (STAGE + ROW_STAGE) + kCW * LVX_SLAB + STAGES * (int)sizeof(TileMeta) + STAGES * 64 + 2 * STAGES * 8 + 128;
+    static_assert(SMEM <= 227 * 1024, "stage ring does not fit the 227 KB of shared memory a CTA can have");
 };
 
 // Everything a consumer needs to know about a tile, prepared once by the producer (64 bytes = four

@@ -31,7 +31,10 @@ def import_reference():
     """Import both reference modules with stubs for absent third-party packages."""
     if REF not in sys.path:
         sys.path.insert(0, REF)
-    sys.modules.setdefault('laspy', types.ModuleType('laspy'))
+    try:                                     # the real laspy, if a wheel ever appears: LAS parity then pins itself (--only las)
+        import laspy                         # noqa: F401
+    except ImportError:
+        sys.modules.setdefault('laspy', types.ModuleType('laspy'))
     for m in ['matplotlib', 'matplotlib.pyplot', 'matplotlib.animation', 'mpl_toolkits',
               'mpl_toolkits.mplot3d']:
         sys.modules.setdefault(m, types.ModuleType(m))
@@ -438,6 +441,94 @@ def config2_fixture(CS, manifest):
     manifest['config2'] = dict(points=int(o[-1]), imu_samples=len(imu), compensated_sha256=sha(np.vstack(out_all)))
 
 
+def cs_run_fixture(CS, manifest):
+    """Whole run of the SECOND simulator past its scanner: the reference's own LiDARMotionSimulator object (CS:1884-1946) drives
+    _apply_motion_compensation (CS:2086-2105) -> _transform_coordinates (CS:2107-2163, target 'vehicle') ->
+    DataExporter.export_point_clouds (CS:1612-1641: .pcd / .xyz / .csv; .las needs laspy) -> LivoxLVXWriter.write_lvx_file
+    (CS:245-374, 'lvx2') on 20 ragged synthetic Mid-70-shaped frames (the ray-marching scanner, CS:1108-1146, is out of scope and
+    returns a handful of points per minute of CPU) against the reference's own trajectory + 200 Hz IMUSimulator output.  Stored:
+    the inputs, the reference's compensated and transformed coordinates, and every output file's bytes + sha256."""
+    import tempfile
+    rng = np.random.default_rng(4711)
+    with tempfile.TemporaryDirectory() as d:
+        cfg = {'random_seed': 42, 'duration': 2.0, 'trajectory_type': 'figure_eight', 'environment_complexity': 'simple', 'max_speed': 12.0,
+               'enable_motion_compensation': True, 'coordinate_system': 'vehicle', 'lvx_format': 'lvx2', 'log_level': 'ERROR',
+               'output_prefix': os.path.join(d, 'run'),
+               'device_info': {'lidar_sn': '3GGDJ6K00200101', 'device_type': 1, 'extrinsic_enable': True, 'roll': 0.01, 'pitch': -0.02,
+                               'yaw': 0.3, 'x': 0.5, 'y': -0.25, 'z': 1.5}}
+        sim = CS.LiDARMotionSimulator(cfg)
+        traj = sim.trajectory_generator.generate_trajectory(duration=2.0, max_speed=12.0, max_angular_vel=0.5)
+        imu = sim.imu_simulator.simulate_imu_data(traj, 2.0)
+        swell = 0.6 * np.sin(np.arange(len(imu))[:, None] * np.array([0.045, 0.027, 0.061]))      # non-trivial rotation rates
+        for smp, dl in zip(imu, swell):
+            smp.gyro_x += dl[0]; smp.gyro_y += dl[1]; smp.gyro_z += dl[2]
+        counts = [400, 0, 1, 513, 96, 97, 300, 1024, 2, 250, 333, 0, 640, 128, 77, 500, 5, 256, 1025, 210]
+        frames, all_pts, all_ts, all_tag, all_ring = [], [], [], [], []
+        for i, n in enumerate(counts):
+            fts = int(i * 0.1 * 1e9)                                                               # CS:2058
+            az = np.radians(rng.uniform(-35.2, 35.2, n)); el = np.radians(rng.uniform(-38.6, 38.6, n))
+            r = rng.uniform(0.05, 90, n)
+            xyz = np.column_stack([r * np.cos(el) * np.cos(az), r * np.cos(el) * np.sin(az), r * np.sin(el)]).reshape(n, 3)
+            inten = rng.integers(0, 256, n); tag = rng.integers(0, 4, n); ring = np.arange(n) % 16
+            ts = fts + np.arange(n, dtype=np.int64) * 1000                                         # CS:1048: 1 us per point
+            pts = [CS.LiDARPoint(x=float(xyz[k, 0]), y=float(xyz[k, 1]), z=float(xyz[k, 2]), intensity=int(inten[k]),
+                                 timestamp=int(ts[k]), ring=int(ring[k]), tag=int(tag[k])) for k in range(n)]
+            frames.append({'frame_id': i, 'timestamp': fts, 'sensor_position': np.zeros(3), 'sensor_orientation': np.zeros(3),
+                           'points': pts, 'frame_duration_ns': int(0.1 * 1e9)})
+            all_pts.append(np.column_stack([xyz, inten.astype(np.float64)]).reshape(n, 4)); all_ts.append(ts)
+            all_tag.append(tag.astype(np.uint8)); all_ring.append(ring.astype(np.int32))
+        comp = sim._apply_motion_compensation(frames, imu)
+        tr = sim._transform_coordinates(comp, CS.CoordinateSystem.VEHICLE, [])
+        assert all(f['motion_compensated'] for f in comp) and all(f['coordinate_system'] == 'vehicle' for f in tr)
+        sim.data_exporter.export_point_clouds(tr, cfg['output_prefix'])
+        sim.lvx_writer.write_lvx_file(cfg['output_prefix'] + '.lvx2', tr, sim.device_info)
+        files = {ext: np.frombuffer(open(cfg['output_prefix'] + '.' + ext, 'rb').read(), np.uint8) for ext in ['pcd', 'xyz', 'csv', 'lvx2']}
+        T = sim.coordinate_transformer.transformations[(CS.CoordinateSystem.SENSOR, CS.CoordinateSystem.VEHICLE)]
+        di = dict(sim.device_info.__dict__)
+    off = np.zeros(len(counts) + 1, np.int64); np.cumsum(counts, out=off[1:])
+    comp_xyz = np.array([[p.x, p.y, p.z] for f in comp for p in f['points']], np.float64).reshape(-1, 3)
+    tr_xyz = np.array([[p.x, p.y, p.z] for f in tr for p in f['points']], np.float64).reshape(-1, 3)
+    np.savez_compressed(os.path.join(HERE, 'cs_run.npz'), pts=np.vstack(all_pts), ts=np.concatenate(all_ts), tag=np.concatenate(all_tag),
+                        ring=np.concatenate(all_ring), frame_off=off, frame_ts=np.array([f['timestamp'] for f in frames], np.int64),
+                        imu_ts=np.array([smp.timestamp for smp in imu], np.int64),
+                        imu_gyro=np.array([[smp.gyro_x, smp.gyro_y, smp.gyro_z] for smp in imu], np.float64),
+                        compensated_xyz=comp_xyz, transformed_xyz=tr_xyz, T_vehicle=T,
+                        device_info_json=np.frombuffer(json.dumps(di).encode(), np.uint8),
+                        file_pcd=files['pcd'], file_xyz=files['xyz'], file_csv=files['csv'], file_lvx2=files['lvx2'])
+    manifest['cs_run'] = dict(frames=len(counts), points=int(off[-1]), imu_samples=len(imu),
+                              **{f'{k}_sha256': sha(v) for k, v in files.items()}, **{f'{k}_bytes': int(len(v)) for k, v in files.items()})
+
+
+def las_fixture(LMC, CS, manifest):
+    """LAS parity hook: needs the REAL laspy.  Runs the reference's two LAS call sites --
+    LiDARMotionSimulator.save_las (LMC:950-963, laspy header defaults) and DataExporter._export_las (CS:1671-1698, scale 0.001,
+    raw intensity, gps_time) -- and stores the files' bytes; tests/test_oracle_golden.py::test_las_parity_pins_itself and
+    tests/test_gpu_parity.py::test_las_file_vs_laspy pick the fixture up.  Without laspy this prints why and writes nothing."""
+    import tempfile
+    try:
+        import laspy
+        ver = laspy.__version__
+        assert hasattr(laspy, 'LasHeader')
+    except Exception as e:                   # noqa: BLE001
+        print(f"las fixture NOT generated: the real laspy is not importable here ({e!r}); LAS parity stays unpinned")
+        return
+    rng = np.random.default_rng(1234)
+    n = 20_000
+    pts = np.column_stack([rng.uniform(-250, 250, (n, 3)), rng.uniform(0, 1, n)])
+    pts[:6, :3] = [[0.005, -0.005, 0.015], [0.025, -0.015, 0.0005], [0.0015, -0.0025, 1e-9], [21474.83, -21474.83, 0.0],
+                   [1.005, 2.675, -1.005], [123.4565, -0.0049999, 99.995]]        # rounding ties of (v - 0) / 0.01 and / 0.001
+    pts5 = np.column_stack([pts[:, :3], np.floor(pts[:, 3] * 255), np.sort(rng.integers(0, 3_600_000_000_000, n)).astype(np.float64)])
+    with tempfile.TemporaryDirectory() as d:
+        with contextlib.redirect_stdout(io.StringIO()):
+            LMC.LiDARMotionSimulator().save_las(pts, os.path.join(d, 'a.las'))
+            CS.DataExporter({})._export_las(pts5, os.path.join(d, 'b.las'))
+        a = np.frombuffer(open(os.path.join(d, 'a.las'), 'rb').read(), np.uint8)
+        b = np.frombuffer(open(os.path.join(d, 'b.las'), 'rb').read(), np.uint8)
+    np.savez_compressed(os.path.join(HERE, 'las_ref.npz'), pts=pts, pts5=pts5, file_lmc=a, file_cs=b,
+                        laspy_version=np.frombuffer(ver.encode(), np.uint8))
+    manifest['las_ref'] = dict(points=n, laspy=ver, lmc_sha256=sha(a), cs_sha256=sha(b))
+
+
 def main():
     LMC, CS = import_reference()
     if len(sys.argv) > 2 and sys.argv[1] == '--only':          # add / refresh single fixtures, keep the rest of the manifest
@@ -446,7 +537,7 @@ def main():
         for name in sys.argv[2:]:
             {'lvx_cs': lambda: lvx_cs_fixture(CS, manifest), 'text_rows': lambda: text_rows_fixture(CS, manifest),
              'coord_frames': lambda: coord_frames_fixture(CS, manifest),
-             'config2': lambda: config2_fixture(CS, manifest),
+             'config2': lambda: config2_fixture(CS, manifest), 'cs_run': lambda: cs_run_fixture(CS, manifest), 'las': lambda: las_fixture(LMC, CS, manifest),
              'outputs': lambda: [outputs_fixture(LMC, n, manifest) for n in ['C1a', 'C2a', 'C3']]}[name]()
         with open(os.path.join(HERE, 'MANIFEST.json'), 'w') as f:
             json.dump(manifest, f, indent=1, sort_keys=True)
@@ -469,6 +560,8 @@ def main():
     text_rows_fixture(CS, manifest)
     coord_frames_fixture(CS, manifest)
     config2_fixture(CS, manifest)
+    cs_run_fixture(CS, manifest)
+    las_fixture(LMC, CS, manifest)
     for name in ['C1a', 'C2a', 'C3']:
         outputs_fixture(LMC, name, manifest)
     with open(os.path.join(HERE, 'MANIFEST.json'), 'w') as f:
