@@ -19,9 +19,9 @@
 //   k_pcd_scan   one CTA: exclusive prefix sum of the tile sizes -> byte offset of every tile
 //   k_pcd_write  per tile: format, lay the lines out in shared memory (block scan of the line lengths) and copy the
 //                tile's contiguous byte range out as one TMA bulk store.  Numbers below 10^4 (every LiDAR coordinate)
-//                take a branch-free path: digits come in pairs from a 100-entry shared-memory table and every
-//                character is stored at a fixed offset from the END of its number, so the stores carry immediate
-//                offsets and no address arithmetic; anything else (>= 10^4, nan, inf) takes the general formatter.
+//                take a branch-free path: digit pairs by arithmetic, characters packed into words in registers and
+//                streamed into the image as aligned 32-bit stores (WordStream below); anything else (>= 10^4, nan,
+//                inf) goes through the general formatter byte by byte.
 #include "lmc_device.cuh"
 
 namespace lmc {
@@ -179,32 +179,67 @@ __device__ __forceinline__ Prep fmt_prep(double v, uint32_t& fl) {
     return p;
 }
 
-// the 100-entry digit-pair table: s_lut[n] = '0' + n / 10 | ('0' + n % 10) << 8
-__device__ __forceinline__ void lut_init(uint16_t* s_lut, int tid) {
-    if (tid < 100) s_lut[tid] = (uint16_t)(0x3030u + (uint32_t)(tid / 10) + ((uint32_t)(tid % 10) << 8));
+// ---- text assembly: a per-thread word stream into the tile image ------------------------------------------------------
+// Byte stores into shared memory were the bottleneck of the first version of this kernel (52 STS.U8 + 20 table LDS per line,
+// ~170 shared-memory wavefronts per warp: the LSU data pipe was 86 % busy).  Now every thread streams its line as aligned
+// 32-bit words: characters are packed in registers (digit pairs by arithmetic, no table), a 1..4-byte piece is appended to
+// a pending word with two funnel shifts, and the fixed 8-byte tail ".dddddd<sep>" of every number leaves as two whole words.
+// Only the first and the last word of a line are shared with the neighbouring lines: those go out with atomicOr into the
+// zero-initialised image (OR commutes, so the result does not depend on the order of the threads).
+__device__ __forceinline__ uint32_t digit_pair(uint32_t n) {          // n < 100 -> '0' + n / 10 | ('0' + n % 10) << 8
+    const uint32_t t = (n * 205u) >> 11;
+    return 0x3030u + t + ((n - 10u * t) << 8);
 }
+struct WordStream {
+    uint32_t* img;        // tile image as words (zero-initialised)
+    uint32_t  wp;         // index of the pending word
+    uint32_t  n;          // bytes already in the pending word (0..3); bytes [0, n) of a line's FIRST word belong to the previous line
+    uint32_t  a0;         // the pending word
+    __device__ __forceinline__ void start(uint32_t* image, uint32_t byte_pos) { img = image; wp = byte_pos >> 2; n = byte_pos & 3u; a0 = 0; }
+    // append the k (0..4) low bytes of chunk (its other bytes must be 0).  FIRST: the word being completed may be the line's first
+    template <bool FIRST>
+    __device__ __forceinline__ void put(uint32_t chunk, uint32_t k) {
+        const uint32_t sh = 8u * n;
+        a0 |= chunk << sh;
+        const uint32_t hi = __funnelshift_l(chunk, 0u, sh);           // the bytes that did not fit (0 when n == 0)
+        n += k;
+        if (n >= 4u) {
+            if (FIRST) atomicOr(img + wp, a0); else img[wp] = a0;
+            wp += 1u; a0 = hi; n -= 4u;
+        }
+    }
+    // append 8 bytes (two whole words leave, the number of pending bytes is unchanged)
+    template <bool FIRST>
+    __device__ __forceinline__ void put8(uint32_t lo, uint32_t hi) {
+        const uint32_t sh = 8u * n;
+        const uint32_t w0 = a0 | (lo << sh);
+        if (FIRST) atomicOr(img + wp, w0); else img[wp] = w0;
+        img[wp + 1u] = __funnelshift_l(lo, hi, sh);
+        a0 = __funnelshift_l(hi, 0u, sh);
+        wp += 2u;
+    }
+    __device__ __forceinline__ void finish() { if (n) atomicOr(img + wp, a0); }   // the line's last word is the next line's first
+};
 
-// Write the prepared number followed by `sep` so that the separator lands at img[end].  Every store is relative to
-// `end`: fraction and '.' at fixed offsets (immediate operands), integer digits predicated on the digit count.
-__device__ __forceinline__ void fmt_emit(uint8_t* img, uint32_t end, const Prep& p, double v, uint8_t sep, const uint16_t* s_lut, uint32_t& fl) {
-    uint8_t* e = img + end;
-    e[0] = sep;
-    if (p.len & kSlowBit) {                                          // general formatter (rare): it writes forwards
-        fmt_write_slow(e - (p.len & ~kSlowBit), v, fl);
+// one prepared number + separator into the stream
+template <bool FIRST>
+__device__ __forceinline__ void fmt_stream(WordStream& ws, const Prep& p, double v, uint32_t sep, uint32_t& fl) {
+    if (p.len & kSlowBit) {                                          // general formatter (rare): bytes through the same stream
+        uint8_t tmp[kNumMax + 3];
+        const int len = fmt_write_slow(tmp, v, fl);
+        for (int k = 0; k < len; ++k) ws.put<FIRST>(tmp[k], 1u);
+        ws.put<FIRST>(sep, 1u);
         return;
     }
-    const uint32_t q1 = p.q / 10000u, r = p.q - q1 * 10000u, q2 = r / 100u, q3 = r - q2 * 100u;
-    const uint32_t i1 = p.ip / 100u, i0 = p.ip - i1 * 100u;
-    const uint32_t c1 = s_lut[q1], c2 = s_lut[q2], c3 = s_lut[q3], d0 = s_lut[i0], d1 = s_lut[i1];
-    e[-1] = (uint8_t)(c3 >> 8); e[-2] = (uint8_t)c3;
-    e[-3] = (uint8_t)(c2 >> 8); e[-4] = (uint8_t)c2;
-    e[-5] = (uint8_t)(c1 >> 8); e[-6] = (uint8_t)c1;
-    e[-7] = '.';
-    e[-8] = (uint8_t)(d0 >> 8);
-    if (p.ip >= 10u) e[-9] = (uint8_t)d0;
-    if (p.ip >= 100u) e[-10] = (uint8_t)(d1 >> 8);
-    if (p.ip >= 1000u) e[-11] = (uint8_t)d1;
-    if ((uint32_t)__double2hiint(v) >> 31) img[end - p.len] = '-';    // the sign is the number's first character
+    const uint32_t neg = (uint32_t)__double2hiint(v) >> 31;
+    const uint32_t nd = p.len - 7u - neg;
+    const uint32_t q1 = p.q / 10000u, r = p.q - q1 * 10000u, q2 = (r * 5243u) >> 19, q3 = r - q2 * 100u;   // r < 10^4: r / 100 exactly
+    const uint32_t p1 = digit_pair(q1), p2 = digit_pair(q2), p3 = digit_pair(q3);
+    const uint32_t i1 = (p.ip * 5243u) >> 19, i0 = p.ip - i1 * 100u;
+    const uint32_t digits = (digit_pair(i1) | (digit_pair(i0) << 16)) >> (8u * (4u - nd));   // the nd integer digits, first digit in byte 0
+    ws.put<FIRST>(neg ? 0x2du : 0u, neg);
+    ws.put<FIRST>(digits, nd);
+    ws.put8<FIRST>(0x2eu | (p1 << 8) | (p2 << 24), (p2 >> 8) | (p3 << 8) | (sep << 24));                  // ".dddddd" + separator
 }
 
 template <bool F64>
@@ -273,12 +308,13 @@ __global__ void __launch_bounds__(kPcdTile) k_pcd_write(const void* __restrict__
                                                         uint8_t* __restrict__ out, uint32_t* __restrict__ status) {
     __shared__ __align__(16) uint8_t s_img[kPcdImg];
     __shared__ uint32_t s_warp[kPcdTile / 32];
-    __shared__ uint16_t s_lut[100];
     const int tid = threadIdx.x;
     const int64_t i = (int64_t)blockIdx.x * kPcdTile + tid;
     const int64_t dst0 = tile_off[blockIdx.x];
     const int phase = (int)(dst0 & 15);
-    lut_init(s_lut, tid);
+    // zero the part of the image this tile can reach (the first / last word of every line is OR-ed in)
+    const int img_words = (int)((phase + (tile_off[blockIdx.x + 1] - dst0) + 3 + 15) / 16) * 4;
+    for (int k = tid * 4; k < img_words; k += kPcdTile * 4) *reinterpret_cast<uint4*>(s_img + 4 * k) = make_uint4(0, 0, 0, 0);
     typename RowT<F64>::T v[4] = { 0, 0, 0, 0 };
     Prep pr[4];
     uint32_t len = 0, fl = 0;
@@ -289,11 +325,15 @@ __global__ void __launch_bounds__(kPcdTile) k_pcd_write(const void* __restrict__
         for (int c = 0; c < 4; ++c) { pr[c] = fmt_prep(v[c], fl); len += pr[c].len & ~kSlowBit; }
     }
     uint32_t total;
-    const uint32_t off = block_scan_excl(len, s_warp, total);       // (its barrier also publishes s_lut)
+    const uint32_t off = block_scan_excl(len, s_warp, total);       // (its barrier also orders the zero fill before the ORs)
     if (i < n) {
-        uint32_t e = (uint32_t)phase + off;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { e += pr[c].len & ~kSlowBit; fmt_emit(s_img, e, pr[c], (double)v[c], c == 3 ? (uint8_t)'\n' : (uint8_t)' ', s_lut, fl); e += 1; }
+        WordStream ws;
+        ws.start(reinterpret_cast<uint32_t*>(s_img), (uint32_t)phase + off);
+        fmt_stream<true>(ws, pr[0], (double)v[0], ' ', fl);
+        fmt_stream<false>(ws, pr[1], (double)v[1], ' ', fl);
+        fmt_stream<false>(ws, pr[2], (double)v[2], ' ', fl);
+        fmt_stream<false>(ws, pr[3], (double)v[3], '\n', fl);
+        ws.finish();
     }
     cta_image_out(out + (dst0 - phase), s_img, phase, phase + (int)total, tid, kPcdTile);        // TMA bulk store of the aligned body
     if (fl != 0 && status != nullptr) atomicOr(status, fl);
