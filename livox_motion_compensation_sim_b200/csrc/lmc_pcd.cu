@@ -22,6 +22,7 @@
 //                take a branch-free path: digit pairs by arithmetic, characters packed into words in registers and
 //                streamed into the image as aligned 32-bit stores (WordStream below); anything else (>= 10^4, nan,
 //                inf) goes through the general formatter byte by byte.
+#include <cstdlib>
 #include "lmc_device.cuh"
 
 namespace lmc {
@@ -29,7 +30,6 @@ namespace lmc {
 constexpr int kPcdTile    = 256;                    // points (= threads) per tile
 constexpr int kNumMax     = 1 + 13 + 1 + 6;         // sign + 13 integer digits + '.' + 6 decimals
 constexpr int kLineMax    = 4 * kNumMax + 4;        // 3 spaces + newline
-constexpr int kPcdImg     = ((kPcdTile * kLineMax + 32 + 15) / 16) * 16;
 
 // One formatted number: integer part, 6 fractional digits as an integer, text length, special-value kind
 struct Num { uint64_t ip; uint32_t fq; uint32_t len; uint32_t kind; bool neg; };   // kind 0 finite, 1 nan, 2 inf
@@ -123,9 +123,10 @@ __device__ __forceinline__ int fmt_write(uint8_t* dst, const Num& t) {
 // kDigitT[k-1] = the smallest double >= 10^k - 5e-7 (tests/test_host.py re-derives them with exact fractions); for a
 // float-valued |v| the same thresholds are 10, 100, 1000, 10000 (the float just below 10^k prints 9...9.99....).
 __device__ __constant__ double kDigitT[4] = { 0x1.3ffffef390860p+3, 0x1.8fffffde7210cp+6, 0x1.f3fffffbce422p+9, 0x1.387fffffbce43p+13 };
-constexpr uint32_t kSlowBit = 0x80000000u;                          // tags a length: the value needs the general formatter
 
-__device__ __noinline__ uint32_t fmt_len_slow(double v, uint32_t& fl) { return fmt_prepare(v, fl).len; }
+// (slow-path helpers return by value: a reference to the caller's flag word or arrays would pin them in local memory)
+__device__ __noinline__ uint2 fmt_len_slow_eval(double v) { uint32_t fl = 0; const uint32_t len = fmt_prepare(v, fl).len; return make_uint2(len, fl); }
+__device__ __forceinline__ uint32_t fmt_len_slow(double v, uint32_t& fl) { const uint2 r = fmt_len_slow_eval(v); fl |= r.y; return r.x; }
 __device__ __noinline__ int fmt_write_slow(uint8_t* dst, double v, uint32_t& fl) { const Num t = fmt_prepare(v, fl); return fmt_write(dst, t); }
 
 // text length of "%.6f" % v, without any digit: four compares
@@ -140,108 +141,7 @@ __device__ __forceinline__ uint32_t fmt_len(float v, uint32_t& fl) {
     return (__float_as_uint(v) >> 31) + 8u + (a >= 10.0f) + (a >= 100.0f) + (a >= 1000.0f);
 }
 
-// One number ready to print: rounded integer part, the 6 fractional digits as an integer, tagged text length
-struct Prep { uint32_t ip, q, len; };
-
-__device__ __forceinline__ void prep_finish(Prep& p, uint32_t ip, uint32_t q, uint32_t neg) {
-    const uint32_t carry = q == 1000000u ? 1u : 0u;                  // 0.9999995 -> 1.000000
-    p.q = carry ? 0u : q;
-    p.ip = ip + carry;
-    p.len = neg + 8u + (p.ip >= 10u) + (p.ip >= 100u) + (p.ip >= 1000u);
-}
-// float4 layout: |v| - trunc(|v|) is exact in f32 and its product with 10^6 = 2^6 * 15625 is exact in f64 (24 + 14 bits),
-// so ONE round-to-nearest-even conversion is printf's rounding of the exact binary value -- no tie handling at all
-__device__ __forceinline__ Prep fmt_prep(float v, uint32_t& fl) {
-    Prep p;
-    const float a = fabsf(v);
-    if (!(a < 10000.0f)) { p.ip = p.q = 0; p.len = fmt_len_slow((double)v, fl) | kSlowBit; return p; }
-    const uint32_t ip = __float2uint_rz(a);
-    const float fr = __fsub_rn(a, __uint2float_rn(ip));
-    prep_finish(p, ip, __double2uint_rn(__dmul_rn((double)fr, 1.0e6)), __float_as_uint(v) >> 31);
-    return p;
-}
-// f64: hi + lo = fr * 10^6 exactly (FMA error term).  RNE(hi) is the answer unless hi sits exactly on a tie k + 0.5 (the only
-// place where the sign of lo can change the decision, since k + 0.5 is itself a double and rounding is monotonic)
-__device__ __forceinline__ Prep fmt_prep(double v, uint32_t& fl) {
-    Prep p;
-    const double a = fabs(v);
-    if (!(a < kDigitT[3])) { p.ip = p.q = 0; p.len = fmt_len_slow(v, fl) | kSlowBit; return p; }
-    const uint32_t ip = __double2uint_rz(a);
-    const double fr = __dsub_rn(a, __uint2double_rn(ip));
-    const double hi = __dmul_rn(fr, 1.0e6);
-    uint32_t q = __double2uint_rn(hi);
-    if (fabs(__dsub_rn(hi, __uint2double_rn(q))) == 0.5) {
-        const double lo = __fma_rn(fr, 1.0e6, -hi);
-        const uint32_t dn = __double2uint_rz(hi);
-        if (lo > 0.0) q = dn + 1u; else if (lo < 0.0) q = dn;
-    }
-    prep_finish(p, ip, q, (uint32_t)__double2hiint(v) >> 31);
-    return p;
-}
-
-// ---- text assembly: a per-thread word stream into the tile image ------------------------------------------------------
-// Byte stores into shared memory were the bottleneck of the first version of this kernel (52 STS.U8 + 20 table LDS per line,
-// ~170 shared-memory wavefronts per warp: the LSU data pipe was 86 % busy).  Now every thread streams its line as aligned
-// 32-bit words: characters are packed in registers (digit pairs by arithmetic, no table), a 1..4-byte piece is appended to
-// a pending word with two funnel shifts, and the fixed 8-byte tail ".dddddd<sep>" of every number leaves as two whole words.
-// Only the first and the last word of a line are shared with the neighbouring lines: those go out with atomicOr into the
-// zero-initialised image (OR commutes, so the result does not depend on the order of the threads).
-__device__ __forceinline__ uint32_t digit_pair(uint32_t n) {          // n < 100 -> '0' + n / 10 | ('0' + n % 10) << 8
-    const uint32_t t = (n * 205u) >> 11;
-    return 0x3030u + t + ((n - 10u * t) << 8);
-}
-struct WordStream {
-    uint32_t* img;        // tile image as words (zero-initialised)
-    uint32_t  wp;         // index of the pending word
-    uint32_t  n;          // bytes already in the pending word (0..3); bytes [0, n) of a line's FIRST word belong to the previous line
-    uint32_t  a0;         // the pending word
-    __device__ __forceinline__ void start(uint32_t* image, uint32_t byte_pos) { img = image; wp = byte_pos >> 2; n = byte_pos & 3u; a0 = 0; }
-    // append the k (0..4) low bytes of chunk (its other bytes must be 0).  FIRST: the word being completed may be the line's first
-    template <bool FIRST>
-    __device__ __forceinline__ void put(uint32_t chunk, uint32_t k) {
-        const uint32_t sh = 8u * n;
-        a0 |= chunk << sh;
-        const uint32_t hi = __funnelshift_l(chunk, 0u, sh);           // the bytes that did not fit (0 when n == 0)
-        n += k;
-        if (n >= 4u) {
-            if (FIRST) atomicOr(img + wp, a0); else img[wp] = a0;
-            wp += 1u; a0 = hi; n -= 4u;
-        }
-    }
-    // append 8 bytes (two whole words leave, the number of pending bytes is unchanged)
-    template <bool FIRST>
-    __device__ __forceinline__ void put8(uint32_t lo, uint32_t hi) {
-        const uint32_t sh = 8u * n;
-        const uint32_t w0 = a0 | (lo << sh);
-        if (FIRST) atomicOr(img + wp, w0); else img[wp] = w0;
-        img[wp + 1u] = __funnelshift_l(lo, hi, sh);
-        a0 = __funnelshift_l(hi, 0u, sh);
-        wp += 2u;
-    }
-    __device__ __forceinline__ void finish() { if (n) atomicOr(img + wp, a0); }   // the line's last word is the next line's first
-};
-
-// one prepared number + separator into the stream
-template <bool FIRST>
-__device__ __forceinline__ void fmt_stream(WordStream& ws, const Prep& p, double v, uint32_t sep, uint32_t& fl) {
-    if (p.len & kSlowBit) {                                          // general formatter (rare): bytes through the same stream
-        uint8_t tmp[kNumMax + 3];
-        const int len = fmt_write_slow(tmp, v, fl);
-        for (int k = 0; k < len; ++k) ws.put<FIRST>(tmp[k], 1u);
-        ws.put<FIRST>(sep, 1u);
-        return;
-    }
-    const uint32_t neg = (uint32_t)__double2hiint(v) >> 31;
-    const uint32_t nd = p.len - 7u - neg;
-    const uint32_t q1 = p.q / 10000u, r = p.q - q1 * 10000u, q2 = (r * 5243u) >> 19, q3 = r - q2 * 100u;   // r < 10^4: r / 100 exactly
-    const uint32_t p1 = digit_pair(q1), p2 = digit_pair(q2), p3 = digit_pair(q3);
-    const uint32_t i1 = (p.ip * 5243u) >> 19, i0 = p.ip - i1 * 100u;
-    const uint32_t digits = (digit_pair(i1) | (digit_pair(i0) << 16)) >> (8u * (4u - nd));   // the nd integer digits, first digit in byte 0
-    ws.put<FIRST>(neg ? 0x2du : 0u, neg);
-    ws.put<FIRST>(digits, nd);
-    ws.put8<FIRST>(0x2eu | (p1 << 8) | (p2 << 24), (p2 >> 8) | (p3 << 8) | (sep << 24));                  // ".dddddd" + separator
-}
-
+// ---- rows ------------------------------------------------------------------------------------------------------------
 template <bool F64>
 __device__ __forceinline__ void load_row(const void* pts, int64_t i, double (&v)[4]) {
     if constexpr (F64) { const double* s = reinterpret_cast<const double*>(pts) + 4 * i; ldg256(s, v[0], v[1], v[2], v[3]); }
@@ -254,6 +154,28 @@ template <bool F64>
 __device__ __forceinline__ void load_row_native(const void* pts, int64_t i, typename RowT<F64>::T (&v)[4]) {
     if constexpr (F64) { const double* s = reinterpret_cast<const double*>(pts) + 4 * i; ldg256(s, v[0], v[1], v[2], v[3]); }
     else { const float4 f = __ldg(reinterpret_cast<const float4*>(pts) + i); v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w; }
+}
+// a thread's two consecutive rows (the formatting kernels work on 2 points per thread)
+template <bool F64>
+__device__ __forceinline__ void rows_load(const void* __restrict__ pts, int64_t row0, bool v0, bool v1, typename RowT<F64>::T (&v)[8]) {
+    using T = typename RowT<F64>::T;
+    if (v0) load_row_native<F64>(pts, row0, reinterpret_cast<T (&)[4]>(v[0]));
+    else { v[0] = v[1] = v[2] = v[3] = 0; }
+    if (v1) load_row_native<F64>(pts, row0 + 1, reinterpret_cast<T (&)[4]>(v[4]));
+    else { v[4] = v[5] = v[6] = v[7] = 0; }
+}
+template <bool F64>
+__device__ __forceinline__ uint32_t rows_len(bool v0, bool v1, const typename RowT<F64>::T (&v)[8], uint32_t& fl) {
+    uint32_t len = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (h == 0 ? v0 : v1) {
+            len += 4u;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) len += fmt_len(v[4 * h + c], fl);
+        }
+    }
+    return len;
 }
 
 __device__ __forceinline__ uint32_t block_scan_excl(uint32_t x, uint32_t* s_warp, uint32_t& total) {
@@ -270,72 +192,297 @@ __device__ __forceinline__ uint32_t block_scan_excl(uint32_t x, uint32_t* s_warp
     return base + inc - x;
 }
 
-template <bool F64>
-__global__ void __launch_bounds__(kPcdTile) k_pcd_len(const void* __restrict__ pts, int64_t n, int64_t* __restrict__ tile_off) {
-    __shared__ uint32_t s_warp[kPcdTile / 32];
-    const int64_t i = (int64_t)blockIdx.x * kPcdTile + threadIdx.x;
-    uint32_t len = 0, fl = 0;
-    if (i < n) {
-        typename RowT<F64>::T v[4];
-        load_row_native<F64>(pts, i, v);
-        len = 4;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) len += fmt_len(v[c], fl);
+// ---- digits: every number of a line as three registers ---------------------------------------------------------------
+// The first version of this formatter spent 646 instructions per point, most of them on digit extraction (divisions by
+// constants per digit pair, a table, byte stores into shared memory).  Now: SWAR -- 4 ASCII digits per 8 integer instructions,
+// no table -- and the characters stay packed in registers until they leave as whole 32-bit words (LineStream).
+constexpr int kFmtThreads = 256;
+constexpr int kFmtTile    = 2 * kFmtThreads;                              // points per tile: 2 consecutive points per thread
+constexpr int kFmtImg     = ((kFmtTile * kLineMax + 32 + 15) / 16) * 16;
+static_assert(kFmtTile == 2 * kPcdTile, "tile_off has kPcdTile granularity: the two halves of a formatting tile");
+
+// x < 10^4 -> its 4 decimal digits as ASCII, thousands in byte 0.  Two 2-digit lanes in one register:
+// h | l << 16 with h = x / 100, l = x % 100; tens of both lanes by one multiply (n * 103 >> 10 == n / 10 for n < 100).
+__device__ __forceinline__ uint32_t swar4(uint32_t x) {
+    const uint32_t h = __umulhi(x, 42949673u);                            // ceil(2^32 / 100): exact quotient for x < 10^4
+    const uint32_t P = (x - 100u * h) * 65536u + h;
+    const uint32_t t = ((P * 103u) >> 10) & 0x000f000fu;
+    return P * 256u + 0x30303030u - 2559u * t;                            // tens + (ones << 8) + "0000", per lane
+}
+
+// One number ready for the stream: the lead (sign + integer digits, ll = 1..5 bytes) and the fixed 8-byte tail ".dddddd<sep>".
+//   T0 = [ll, d, d, d] (ll rides in byte 0, where the '.' goes),  T1 = [d, d, d, sep]
+//   ll <= 4: L0 holds the ll lead bytes;  ll == 5: "-dddd", L0 holds the four digits;
+//   ll & kPieceSlow: the general formatter prints it (|v| >= 10^4, nan, inf): L0 = text length incl. separator, T1 = the last
+//   four bytes of the text (what the next thread's first word needs)
+struct Piece { uint32_t L0, T0, T1; };
+constexpr uint32_t kPieceSlow = 0x80u;
+__device__ __forceinline__ uint32_t piece_ll(const Piece& p) { return p.T0 & 0xffu; }
+__device__ __forceinline__ uint32_t piece_len(const Piece& p) { const uint32_t ll = piece_ll(p); return (ll & kPieceSlow) ? p.L0 : ll + 8u; }
+
+__device__ __forceinline__ void piece_finish(Piece& p, uint32_t ip, uint32_t q, uint32_t neg, uint32_t sepw) {
+    const uint32_t carry = q == 1000000u ? 1u : 0u;                      // 0.9999995 -> 1.000000
+    q = carry ? 0u : q;
+    ip += carry;
+    const uint32_t A = swar4(ip);
+    const uint32_t lz = (uint32_t)(__ffs((int)((A ^ 0x30303030u) | 0x01000000u)) - 1) >> 3;   // leading zero digits, at most 3
+    const uint32_t digits = A >> (8u * lz), ll = 4u - lz + neg;
+    p.L0 = ll == 5u ? digits : ((digits << (8u * neg)) | (neg ? 0x2du : 0u));
+    const uint32_t q1 = __umulhi(q, 429497u), r = q - q1 * 10000u;       // ceil(2^32 / 10^4): exact for q < 10^6
+    const uint32_t C = swar4(r);
+    const uint32_t t = (q1 * 205u) >> 11;                                 // q1 / 10 for q1 < 100
+    const uint32_t X = q1 * 65536u + 0x303000u - 655104u * t + ll;        // ll, tens, ones of q1 in bytes 0..2
+    p.T0 = __byte_perm(X, C, 0x4210);
+    p.T1 = __byte_perm(C, sepw, 0x4321);
+}
+__device__ __noinline__ uint3 piece_slow_eval(double v, uint32_t sepw) {     // {T1, text length incl. separator, status flags}
+    uint32_t fl = 0;
+    const Num t = fmt_prepare(v, fl);
+    uint32_t t1;
+    if (t.kind) t1 = (t.kind == 1 ? 0x006e616eu : 0x00666e69u) | (sepw << 24);            // "nan" / "inf" + separator
+    else t1 = __byte_perm(swar4(t.fq % 10000u), sepw, 0x4321);
+    return make_uint3(t1, t.len + 1u, fl);
+}
+__device__ __forceinline__ void piece_slow(Piece& p, double v, uint32_t sepw, uint32_t& fl) {
+    const uint3 r = piece_slow_eval(v, sepw);
+    p.L0 = r.y; p.T0 = kPieceSlow; p.T1 = r.x;
+    fl |= r.z;
+}
+// The fast formulas run unconditionally on every number (a slow number -- |v| >= 10^4, nan, inf -- just yields garbage that the
+// thread's ONE fix-up branch replaces): no branch per number in the common case.
+// float4 layout: |v| - trunc(|v|) is exact in f32 and its product with 10^6 = 2^6 * 15625 is exact in f64 (24 + 14 bits),
+// so ONE round-to-nearest-even conversion is printf's rounding of the exact binary value -- no tie handling at all
+__device__ __forceinline__ bool piece_fast(Piece& p, float v, uint32_t sepw) {
+    const float a = fabsf(v);
+    const uint32_t ip = __float2uint_rz(a);
+    const float fr = __fsub_rn(a, __uint2float_rn(ip));
+    piece_finish(p, ip, __double2uint_rn(__dmul_rn((double)fr, 1.0e6)), __float_as_uint(v) >> 31, sepw);
+    return !(a < 10000.0f);
+}
+// f64: hi + lo = fr * 10^6 exactly (FMA error term).  RNE(hi) is the answer unless hi sits exactly on a tie k + 0.5 (the only
+// place where the sign of lo can change the decision, since k + 0.5 is itself a double and rounding is monotonic)
+__device__ __forceinline__ bool piece_fast(Piece& p, double v, uint32_t sepw) {
+    const double a = fabs(v);
+    const uint32_t ip = __double2uint_rz(a);
+    const double fr = __dsub_rn(a, __uint2double_rn(ip));
+    const double hi = __dmul_rn(fr, 1.0e6);
+    uint32_t q = __double2uint_rn(hi);
+    if (fabs(__dsub_rn(hi, __uint2double_rn(q))) == 0.5) {
+        const double lo = __fma_rn(fr, 1.0e6, -hi);
+        const uint32_t dn = __double2uint_rz(hi);
+        if (lo > 0.0) q = dn + 1u; else if (lo < 0.0) q = dn;
     }
-    uint32_t total;
-    block_scan_excl(len, s_warp, total);
-    if (threadIdx.x == 0) tile_off[blockIdx.x + 1] = total;       // sizes now, offsets after k_pcd_scan
+    piece_finish(p, ip, q, (uint32_t)__double2hiint(v) >> 31, sepw);
+    return !(a < kDigitT[3]);
 }
-
-// one CTA: tile_off[0] = 0; tile_off[t+1] = sum of sizes[0..t]   (in place)
-__global__ void __launch_bounds__(1024) k_pcd_scan(int64_t* __restrict__ tile_off, int64_t n_tiles) {
-    __shared__ int64_t s_part[1024];
-    const int t = threadIdx.x;
-    const int64_t per = (n_tiles + 1023) / 1024;
-    const int64_t b = t * per, e = b + per < n_tiles ? b + per : n_tiles;
-    int64_t sum = 0;
-    for (int64_t k = b; k < e; ++k) sum += tile_off[k + 1];
-    s_part[t] = sum;
-    __syncthreads();
-    if (t == 0) { int64_t acc = 0; for (int k = 0; k < 1024; ++k) { const int64_t v = s_part[k]; s_part[k] = acc; acc += v; } tile_off[0] = 0; }
-    __syncthreads();
-    int64_t acc = s_part[t];
-    for (int64_t k = b; k < e; ++k) { acc += tile_off[k + 1]; tile_off[k + 1] = acc; }
-}
-
+__device__ __forceinline__ bool is_slow(float v) { return !(fabsf(v) < 10000.0f); }
+__device__ __forceinline__ bool is_slow(double v) { return !(fabs(v) < kDigitT[3]); }
+// the 8 numbers of a thread's two rows; returns the text length of both lines.  special: some piece needs more than
+// put(lead) + put8(tail) in the stream (a slow number or a 5-byte lead "-dddd")
 template <bool F64>
-__global__ void __launch_bounds__(kPcdTile) k_pcd_write(const void* __restrict__ pts, int64_t n, const int64_t* __restrict__ tile_off,
-                                                        uint8_t* __restrict__ out, uint32_t* __restrict__ status) {
-    __shared__ __align__(16) uint8_t s_img[kPcdImg];
-    __shared__ uint32_t s_warp[kPcdTile / 32];
+__device__ __forceinline__ uint32_t rows_pieces(bool v0, bool v1, const typename RowT<F64>::T (&v)[8], Piece (&pc)[8], bool& special, uint32_t& fl) {
+    bool slow = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) slow |= piece_fast(pc[k], v[k], (k & 3) == 3 ? 0x0au : 0x20u);      // (invalid rows hold zeros: "0.000000")
+    if (slow) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (is_slow(v[k])) piece_slow(pc[k], (double)v[k], (k & 3) == 3 ? 0x0au : 0x20u, fl);
+    }
+    uint32_t len = 0, odd = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const bool valid = k < 4 ? v0 : v1;
+        if (valid) { len += piece_len(pc[k]); odd |= piece_ll(pc[k]) + 3u; }      // bit 3 or 7 set <=> ll > 4
+    }
+    special = (odd & 0x88u) != 0u;
+    return len;
+}
+
+// ---- text assembly: the thread's two lines as a stream of aligned 32-bit words into the tile image ----------------------
+// (byte stores were the bottleneck of the first version: 52 STS.U8 + 20 table LDS per line, the LSU data pipe 86 % busy; an
+// intermediate version OR-ed the word shared by two neighbouring lines into a zero-filled image with shared-memory atomics.)
+// A 1..4-byte piece is appended to a pending word with two funnel shifts, the fixed 8-byte tail of every number leaves as two
+// whole words.  The word a thread shares with its predecessor starts from that thread's last bytes (handed over by shuffle /
+// shared memory before the stream starts), the word it shares with its successor is left to the successor: every word of
+// the image is stored exactly once, complete -- no atomics, no zero fill.
+struct LineStream {
+    uint32_t addr, sh, a0;          // pending word: its shared-memory address, 8 x the bytes already in it (0, 8, 16, 24), its value
+    __device__ __forceinline__ void sts(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+    // the pending word starts with the last (pos & 3) bytes of the previous thread's text (prev_t1 = that text's last 4 bytes)
+    __device__ __forceinline__ void start(uint32_t img_s, uint32_t pos, uint32_t prev_t1) {
+        addr = img_s + (pos & ~3u); sh = 8u * (pos & 3u); a0 = __funnelshift_l(prev_t1, 0u, sh);
+    }
+    __device__ __forceinline__ void put(uint32_t chunk, uint32_t k) {   // the k (1..4) low bytes of chunk, the others 0
+        const uint32_t w0 = a0 | (chunk << sh);
+        const uint32_t hi = __funnelshift_l(chunk, 0u, sh);               // the bytes that did not fit (0 when sh == 0)
+        const uint32_t nsh = sh + 8u * k;
+        const bool full = nsh >= 32u;
+        if (full) sts(addr, w0);
+        addr += full ? 4u : 0u; a0 = full ? hi : w0; sh = nsh & 31u;
+    }
+    __device__ __forceinline__ void put8(uint32_t lo, uint32_t hi) {    // 8 bytes: two whole words leave
+        sts(addr, a0 | (lo << sh));
+        sts(addr + 4u, __funnelshift_l(lo, hi, sh));
+        a0 = __funnelshift_l(hi, 0u, sh);
+        addr += 8u;
+    }
+    __device__ __forceinline__ void flush() { if (sh) sts(addr, a0); }   // only where no later thread completes the word
+};
+template <bool F64>
+__device__ __noinline__ uint3 stream_slow(uint32_t addr, uint32_t sh, uint32_t a0, const void* pts, int64_t row, int c, uint32_t sep) {
+    LineStream ws{addr, sh, a0};
+    double v[4];
+    load_row<F64>(pts, row, v);                                          // (re-read: nothing of a slow number is kept in registers)
+    uint8_t tmp[kNumMax + 3];
+    uint32_t fl = 0;
+    const int len = fmt_write_slow(tmp, v[c], fl);
+    for (int k = 0; k < len; ++k) ws.put(tmp[k], 1u);
+    ws.put(sep, 1u);
+    return make_uint3(ws.addr, ws.sh, ws.a0);
+}
+template <bool F64>
+__device__ __forceinline__ void stream_piece(LineStream& ws, const Piece& p, const void* pts, int64_t row, int c, uint32_t sep) {
+    const uint32_t ll = piece_ll(p);
+    if (ll > 4u) {                                                       // rare: "-dddd" or the general formatter
+        if (ll & kPieceSlow) { const uint3 r = stream_slow<F64>(ws.addr, ws.sh, ws.a0, pts, row, c, sep); ws.addr = r.x; ws.sh = r.y; ws.a0 = r.z; return; }
+        ws.put(0x2du, 1u); ws.put(p.L0, 4u);
+    } else ws.put(p.L0, ll);
+    ws.put8((p.T0 & 0xffffff00u) | 0x2eu, p.T1);
+}
+// both lines of a thread: rows row0 / row0 + 1 start at byte `pos` of the image; `last`: the tile's last line is this thread's;
+// special (rows_pieces): take the general route with its per-piece tests
+template <bool F64>
+__device__ __forceinline__ void rows_stream(uint32_t img_s, uint32_t pos, uint32_t prev_t1, bool v0, bool v1, bool last, bool special,
+                                            const Piece (&pc)[8], const void* pts, int64_t row0) {
+    if (!v0) return;
+    LineStream ws;
+    ws.start(img_s, pos, prev_t1);
+    if (!special) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { ws.put(pc[c].L0, piece_ll(pc[c])); ws.put8((pc[c].T0 & 0xffffff00u) | 0x2eu, pc[c].T1); }
+        if (v1) {
+#pragma unroll
+            for (int c = 4; c < 8; ++c) { ws.put(pc[c].L0, piece_ll(pc[c])); ws.put8((pc[c].T0 & 0xffffff00u) | 0x2eu, pc[c].T1); }
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) stream_piece<F64>(ws, pc[c], pts, row0, c, c == 3 ? 0x0au : 0x20u);
+        if (v1) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) stream_piece<F64>(ws, pc[4 + c], pts, row0 + 1, c, c == 3 ? 0x0au : 0x20u);
+        }
+    }
+    if (last) ws.flush();                                                // nobody else completes the tile's last word
+}
+
+// ---- two-call protocol: k_pcd_len + k_pcd_scan, then k_pcd_write -------------------------------------------------------
+// sizes of both 256-point halves of a 512-point tile (2 points per thread): tile_off[t + 1] = bytes of half t, offsets after k_pcd_scan
+template <bool F64>
+__global__ void __launch_bounds__(kFmtThreads) k_pcd_len(const void* __restrict__ pts, int64_t n, int64_t* __restrict__ tile_off) {
+    __shared__ uint32_t s_warp[kFmtThreads / 32];
     const int tid = threadIdx.x;
-    const int64_t i = (int64_t)blockIdx.x * kPcdTile + tid;
-    const int64_t dst0 = tile_off[blockIdx.x];
-    const int phase = (int)(dst0 & 15);
-    // zero the part of the image this tile can reach (the first / last word of every line is OR-ed in)
-    const int img_words = (int)((phase + (tile_off[blockIdx.x + 1] - dst0) + 3 + 15) / 16) * 4;
-    for (int k = tid * 4; k < img_words; k += kPcdTile * 4) *reinterpret_cast<uint4*>(s_img + 4 * k) = make_uint4(0, 0, 0, 0);
-    typename RowT<F64>::T v[4] = { 0, 0, 0, 0 };
-    Prep pr[4];
-    uint32_t len = 0, fl = 0;
-    if (i < n) {
-        load_row_native<F64>(pts, i, v);
-        len = 4;
+    const int64_t row0 = (int64_t)blockIdx.x * kFmtTile + 2 * tid;
+    typename RowT<F64>::T v[8];
+    uint32_t fl = 0;
+    rows_load<F64>(pts, row0, row0 < n, row0 + 1 < n, v);
+    const uint32_t sum = __reduce_add_sync(0xffffffffu, rows_len<F64>(row0 < n, row0 + 1 < n, v, fl));
+    if ((tid & 31) == 0) s_warp[tid >> 5] = sum;
+    __syncthreads();
+    const int64_t n256 = (n + kPcdTile - 1) / kPcdTile, h = 2 * (int64_t)blockIdx.x + (tid >> 7);
+    if ((tid & 127) == 0 && h < n256) { const uint32_t* s = s_warp + 4 * (tid >> 7); tile_off[h + 1] = s[0] + s[1] + s[2] + s[3]; }
+}
+
+// sizes -> offsets, in place, without scratch memory: tile_off[0] = 0, tile_off[t + 1] = sum of sizes[0..t].
+//   pass 1 (one CTA per chunk of 1024 entries): inclusive scan inside the chunk -> its last entry is the chunk total
+//   pass 2 (one CTA): the chunk totals, which sit 1024 entries apart, become global offsets
+//   pass 3 (one CTA per chunk): every other entry of chunk c > 0 gets the (now global) last entry of chunk c - 1 added
+// All accesses coalesced; the single-CTA scan this replaces walked 137 consecutive entries per thread and took 149 us for 140 k tiles.
+constexpr int kScanChunk = 1024;
+__device__ __forceinline__ int64_t cta_scan_incl(int64_t x, int64_t* s_warp) {          // 1024 threads
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { pr[c] = fmt_prep(v[c], fl); len += pr[c].len & ~kSlowBit; }
+    for (int o = 1; o < 32; o <<= 1) { const int64_t t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        int64_t y = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int64_t t = __shfl_up_sync(0xffffffffu, y, o); if (lane >= o) y += t; }
+        s_warp[lane] = y;
     }
-    uint32_t total;
-    const uint32_t off = block_scan_excl(len, s_warp, total);       // (its barrier also orders the zero fill before the ORs)
-    if (i < n) {
-        WordStream ws;
-        ws.start(reinterpret_cast<uint32_t*>(s_img), (uint32_t)phase + off);
-        fmt_stream<true>(ws, pr[0], (double)v[0], ' ', fl);
-        fmt_stream<false>(ws, pr[1], (double)v[1], ' ', fl);
-        fmt_stream<false>(ws, pr[2], (double)v[2], ' ', fl);
-        fmt_stream<false>(ws, pr[3], (double)v[3], '\n', fl);
-        ws.finish();
+    __syncthreads();
+    return x + (w ? s_warp[w - 1] : 0);
+}
+__global__ void __launch_bounds__(kScanChunk) k_pcd_scan_chunks(int64_t* __restrict__ tile_off, int64_t n_tiles) {
+    __shared__ int64_t s_warp[32];
+    const int64_t k = (int64_t)blockIdx.x * kScanChunk + threadIdx.x;
+    const int64_t x = cta_scan_incl(k < n_tiles ? tile_off[k + 1] : 0, s_warp);
+    if (k < n_tiles) tile_off[k + 1] = x;
+    if (k == 0) tile_off[0] = 0;
+}
+__global__ void __launch_bounds__(kScanChunk) k_pcd_scan_totals(int64_t* __restrict__ tile_off, int64_t n_tiles, int64_t n_chunks) {
+    __shared__ int64_t s_warp[32];
+    __shared__ int64_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t c0 = 0; c0 < n_chunks; c0 += kScanChunk) {
+        const int64_t c = c0 + threadIdx.x;
+        const int64_t last = (c + 1) * kScanChunk < n_tiles ? (c + 1) * kScanChunk : n_tiles;      // index of chunk c's last entry
+        const int64_t x = cta_scan_incl(c < n_chunks ? tile_off[last] : 0, s_warp) + s_carry;
+        __syncthreads();
+        if (c < n_chunks) tile_off[last] = x;
+        if (threadIdx.x == kScanChunk - 1) s_carry = x;
+        __syncthreads();
     }
-    cta_image_out(out + (dst0 - phase), s_img, phase, phase + (int)total, tid, kPcdTile);        // TMA bulk store of the aligned body
+}
+__global__ void __launch_bounds__(kScanChunk) k_pcd_scan_add(int64_t* __restrict__ tile_off, int64_t n_tiles) {
+    const int64_t c = (int64_t)blockIdx.x + 1, k = c * kScanChunk + threadIdx.x;
+    const int64_t last = (c + 1) * kScanChunk < n_tiles ? (c + 1) * kScanChunk : n_tiles;
+    if (k + 1 < last) tile_off[k + 1] += tile_off[c * kScanChunk];      // (entry `last` is already global)
+}
+static cudaError_t launch_tile_scan(int64_t* tile_off, int64_t tiles, cudaStream_t st) {
+    if (tiles <= 0) return cudaMemsetAsync(tile_off, 0, sizeof(int64_t), st);
+    const int64_t chunks = (tiles + kScanChunk - 1) / kScanChunk;
+    k_pcd_scan_chunks<<<(unsigned)chunks, kScanChunk, 0, st>>>(tile_off, tiles);
+    if (chunks > 1) {
+        k_pcd_scan_totals<<<1, kScanChunk, 0, st>>>(tile_off, tiles, chunks);
+        k_pcd_scan_add<<<(unsigned)(chunks - 1), kScanChunk, 0, st>>>(tile_off, tiles);
+    }
+    return cudaGetLastError();
+}
+
+// one 512-point tile per CTA: digits in registers, block scan of the line lengths, word stream into the image (laid out at the
+// destination's 16-byte phase), one TMA bulk store
+template <bool F64>
+__global__ void __launch_bounds__(kFmtThreads, F64 ? 3 : 4) k_pcd_write(const void* __restrict__ pts, int64_t n, const int64_t* __restrict__ tile_off,
+                                                                        uint8_t* __restrict__ out, uint32_t* __restrict__ status) {
+    extern __shared__ __align__(16) uint8_t s_img[];
+    __shared__ uint32_t s_warp[kFmtThreads / 32], s_edge[kFmtThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t dst0 = __ldg(tile_off + 2 * (int64_t)blockIdx.x);
+    const int64_t row0 = (int64_t)blockIdx.x * kFmtTile + 2 * tid;
+    const int64_t rest = n - (int64_t)blockIdx.x * kFmtTile;
+    const int m = (int)(rest < kFmtTile ? rest : kFmtTile);
+    const bool v0 = 2 * tid < m, v1 = 2 * tid + 1 < m;
+    typename RowT<F64>::T v[8];
+    rows_load<F64>(pts, row0, v0, v1, v);
+    Piece pc[8];
+    uint32_t fl = 0;
+    bool special;
+    const uint32_t len = rows_pieces<F64>(v0, v1, v, pc, special, fl);
+    uint32_t inc = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    uint32_t prev_t1 = __shfl_up_sync(0xffffffffu, pc[7].T1, 1);         // the last four bytes of the previous thread's text
+    if (lane == 31) { s_warp[w] = inc; s_edge[w] = pc[7].T1; }
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < kFmtThreads / 32; ++k) { const uint32_t t = s_warp[k]; if (k < w) base += t; total += t; }
+    if (lane == 0) prev_t1 = w ? s_edge[w - 1] : 0u;
+    const int phase = (int)(dst0 & 15);
+    rows_stream<F64>(smem_u32(s_img), (uint32_t)phase + base + inc - len, prev_t1, v0, v1, 2 * tid + 2 >= m, special, pc, pts, row0);
+    cta_image_out(out + (dst0 - phase), s_img, phase, phase + (int)total, tid, kFmtThreads);     // TMA bulk store of the aligned body
     if (fl != 0 && status != nullptr) atomicOr(status, fl);
 }
 
@@ -513,8 +660,7 @@ cudaError_t launch_text_size(bool f64, const void* rows, int64_t n, int32_t n_co
         if (f64) k_text_len<true><<<(unsigned)tiles, kPcdTile, 0, st>>>(rows, n, F, tile_off);
         else     k_text_len<false><<<(unsigned)tiles, kPcdTile, 0, st>>>(rows, n, F, tile_off);
     }
-    k_pcd_scan<<<1, 1024, 0, st>>>(tile_off, tiles);
-    return cudaGetLastError();
+    return launch_tile_scan(tile_off, tiles, st);
 }
 
 cudaError_t launch_text_write(bool f64, const void* rows, int64_t n, int32_t n_cols, int32_t row_stride, const int32_t* col, const int32_t* dec,
@@ -534,14 +680,13 @@ cudaError_t launch_text_write(bool f64, const void* rows, int64_t n, int32_t n_c
 }
 
 cudaError_t launch_pcd_size(bool f64, const void* pts, int64_t n, int64_t* tile_off, cudaStream_t st) {
-    const int64_t tiles = (n + kPcdTile - 1) / kPcdTile;
+    const int64_t tiles = (n + kPcdTile - 1) / kPcdTile, ctas = (n + kFmtTile - 1) / kFmtTile;
     if (tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
-    if (tiles > 0) {
-        if (f64) k_pcd_len<true><<<(unsigned)tiles, kPcdTile, 0, st>>>(pts, n, tile_off);
-        else     k_pcd_len<false><<<(unsigned)tiles, kPcdTile, 0, st>>>(pts, n, tile_off);
+    if (ctas > 0) {
+        if (f64) k_pcd_len<true><<<(unsigned)ctas, kFmtThreads, 0, st>>>(pts, n, tile_off);
+        else     k_pcd_len<false><<<(unsigned)ctas, kFmtThreads, 0, st>>>(pts, n, tile_off);
     }
-    k_pcd_scan<<<1, 1024, 0, st>>>(tile_off, tiles);
-    return cudaGetLastError();
+    return launch_tile_scan(tile_off, tiles, st);
 }
 
 cudaError_t launch_pcd_row_off(bool f64, const void* pts, int64_t n, const int64_t* tile_off, const int64_t* rows, int32_t n_rows,
@@ -554,10 +699,20 @@ cudaError_t launch_pcd_row_off(bool f64, const void* pts, int64_t n, const int64
 }
 
 cudaError_t launch_pcd_write(bool f64, const void* pts, int64_t n, const int64_t* tile_off, uint8_t* out, uint32_t* status, cudaStream_t st) {
-    const int64_t tiles = (n + kPcdTile - 1) / kPcdTile;
-    if (tiles == 0) return cudaSuccess;
-    if (f64) k_pcd_write<true><<<(unsigned)tiles, kPcdTile, 0, st>>>(pts, n, tile_off, out, status);
-    else     k_pcd_write<false><<<(unsigned)tiles, kPcdTile, 0, st>>>(pts, n, tile_off, out, status);
+    const int64_t ctas = (n + kFmtTile - 1) / kFmtTile;
+    if (ctas == 0) return cudaSuccess;
+    if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (attr_dev != dev) {
+        if ((e = cudaFuncSetAttribute(k_pcd_write<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmtImg)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(k_pcd_write<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFmtImg)) != cudaSuccess) return e;
+        attr_dev = dev;
+    }
+    if (f64) k_pcd_write<true><<<(unsigned)ctas, kFmtThreads, kFmtImg, st>>>(pts, n, tile_off, out, status);
+    else     k_pcd_write<false><<<(unsigned)ctas, kFmtThreads, kFmtImg, st>>>(pts, n, tile_off, out, status);
     return cudaGetLastError();
 }
 

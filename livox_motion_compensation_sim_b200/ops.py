@@ -357,21 +357,28 @@ def build_lvx_cs(pts: torch.Tensor, tag: Optional[torch.Tensor], frame_off: torc
     return out, status
 
 
-@_on_tensor_device
-def pcd_ascii_body(pts: torch.Tensor):
-    """(N2) LMC:946-947 on the device: one '%.6f %.6f %.6f %.6f\\n' line per row, byte-identical to the
-    reference's f-string formatting.  Returns (uint8 text tensor, status flags tensor)."""
+def _pcd_format(pts: torch.Tensor):
+    """LMC:946-947 for every row of pts -> (text, tile_off, status): lmc_pcd_ascii_size_* (line lengths need no digits: four
+    compares per number), one host read of the total, lmc_pcd_ascii_write_* into the exactly sized buffer."""
     f64 = _layout(pts)
     n = pts.shape[0]
     tiles = (n + C.PCD_TILE - 1) // C.PCD_TILE
     tile_off = torch.empty(tiles + 1, dtype=torch.int64, device=pts.device)
     status = torch.zeros(1, dtype=torch.int32, device=pts.device)
     L = C.lib()
-    C.check((L.lmc_pcd_ascii_size_f64 if f64 else L.lmc_pcd_ascii_size_f32)(_req(pts, pts.dtype, "pts", (4,)), n, tile_off.data_ptr(), _stream_ptr()))
+    ptr = _req(pts, pts.dtype, "pts", (4,))
+    C.check((L.lmc_pcd_ascii_size_f64 if f64 else L.lmc_pcd_ascii_size_f32)(ptr, n, tile_off.data_ptr(), _stream_ptr()))
     total = int(tile_off[-1].item())                       # the one host sync: the text buffer has to be sized
     out = torch.empty(total, dtype=torch.uint8, device=pts.device)
-    C.check((L.lmc_pcd_ascii_write_f64 if f64 else L.lmc_pcd_ascii_write_f32)(_req(pts, pts.dtype, "pts", (4,)), n, tile_off.data_ptr(),
-                                                                              out.data_ptr(), status.data_ptr(), _stream_ptr()))
+    C.check((L.lmc_pcd_ascii_write_f64 if f64 else L.lmc_pcd_ascii_write_f32)(ptr, n, tile_off.data_ptr(), out.data_ptr(), status.data_ptr(), _stream_ptr()))
+    return out, tile_off, status
+
+
+@_on_tensor_device
+def pcd_ascii_body(pts: torch.Tensor):
+    """(N2) LMC:946-947 on the device: one '%.6f %.6f %.6f %.6f\\n' line per row, byte-identical to the
+    reference's f-string formatting.  Returns (uint8 text tensor, status flags tensor)."""
+    out, _, status = _pcd_format(pts)
     return out, status
 
 
@@ -383,20 +390,12 @@ def pcd_ascii_frames(pts: torch.Tensor, frame_off: torch.Tensor):
     whole text is the body of the merged file (np.vstack order, LMC:888 / 897)."""
     f64 = _layout(pts)
     n = pts.shape[0]
-    tiles = (n + C.PCD_TILE - 1) // C.PCD_TILE
-    tile_off = torch.empty(tiles + 1, dtype=torch.int64, device=pts.device)
-    status = torch.zeros(1, dtype=torch.int32, device=pts.device)
+    out, tile_off, status = _pcd_format(pts)
     nq = frame_off.shape[0]
     byte_off = torch.empty(nq, dtype=torch.int64, device=pts.device)
     L = C.lib()
-    ptr = _req(pts, pts.dtype, "pts", (4,))
-    C.check((L.lmc_pcd_ascii_size_f64 if f64 else L.lmc_pcd_ascii_size_f32)(ptr, n, tile_off.data_ptr(), _stream_ptr()))
     C.check((L.lmc_pcd_ascii_row_offsets_f64 if f64 else L.lmc_pcd_ascii_row_offsets_f32)(
-        ptr, n, tile_off.data_ptr(), _req(frame_off, torch.int64, "frame_off"), nq, byte_off.data_ptr(), _stream_ptr()))
-    total = int(tile_off[-1].item())                       # the one host sync: the text buffer has to be sized
-    out = torch.empty(total, dtype=torch.uint8, device=pts.device)
-    C.check((L.lmc_pcd_ascii_write_f64 if f64 else L.lmc_pcd_ascii_write_f32)(ptr, n, tile_off.data_ptr(), out.data_ptr(), status.data_ptr(),
-                                                                              _stream_ptr()))
+        _req(pts, pts.dtype, "pts", (4,)), n, tile_off.data_ptr(), _req(frame_off, torch.int64, "frame_off"), nq, byte_off.data_ptr(), _stream_ptr()))
     return out, byte_off, status
 
 

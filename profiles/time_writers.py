@@ -46,10 +46,13 @@ def main():
     def add(name, ms, nbytes):
         res[name] = {"ms": ms, "Gpts_per_s": n / ms / 1e6, "GBps": nbytes / ms / 1e6, "frac": nbytes / ms / 1e6 / peak}
     txt = ops.pcd_ascii_body(raw)[0].numel()
-    add("pcd_ascii_f32", t_ms(lambda: ops.pcd_ascii_body(raw)), 2 * n * 16 + txt)
+    add("pcd_ascii_f32", t_ms(lambda: ops.pcd_ascii_body(raw)), 2 * n * 16 + txt)                 # the points are read twice: size pass, write pass
     txt64 = ops.pcd_ascii_body(raw64)[0].numel()
     add("pcd_ascii_f64", t_ms(lambda: ops.pcd_ascii_body(raw64)), 2 * n * 32 + txt64)
     add("pcd_ascii_frames_f32", t_ms(lambda: ops.pcd_ascii_frames(raw, off_d)), 2 * n * 16 + txt)
+    if len(sys.argv) > 1 and sys.argv[1] == "pcd":                 # A/B runs of the formatter alone
+        print(json.dumps(res))
+        return
     add("lvx_v11", t_ms(lambda: ops.build_lvx_v11(raw, off_d, fpos_d, ft_d, id_d, P)), n * 16 + int(fpos[-1]))
     add("lvx2", t_ms(lambda: ops.build_lvx_cs(raw, None, off_d, ts_d, bytes(88), C.LVXCS_LVX2, P)), n * 16 + 88 + 45 * F + 14 * n)
     add("las_pf3", t_ms(lambda: ops.build_las_pf3(raw, scale=(0.001,) * 3)), n * 16 + 227 + 34 * n)

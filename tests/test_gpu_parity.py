@@ -796,6 +796,33 @@ def test_pcd_ascii_frames_one_pass(f64):
         assert t[b[i]:b[i + 1]] == want, i
 
 
+@pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
+def test_pcd_ascii_tile_edges_and_slow_numbers(f64):
+    """The formatter works on 512-point tiles of 2 points per thread, whole words per store, the word shared by two threads
+    completed by the second one: sizes around the tile / half-tile / pair boundaries, every lead length (1..5 bytes: sign x 1..4
+    digits), slow numbers (>= 10^4, nan, inf) anywhere in a line incl. the last column of a thread's last line and whole runs of
+    them, carries into the next digit count -- against CPython; and tile_off[-1] == the text size."""
+    rng = np.random.default_rng(77)
+    for n in (0, 1, 2, 3, 255, 256, 257, 511, 512, 513, 1023, 1025, 5 * 512 + 301, 200_003, 1024 * 256 + 5, 2 * 1024 * 256 + 700):
+        mag = 10.0 ** rng.integers(-3, 4, (n, 4))
+        pts = rng.uniform(-1, 1, (n, 4)) * mag
+        if n > 8:
+            pts[1, 3] = 12345.678; pts[2, 0] = np.nan; pts[3, 3] = np.inf; pts[4, 3] = -np.inf; pts[5, 1] = -9999.9999996
+            pts[6] = [0.9999995, -0.9999995, 9.9999995, 999.9999995]; pts[7] = [-0.0, 0.0, 5e-7, 1.5e-6]; pts[n - 1, 3] = -98765.4321
+        if n > 600:
+            pts[511, 3] = 1e9; pts[512, 0] = -1e9; pts[513:520, :] = np.nan
+        if not f64:
+            pts = pts.astype(np.float32)
+        want = "".join("%.6f %.6f %.6f %.6f\n" % tuple(r) for r in pts.astype(np.float64)).encode()
+        body, tile_off, status = ops._pcd_format(dev(pts))
+        assert body.cpu().numpy().tobytes() == want, n
+        assert int(status.item()) == 0 and int(tile_off[-1].item()) == len(want), n
+        t = tile_off.cpu().numpy()
+        assert t[0] == 0 and (np.diff(t) >= 0).all() and len(t) == (n + 255) // 256 + 1
+        if n > 256:
+            assert t[1] == len("".join("%.6f %.6f %.6f %.6f\n" % tuple(r) for r in pts[:256].astype(np.float64)))
+
+
 def test_save_results_files_are_save_pcd_files(golden, tmp_path):
     """save_results writes every per-frame / merged PCD from the batched pass: byte-identical to save_pcd frame by
     frame (which is pinned to the reference's file bytes), with the reference's merge guards; results come back
