@@ -321,6 +321,57 @@ def modeb_fixture(CS, manifest):
                              lvx2_sha256=sha(rec))
 
 
+def modeb_tiers_fixture(CS, manifest):
+    """The same reference path (CS:1435-1536 + 365-374) at gyro rates up to ~12 rad/s: per-point angles from 0 to ~1.2 rad,
+    so every sin / cos tier of the device code (|a| < 2^-4, <= 2^-3, <= 0.5, library) meets the reference's np.sin / np.cos."""
+    rng = np.random.default_rng(1234)
+    cfg = {'random_seed': 42, 'duration': 1.0, 'trajectory_type': 'figure_eight', 'max_speed': 12.0}
+    tg = CS.TrajectoryGenerator('figure_eight', seed=42)
+    traj = tg.generate_trajectory(1.0, dt=0.1, max_speed=12.0)
+    imu = CS.IMUSimulator(cfg).simulate_imu_data(traj, 1.0)
+    imu_ts = np.array([s.timestamp for s in imu], np.int64)
+    amp = np.linspace(0.05, 12.0, len(imu))[:, None]
+    swell = amp * np.sin(np.arange(len(imu))[:, None] * np.array([0.11, 0.071, 0.13]) + np.array([0.3, 1.1, 2.0]))
+    for s, d in zip(imu, swell):
+        s.gyro_x += d[0]; s.gyro_y += d[1]; s.gyro_z += d[2]
+    imu_gyro = np.array([[s.gyro_x, s.gyro_y, s.gyro_z] for s in imu], np.float64)
+    mc = CS.MotionCompensator({'enable_motion_compensation': True})
+    frame_starts = [0, 100_000_000, 300_000_000, 500_000_000, 700_000_000, 880_000_000]
+    counts = [400, 401, 399, 400, 402, 400]
+    all_pts, all_ts, all_out, all_tag = [], [], [], []
+    lvx2 = io.BytesIO()
+    w = CS.LivoxLVXWriter('lvx2')
+    for fs, n in zip(frame_starts, counts):
+        az = np.radians(rng.uniform(-35.2, 35.2, n)); el = np.radians(rng.uniform(-38.6, 38.6, n))
+        r = rng.uniform(0.05, 90, n)
+        xyz = np.column_stack([r * np.cos(el) * np.cos(az), r * np.cos(el) * np.sin(az), r * np.sin(el)])
+        inten = rng.integers(0, 256, n)
+        ts = fs + np.arange(n, dtype=np.int64) * (100_000_000 // n) + rng.integers(0, 7, n)
+        tag = rng.integers(0, 2, n)
+        pts = [CS.LiDARPoint(x=float(xyz[i, 0]), y=float(xyz[i, 1]), z=float(xyz[i, 2]), intensity=int(inten[i]),
+                             timestamp=int(ts[i]), ring=i % 16, tag=int(tag[i])) for i in range(n)]
+        comp = mc.compensate_point_cloud(pts, imu, fs, 100_000_000)
+        out = np.array([[p.x, p.y, p.z, p.intensity] for p in comp], np.float64).reshape(n, 4)
+        all_pts.append(np.column_stack([xyz, inten.astype(np.float64)])); all_ts.append(ts)
+        all_out.append(out); all_tag.append(tag.astype(np.uint8))
+        fbuf = io.BytesIO()
+        w._write_frame_lvx2(fbuf, {'points': comp, 'timestamp': fs}, 0)
+        lvx2.write(fbuf.getvalue()[24 + 21:])       # skip 24-B frame header + 21-B package header
+    off = np.zeros(len(counts) + 1, np.int64)
+    np.cumsum(counts, out=off[1:])
+    rec = np.frombuffer(lvx2.getvalue(), np.uint8).reshape(-1, 14)
+    # per-point angle magnitudes (what picks the tier), for the test's coverage assertion
+    tsa, fsa = np.concatenate(all_ts), np.repeat(np.array(frame_starts, np.int64), counts)
+    g = np.column_stack([np.interp(tsa, imu_ts, imu_gyro[:, c]) for c in range(3)])
+    amax = np.abs(g * ((tsa - fsa) * 1e-9)[:, None]).max(axis=1)
+    np.savez_compressed(os.path.join(HERE, 'modeb_tiers.npz'), pts=np.vstack(all_pts), ts=tsa,
+                        tag=np.concatenate(all_tag), frame_off=off, frame_start=np.array(frame_starts, np.int64),
+                        imu_ts=imu_ts, imu_gyro=imu_gyro, compensated=np.vstack(all_out), lvx2_records=rec, angle_max=amax)
+    manifest['modeb_tiers'] = dict(points=int(off[-1]), imu_samples=len(imu), compensated_sha256=sha(np.vstack(all_out)),
+                                   lvx2_sha256=sha(rec), tier_counts=[int((amax < 0.0625).sum()), int(((amax >= 0.0625) & (amax <= 0.125)).sum()),
+                                                                      int(((amax > 0.125) & (amax <= 0.5)).sum()), int((amax > 0.5).sum())])
+
+
 def lvx_cs_fixture(CS, manifest):
     """Reference LivoxLVXWriter.write_lvx_file (CS:245-374) for 'lvx2', 'lvx3' and 'lvx' on ragged synthetic
     frames (one empty, one of a single point, one above 1024 points) with a non-trivial DeviceInfo."""
@@ -537,7 +588,7 @@ def main():
         for name in sys.argv[2:]:
             {'lvx_cs': lambda: lvx_cs_fixture(CS, manifest), 'text_rows': lambda: text_rows_fixture(CS, manifest),
              'coord_frames': lambda: coord_frames_fixture(CS, manifest),
-             'config2': lambda: config2_fixture(CS, manifest), 'cs_run': lambda: cs_run_fixture(CS, manifest), 'las': lambda: las_fixture(LMC, CS, manifest),
+             'config2': lambda: config2_fixture(CS, manifest), 'modeb_tiers': lambda: modeb_tiers_fixture(CS, manifest), 'cs_run': lambda: cs_run_fixture(CS, manifest), 'las': lambda: las_fixture(LMC, CS, manifest),
              'outputs': lambda: [outputs_fixture(LMC, n, manifest) for n in ['C1a', 'C2a', 'C3']]}[name]()
         with open(os.path.join(HERE, 'MANIFEST.json'), 'w') as f:
             json.dump(manifest, f, indent=1, sort_keys=True)
@@ -554,6 +605,7 @@ def main():
     lvx_type2_fixture(LMC, manifest)
     lvx_file_fixture(LMC, manifest)
     modeb_fixture(CS, manifest)
+    modeb_tiers_fixture(CS, manifest)
     coord_chain_fixture(CS, manifest)
     pcd_fixture(LMC, manifest)
     lvx_cs_fixture(CS, manifest)

@@ -261,6 +261,30 @@ def test_mode_b_vs_reference(golden, path):
     assert np.array_equal(got[:, 3], g['pts'][:, 3])
 
 
+@pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
+def test_mode_b_all_trig_tiers_vs_reference(golden, path, f64):
+    """Every sin / cos tier of the device code (degree-9/8 below 2^-4, degree-11/12 to 2^-3, degree-15/16 to 0.5, library beyond)
+    against the real MotionCompensator's np.sin / np.cos at gyro rates up to ~12 rad/s (golden modeb_tiers.npz), both kernel paths."""
+    g = golden("modeb_tiers.npz")
+    spec = ops.ExportSpec(lvx=True, lvx_mode=C.LVX2_OF_OUTPUT, tag=dev(g['tag']))
+    if f64:
+        pts_d, ts_d = dev(g['pts']), dev(g['ts'])
+    else:                                   # float4 layout + u32 ns offsets: same arithmetic on the f32-rounded inputs
+        pts_d = dev(g['pts'].astype(np.float32))
+        ts_d = dev((g['ts'] - np.repeat(g['frame_start'], np.diff(g['frame_off']))).astype(np.uint32))
+    out, b = ops.deskew_gyro(pts_d, ts_d, dev(g['frame_off']), dev(g['frame_start']), dev(g['imu_ts']), dev(g['imu_gyro']), export=spec)
+    got = out.cpu().numpy().astype(np.float64)
+    if f64:
+        err = np.abs(got - g['compensated']).max()
+        rec = b.lvx14.cpu().numpy()
+        mism = int((rec != g['lvx2_records']).any(axis=1).sum())
+        print(f"mode B tiers: max |d| = {err:.3e} m, LVX2 record mismatches = {mism} / {len(rec)}")
+        assert err <= 1e-11 and mism == 0 and b.flags() == 0
+    else:
+        want = orc.C.deskew_gyro_f64(g['pts'].astype(np.float32).astype(np.float64), g['ts'], g['frame_off'], g['frame_start'], g['imu_ts'], g['imu_gyro'])
+        assert np.abs(got - want).max() <= 1e-5 and np.abs(got - g['compensated']).max() <= TOL_M
+
+
 def test_mode_b_empty_imu_copies(golden):
     g = golden("modeb.npz")
     out, _ = ops.deskew_gyro(dev(g['pts']), dev(g['ts']), dev(g['frame_off']), dev(g['frame_start']),
