@@ -17,6 +17,7 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
+from . import _trace
 from . import _capi as C
 from . import ops
 
@@ -62,6 +63,7 @@ class MotionCompensator:
         return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(self.device)
 
     # -- array API ---------------------------------------------------------------------------
+    @_trace.traced("MotionCompensator.compensate_arrays")
     def compensate_arrays(self, pts: np.ndarray, ts: np.ndarray, frame_off: np.ndarray, frame_start: np.ndarray,
                           imu_ts: np.ndarray, imu_gyro: np.ndarray, *, lvx2: bool = False,
                           tag: Optional[np.ndarray] = None):
@@ -91,6 +93,7 @@ class MotionCompensator:
         return out.cpu().numpy(), rec
 
     # -- the reference's operator (CS:1435-1480) ---------------------------------------------------
+    @_trace.traced("MotionCompensator.compensate_point_cloud")
     def compensate_point_cloud(self, points: List[LiDARPoint], imu_data: List[IMUData],
                                frame_start_time: int, frame_duration_ns: int) -> List[LiDARPoint]:
         """Apply motion compensation to point cloud using IMU data (one frame)."""
@@ -107,6 +110,7 @@ class MotionCompensator:
                            timestamp=p.timestamp, ring=p.ring, tag=p.tag) for o, p in zip(out, points)]
 
     # -- batched CS:2086-2105 (_apply_motion_compensation) -----------------------------------------
+    @_trace.traced("MotionCompensator.compensate_frames")
     def compensate_frames(self, frames_data: List[Dict], imu_data: List[IMUData]) -> List[Dict]:
         """All frames in one device call; returns new frame dicts with 'motion_compensated': True."""
         if not self.enable_compensation or not imu_data:

@@ -21,6 +21,8 @@ import torch
 from . import _capi as C
 from . import ops
 
+from . import _trace
+
 
 class CoordinateSystem:                 # CS:145-151
     SENSOR = "sensor"
@@ -77,12 +79,18 @@ class CoordinateTransformer:
         T[:3, 3] = translation
         return T
 
+    @_trace.traced("CoordinateTransformer.transform_points")
     def transform_points(self, points: np.ndarray, from_frame: str, to_frame: str) -> np.ndarray:
         """CS:214-233: (n,3) -> (n,3) in the target frame; unknown pair -> points returned unchanged.
         n == 1 reproduces the reference's single-point (gemv) summation order, n >= 2 the dgemm order."""
         if (from_frame, to_frame) not in self.transformations:
             return points
         points = np.asarray(points, np.float64)
+        if points.ndim != 2 or points.shape[1] != 3:
+            # CS:223-228 treats any other width as already homogeneous (column 3 multiplies the translation, other widths fail
+            # in the matmul); none of the reference's own callers does that, and the device kernel fixes w = 1 -- refuse
+            # instead of silently computing something else
+            raise ValueError(f"transform_points expects (n, 3) points, got {points.shape}")
         n = len(points)
         if n == 0:
             return points[:, :3].copy()
@@ -92,6 +100,7 @@ class CoordinateTransformer:
         return out.cpu().numpy()[:, :3]
 
     # -- batched CS:2107-2163 (_transform_coordinates) ---------------------------------------------
+    @_trace.traced("CoordinateTransformer.transform_frames")
     def transform_frames(self, frames_data: List[Dict], target_system: str, utm_offsets: Optional[np.ndarray] = None) -> List[Dict]:
         """All frames in one device call.  The reference transforms ONE point per ``transform_points`` call
         (CS:2117-2138), so the single-point summation order applies to every point.  For the UTM target

@@ -17,6 +17,7 @@ from typing import Dict, List
 import numpy as np
 import torch
 
+from . import _trace
 from . import _capi as C
 from . import ops
 
@@ -60,6 +61,7 @@ class DataExporter:
         return text.cpu().numpy().tobytes()
 
     # -- CS:1612-1641 ----------------------------------------------------------------------------
+    @_trace.traced("DataExporter.export_point_clouds")
     def export_point_clouds(self, frames_data: List[Dict], output_prefix: str = "lidar_data"):
         points = merge_frames(frames_data)
         if len(points) == 0:                                       # CS:1622-1624

@@ -16,6 +16,8 @@ from dataclasses import dataclass
 
 import numpy as np
 
+from . import _trace
+
 POINTS_PER_PACKAGE = 96          # LMC:48
 RECORD = 14
 PKG_HEADER = 22
@@ -167,6 +169,7 @@ class LivoxLVXWriter:
         self.format_version = format_version
         self.device = device
 
+    @_trace.traced("LivoxLVXWriter.build_bytes")
     def build_bytes(self, frames_data, device_info) -> np.ndarray:
         import torch
         from . import _capi as C
@@ -184,6 +187,7 @@ class LivoxLVXWriter:
             raise struct.error("argument out of range")                                 # struct.pack beyond the field, CS:372-373 / 319-320
         return data.cpu().numpy()
 
+    @_trace.traced("LivoxLVXWriter.write_lvx_file")
     def write_lvx_file(self, filename: str, frames_data, device_info) -> None:
         data = self.build_bytes(frames_data, device_info)
         with open(filename, 'wb') as f:

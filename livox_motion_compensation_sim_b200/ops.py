@@ -10,6 +10,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _capi as C
+from . import _trace
 
 
 def _stream_ptr() -> int:
@@ -41,7 +42,7 @@ def _on_tensor_device(fn):
             visit(v)
         if dev is None:
             return fn(*args, **kwargs)                      # no CUDA tensor: the operator's own checks raise
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _trace.span("lmc." + fn.__name__):
             return fn(*args, **kwargs)
     return wrapper
 

@@ -14,6 +14,7 @@ from typing import List, Optional
 import numpy as np
 import torch
 
+from . import _trace
 from . import _capi as C
 from . import ops
 
@@ -75,8 +76,7 @@ class StreamingAligner:
             self.sample_ts = torch.empty(S, dtype=torch.int64, device=self.device)
             self.seg = torch.empty((S, 22), dtype=torch.float64, device=self.device)
         F = len(self.frame_off) - 1
-        # chunk boundaries at whole frames, ~chunk_points each, point-aligned to 8 so every
-        # chunk's slice of the 14-byte record array starts 16-byte aligned on the host side
+        # chunk boundaries at whole frames, ~chunk_points each
         cuts = [0]
         while cuts[-1] < F:
             target = self.frame_off[cuts[-1]] + chunk_points
@@ -104,6 +104,7 @@ class StreamingAligner:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
+    @_trace.traced("StreamingAligner.run")
     def run(self, hs: HostStream) -> None:
         """One pass over the whole host stream.  Returns after all copies are enqueued; call
         torch.cuda.synchronize() (or wait on the streams) before reading hs.out / hs.lvx14."""
@@ -113,6 +114,7 @@ class StreamingAligner:
         ev_out: List[Optional[torch.cuda.Event]] = [None] * self.nbuf
         self.launches = self.h2d_bytes = self.d2h_bytes = 0
         cur = torch.cuda.current_stream(self.device)
+        self.d_status.zero_()                                        # NaN / overflow flags of THIS pass (flags() / raise_for_flags())
         for s in (self.s_in, self.s_k, self.s_out):
             s.wait_stream(cur)
         if self.pose_samples is not None:                           # pose stream: H2D + segment table on the device
@@ -166,3 +168,16 @@ class StreamingAligner:
                 ev_out[sl] = e
         for s in (self.s_in, self.s_k, self.s_out):
             cur.wait_stream(s)
+
+    def flags(self) -> int:
+        """NaN / overflow bits (C.FLAG_*) of the last run(); synchronises the device."""
+        torch.cuda.synchronize(self.device)
+        return int(self.d_status.item())
+
+    def raise_for_flags(self) -> None:
+        """What the reference's packer would have raised on the same stream (LMC:257 int(nan) -> ValueError)."""
+        f = self.flags()
+        if f & C.FLAG_NAN:
+            raise ValueError("cannot convert float NaN to integer")
+        if f & C.FLAG_OVERFLOW:
+            raise OverflowError("LVX record field out of range")

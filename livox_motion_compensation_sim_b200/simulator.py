@@ -22,6 +22,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import torch
 
+from . import _trace
 from . import _capi as C
 from . import frames as FR
 from . import ops
@@ -58,10 +59,12 @@ class LiDARMotionSimulator:
             # 'hold_next' = the reference's per-frame pose (LMC:802-812); 'slerp' = per-point deskew: every point's
             # timestamp is bracketed in the trajectory samples, orientation SLERPed, position lerped (north_star Mode C)
             'pose_interpolation': 'hold_next',
-            # results come back in page-locked host memory from torch's caching host allocator (a D2H copy into a fresh
-            # pageable array runs at ~2 GB/s: 30 of the 42 ms of an align_frames call on the reference's own run shapes);
-            # False = stage through the reusable pinned buffer and copy into an ordinary NumPy array
-            'pinned_results': True,
+            # False (default): results are ordinary NumPy arrays -- D2H into one reusable pinned staging buffer, then a threaded
+            # copy (lmc_host_copy); nothing stays page-locked behind the caller's back.
+            # True: opt-in throughput knob -- results ARE page-locked blocks of torch's caching host allocator (no second copy:
+            # align_frames 42 -> 7 ms on the reference's run shapes), which stay locked as long as any per-frame view of them
+            # lives and are cached afterwards (~2 x 2 GB for the reference's default run)
+            'pinned_results': False,
         }
 
     def _validate_config(self, config: Dict) -> None:
@@ -99,7 +102,7 @@ class LiDARMotionSimulator:
         """Device result -> host array the caller owns."""
         if t.device.type != 'cuda' or t.numel() == 0:
             return t.cpu().numpy()
-        if self.config.get('pinned_results', True):
+        if self.config.get('pinned_results', False):
             h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)      # cached block after the first call of a size
             h.copy_(t)
             return h.numpy()                                              # keeps the pinned block alive while referenced
@@ -138,6 +141,7 @@ class LiDARMotionSimulator:
         return out.cpu().numpy()
 
     # ------------------------------------------------------------------ (N4) LMC:701-770
+    @_trace.traced("LiDARMotionSimulator.scan_all")
     def scan_all(self, environment, positions, eulers, keep_device: bool = False) -> List[np.ndarray]:
         """scan_environment for every frame in ONE device pass (range / FOV cull, compaction, subsample);
         the noise is drawn on the host from the global NumPy RNG exactly as LMC:767 does, so a seeded
@@ -159,6 +163,7 @@ class LiDARMotionSimulator:
         return self.scan_all(environment, [sensor_pose['position']], [sensor_pose['orientation']])[0]
 
     # ------------------------------------------------------------------ (a2)+(a3) batched
+    @_trace.traced("LiDARMotionSimulator.align_frames")
     def align_frames(self, frames: Sequence[np.ndarray], positions: np.ndarray, eulers: np.ndarray,
                      export: Optional[ops.ExportSpec] = None):
         """The reference's frame loop body LMC:826-832 for every frame at once.
@@ -181,6 +186,7 @@ class LiDARMotionSimulator:
         return self._to_host(out), off, bufs
 
     # ------------------------------------------------------------------ LMC:778-858
+    @_trace.traced("LiDARMotionSimulator.run_simulation")
     def run_simulation(self, frame_source=None):
         """Run the simulation with the alignment step on the B200.
 
@@ -240,6 +246,7 @@ class LiDARMotionSimulator:
                 'gps_alt': p[2], 'imu_roll': o[0], 'imu_pitch': o[1], 'imu_yaw': o[2],
                 'vel_x': v[0], 'vel_y': v[1], 'vel_z': v[2]}
 
+    @_trace.traced("LiDARMotionSimulator.align_scans")
     def align_scans(self, raw_scans: List[dict], export: Optional[ops.ExportSpec] = None) -> List[np.ndarray]:
         """Batched LMC:826-832 over the reference's raw_scans list; keeps the merged buffer and the
         export buffers on ``self`` (last_merged / last_frame_off / last_export)."""
@@ -250,6 +257,7 @@ class LiDARMotionSimulator:
         self.last_merged, self.last_frame_off, self.last_export = merged, off, bufs
         return FR.split_frames(merged, off)
 
+    @_trace.traced("LiDARMotionSimulator.deskew_scans")
     def deskew_scans(self, raw_scans: List[dict], trajectory: Dict, export: Optional[ops.ExportSpec] = None,
                      _device_raw=None) -> List[np.ndarray]:
         """Per-point deskew + alignment (north_star Mode C; the reference has no such step -- parity is against the
@@ -270,13 +278,13 @@ class LiDARMotionSimulator:
         if flat_d is None:
             flat_d = self._to_dev(flat)
         period_ns = int(round(1e9 / float(self.config['lidar_fps'])))
-        fstart = np.array([int(s['timestamp'] * 1e9) for s in raw_scans], np.int64)
+        fstart = np.round(np.array([s['timestamp'] for s in raw_scans], np.float64) * 1e9).astype(np.int64)   # same conversion as the sample times below
         ts = np.empty(n, np.int64)
         for i, s in enumerate(raw_scans):
             m = int(off[i + 1] - off[i])
             if m:
                 pt = s.get('point_times')
-                ts[off[i]:off[i + 1]] = pt if pt is not None else fstart[i] + np.arange(m, dtype=np.int64) * (period_ns // m)
+                ts[off[i]:off[i + 1]] = pt if pt is not None else fstart[i] + (np.arange(m, dtype=np.int64) * period_ns) // m
         s_ts = np.round(np.asarray(trajectory['time'], np.float64) * 1e9).astype(np.int64)
         quat = Rotation.from_euler('xyz', np.asarray(trajectory['orientation_imu'], np.float64)).as_quat()
         seg = ops.build_slerp_table(self._to_dev(quat), self._to_dev(np.asarray(trajectory['position_gps'], np.float64)), self._to_dev(s_ts))
@@ -334,6 +342,7 @@ class LiDARMotionSimulator:
                 bufs.las_intensity.cpu().numpy())
 
     # ------------------------------------------------------------------ LMC:860-930 (hot-path outputs)
+    @_trace.traced("LiDARMotionSimulator.save_results")
     def save_results(self, results, output_dir='lidar_simulation_output'):
         """Writes the reference's hot-path outputs under the reference's names:
         aligned_scans_pcd/aligned_frame_%04d.pcd, raw_scans_pcd/frame_%04d.pcd, merged_aligned.pcd,
@@ -396,6 +405,7 @@ class LiDARMotionSimulator:
                     raise OverflowError("save_pcd: |value| >= 9.2e12 is outside the device formatter's range")
                 f.write(body.cpu().numpy().tobytes())
 
+    @_trace.traced("LiDARMotionSimulator.save_pcd_frames")
     def save_pcd_frames(self, frames: Sequence[np.ndarray], filenames: Sequence[str], merged_filename: Optional[str] = None):
         """save_pcd for a whole list of frames (LMC:870-884) plus their np.vstack (LMC:893-899) with ONE upload and
         ONE formatting pass: the frame-major buffer is formatted once, frame f's file body is the byte range between
@@ -429,6 +439,7 @@ class LiDARMotionSimulator:
                     f.write(text)
         return pts_d
 
+    @_trace.traced("LiDARMotionSimulator.save_las")
     def save_las(self, points, filename, _device_pts: Optional[torch.Tensor] = None):
         """merged_aligned.las (LMC:950-963): LAS 1.2 / point format 3 with the laspy header defaults the
         reference relies on (scale 0.01, offset 0; config 'las_scale' / 'las_offset'), intensity scaled to
@@ -444,6 +455,7 @@ class LiDARMotionSimulator:
         with open(filename, 'wb') as f:
             f.write(memoryview(self._to_host(data)))
 
+    @_trace.traced("LiDARMotionSimulator.save_lvx")
     def save_lvx(self, results, base_filename):
         """lidar_data.lvx with the LVX v1.1 container of LMC:58-250 around device-quantised records."""
         data = self.build_lvx_bytes(results)

@@ -708,6 +708,8 @@ def test_transform_frames_vs_reference(golden):
         assert [len(r['points']) for r in res] == list(np.diff(off)) and all(r['coordinate_system'] == k for r in res)
         assert np.array_equal(xyz(res), g['out_' + k])
         assert res[0]['points'][3].intensity == 3 and res[0]['points'][3].tag == 0
+    with pytest.raises(ValueError):                                   # (n,4) is 'already homogeneous' in CS:223-228: refused, not silently w = 1
+        ct.transform_points(np.ones((3, 4)), "sensor", "local")
     # one point through transform_points: same single-point order
     assert np.array_equal(ct.transform_points(g['pts'][7:8], "sensor", "local"), g['out_local'][7:8])
     # UTM: offsets per frame, or untouched without them (utm package absent, CS:2133-2134)
@@ -859,9 +861,10 @@ def test_save_results_files_are_save_pcd_files(golden, tmp_path):
                   'points_local': g['raw'][off[i]:off[i + 1]] if off[i + 1] > off[i] else np.array([]).reshape(0, 4),
                   'sensor_pose': {'position': g['pose_position'][i], 'orientation': g['pose_euler'][i], 'velocity': np.zeros(3)}}
                  for i in range(F)]
-    sim = LiDARMotionSimulator()
+    sim = LiDARMotionSimulator({'pinned_results': True})
     aligned = sim.align_scans(raw_scans)
-    sim2 = LiDARMotionSimulator({'pinned_results': False})
+    sim2 = LiDARMotionSimulator()
+    assert sim2.config['pinned_results'] is False          # page-locked results are opt-in
     aligned2 = sim2.align_scans(raw_scans)
     assert all(a.tobytes() == b.tobytes() for a, b in zip(aligned, aligned2))
     assert sim.last_merged.tobytes() == g['aligned'].tobytes() == sim2.last_merged.tobytes()
@@ -952,8 +955,8 @@ def test_run_simulation_slerp_pose_interpolation(golden):
     assert sha(got) != MAN['lmc']['C3']['aligned_sha256']              # ... and the alignment really is per point now
     # oracle: per-point times as deskew_scans defines them, SciPy Slerp + lerp over the trajectory samples
     period = int(round(1e9 / cfg['lidar_fps']))
-    ts = np.concatenate([int(s['timestamp'] * 1e9) + np.arange(len(s['points_local']), dtype=np.int64) * (period // max(len(s['points_local']), 1))
-                         for s in res['raw_scans']])
+    ts = np.concatenate([int(np.round(s['timestamp'] * 1e9)) + (np.arange(len(s['points_local']), dtype=np.int64) * period) // max(len(s['points_local']), 1)
+                         for s in res['raw_scans']])           # ONE time base: frame starts rounded like the sample times, offsets (i * period) // m
     s_ts = np.round(g['traj_time'] * 1e9).astype(np.int64)
     quat = Rotation.from_euler('xyz', g['traj_orientation_imu']).as_quat()
     want = orc.slerp_deskew_scipy(raw, ts, s_ts, quat, g['traj_position_gps'])
@@ -1214,6 +1217,18 @@ def test_host_buffer_pipeline_equals_resident(mode):
         torch.cuda.synchronize()
     assert torch.equal(hs.out, want.cpu()) and torch.equal(hs.lvx14, wb.lvx14.cpu())
     assert sa.h2d_bytes == N * (16 + (4 if mode == "slerp" else 0)) and sa.d2h_bytes == N * 30
+    assert sa.flags() == 0
+    sa.raise_for_flags()
+    # a NaN coordinate: where the reference's packer raises (LMC:257 int(nan)) the pass reports it -- and the flag is per pass
+    bad = hs.pts[N // 2, 1].item()
+    hs.pts[N // 2, 1] = float("nan")
+    sa.run(hs)
+    assert sa.flags() & C.FLAG_NAN
+    with pytest.raises(ValueError):
+        sa.raise_for_flags()
+    hs.pts[N // 2, 1] = bad
+    sa.run(hs)
+    assert sa.flags() == 0 and torch.equal(hs.out, want.cpu())
     if mode == "slerp":                                     # pose stream from the host: table built on the device inside run()
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()   # noqa: E731
         sb = StreamingAligner(DEV, st.frame_off, st.frame_start, mode="slerp", chunk_points=30_000, lvx=True,

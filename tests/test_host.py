@@ -416,3 +416,36 @@ def test_pcd_digit_count_thresholds_are_exact():
         assert Fraction(below) < thr < Fraction(c)
         assert "%.6f" % c == "1" + "0" * k + ".000000" and "%.6f" % below == "9" * k + ".999999"
         assert len("%.6f" % -c) == k + 9 and len("%.6f" % -below) == k + 8
+
+
+def test_nvtx_spans_are_off_by_default_and_balanced():
+    """_trace: ranges only when enabled (LMC_NVTX=1 / enable()); a raising body still closes its range."""
+    from livox_motion_compensation_sim_b200 import _trace
+    assert not _trace.enabled() or os.environ.get("LMC_NVTX", "0") not in ("", "0")
+    calls = []
+
+    @_trace.traced("t.f")
+    def f(x):
+        calls.append(_trace.depth())
+        if x < 0:
+            raise ValueError("neg")
+        return x + 1
+    was = _trace.enabled()
+    try:
+        _trace.enable(False)
+        assert f(1) == 2 and calls[-1] == 0
+        import torch
+        pushed = []
+        orig = torch.cuda.nvtx.range_push, torch.cuda.nvtx.range_pop
+        torch.cuda.nvtx.range_push = lambda name: pushed.append(name)
+        torch.cuda.nvtx.range_pop = lambda: pushed.append("pop")
+        try:
+            _trace.enable(True)
+            assert f(2) == 3 and calls[-1] == 1
+            with pytest.raises(ValueError):
+                f(-1)
+            assert _trace.depth() == 0 and pushed == ["t.f", "pop", "t.f", "pop"]
+        finally:
+            torch.cuda.nvtx.range_push, torch.cuda.nvtx.range_pop = orig
+    finally:
+        _trace.enable(was)
