@@ -452,11 +452,18 @@ def _redecide_uncertain(env, pos, Rm, flags, fov_h, fov_v, range_min) -> int:
     if fi.numel() == 0:
         return 0
     e = env[pi][:, :3].cpu().numpy()
-    p = pos[fi].cpu().numpy()
-    R = Rm[fi].cpu().numpy().reshape(-1, 3, 3)
+    fi_h = fi.cpu().numpy()
+    p = pos.cpu().numpy()[fi_h]
+    Rall = Rm.cpu().numpy().reshape(-1, 3, 3)
     rel = e - p
     d2 = np.sum(rel ** 2, axis=1)
-    rot = np.stack([(R[k].T @ rel[k:k + 1].T).T[0] for k in range(len(rel))])
+    rot = np.empty_like(rel)
+    # one matmul per FRAME that has flagged points (torch.nonzero is frame-major, so each frame's points are one slice) --
+    # the reference's own expression (LMC:726: R.T @ rel.T over the frame's points), not a Python iteration per point
+    starts = np.flatnonzero(np.r_[True, fi_h[1:] != fi_h[:-1]])
+    ends = np.r_[starts[1:], len(fi_h)]
+    for a, b in zip(starts, ends):
+        rot[a:b] = (Rall[fi_h[a]].T @ rel[a:b].T).T
     x, y, z = rot[:, 0], rot[:, 1], rot[:, 2]
     ranges = np.sqrt(d2)
     azimuth = np.arctan2(y, x) * 180 / np.pi
