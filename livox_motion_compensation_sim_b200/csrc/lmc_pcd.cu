@@ -525,6 +525,28 @@ struct TextNum { uint64_t ip; uint32_t fq; uint32_t len; uint8_t kind; bool neg;
 
 __device__ __constant__ double kPow10d[10] = { 1.0, 10.0, 100.0, 1.0e3, 1.0e4, 1.0e5, 1.0e6, 1.0e7, 1.0e8, 1.0e9 };
 
+// Digit count of the ROUNDED integer part of "%.{d}f" % a without making a digit: the printed value reaches 10^k exactly when
+// a >= 10^k - 0.5 * 10^-d (a tie there goes to the even neighbour, and 10^(k+d) is even), so the count is found by comparing with
+// kTextT[d][k] = the smallest double >= that real number (generated with exact fractions; tests/test_host.py re-derives the table).
+// Which k to compare with follows from the binary exponent: 2^e <= a < 2^(e+1) has floor(e * log10 2) + 1 or + 2 digits.
+__device__ const double kTextT[10][20] = {
+    { 0.0, 0x1.3000000000000p+3, 0x1.8e00000000000p+6, 0x1.f3c0000000000p+9, 0x1.387c000000000p+13, 0x1.869f800000000p+16, 0x1.e847f00000000p+19, 0x1.312cff0000000p+23, 0x1.7d783fe000000p+26, 0x1.dcd64ffc00000p+29, 0x1.2a05f1ffc0000p+33, 0x1.74876e7ff8000p+36, 0x1.d1a94a1fff000p+39, 0x1.2309ce53fff00p+43, 0x1.6bcc41e8fffe0p+46, 0x1.c6bf52633fffcp+49, 0x1.1c37937e08000p+53, 0x1.6345785d8a000p+56, 0x1.bc16d674ec800p+59, 0x1.158e460913d00p+63 },
+    { 0.0, 0x1.3e66666666667p+3, 0x1.8fccccccccccdp+6, 0x1.f3f999999999ap+9, 0x1.387f99999999ap+13, 0x1.869ff33333334p+16, 0x1.e847fe6666667p+19, 0x1.312cffe666667p+23, 0x1.7d783ffcccccdp+26, 0x1.dcd64fff9999ap+29, 0x1.2a05f1fff999ap+33, 0x1.74876e7fff334p+36, 0x1.d1a94a1fffe67p+39, 0x1.2309ce53fffe7p+43, 0x1.6bcc41e8ffffdp+46, 0x1.c6bf526340000p+49, 0x1.1c37937e08000p+53, 0x1.6345785d8a000p+56, 0x1.bc16d674ec800p+59, 0x1.158e460913d00p+63 },
+    { 0.0, 0x1.3fd70a3d70a3ep+3, 0x1.8ffae147ae148p+6, 0x1.f3ff5c28f5c29p+9, 0x1.387ff5c28f5c3p+13, 0x1.869ffeb851eb9p+16, 0x1.e847ffd70a3d8p+19, 0x1.312cfffd70a3ep+23, 0x1.7d783fffae148p+26, 0x1.dcd64ffff5c29p+29, 0x1.2a05f1ffff5c3p+33, 0x1.74876e7fffeb9p+36, 0x1.d1a94a1ffffd8p+39, 0x1.2309ce53ffffep+43, 0x1.6bcc41e900000p+46, 0x1.c6bf526340000p+49, 0x1.1c37937e08000p+53, 0x1.6345785d8a000p+56, 0x1.bc16d674ec800p+59, 0x1.158e460913d00p+63 },
+    { 0.0, 0x1.3ffbe76c8b43ap+3, 0x1.8fff7ced91688p+6, 0x1.f3ffef9db22d1p+9, 0x1.387ffef9db22ep+13, 0x1.869fffdf3b646p+16, 0x1.e847fffbe76c9p+19, 0x1.312cffffbe76dp+23, 0x1.7d783ffff7ceep+26, 0x1.dcd64ffffef9ep+29, 0x1.2a05f1ffffefap+33, 0x1.74876e7ffffe0p+36, 0x1.d1a94a1fffffcp+39, 0x1.2309ce5400000p+43, 0x1.6bcc41e900000p+46, 0x1.c6bf526340000p+49, 0x1.1c37937e08000p+53, 0x1.6345785d8a000p+56, 0x1.bc16d674ec800p+59, 0x1.158e460913d00p+63 },
+    { 0.0, 0x1.3fff972474539p+3, 0x1.8ffff2e48e8a8p+6, 0x1.f3fffe5c91d15p+9, 0x1.387fffe5c91d2p+13, 0x1.869ffffcb923bp+16, 0x1.e847ffff97248p+19, 0x1.312cfffff9725p+23, 0x1.7d783fffff2e5p+26, 0x1.dcd64fffffe5dp+29, 0x1.2a05f1fffffe6p+33, 0x1.74876e7fffffdp+36, 0x1.d1a94a2000000p+39, 0x1.2309ce5400000p+43, 0x1.6bcc41e900000p+46, 0x1.c6bf526340000p+49, 0x1.1c37937e08000p+53, 0x1.6345785d8a000p+56, 0x1.bc16d674ec800p+59, 0x1.158e460913d00p+63 },
+    { 0.0, 0x1.3ffff583a53b9p+3, 0x1.8ffffeb074a78p+6, 0x1.f3ffffd60e94fp+9, 0x1.387ffffd60e95p+13, 0x1.869fffffac1d3p+16, 0x1.e847fffff583bp+19, 0x1.312cffffff584p+23, 0x1.7d783fffffeb1p+26, 0x1.dcd64ffffffd7p+29, 0x1.2a05f1ffffffep+33, 0x1.74876e8000000p+36, 0x1.d1a94a2000000p+39, 0x1.2309ce5400000p+43, 0x1.6bcc41e900000p+46, 0x1.c6bf526340000p+49, 0x1.1c37937e08000p+53, 0x1.6345785d8a000p+56, 0x1.bc16d674ec800p+59, 0x1.158e460913d00p+63 },
+    { 0.0, 0x1.3ffffef390860p+3, 0x1.8fffffde7210cp+6, 0x1.f3fffffbce422p+9, 0x1.387fffffbce43p+13, 0x1.869ffffff79c9p+16, 0x1.e847fffffef3ap+19, 0x1.312cffffffef4p+23, 0x1.7d783ffffffdfp+26, 0x1.dcd64fffffffcp+29, 0x1.2a05f20000000p+33, 0x1.74876e8000000p+36, 0x1.d1a94a2000000p+39, 0x1.2309ce5400000p+43, 0x1.6bcc41e900000p+46, 0x1.c6bf526340000p+49, 0x1.1c37937e08000p+53, 0x1.6345785d8a000p+56, 0x1.bc16d674ec800p+59, 0x1.158e460913d00p+63 },
+    { 0.0, 0x1.3fffffe5280d7p+3, 0x1.8ffffffca501bp+6, 0x1.f3ffffff94a04p+9, 0x1.387ffffff94a1p+13, 0x1.869fffffff295p+16, 0x1.e847ffffffe53p+19, 0x1.312cfffffffe6p+23, 0x1.7d783fffffffdp+26, 0x1.dcd6500000000p+29, 0x1.2a05f20000000p+33, 0x1.74876e8000000p+36, 0x1.d1a94a2000000p+39, 0x1.2309ce5400000p+43, 0x1.6bcc41e900000p+46, 0x1.c6bf526340000p+49, 0x1.1c37937e08000p+53, 0x1.6345785d8a000p+56, 0x1.bc16d674ec800p+59, 0x1.158e460913d00p+63 },
+    { 0.0, 0x1.3ffffffd50ce3p+3, 0x1.8fffffffaa19dp+6, 0x1.f3fffffff5434p+9, 0x1.387fffffff544p+13, 0x1.869fffffffea9p+16, 0x1.e847fffffffd6p+19, 0x1.312cffffffffep+23, 0x1.7d78400000000p+26, 0x1.dcd6500000000p+29, 0x1.2a05f20000000p+33, 0x1.74876e8000000p+36, 0x1.d1a94a2000000p+39, 0x1.2309ce5400000p+43, 0x1.6bcc41e900000p+46, 0x1.c6bf526340000p+49, 0x1.1c37937e08000p+53, 0x1.6345785d8a000p+56, 0x1.bc16d674ec800p+59, 0x1.158e460913d00p+63 },
+    { 0.0, 0x1.3fffffffbb47ep+3, 0x1.8ffffffff7690p+6, 0x1.f3fffffffeed2p+9, 0x1.387fffffffeeep+13, 0x1.869ffffffffdep+16, 0x1.e847ffffffffcp+19, 0x1.312d000000000p+23, 0x1.7d78400000000p+26, 0x1.dcd6500000000p+29, 0x1.2a05f20000000p+33, 0x1.74876e8000000p+36, 0x1.d1a94a2000000p+39, 0x1.2309ce5400000p+43, 0x1.6bcc41e900000p+46, 0x1.c6bf526340000p+49, 0x1.1c37937e08000p+53, 0x1.6345785d8a000p+56, 0x1.bc16d674ec800p+59, 0x1.158e460913d00p+63 },
+};
+__device__ __forceinline__ uint32_t text_nd(double a, int d) {        // 0 <= a < 2^64
+    const int e = (int)(((uint32_t)__double2hiint(a) >> 20) & 0x7ffu) - 1023;
+    const int k0 = e > 0 ? (e * 1233) >> 12 : 0;
+    return (uint32_t)k0 + 1u + (a >= __ldg(&kTextT[d][k0 + 1]) ? 1u : 0u);
+}
+
 // Same exact-FP64 scheme as fmt_prepare: ip = trunc(|v|) (exact below 2^64), fr = |v| - ip (exact),
 // hi + lo = fr * 10^d exactly (10^d has <= 21 significant bits), q = floor(hi), tie test on (hi - q) - 0.5
 // with lo as the tie breaker; ties go to the even last printed digit (ip's when d == 0).
@@ -538,13 +560,22 @@ __device__ __forceinline__ TextNum fmtg_prepare(double v, int d, uint32_t& fl) {
         uint64_t ip = __double2ull_rz(a);
         const double fr = __dsub_rn(a, __ull2double_rn(ip));
         const double p10 = kPow10d[d];
-        const double hi = __dmul_rn(fr, p10), lo = __fma_rn(fr, p10, -hi);
-        uint32_t q = __double2uint_rz(hi);
-        const double dd = __dsub_rn(__dsub_rn(hi, __uint2double_rn(q)), 0.5);
-        const bool odd = d ? (q & 1u) : (uint32_t)(ip & 1ull);
-        if (dd > 0.0 || (dd == 0.0 && (lo > 0.0 || (lo == 0.0 && odd)))) q += 1;
+        const double hi = __dmul_rn(fr, p10);
+        // RNE(hi) is the answer unless hi sits exactly on a tie k + 0.5 -- the only place where the FMA error term lo = fr * 10^d - hi
+        // can change the decision (k + 0.5 is itself a double and rounding is monotonic); an exact tie goes to the even last
+        // printed digit (ip's when d == 0)
+        uint32_t q = __double2uint_rn(hi);
+        if (fabs(__dsub_rn(hi, __uint2double_rn(q))) == 0.5) {
+            const double lo = __fma_rn(fr, p10, -hi);
+            const uint32_t dn = __double2uint_rz(hi);
+            if (lo > 0.0) q = dn + 1u;
+            else if (lo < 0.0) q = dn;
+            else q = dn + ((d ? (dn & 1u) : (uint32_t)(ip & 1ull)) ? 1u : 0u);
+        }
         if (q >= kPow10[d]) { q -= kPow10[d]; ip += 1; }
         t.ip = ip; t.fq = q;
+        t.len = (t.neg ? 1u : 0u) + text_nd(a, d) + (d ? 1u + (uint32_t)d : 0u);
+        return t;
     } else if (a != a) {
         t.kind = 1; t.len = 3u; return t;
     } else if (isinf(a)) {
@@ -552,41 +583,15 @@ __device__ __forceinline__ TextNum fmtg_prepare(double v, int d, uint32_t& fl) {
     } else {
         fl |= LMC_FLAG_OVERFLOW; t.ip = 0xffffffffffffffffull;
     }
-    uint32_t nd;
-    if (t.ip < 1000000ull) {
-        const uint32_t x = (uint32_t)t.ip;
-        nd = 1u + (x >= 10u) + (x >= 100u) + (x >= 1000u) + (x >= 10000u) + (x >= 100000u);
-    } else {
-        nd = 7;
-        for (uint64_t x = t.ip / 1000000ull; x >= 10; x /= 10) ++nd;
-    }
-    t.len = (t.neg ? 1u : 0u) + nd + (d ? 1u + (uint32_t)d : 0u);
+    t.len = (t.neg ? 1u : 0u) + 20u + (d ? 1u + (uint32_t)d : 0u);     // finite >= 2^64: saturated to 2^64 - 1 (20 digits), flagged
     return t;
 }
-
-__device__ __forceinline__ int fmtg_write(uint8_t* dst, int d, const TextNum& t) {
-    if (t.kind) {
-        int o = 0;
-        if (t.kind == 2 && t.neg) dst[o++] = '-';
-        if (t.kind == 1) { dst[o] = 'n'; dst[o + 1] = 'a'; dst[o + 2] = 'n'; }
-        else             { dst[o] = 'i'; dst[o + 1] = 'n'; dst[o + 2] = 'f'; }
-        return o + 3;
-    }
-    int o = (int)t.len;
-    if (d) {
-        uint32_t fp = t.fq;
-        for (int k = 0; k < d; ++k) { dst[--o] = (uint8_t)('0' + fp % 10u); fp /= 10u; }
-        dst[--o] = '.';
-    }
-    if (t.ip < 1000000000ull) {
-        uint32_t x = (uint32_t)t.ip;
-        do { dst[--o] = (uint8_t)('0' + x % 10u); x /= 10u; } while (x);
-    } else {
-        uint64_t ip = t.ip;
-        do { dst[--o] = (uint8_t)('0' + (uint32_t)(ip % 10ull)); ip /= 10ull; } while (ip);
-    }
-    if (t.neg) dst[--o] = '-';
-    return (int)t.len;
+// text length of "%.{d}f" % v: no digits, one table compare
+__device__ __noinline__ uint2 text_len_slow_eval(double v, int d) { uint32_t fl = 0; const uint32_t len = fmtg_prepare(v, d, fl).len; return make_uint2(len, fl); }
+__device__ __forceinline__ uint32_t text_len(double v, int d, uint32_t& fl) {
+    const double a = fabs(v);
+    if (!(a < 18446744073709551616.0)) { const uint2 r = text_len_slow_eval(v, d); fl |= r.y; return r.x; }     // nan, inf, >= 2^64
+    return ((uint32_t)__double2hiint(v) >> 31) + text_nd(a, d) + (d ? 1u + (uint32_t)d : 0u);
 }
 
 template <bool F64>
@@ -595,24 +600,128 @@ __device__ __forceinline__ double load_cell(const void* rows, int64_t idx) {
     else return (double)__ldg(reinterpret_cast<const float*>(rows) + idx);
 }
 
-template <bool F64>
+// The format is a launch parameter (TextFmt), but every runtime test on it sits inside the per-number code: the three formats the
+// second simulator writes -- pcd '%.6f %.6f %.6f %.0f %.0f', xyz '%.6f' x 3, csv '%.6f' x 5, identity column pick (CS:1664 / 1703 /
+// 1711) -- are compiled with the column count and the decimals as template constants (NC > 0, DP = 4 bits per column); anything
+// else runs the same code with NC = 0 and reads them from F.
+template <int NC, uint32_t DP> struct TextSpec {
+    static __device__ __forceinline__ int ncols(const TextFmt& F) { return NC ? NC : F.n_cols; }
+    static __device__ __forceinline__ int dec(const TextFmt& F, int c) { return NC ? (int)((DP >> (4 * c)) & 15u) : F.dec[c]; }
+    static __device__ __forceinline__ int64_t cell(const TextFmt& F, int64_t i, int c) { return NC ? i * F.row_stride + c : i * F.row_stride + F.col[c]; }
+};
+
+// size pass: the rows' text lengths summed per 256-row tile (warp redux, no scan)
+template <bool F64, int NC, uint32_t DP>
 __global__ void __launch_bounds__(kPcdTile) k_text_len(const void* __restrict__ rows, int64_t n, const __grid_constant__ TextFmt F, int64_t* __restrict__ tile_off) {
+    using S = TextSpec<NC, DP>;
     __shared__ uint32_t s_warp[kPcdTile / 32];
     const int64_t i = (int64_t)blockIdx.x * kPcdTile + threadIdx.x;
     uint32_t len = 0, fl = 0;
     if (i < n) {
-        len = (uint32_t)F.n_cols;                                    // separators + newline
+        len = (uint32_t)S::ncols(F);                                 // separators + newline
 #pragma unroll
-        for (int c = 0; c < kTextCols; ++c) if (c < F.n_cols) len += fmtg_prepare(load_cell<F64>(rows, i * F.row_stride + F.col[c]), F.dec[c], fl).len;
+        for (int c = 0; c < kTextCols; ++c) if (c < S::ncols(F)) len += text_len(load_cell<F64>(rows, S::cell(F, i, c)), S::dec(F, c), fl);
     }
-    uint32_t total;
-    block_scan_excl(len, s_warp, total);
-    if (threadIdx.x == 0) tile_off[blockIdx.x + 1] = total;
+    const uint32_t sum = __reduce_add_sync(0xffffffffu, len);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int k = 0; k < kPcdTile / 32; ++k) total += s_warp[k];
+        tile_off[blockIdx.x + 1] = total;
+    }
 }
 
-template <bool F64>
+// Word stream of one row into the (zero-filled) tile image.  Rows of the generic writer are heterogeneous (any mix of column
+// widths), so the word a row shares with its predecessor is not handed over in registers as in the PCD writer: the row's FIRST
+// completed word and its last partial word are OR-ed into the image (shared-memory atomics commute), every word in between is
+// a plain store.
+struct TextStream {
+    uint32_t addr, sh, a0; bool first;
+    __device__ __forceinline__ void start(uint32_t img_s, uint32_t pos) { addr = img_s + (pos & ~3u); sh = 8u * (pos & 3u); a0 = 0u; first = true; }
+    // MODE 0: plain store; 1: OR (the word may be the one shared with the previous row); 2: decide at run time (generic formats)
+    template <int MODE>
+    __device__ __forceinline__ void out(uint32_t w) {
+        if (MODE == 1 || (MODE == 2 && first)) { asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(addr), "r"(w) : "memory"); first = false; }
+        else asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(w) : "memory");
+        addr += 4u;
+    }
+    template <int MODE>
+    __device__ __forceinline__ void put(uint32_t chunk, uint32_t k) {   // the k (1..4) low bytes of chunk, the others 0
+        const uint32_t w0 = a0 | (chunk << sh);
+        const uint32_t hi = __funnelshift_l(chunk, 0u, sh);
+        const uint32_t nsh = sh + 8u * k;
+        if (nsh >= 32u) { out<MODE>(w0); a0 = hi; } else a0 = w0;
+        sh = nsh & 31u;
+    }
+    template <int MODE>
+    __device__ __forceinline__ void put4(uint32_t w) { out<MODE>(a0 | (w << sh)); a0 = __funnelshift_l(w, 0u, sh); }
+    __device__ __forceinline__ void finish() { if (sh) asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(addr), "r"(a0) : "memory"); }
+};
+// x < 10^8 printed with nd (1..8) digits / with all 8 digits
+template <int MODE>
+__device__ __forceinline__ void emit_u8(TextStream& ts, uint32_t x, uint32_t nd) {
+    if (nd > 4u) {
+        const uint32_t h = (uint32_t)(((uint64_t)x * 3518437209ull) >> 45);       // x / 10^4, exact for 32-bit x
+        ts.put<MODE>(swar4(h) >> (8u * (8u - nd)), nd - 4u);
+        ts.put4<MODE>(swar4(x - h * 10000u));
+    } else ts.put<MODE>(swar4(x) >> (8u * (4u - nd)), nd);
+}
+template <int MODE>
+__device__ __forceinline__ void emit_u8_full(TextStream& ts, uint32_t x) {
+    const uint32_t h = (uint32_t)(((uint64_t)x * 3518437209ull) >> 45);
+    ts.put4<MODE>(swar4(h));
+    ts.put4<MODE>(swar4(x - h * 10000u));
+}
+// one number + separator: sign, integer digits in groups of four (SWAR), fraction, separator
+template <int MODE>
+__device__ __forceinline__ void emit_number(TextStream& ts, const TextNum& t, int d, uint32_t sep) {
+    if (t.kind) {                                                      // "nan" | "inf" | "-inf"
+        if (t.kind == 2 && t.neg) ts.put<MODE>(0x2du, 1u);
+        ts.put<MODE>(t.kind == 1 ? 0x006e616eu : 0x00666e69u, 3u);
+        ts.put<MODE>(sep, 1u);
+        return;
+    }
+    if (t.neg) ts.put<MODE>(0x2du, 1u);
+    const uint32_t nd = t.len - (t.neg ? 1u : 0u) - (d ? 1u + (uint32_t)d : 0u);
+    if (t.ip < 100000000ull) emit_u8<MODE>(ts, (uint32_t)t.ip, nd);
+    else if (t.ip < 10000000000000000ull) {
+        const uint64_t h = t.ip / 100000000ull;
+        emit_u8<MODE>(ts, (uint32_t)h, nd - 8u);
+        emit_u8_full<MODE>(ts, (uint32_t)(t.ip - h * 100000000ull));
+    } else {
+        const uint64_t h = t.ip / 10000000000000000ull, r = t.ip - h * 10000000000000000ull, m = r / 100000000ull;
+        emit_u8<MODE>(ts, (uint32_t)h, nd - 16u);
+        emit_u8_full<MODE>(ts, (uint32_t)m);
+        emit_u8_full<MODE>(ts, (uint32_t)(r - m * 100000000ull));
+    }
+    if (d) {
+        // the d fraction digits = the last d characters of the 9-digit zero-padded fq
+        const uint32_t top = t.fq / 100000000u, r8 = t.fq - top * 100000000u;
+        const uint32_t h = (uint32_t)(((uint64_t)r8 * 3518437209ull) >> 45);
+        const uint64_t ab = (uint64_t)swar4(h) | ((uint64_t)swar4(r8 - h * 10000u) << 32);      // 8 digits, most significant in byte 0
+        if (d == 6) {                                                  // ".dddddd<sep>": two whole words
+            const uint64_t x = ab >> 16;
+            ts.put4<MODE>(0x2eu | ((uint32_t)x << 8));
+            ts.put4<MODE>(((uint32_t)x >> 24) | ((uint32_t)(x >> 32) << 8) | (sep << 24));
+            return;
+        }
+        ts.put<MODE>(0x2eu, 1u);
+        if (d == 9) ts.put<MODE>(0x30u + top, 1u);
+        const uint32_t dd = d == 9 ? 8u : (uint32_t)d;
+        const uint64_t x = ab >> (8u * (8u - dd));
+        if (dd > 4u) { ts.put4<MODE>((uint32_t)x); ts.put<MODE>((uint32_t)(x >> 32), dd - 4u); }
+        else ts.put<MODE>((uint32_t)x, dd);
+    }
+    ts.put<MODE>(sep, 1u);
+}
+
+// write pass: one row per thread, 256 rows per tile; exact (ip, fq) per number by fmtg_prepare, digits by SWAR groups, word stream
+template <bool F64, int NC, uint32_t DP>
 __global__ void __launch_bounds__(kPcdTile) k_text_write(const void* __restrict__ rows, int64_t n, const __grid_constant__ TextFmt F,
                                                          const int64_t* __restrict__ tile_off, uint8_t* __restrict__ out, uint32_t* __restrict__ status) {
+    using S = TextSpec<NC, DP>;
     extern __shared__ __align__(16) uint8_t s_dyn[];                 // the tile's text image, sized by the host from the format
     __shared__ uint32_t s_warp[kPcdTile / 32];
     uint8_t* s_img = s_dyn;
@@ -620,25 +729,44 @@ __global__ void __launch_bounds__(kPcdTile) k_text_write(const void* __restrict_
     const int64_t i = (int64_t)blockIdx.x * kPcdTile + tid;
     const int64_t dst0 = tile_off[blockIdx.x];
     const int phase = (int)(dst0 & 15);
+    // zero the part of the image this tile can reach (row edges are OR-ed in)
+    const int img_words = (int)((phase + (tile_off[blockIdx.x + 1] - dst0) + 3 + 15) / 16) * 4;
+    for (int k = tid * 4; k < img_words; k += kPcdTile * 4) *reinterpret_cast<uint4*>(s_img + 4 * k) = make_uint4(0, 0, 0, 0);
     TextNum t[kTextCols];
     uint32_t len = 0, fl = 0;
     if (i < n) {
-        len = (uint32_t)F.n_cols;
+        len = (uint32_t)S::ncols(F);
 #pragma unroll
-        for (int c = 0; c < kTextCols; ++c) if (c < F.n_cols) {
-            t[c] = fmtg_prepare(load_cell<F64>(rows, i * F.row_stride + F.col[c]), F.dec[c], fl);
+        for (int c = 0; c < kTextCols; ++c) if (c < S::ncols(F)) {
+            t[c] = fmtg_prepare(load_cell<F64>(rows, S::cell(F, i, c)), S::dec(F, c), fl);
             len += t[c].len;
         }
     }
     uint32_t total;
-    const uint32_t off = block_scan_excl(len, s_warp, total);
+    const uint32_t off = block_scan_excl(len, s_warp, total);       // (its barrier also orders the zero fill before the ORs)
     if (i < n) {
-        uint8_t* d = s_img + phase + off;
+        TextStream ts;
+        ts.start(smem_u32(s_img), (uint32_t)phase + off);
+        const uint32_t sep = (uint32_t)F.sep;
+        // compiled formats start with a '%.6f' column (>= 9 bytes): the word shared with the previous row completes inside it
+        if (S::ncols(F) > 0) emit_number<NC ? 1 : 2>(ts, t[0], S::dec(F, 0), S::ncols(F) == 1 ? 0x0au : sep);
 #pragma unroll
-        for (int c = 0; c < kTextCols; ++c) if (c < F.n_cols) { d += fmtg_write(d, F.dec[c], t[c]); *d++ = c == F.n_cols - 1 ? (uint8_t)'\n' : F.sep; }
+        for (int c = 1; c < kTextCols; ++c) if (c < S::ncols(F)) emit_number<NC ? 0 : 2>(ts, t[c], S::dec(F, c), c == S::ncols(F) - 1 ? 0x0au : sep);
+        ts.finish();
     }
     cta_image_out(out + (dst0 - phase), s_img, phase, phase + (int)total, tid, kPcdTile);
     if (fl != 0 && status != nullptr) atomicOr(status, fl);
+}
+
+// the compiled formats (TextSpec): decimals 4 bits per column, identity column pick
+constexpr uint32_t kDpPcd = 0x00666u, kDpXyz = 0x666u, kDpCsv = 0x66666u;
+static int text_spec_of(int32_t n_cols, const int32_t* col, const int32_t* dec) {      // 0 generic, 1 pcd, 2 xyz, 3 csv
+    uint32_t dp = 0;
+    for (int c = 0; c < n_cols; ++c) { if (col[c] != c) return 0; dp |= (uint32_t)dec[c] << (4 * c); }
+    if (n_cols == 5 && dp == kDpPcd) return 1;
+    if (n_cols == 3 && dp == kDpXyz) return 2;
+    if (n_cols == 5 && dp == kDpCsv) return 3;
+    return 0;
 }
 
 static TextFmt make_fmt(int32_t n_cols, int32_t row_stride, const int32_t* col, const int32_t* dec, uint8_t sep, int& img_bytes) {
@@ -657,26 +785,46 @@ cudaError_t launch_text_size(bool f64, const void* rows, int64_t n, int32_t n_co
     int img;
     const TextFmt F = make_fmt(n_cols, row_stride, col, dec, sep, img);
     if (tiles > 0) {
-        if (f64) k_text_len<true><<<(unsigned)tiles, kPcdTile, 0, st>>>(rows, n, F, tile_off);
-        else     k_text_len<false><<<(unsigned)tiles, kPcdTile, 0, st>>>(rows, n, F, tile_off);
+        const unsigned g = (unsigned)tiles;
+#define LMC_TEXT_LEN(NC, DP) do { if (f64) k_text_len<true, NC, DP><<<g, kPcdTile, 0, st>>>(rows, n, F, tile_off); \
+                                  else     k_text_len<false, NC, DP><<<g, kPcdTile, 0, st>>>(rows, n, F, tile_off); } while (0)
+        switch (text_spec_of(n_cols, col, dec)) {
+        case 1:  LMC_TEXT_LEN(5, kDpPcd); break;
+        case 2:  LMC_TEXT_LEN(3, kDpXyz); break;
+        case 3:  LMC_TEXT_LEN(5, kDpCsv); break;
+        default: LMC_TEXT_LEN(0, 0u); break;
+        }
+#undef LMC_TEXT_LEN
     }
     return launch_tile_scan(tile_off, tiles, st);
 }
 
+template <bool F64, int NC, uint32_t DP>
+static cudaError_t launch_text_write_as(const void* rows, int64_t n, const TextFmt& F, int img, const int64_t* tile_off, uint8_t* out,
+                                        uint32_t* status, unsigned tiles, cudaStream_t st) {
+    if (img > 48 * 1024) {                                           // widest formats only (6 columns x 9 decimals = 49 KB)
+        cudaError_t e = cudaFuncSetAttribute(k_text_write<F64, NC, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, img);
+        if (e != cudaSuccess) return e;
+    }
+    k_text_write<F64, NC, DP><<<tiles, kPcdTile, img, st>>>(rows, n, F, tile_off, out, status);
+    return cudaGetLastError();
+}
 cudaError_t launch_text_write(bool f64, const void* rows, int64_t n, int32_t n_cols, int32_t row_stride, const int32_t* col, const int32_t* dec,
                               uint8_t sep, const int64_t* tile_off, uint8_t* out, uint32_t* status, cudaStream_t st) {
     const int64_t tiles = (n + kPcdTile - 1) / kPcdTile;
     if (tiles == 0) return cudaSuccess;
     int img;
     const TextFmt F = make_fmt(n_cols, row_stride, col, dec, sep, img);
-    cudaError_t e = cudaSuccess;
-    if (img > 48 * 1024)                                             // widest formats only (6 columns x 9 decimals = 49 KB)
-        e = f64 ? cudaFuncSetAttribute(k_text_write<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, img)
-                : cudaFuncSetAttribute(k_text_write<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, img);
-    if (e != cudaSuccess) return e;
-    if (f64) k_text_write<true><<<(unsigned)tiles, kPcdTile, img, st>>>(rows, n, F, tile_off, out, status);
-    else     k_text_write<false><<<(unsigned)tiles, kPcdTile, img, st>>>(rows, n, F, tile_off, out, status);
-    return cudaGetLastError();
+    const unsigned g = (unsigned)tiles;
+#define LMC_TEXT_WRITE(NC, DP) (f64 ? launch_text_write_as<true, NC, DP>(rows, n, F, img, tile_off, out, status, g, st) \
+                                    : launch_text_write_as<false, NC, DP>(rows, n, F, img, tile_off, out, status, g, st))
+    switch (text_spec_of(n_cols, col, dec)) {
+    case 1:  return LMC_TEXT_WRITE(5, kDpPcd);
+    case 2:  return LMC_TEXT_WRITE(3, kDpXyz);
+    case 3:  return LMC_TEXT_WRITE(5, kDpCsv);
+    default: return LMC_TEXT_WRITE(0, 0u);
+    }
+#undef LMC_TEXT_WRITE
 }
 
 cudaError_t launch_pcd_size(bool f64, const void* pts, int64_t n, int64_t* tile_off, cudaStream_t st) {

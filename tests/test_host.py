@@ -418,6 +418,40 @@ def test_pcd_digit_count_thresholds_are_exact():
         assert len("%.6f" % -c) == k + 9 and len("%.6f" % -below) == k + 8
 
 
+def test_text_digit_count_table_is_exact():
+    """csrc/lmc_pcd.cu: kTextT[d][k] = the smallest double >= 10^k - 0.5 * 10^-d, and the exponent-based choice of k
+    (text_nd): re-derive all 190 constants with exact fractions, check the boundary doubles against CPython's formatting,
+    and replay text_nd on the host for random magnitudes and every d."""
+    import math
+    from fractions import Fraction
+    src = open(os.path.join(ROOT, "livox_motion_compensation_sim_b200", "csrc", "lmc_pcd.cu")).read()
+    m = re.search(r"kTextT\[10\]\[20\]\s*=\s*\{(.*?)\n\};", src, re.S)
+    rows = re.findall(r"\{([^{}]*)\}", m.group(1))
+    T = [[float.fromhex(t.strip()) if "x" in t else float(t) for t in r.split(",")] for r in rows]
+    assert len(T) == 10 and all(len(r) == 20 for r in T)
+    for d in range(10):
+        for k in range(1, 20):
+            thr = Fraction(10) ** k - Fraction(1, 2) / Fraction(10) ** d
+            c = T[d][k]
+            below = math.nextafter(c, 0.0)
+            assert Fraction(below) < thr <= Fraction(c), (d, k)
+            assert len(("%%.%df" % d) % c) == k + 1 + (d + 1 if d else 0), (d, k)
+            assert len(("%%.%df" % d) % below) == k + (d + 1 if d else 0), (d, k)
+
+    def text_nd(a, d):
+        e = (struct.unpack("<Q", struct.pack("<d", a))[0] >> 52 & 0x7ff) - 1023
+        k0 = (e * 1233) >> 12 if e > 0 else 0
+        return k0 + 1 + (1 if a >= T[d][k0 + 1] else 0)
+    import struct
+    rng = np.random.default_rng(5)
+    vals = np.concatenate([10.0 ** rng.uniform(-12, 19.2, 20000), [0.0, 0.5, 1.5, 2.5, 9.5, 0.95, 0.995, 5e-324, 2.0 ** 63, 2.0 ** 64 - 2048.0],
+                           [math.nextafter(10.0 ** k, 0.0) for k in range(1, 20)], [10.0 ** k for k in range(0, 20)]])
+    for d in range(10):
+        for a in vals[:: (1 if d in (0, 6) else 7)]:
+            txt = ("%%.%df" % d) % a
+            assert text_nd(float(a), d) == len(txt.split(".")[0]), (a, d, txt)
+
+
 def test_nvtx_spans_are_off_by_default_and_balanced():
     """_trace: ranges only when enabled (LMC_NVTX=1 / enable()); a raising body still closes its range."""
     from livox_motion_compensation_sim_b200 import _trace
