@@ -492,7 +492,7 @@ def main_b200(args):
                     fn()
                 e1.record(); torch.cuda.synchronize()
                 return e0.elapsed_time(e1) / reps
-            lvx_ms = t_ms(lambda: ops.build_lvx_v11(raw, offw, fpos_d, ftw, idw, P))
+            lvx_ms = t_ms(lambda: ops.build_lvx_v11(raw, offw, fpos_d, ftw, idw, P, size=int(fpos[-1])))
             lvx_bytes = int(fpos[-1])
             pcd_ms = t_ms(lambda: ops.pcd_ascii_body(raw))
             pcd_bytes = int(ops.pcd_ascii_body(raw)[0].numel())

@@ -265,13 +265,14 @@ def transform_homog(pts: torch.Tensor, T, order: int = C.HOMOG_BATCH, out: Optio
 
 @_on_tensor_device
 def build_lvx_v11(pts: torch.Tensor, frame_off: torch.Tensor, frame_pos: torch.Tensor, frame_time: torch.Tensor,
-                  frame_id: torch.Tensor, max_frame_points: int):
+                  frame_id: torch.Tensor, max_frame_points: int, size: Optional[int] = None):
     """(N1) LMC:58-250 on the device: RAW points -> the complete LVX v1.1 file image (uint8 tensor).
-    frame_pos (int64[F+1], byte offsets incl. the 88-byte preamble) comes from lvx.frame_layout().
+    frame_pos (int64[F+1], byte offsets incl. the 88-byte preamble) comes from lvx.frame_layout(); size = its last entry.
     Returns (file bytes tensor, status flags tensor)."""
     f64 = _layout(pts)
     F = frame_off.shape[0] - 1
-    size = int(frame_pos[-1].item())
+    if size is None:
+        size = int(frame_pos[-1].item())                    # (a host sync: pass the file size when the layout was made on the host)
     out = torch.empty(size, dtype=torch.uint8, device=pts.device)
     status = torch.zeros(1, dtype=torch.int32, device=pts.device)
     fn = C.lib().lmc_lvx_v11_build_f64 if f64 else C.lib().lmc_lvx_v11_build_f32

@@ -473,7 +473,7 @@ class LiDARMotionSimulator:
         ids = np.array([s['frame_id'] for s in scans], np.int64)
         _, fpos = frame_layout(off)
         data, status = ops.build_lvx_v11(self._to_dev(flat), self._to_dev(off), self._to_dev(fpos), self._to_dev(ts),
-                                         self._to_dev(ids), int(np.diff(off).max()))
+                                         self._to_dev(ids), int(np.diff(off).max()), size=int(fpos[-1]))
         bufs = ops.ExportBuffers(status=status)
         bufs.raise_for_flags()
         return self._to_host(data)

@@ -53,7 +53,7 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "pcd":                 # A/B runs of the formatter alone
         print(json.dumps(res))
         return
-    add("lvx_v11", t_ms(lambda: ops.build_lvx_v11(raw, off_d, fpos_d, ft_d, id_d, P)), n * 16 + int(fpos[-1]))
+    add("lvx_v11", t_ms(lambda: ops.build_lvx_v11(raw, off_d, fpos_d, ft_d, id_d, P, size=int(fpos[-1]))), n * 16 + int(fpos[-1]))
     add("lvx2", t_ms(lambda: ops.build_lvx_cs(raw, None, off_d, ts_d, bytes(88), C.LVXCS_LVX2, P)), n * 16 + 88 + 45 * F + 14 * n)
     add("las_pf3", t_ms(lambda: ops.build_las_pf3(raw, scale=(0.001,) * 3)), n * 16 + 227 + 34 * n)
     rows5 = torch.cat([raw64, torch.arange(n, device=dev, dtype=torch.float64).unsqueeze(1) * 1000.0], dim=1).contiguous()
