@@ -13,8 +13,11 @@
  * PARITY UNPINNED for (i) the LAS scale/offset quantiser, whose arithmetic lives in
  * the un-vendored, un-pinned third-party `laspy` (call sites
  * lidar_motion_compensation.py:950-963 and livox_mid70_complete_simulator.py:1671-1698)
- * and is restated here from the LAS 1.2 spec + laspy 2.x behaviour, and (ii) Mode C
- * (pose-interp deskew), which has no implementation anywhere in the reference.
+ * and is restated here from the LAS 1.2 spec + laspy 2.x behaviour, and (ii) the ROTATION
+ * half of Mode C (pose-interp deskew): the reference has no per-point SLERP anywhere.  Its
+ * bracket search + position lerp ARE pinned: with identity orientations Mode C equals the
+ * reference's own IMUSimulator._interpolate_trajectory (CS:1248-1275, np.interp), golden
+ * tests/golden/modec_lerp.npz.
  *
  * Reference citations use LMC = lidar_motion_compensation.py and
  * CS = livox_mid70_complete_simulator.py.
@@ -275,9 +278,10 @@ void orc_deskew_gyro_f64(const double* pts, const int64_t* ts, const int64_t* fr
 
 /* ------------------------------------------------------------------------------------
  * Mode C: per-point pose-interp deskew (north_star: binary search + SLERP + lerp).
- * PARITY UNPINNED -- no reference implementation exists (docs/Master Guide.md:339-367
- * is a body-less sketch).  Definition (validated against scipy Slerp + lerp in
- * oracle/lmc_oracle.py::slerp_deskew_scipy):
+ * PARITY UNPINNED for the rotation -- no reference implementation exists (docs/Master
+ * Guide.md:339-367 is a body-less sketch); bracket + position lerp pinned by the reference's
+ * np.interp trajectory interpolation (CS:1248-1275, golden modec_lerp.npz).  Definition
+ * (validated against scipy Slerp + lerp in oracle/lmc_oracle.py::slerp_deskew_scipy):
  *   k = bracket_right(sample_ts, ts)  (same bracket rule as a7, clamped at both ends)
  *   alpha = (ts - t_k) * inv_dt_k,  inv_dt_k = 1.0 / (double)(t_{k+1} - t_k) from the table
  *           (a per-segment reciprocal instead of a per-point division: <= 1 ulp from the quotient)

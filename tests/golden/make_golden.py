@@ -372,6 +372,31 @@ def modeb_tiers_fixture(CS, manifest):
                                                                       int(((amax > 0.125) & (amax <= 0.5)).sum()), int((amax > 0.5).sum())])
 
 
+def modec_lerp_fixture(CS, manifest):
+    """The reference has no per-point pose interpolation as a whole (Mode C is the north_star's), but it does interpolate a
+    trajectory to arbitrary times: IMUSimulator._interpolate_trajectory (CS:1248-1275, np.interp over trajectory['time']).  That pins
+    the bracket search and the POSITION lerp of Mode C: with identity orientations Mode C's output is p + lerp(position)(t)."""
+    rng = np.random.default_rng(2024)
+    tg = CS.TrajectoryGenerator('figure_eight', seed=7)
+    traj = tg.generate_trajectory(3.0, dt=0.005, max_speed=15.0)                 # 200 Hz samples
+    t_s = np.asarray(traj['time'], np.float64)
+    sample_ts = np.round(t_s * 1e9).astype(np.int64)
+    tt = sample_ts.astype(np.float64) * 1e-9                                      # the times both sides interpolate over
+    traj = dict(traj); traj['time'] = tt
+    n = 6000
+    ts = np.sort(rng.integers(sample_ts[0] - 30_000_000, sample_ts[-1] + 30_000_000, n)).astype(np.int64)
+    ts[:40] = sample_ts[rng.integers(0, len(sample_ts), 40)]                     # exactly on samples
+    ts = np.sort(ts)
+    imu = CS.IMUSimulator({'random_seed': 1})
+    interp = imu._interpolate_trajectory(traj, ts.astype(np.float64) * 1e-9)
+    pts = np.column_stack([rng.uniform(-50, 50, (n, 3)), rng.uniform(0, 1, n)])
+    pos = np.column_stack([traj['x'], traj['y'], traj['z']]).astype(np.float64)
+    np.savez_compressed(os.path.join(HERE, 'modec_lerp.npz'), pts=pts, ts=ts, sample_ts=sample_ts, sample_pos=pos,
+                        ref_position=interp['position'], ref_orientation=interp['orientation'],
+                        sample_euler=np.column_stack([traj['roll'], traj['pitch'], traj['yaw']]).astype(np.float64))
+    manifest['modec_lerp'] = dict(points=n, samples=len(sample_ts), position_sha256=sha(interp['position']))
+
+
 def lvx_cs_fixture(CS, manifest):
     """Reference LivoxLVXWriter.write_lvx_file (CS:245-374) for 'lvx2', 'lvx3' and 'lvx' on ragged synthetic
     frames (one empty, one of a single point, one above 1024 points) with a non-trivial DeviceInfo."""
@@ -588,7 +613,7 @@ def main():
         for name in sys.argv[2:]:
             {'lvx_cs': lambda: lvx_cs_fixture(CS, manifest), 'text_rows': lambda: text_rows_fixture(CS, manifest),
              'coord_frames': lambda: coord_frames_fixture(CS, manifest),
-             'config2': lambda: config2_fixture(CS, manifest), 'modeb_tiers': lambda: modeb_tiers_fixture(CS, manifest), 'cs_run': lambda: cs_run_fixture(CS, manifest), 'las': lambda: las_fixture(LMC, CS, manifest),
+             'config2': lambda: config2_fixture(CS, manifest), 'modeb_tiers': lambda: modeb_tiers_fixture(CS, manifest), 'modec_lerp': lambda: modec_lerp_fixture(CS, manifest), 'cs_run': lambda: cs_run_fixture(CS, manifest), 'las': lambda: las_fixture(LMC, CS, manifest),
              'outputs': lambda: [outputs_fixture(LMC, n, manifest) for n in ['C1a', 'C2a', 'C3']]}[name]()
         with open(os.path.join(HERE, 'MANIFEST.json'), 'w') as f:
             json.dump(manifest, f, indent=1, sort_keys=True)
@@ -606,6 +631,7 @@ def main():
     lvx_file_fixture(LMC, manifest)
     modeb_fixture(CS, manifest)
     modeb_tiers_fixture(CS, manifest)
+    modec_lerp_fixture(CS, manifest)
     coord_chain_fixture(CS, manifest)
     pcd_fixture(LMC, manifest)
     lvx_cs_fixture(CS, manifest)

@@ -495,6 +495,27 @@ def test_mode_c_staged_rows_fallbacks(case):
     assert np.array_equal(b.lvx14.cpu().numpy(), orc.C.quantize_lvx_type2(pts64)[0])
 
 
+@pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
+def test_mode_c_bracket_and_lerp_vs_reference_interpolation(golden, path, f64):
+    """Device Mode C with identity orientations == p + the REAL reference's trajectory interpolation (np.interp, CS:1248-1275) at the
+    points' times: bracket search, both clamps, times exactly on samples, position lerp -- the half of Mode C the reference implements
+    (golden modec_lerp.npz); the device-built segment table is used, as in the product path."""
+    g = golden("modec_lerp.npz")
+    S, n = len(g['sample_ts']), len(g['pts'])
+    quat = np.tile(np.array([0.0, 0.0, 0.0, 1.0]), (S, 1))
+    seg = ops.build_slerp_table(dev(quat), dev(g['sample_pos']), dev(g['sample_ts']))
+    want = g['pts'][:, :3] + g['ref_position']
+    fs = np.array([g['ts'][0]], np.int64)
+    if f64:
+        out, _ = ops.deskew_slerp(dev(g['pts']), dev(g['ts']), dev(np.array([0, n], np.int64)), dev(fs), dev(g['sample_ts']), seg)
+        assert np.abs(out.cpu().numpy()[:, :3] - want).max() <= 1e-9
+    else:
+        p32 = g['pts'].astype(np.float32)
+        out, _ = ops.deskew_slerp(dev(p32), dev((g['ts'] - fs[0]).astype(np.uint32)), dev(np.array([0, n], np.int64)), dev(fs), dev(g['sample_ts']), seg)
+        want32 = p32[:, :3].astype(np.float64) + g['ref_position']
+        assert np.abs(out.cpu().numpy().astype(np.float64)[:, :3] - want32).max() <= 1e-5      # one f32 rounding of coordinates up to ~100 m
+
+
 def test_mode_c_hold_next_is_mode_a():
     """Mode A == Mode C with the interpolation weight forced to hold-next: bit-identical."""
     F = 25
