@@ -733,13 +733,34 @@ __global__ void __launch_bounds__(kPcdTile) k_text_write(const void* __restrict_
     const int img_words = (int)((phase + (tile_off[blockIdx.x + 1] - dst0) + 3 + 15) / 16) * 4;
     for (int k = tid * 4; k < img_words; k += kPcdTile * 4) *reinterpret_cast<uint4*>(s_img + 4 * k) = make_uint4(0, 0, 0, 0);
     TextNum t[kTextCols];
+    [[maybe_unused]] Piece pc[kTextCols];
+    [[maybe_unused]] bool slow6 = false;                             // compiled formats: some '%.6f' column of the row is not a fast number
     uint32_t len = 0, fl = 0;
     if (i < n) {
         len = (uint32_t)S::ncols(F);
+        if constexpr (NC > 0) {
+            // compiled formats: '%.6f' columns take the PCD writer's three-register pieces (|v| < 10^4 after rounding: every coordinate a
+            // LiDAR produces; 63 instead of ~150 instructions per number), the other columns the generic exact split
+            double v[NC];
 #pragma unroll
-        for (int c = 0; c < kTextCols; ++c) if (c < S::ncols(F)) {
-            t[c] = fmtg_prepare(load_cell<F64>(rows, S::cell(F, i, c)), S::dec(F, c), fl);
-            len += t[c].len;
+            for (int c = 0; c < NC; ++c) {
+                v[c] = load_cell<F64>(rows, S::cell(F, i, c));
+                if (S::dec(F, c) == 6) slow6 |= piece_fast(pc[c], v[c], c == NC - 1 ? 0x0au : (uint32_t)F.sep);
+                else { t[c] = fmtg_prepare(v[c], S::dec(F, c), fl); len += t[c].len; }
+            }
+            if (slow6) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) if (S::dec(F, c) == 6) { t[c] = fmtg_prepare(v[c], 6, fl); len += t[c].len; }
+            } else {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) if (S::dec(F, c) == 6) len += piece_ll(pc[c]) + 7u;      // lead + ".dddddd" (separators counted above)
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < kTextCols; ++c) if (c < S::ncols(F)) {
+                t[c] = fmtg_prepare(load_cell<F64>(rows, S::cell(F, i, c)), S::dec(F, c), fl);
+                len += t[c].len;
+            }
         }
     }
     uint32_t total;
@@ -748,10 +769,28 @@ __global__ void __launch_bounds__(kPcdTile) k_text_write(const void* __restrict_
         TextStream ts;
         ts.start(smem_u32(s_img), (uint32_t)phase + off);
         const uint32_t sep = (uint32_t)F.sep;
-        // compiled formats start with a '%.6f' column (>= 9 bytes): the word shared with the previous row completes inside it
-        if (S::ncols(F) > 0) emit_number<NC ? 1 : 2>(ts, t[0], S::dec(F, 0), S::ncols(F) == 1 ? 0x0au : sep);
+        if constexpr (NC > 0) {
+            // (compiled formats start with a '%.6f' column, >= 9 bytes: the word shared with the previous row completes inside it)
 #pragma unroll
-        for (int c = 1; c < kTextCols; ++c) if (c < S::ncols(F)) emit_number<NC ? 0 : 2>(ts, t[c], S::dec(F, c), c == S::ncols(F) - 1 ? 0x0au : sep);
+            for (int c = 0; c < NC; ++c) {
+                constexpr int kFirst = 1, kRest = 0;
+                if (S::dec(F, c) == 6 && !slow6) {
+                    const uint32_t ll = piece_ll(pc[c]);
+                    if (c == 0) {
+                        if (ll > 4u) { ts.put<kFirst>(0x2du, 1u); ts.put<kFirst>(pc[c].L0, 4u); } else ts.put<kFirst>(pc[c].L0, ll);
+                        ts.put4<kFirst>((pc[c].T0 & 0xffffff00u) | 0x2eu); ts.put4<kFirst>(pc[c].T1);
+                    } else {
+                        if (ll > 4u) { ts.put<kRest>(0x2du, 1u); ts.put<kRest>(pc[c].L0, 4u); } else ts.put<kRest>(pc[c].L0, ll);
+                        ts.put4<kRest>((pc[c].T0 & 0xffffff00u) | 0x2eu); ts.put4<kRest>(pc[c].T1);
+                    }
+                } else if (c == 0) emit_number<kFirst>(ts, t[c], S::dec(F, c), c == NC - 1 ? 0x0au : sep);
+                else emit_number<kRest>(ts, t[c], S::dec(F, c), c == NC - 1 ? 0x0au : sep);
+            }
+        } else {
+            if (S::ncols(F) > 0) emit_number<2>(ts, t[0], S::dec(F, 0), S::ncols(F) == 1 ? 0x0au : sep);
+#pragma unroll
+            for (int c = 1; c < kTextCols; ++c) if (c < S::ncols(F)) emit_number<2>(ts, t[c], S::dec(F, c), c == S::ncols(F) - 1 ? 0x0au : sep);
+        }
         ts.finish();
     }
     cta_image_out(out + (dst0 - phase), s_img, phase, phase + (int)total, tid, kPcdTile);
