@@ -1110,6 +1110,45 @@ def test_no_write_outside_buffers(f64, path):
     assert bool((li_f.view(torch.int16)[:G + b] == 0x5A5A).all()) and bool((li_f.view(torch.int16)[G + e:] == 0x5A5A).all())
 
 
+@pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
+def test_text_writers_stay_inside_their_buffers(f64):
+    """Home-made memcheck for the two text writers (word stream + TMA bulk store of a tile image laid out at the destination's
+    16-byte phase): the exactly sized text lives inside a larger allocation filled with a sentinel, at the 32-byte alignment the
+    C ABI asks for; after _write the guard bytes on both sides are untouched and the text equals CPython's."""
+    rng = np.random.default_rng(9)
+    G = 4096
+    L = C.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    for n in (1, 255, 513, 70_001):
+        pts = rng.uniform(-1500, 1500, (n, 4)); pts[::13, 2] = 1e7; pts[::17, 0] = np.nan
+        pts = pts if f64 else pts.astype(np.float32)
+        d = dev(pts)
+        tile_off = torch.empty((n + 255) // 256 + 1, dtype=torch.int64, device=DEV)
+        status = torch.zeros(1, dtype=torch.int32, device=DEV)
+        C.check((L.lmc_pcd_ascii_size_f64 if f64 else L.lmc_pcd_ascii_size_f32)(d.data_ptr(), n, tile_off.data_ptr(), stream))
+        total = int(tile_off[-1].item())
+        full = torch.full((total + 2 * G,), 0xA5, dtype=torch.uint8, device=DEV)
+        C.check((L.lmc_pcd_ascii_write_f64 if f64 else L.lmc_pcd_ascii_write_f32)(d.data_ptr(), n, tile_off.data_ptr(), full[G:].data_ptr(), status.data_ptr(), stream))
+        torch.cuda.synchronize()
+        h = full.cpu().numpy()
+        assert (h[:G] == 0xA5).all() and (h[G + total:] == 0xA5).all(), n
+        assert h[G:G + total].tobytes() == "".join("%.6f %.6f %.6f %.6f\n" % tuple(r) for r in pts.astype(np.float64)).encode(), n
+        # generic rows: the second simulator's .pcd format over 5 f64 / f32 columns
+        rows = np.column_stack([pts[:, :3].astype(np.float64), rng.integers(0, 256, n).astype(np.float64), 1.7e18 + np.arange(n) * 1000.0])
+        rows = rows if f64 else rows.astype(np.float32)
+        r = dev(rows)
+        ca = (C.ctypes.c_int32 * 5)(0, 1, 2, 3, 4); da = (C.ctypes.c_int32 * 5)(6, 6, 6, 0, 0)
+        fs, fw = (L.lmc_text_rows_size_f64, L.lmc_text_rows_write_f64) if f64 else (L.lmc_text_rows_size_f32, L.lmc_text_rows_write_f32)
+        C.check(fs(r.data_ptr(), n, 5, 5, ca, da, ord(" "), tile_off.data_ptr(), stream))
+        total = int(tile_off[-1].item())
+        full = torch.full((total + 2 * G,), 0xA5, dtype=torch.uint8, device=DEV)
+        C.check(fw(r.data_ptr(), n, 5, 5, ca, da, ord(" "), tile_off.data_ptr(), full[G:].data_ptr(), status.data_ptr(), stream))
+        torch.cuda.synchronize()
+        h = full.cpu().numpy()
+        assert (h[:G] == 0xA5).all() and (h[G + total:] == 0xA5).all(), n
+        assert h[G:G + total].tobytes() == "".join("%.6f %.6f %.6f %.0f %.0f\n" % tuple(x) for x in rows.astype(np.float64)).encode(), n
+
+
 @pytest.mark.parametrize("mode", ["rigid", "slerp"])
 @pytest.mark.parametrize("f64", [True, False], ids=["f64", "f32"])
 def test_lean_lvx_bulk_store_epilogue_with_ragged_shards(mode, f64):
