@@ -52,7 +52,7 @@ VARIANTS = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel (ncu --set full, profiles/)
-NCU_TRAFFIC = {("V5", N_FRAMES, PTS_PER_FRAME): 18.098e9, ("V1", N_FRAMES, PTS_PER_FRAME): 11.489e9, ("V2", N_FRAMES, PTS_PER_FRAME): 16.518e9, ("V4b", N_FRAMES, PTS_PER_FRAME): 12.948e9}
+NCU_TRAFFIC = {("V5", N_FRAMES, PTS_PER_FRAME): 18.100e9, ("V1", N_FRAMES, PTS_PER_FRAME): 11.489e9, ("V2", N_FRAMES, PTS_PER_FRAME): 16.518e9, ("V4b", N_FRAMES, PTS_PER_FRAME): 12.948e9}
 
 
 def parse():
