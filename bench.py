@@ -804,7 +804,7 @@ def main_b200(args):
                        "l2": f"inputs {N * (16 + 4) / 1e9:.1f} GB >> 126 MB L2: no flush needed", "parallelism": f"frame-sharded x{world}",
                        "status_flags": flags},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC.get((args.variant, F, P)), "traffic_source": f"profiles/r01_ncu_{args.variant.lower()}_summary.md (dram__bytes_read + dram__bytes_write of one launch, ncu --set full)" if (args.variant, F, P) in NCU_TRAFFIC else None, "peak_source": peak_src, "kernel_ms": kern_ms,
+                         "traffic": NCU_TRAFFIC.get((args.variant, F, P)), "traffic_source": f"profiles/{'r02' if args.variant in ('V5', 'V4b') else 'r01'}_ncu_{args.variant.lower()}_summary.md (dram__bytes_read + dram__bytes_write of one launch, ncu --set full)" if (args.variant, F, P) in NCU_TRAFFIC else None, "peak_source": peak_src, "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": N * bpp, "frac_of_nominal_8TBps": achieved / 8000.0},
             "clocks": clocks, "gpu_launches": args.steps, "e2e": e2e, "cpu_baseline": cpu,
         }
