@@ -342,16 +342,36 @@ __device__ __forceinline__ uint32_t q_u8_copy(double w, uint32_t& fl) {
 // The quotient is formed with the host-rounded reciprocal and two Markstein corrections
 // (q += fma(-s, q, a) * rcp), which yields the correctly rounded a / s -- identical to the IEEE
 // division the restatement uses, at 5 FP64 ops instead of a ~25-instruction division sequence.
-__device__ __forceinline__ int32_t q_las(double v, double scale, double rcp, double off, uint32_t& fl) {
+// exact route (rare: within 2^-20 of a tie, NaN, inf, |q| >= 2^31 - 1): {X, flags}
+__device__ __forceinline__ int2 q_las_exact_body(double v, double scale, double rcp, double off) {
     const double a = __dsub_rn(v, off);
     double q = __dmul_rn(a, rcp);
+    uint32_t fl = 0;
     if (fabs(q) < 1.0e300) {                        // finite, far from overflow: refine
         q = __fma_rn(__fma_rn(-scale, q, a), rcp, q);
         q = __fma_rn(__fma_rn(-scale, q, a), rcp, q);
     }
     if (v != v) fl |= LMC_FLAG_NAN;
     if (q >= 2147483647.5 || q < -2147483648.5) fl |= LMC_FLAG_OVERFLOW;
-    return __double2int_rn(q);                      // round-half-even, saturates
+    return make_int2(__double2int_rn(q), (int)fl);  // round-half-even, saturates
+}
+static __device__ __noinline__ int2 q_las_exact(double v, double scale, double rcp, double off) { return q_las_exact_body(v, scale, rcp, off); }
+// OOL: the exact route as a call (Mode A + LAS: +1.6 %) or inline (Mode C + LAS, which is register-starved: the call's register
+// shuffling costs it 4-6 %) -- same-box A/B, profiles/r02_ab_las.log
+template <bool OOL = true>
+__device__ __forceinline__ int32_t q_las(double v, double scale, double rcp, double off, uint32_t& fl) {
+    // Only the INTEGER np.round(a / scale) is wanted.  q = a * RN(1/scale) is within 2 ulp of the correctly rounded quotient, i.e.
+    // within 2^-21 of it for |q| < 2^31; unless q lies that close to a tie k + 0.5 both round to the same integer, and the two
+    // Markstein corrections of the exact route are not needed.  d = q - rint(q) is exact; the two range tests run on high words
+    // (integer ALU): NaN / inf / |q| >= 2^31 - 1 and everything within 2^-20 of a tie take the exact route.
+    const double q = __dmul_rn(__dsub_rn(v, off), rcp);
+    const int32_t X = __double2int_rn(q);
+    const double d = __dsub_rn(q, (double)X);
+    const uint32_t hq = (uint32_t)__double2hiint(q) & 0x7fffffffu, hd = (uint32_t)__double2hiint(d) & 0x7fffffffu;
+    if (hq < 0x41DFFFFFu && hd < 0x3FDFFFFEu) return X;
+    const int2 r = OOL ? q_las_exact(v, scale, rcp, off) : q_las_exact_body(v, scale, rcp, off);
+    fl |= (uint32_t)r.y;
+    return r.x;
 }
 // LMC:961 (w*65535).astype(uint16) | CS:1686 w.astype(uint16): truncate, wrap modulo 2^16
 __device__ __forceinline__ uint32_t q_las_intensity(double w, int mode, uint32_t& fl) {
@@ -792,12 +812,12 @@ __device__ __forceinline__ void store_pair(void* base, int64_t p, bool va, bool 
 }
 
 // LAS integer stores of one pair (SoA, 64-bit per array for a full pair)
-template <bool FULL>
+template <bool FULL, bool OOL = true>
 __device__ __forceinline__ void store_las_pair(const Params& P, int64_t p, bool va, bool vb, const Pt& a, const Pt& b, uint32_t& fl) {
     if (P.las_x != nullptr) {
         int32_t X[2] = {0, 0}, Y[2] = {0, 0}, Z[2] = {0, 0};
-        if (FULL || va) { X[0] = q_las(a.x, P.las_scale[0], P.las_rcp[0], P.las_off[0], fl); Y[0] = q_las(a.y, P.las_scale[1], P.las_rcp[1], P.las_off[1], fl); Z[0] = q_las(a.z, P.las_scale[2], P.las_rcp[2], P.las_off[2], fl); }
-        if (FULL || vb) { X[1] = q_las(b.x, P.las_scale[0], P.las_rcp[0], P.las_off[0], fl); Y[1] = q_las(b.y, P.las_scale[1], P.las_rcp[1], P.las_off[1], fl); Z[1] = q_las(b.z, P.las_scale[2], P.las_rcp[2], P.las_off[2], fl); }
+        if (FULL || va) { X[0] = q_las<OOL>(a.x, P.las_scale[0], P.las_rcp[0], P.las_off[0], fl); Y[0] = q_las<OOL>(a.y, P.las_scale[1], P.las_rcp[1], P.las_off[1], fl); Z[0] = q_las<OOL>(a.z, P.las_scale[2], P.las_rcp[2], P.las_off[2], fl); }
+        if (FULL || vb) { X[1] = q_las<OOL>(b.x, P.las_scale[0], P.las_rcp[0], P.las_off[0], fl); Y[1] = q_las<OOL>(b.y, P.las_scale[1], P.las_rcp[1], P.las_off[1], fl); Z[1] = q_las<OOL>(b.z, P.las_scale[2], P.las_rcp[2], P.las_off[2], fl); }
         if (FULL || (va && vb)) {
             *reinterpret_cast<int2*>(P.las_x + p) = make_int2(X[0], X[1]);
             *reinterpret_cast<int2*>(P.las_y + p) = make_int2(Y[0], Y[1]);

@@ -49,9 +49,11 @@ __global__ void __launch_bounds__(kLasThreads) k_las_records(const __grid_consta
         const int64_t i = first + j;
         if constexpr (F64) { const double* s = reinterpret_cast<const double*>(L.pts) + 4 * i; ldg256(s, p.x, p.y, p.z, p.w); }
         else { const float4 v = __ldg(reinterpret_cast<const float4*>(L.pts) + i); p = Pt{ (double)v.x, (double)v.y, (double)v.z, (double)v.w }; }
-        const int32_t X = q_las(p.x, L.scale[0], L.rcp[0], L.off[0], fl);
-        const int32_t Y = q_las(p.y, L.scale[1], L.rcp[1], L.off[1], fl);
-        const int32_t Z = q_las(p.z, L.scale[2], L.rcp[2], L.off[2], fl);
+        // (the always-exact route: this kernel is bound by its 34-byte records, not by FP64 -- the tie test of q_las costs it 2 %)
+        const int2 qx = q_las_exact_body(p.x, L.scale[0], L.rcp[0], L.off[0]), qy = q_las_exact_body(p.y, L.scale[1], L.rcp[1], L.off[1]),
+                   qz = q_las_exact_body(p.z, L.scale[2], L.rcp[2], L.off[2]);
+        const int32_t X = qx.x, Y = qy.x, Z = qz.x;
+        fl |= (uint32_t)(qx.y | qy.y | qz.y);
         const uint32_t I = q_las_intensity(p.w, L.intensity_mode, fl);
         mn[0] = min(mn[0], X); mx[0] = max(mx[0], X); mn[1] = min(mn[1], Y); mx[1] = max(mx[1], Y); mn[2] = min(mn[2], Z); mx[2] = max(mx[2], Z);
         // the record starts at an odd address (227 + 34 j): one byte, sixteen aligned halfwords, one byte

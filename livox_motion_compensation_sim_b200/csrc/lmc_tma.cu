@@ -250,7 +250,7 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
             for (int r = 0; r < P.n_peers; ++r)
                 if (P.peer_out[r] != nullptr) store_pair<F64, FULL>(P.peer_out[r], p, va, vb, o[0], o[1]);
         }
-        if (do_las) store_las_pair<FULL>(P, p, va, vb, o[0], o[1], fl);
+        if (do_las) store_las_pair<FULL, MODE == kRigid>(P, p, va, vb, o[0], o[1], fl);
         if constexpr (GEN || LVX2) {
             if (do_lvx) {
                 uint32_t x[2] = {0, 0}, y[2] = {0, 0}, z[2] = {0, 0}, rt[2] = {0, 0};
