@@ -556,6 +556,11 @@ __device__ __forceinline__ TextNum fmtg_prepare(double v, int d, uint32_t& fl) {
     t.neg = bits >> 63;
     t.ip = 0; t.fq = 0; t.kind = 0;
     const double a = fabs(v);
+    if (d == 0 && a < 18446744073709551616.0) {      // '%.0f': one round-to-nearest-even conversion IS the answer (a < 2^64 - 1024)
+        t.ip = __double2ull_rn(a);
+        t.len = (t.neg ? 1u : 0u) + text_nd(a, 0);
+        return t;
+    }
     if (a < 18446744073709551616.0) {                // 2^64
         uint64_t ip = __double2ull_rz(a);
         const double fr = __dsub_rn(a, __ull2double_rn(ip));
