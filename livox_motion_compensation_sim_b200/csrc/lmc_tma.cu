@@ -16,6 +16,7 @@
 //                   output side needs no CTA-wide barrier at all.
 //
 // Edge tiles (a shard's ragged first / last tile) skip TMA and take guarded global loads.
+#include <cstdlib>
 #include <type_traits>
 #include "lmc_device.cuh"
 
@@ -98,7 +99,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // kExMc (with kExOut | kExLvx): fused merged-cloud assembly through the NVSwitch multicast mapping of the symmetric buffers --
 // every result of a full tile leaves as ONE multimem.st (the switch replicates it into every rank's copy, this rank's
 // included) instead of a local store plus one store per peer; ragged edge tiles fall back to local + per-peer stores.
-constexpr int kExOut = 1, kExLvx = 2, kExLas = 4, kExGeneric = 8, kExLvx2 = 16, kExMc = 32;
+// kExPb (with kExOut | kExLvx): fused merged-cloud assembly by TMA BULK stores -- the warp writes its results back over its own
+// points in the stage, and its contiguous run of the tile (aligned cloud) plus its record slab leave as one bulk store per
+// destination (this rank's copy and every peer's over NVLink) instead of one register store per result and peer.
+constexpr int kExOut = 1, kExLvx = 2, kExLas = 4, kExGeneric = 8, kExLvx2 = 16, kExMc = 32, kExPb = 64;
 
 // 16 bytes to the multicast address (PTX multimem.st; the switch fans the write out to every member of the group)
 __device__ __forceinline__ void mc_st128(void* mc, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -117,6 +121,7 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
     constexpr int PPT = Cfg::PPT;
     constexpr bool GEN = EX == kExGeneric;
     constexpr bool MC = !GEN && (EX & kExMc);                    // full tiles: multimem.st only; edge tiles: local + per-peer stores
+    constexpr bool PB = !GEN && (EX & kExPb) && !F64;            // full tiles: results written back into the stage, bulk stores per destination
     const bool do_out = GEN ? P.out != nullptr : bool(EX & kExOut);
     const bool do_lvx = GEN ? P.lvx14 != nullptr : bool(EX & kExLvx);
     const bool do_las = GEN ? (P.las_x != nullptr || P.las_int != nullptr) : bool(EX & kExLas);
@@ -199,7 +204,8 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
         }
         // with staged pose rows the stage is still being read by ctx.pair() below: release it after the last pair's math
         constexpr bool ROWS_STAGED = FULL && !GEN && MODE == kSlerp && !F64;   // (f64 tiles are one pair per thread: holding the stage through the math costs more than the row reads)
-        if (j == PPT - 1 && !ROWS_STAGED) {                  // everything this warp needs from the stage is in registers
+        constexpr bool PB_FULL = PB && FULL;                 // the stage is the staging buffer of the bulk stores: released after they have read it
+        if (j == PPT - 1 && !ROWS_STAGED && !PB_FULL) {      // everything this warp needs from the stage is in registers
             __syncwarp();
             if (lane == 0) mbar_arrive(empty_bar);
         }
@@ -224,7 +230,7 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
             if (va) o[0] = ctx.one(P, fr[0], single[0], fsv[0], tsv[0], in[0]);
             if (vb) o[1] = ctx.one(P, fr[1], single[1], fsv[1], tsv[1], in[1]);
         }
-        if (j == PPT - 1 && ROWS_STAGED) {
+        if (j == PPT - 1 && ROWS_STAGED && !PB_FULL) {
             __syncwarp();
             if (lane == 0) mbar_arrive(empty_bar);
         }
@@ -232,7 +238,11 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
             if constexpr (F64) store_pair<true, FULL>(P.out, p, va, vb, o[0], o[1]);
             else {
                 float* dst = reinterpret_cast<float*>(P.out) + 4 * p;
-                if constexpr (MC && FULL) {
+                if constexpr (PB_FULL) {
+                    float4* sp = reinterpret_cast<float4*>(const_cast<uint8_t*>(s_pts)) + 2 * q;       // over the pair's own input
+                    sp[0] = make_float4((float)o[0].x, (float)o[0].y, (float)o[0].z, wraw[0]);
+                    sp[1] = make_float4((float)o[1].x, (float)o[1].y, (float)o[1].z, wraw[1]);
+                } else if constexpr (MC && FULL) {
                     float* mc = reinterpret_cast<float*>(P.mc_out) + 4 * p;
                     mc_st128(mc, __float_as_uint((float)o[0].x), __float_as_uint((float)o[0].y), __float_as_uint((float)o[0].z), __float_as_uint(wraw[0]));
                     mc_st128(mc + 4, __float_as_uint((float)o[1].x), __float_as_uint((float)o[1].y), __float_as_uint((float)o[1].z), __float_as_uint(wraw[1]));
@@ -245,7 +255,7 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
                 }
             }
         }
-        if constexpr (GEN || (MC && !FULL)) {
+        if constexpr (GEN || ((MC || PB) && !FULL)) {
             // fused merged-cloud assembly: the same pair goes to every peer's copy of the merged buffer
             for (int r = 0; r < P.n_peers; ++r)
                 if (P.peer_out[r] != nullptr) store_pair<F64, FULL>(P.peer_out[r], p, va, vb, o[0], o[1]);
@@ -265,7 +275,24 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
         const int64_t wfirst = base + 2 * (int64_t)(cw * PPT) * 32;          // first point of the warp's block
         uint8_t* g = P.lvx14 + 14 * wfirst;
         constexpr int NB = PPT * 64 * 14;
-        if constexpr (MC && FULL) {
+        if constexpr (PB && FULL) {
+            // the warp's PPT x 64 results are one contiguous run of the stage (16 bytes per point) and of every destination
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                constexpr uint32_t OB = PPT * 64 * 16;
+                const uint8_t* src = s_pts + 16 * (size_t)(cw * PPT) * 64;
+                bulk_s2g(reinterpret_cast<uint8_t*>(P.out) + 16 * wfirst, src, OB);
+                bulk_s2g(g, slab, NB);
+                for (int r = 0; r < P.n_peers; ++r) {
+                    if (P.peer_out[r] != nullptr) bulk_s2g(reinterpret_cast<uint8_t*>(P.peer_out[r]) + 16 * wfirst, src, OB);
+                    if (P.peer_lvx[r] != nullptr) bulk_s2g(P.peer_lvx[r] + 14 * wfirst, slab, NB);
+                }
+                bulk_commit();
+                bulk_wait_read0();                                   // stage and slab have been read: hand the stage back
+                mbar_arrive(empty_bar);
+            }
+        } else if constexpr (MC && FULL) {
             __syncwarp();
             uint8_t* mc = P.mc_lvx + 14 * wfirst;
             for (int i = lane; i < NB / 16; i += 32) {
@@ -289,7 +316,7 @@ __device__ __forceinline__ void consume_tile(const Params& P, const TileInfo& ti
                 for (int i = a1 + lane; i < b1; i += 32) g[i] = slab[i];
             }
         }
-        if constexpr (GEN || (MC && !FULL)) {
+        if constexpr (GEN || ((MC || PB) && !FULL)) {
             for (int r = 0; r < P.n_peers; ++r) {
                 uint8_t* gp = P.peer_lvx[r];
                 if (gp == nullptr) continue;
@@ -427,7 +454,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) k_stream(const __grid_const
             else         consume_tile<F64, MODE, EX, false>(P, ti, s_meta[s], st, st + Cfg::PTS_STAGE, st + Cfg::PTS_STAGE + Cfg::TS_STAGE, slab, empty0 + 8 * s, ctx, fl, warp, lane);
             if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
-        if constexpr (GEN || (EX & kExLvx)) { if (lane == 0) bulk_wait0(); }                   // bulk store of the last tile
+        if constexpr (GEN || (EX & kExLvx)) { if (lane == 0) bulk_wait0(); }                   // bulk stores of the last tile (all destinations)
         if (fl != 0 && P.status != nullptr) atomicOr(P.status, fl);
     }
 }
@@ -477,14 +504,17 @@ static cudaError_t launch_stream(const Params& P, cudaStream_t st, bool force, b
         const int mask = (P.out ? kExOut : 0) | (P.lvx14 ? kExLvx : 0) | ((P.las_x || P.las_int) ? kExLas : 0);
         const bool lvx2 = P.lvx14 && P.lvx_mode == LMC_LVX2_OF_OUTPUT;
         const bool mc = P.mc_out != nullptr && P.mc_lvx != nullptr;           // multicast merge: lean out + LVX kernel, float4 layout
+        static const bool pb_on = [] { const char* e = getenv("LMC_PEER_BULK"); return !(e && e[0] == '0'); }();   // (experiments: LMC_PEER_BULK=0 keeps the register peer stores)
+        const bool pb = pb_on && !mc && P.n_peers > 0 && MODE != kGyro && !F64 && mask == (kExOut | kExLvx) && !lvx2;
         if (mc && !(MODE != kGyro && !F64 && mask == (kExOut | kExLvx) && !lvx2)) return cudaErrorInvalidValue;
-        bool lean = (P.n_peers == 0 || mc) && (!lvx2 || MODE == kGyro) && (!(mask & kExLas) || (P.las_x && P.las_int));
+        bool lean = (P.n_peers == 0 || mc || pb) && (!lvx2 || MODE == kGyro) && (!(mask & kExLas) || (P.las_x && P.las_int));
         if (MODE == kSlerp) lean = lean && P.hold_idx == nullptr && P.ts != nullptr && P.n_samp >= 2 && P.n_samp < 0x7fffffffLL &&
                                    (F64 || P.frame_start != nullptr);
         if (MODE == kGyro)  lean = lean && P.ts != nullptr && P.frame_start != nullptr && P.n_samp >= 2 && P.n_samp < 0x7fffffffLL;
         if (mc && !lean) return cudaErrorInvalidValue;
         if constexpr (MODE != kGyro && !F64) {
             if (lean && mc) return launch_stream_ex<F64, MODE, kExOut | kExLvx | kExMc>(P, st, grid, tile0, n_tiles);
+            if (lean && pb) return launch_stream_ex<F64, MODE, kExOut | kExLvx | kExPb>(P, st, grid, tile0, n_tiles);
         }
         if (lean) {
             if (mask == kExOut)            return launch_stream_ex<F64, MODE, kExOut>(P, st, grid, tile0, n_tiles);
