@@ -137,6 +137,23 @@ __device__ __forceinline__ void cta_image_out(uint8_t* g, const uint8_t* img, in
     if (body) bulk_wait_read0();
 }
 
+// A file writer's CTA walks its points as j = tid + k * T: load all K rows first (K independent 16/32-byte loads in flight per
+// thread instead of one round trip per loop iteration), then quantise.  Rows at or beyond npts are not touched.
+template <bool F64> struct RawRow;
+template <> struct RawRow<false> { float4 v;        __device__ __forceinline__ Pt pt() const { return Pt{ (double)v.x, (double)v.y, (double)v.z, (double)v.w }; } };
+template <> struct RawRow<true>  { double x, y, z, w; __device__ __forceinline__ Pt pt() const { return Pt{ x, y, z, w }; } };
+template <bool F64, int K, int T>
+__device__ __forceinline__ void load_rows_strided(const void* __restrict__ pts, int64_t first, int tid, int npts, RawRow<F64> (&r)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = tid + k * T;
+        if (j < npts) {
+            if constexpr (F64) ldg256(reinterpret_cast<const double*>(pts) + 4 * (first + j), r[k].x, r[k].y, r[k].z, r[k].w);
+            else r[k].v = __ldg(reinterpret_cast<const float4*>(pts) + (first + j));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Reference operation orders
 // ------------------------------------------------------------------------------------------

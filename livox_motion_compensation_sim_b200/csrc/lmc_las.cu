@@ -44,32 +44,79 @@ __global__ void __launch_bounds__(kLasThreads) k_las_records(const __grid_consta
     __syncthreads();
     uint32_t fl = 0;
     int32_t mn[3] = { INT32_MAX, INT32_MAX, INT32_MAX }, mx[3] = { INT32_MIN, INT32_MIN, INT32_MIN };
-    for (int j = tid; j < cnt; j += kLasThreads) {
-        Pt p;
-        const int64_t i = first + j;
-        if constexpr (F64) { const double* s = reinterpret_cast<const double*>(L.pts) + 4 * i; ldg256(s, p.x, p.y, p.z, p.w); }
-        else { const float4 v = __ldg(reinterpret_cast<const float4*>(L.pts) + i); p = Pt{ (double)v.x, (double)v.y, (double)v.z, (double)v.w }; }
-        // (the always-exact route: this kernel is bound by its 34-byte records, not by FP64 -- the tie test of q_las costs it 2 %)
+    // (the always-exact quantiser route: this kernel is bound by its 34-byte records, not by FP64 -- the tie test of q_las costs it 2 %)
+    auto quantise = [&](const Pt& p, uint32_t (&q)[4]) {
         const int2 qx = q_las_exact_body(p.x, L.scale[0], L.rcp[0], L.off[0]), qy = q_las_exact_body(p.y, L.scale[1], L.rcp[1], L.off[1]),
                    qz = q_las_exact_body(p.z, L.scale[2], L.rcp[2], L.off[2]);
-        const int32_t X = qx.x, Y = qy.x, Z = qz.x;
         fl |= (uint32_t)(qx.y | qy.y | qz.y);
-        const uint32_t I = q_las_intensity(p.w, L.intensity_mode, fl);
-        mn[0] = min(mn[0], X); mx[0] = max(mx[0], X); mn[1] = min(mn[1], Y); mx[1] = max(mx[1], Y); mn[2] = min(mn[2], Z); mx[2] = max(mx[2], Z);
-        // the record starts at an odd address (227 + 34 j): one byte, sixteen aligned halfwords, one byte
-        uint8_t* r = img + j * kLasRec;
-        const uint64_t gb = (uint64_t)__double_as_longlong(L.gps_time ? __ldg(L.gps_time + i) : 0.0);
-        // bytes 0-11 X Y Z | 12-13 intensity | 14-19 return byte, classification, scan angle, user data, point source id = 0
-        // | 20-27 gps_time | 28-33 R G B = 0
-        const uint32_t W[9] = { (uint32_t)X, (uint32_t)Y, (uint32_t)Z, I & 0xffffu, 0u, (uint32_t)gb, (uint32_t)(gb >> 32), 0u, 0u };
-        r[0] = (uint8_t)W[0];
-        uint16_t* h = reinterpret_cast<uint16_t*>(r + 1);
+        mn[0] = min(mn[0], qx.x); mx[0] = max(mx[0], qx.x); mn[1] = min(mn[1], qy.x); mx[1] = max(mx[1], qy.x); mn[2] = min(mn[2], qz.x); mx[2] = max(mx[2], qz.x);
+        q[0] = (uint32_t)qx.x; q[1] = (uint32_t)qy.x; q[2] = (uint32_t)qz.x; q[3] = q_las_intensity(p.w, L.intensity_mode, fl) & 0xffffu;
+    };
+    // record bytes: 0-11 X Y Z | 12-13 intensity | 14-19 return byte, classification, scan angle, user data, point source id = 0
+    // | 20-27 gps_time | 28-33 R G B = 0
+    if (cnt == kLasTile) {
+        // Full tile: a thread owns two consecutive records = 68 bytes = 17 words w[], which start m = phase & 3 bytes into a
+        // shared-memory word.  The words are shifted in registers (funnel shifts) and stored as 32-bit words at an odd word stride
+        // (conflict-free); the word two neighbouring threads share is merged by a shuffle, the warp's two end words go byte-wise.
+        const int64_t i = first + 2 * tid;
+        Pt a, b;
+        const bool al32 = ((reinterpret_cast<uintptr_t>(L.pts) + (F64 ? 32 : 16) * (uintptr_t)first) & 31) == 0;
+        if (F64 || al32) load_pair<F64, true>(L.pts, i, true, true, a, b);
+        else             load_pair<F64, false>(L.pts, i, true, false, a, b), load_pair<F64, false>(L.pts, i + 1, true, false, b, b);
+        uint64_t g0 = 0, g1 = 0;
+        if (L.gps_time) { g0 = (uint64_t)__double_as_longlong(__ldg(L.gps_time + i)); g1 = (uint64_t)__double_as_longlong(__ldg(L.gps_time + i + 1)); }
+        uint32_t qa[4], qb[4];
+        quantise(a, qa); quantise(b, qb);
+        const uint32_t g0l = (uint32_t)g0, g0h = (uint32_t)(g0 >> 32), g1l = (uint32_t)g1, g1h = (uint32_t)(g1 >> 32);
+        const uint32_t w[17] = { qa[0], qa[1], qa[2], qa[3], 0u, g0l, g0h, 0u,
+                                 qb[0] << 16, (qb[0] >> 16) | (qb[1] << 16), (qb[1] >> 16) | (qb[2] << 16), (qb[2] >> 16) | (qb[3] << 16), 0u,
+                                 g1l << 16, (g1l >> 16) | (g1h << 16), g1h >> 16, 0u };
+        const int m = phase & 3;
+        const uint32_t sh = 8u * (uint32_t)m;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_img + (phase & ~3)) + 17 * tid;      // word holding the pair's first byte
+        const uint32_t o0 = w[0] << sh;                                                    // bytes m..3 of word 0
+        const uint32_t o17 = __funnelshift_l(w[16], 0u, sh);                               // bytes 0..m-1 of word 17 (0 when m == 0)
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int b = 1 + 2 * k;                                  // first byte of this halfword
-            h[k] = (b & 3) == 1 ? (uint16_t)(W[b >> 2] >> 8) : (uint16_t)((W[b >> 2] >> 24) | (W[(b >> 2) + 1] << 8));
+        for (int k = 1; k < 17; ++k) dst[k] = __funnelshift_l(w[k - 1], w[k], sh);
+        const uint32_t nxt = __shfl_down_sync(0xffffffffu, o0, 1);
+        const int lane = tid & 31;
+        if (lane != 31) dst[17] = o17 | nxt;
+        else {
+            uint8_t* e = reinterpret_cast<uint8_t*>(dst + 17);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) if (k < m) e[k] = (uint8_t)(o17 >> (8 * k));
         }
-        r[33] = 0;
+        if (lane == 0) {
+            uint8_t* e = reinterpret_cast<uint8_t*>(dst);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (k >= m) e[k] = (uint8_t)(o0 >> (8 * k));
+        }
+    } else {
+        for (int j = tid; j < cnt; j += kLasThreads) {
+            Pt p, unused;
+            const int64_t i = first + j;
+            load_pair<F64, false>(L.pts, i, true, false, p, unused);
+            uint32_t q[4];
+            quantise(p, q);
+            // the record starts at an odd address (227 + 34 j): one byte, sixteen aligned halfwords, one byte
+            uint8_t* r = img + j * kLasRec;
+            const uint64_t gb = (uint64_t)__double_as_longlong(L.gps_time ? __ldg(L.gps_time + i) : 0.0);
+            const uint32_t W[9] = { q[0], q[1], q[2], q[3], 0u, (uint32_t)gb, (uint32_t)(gb >> 32), 0u, 0u };
+            if ((reinterpret_cast<uintptr_t>(r) & 1) != 0) {
+                r[0] = (uint8_t)W[0];
+                uint16_t* h = reinterpret_cast<uint16_t*>(r + 1);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int bb = 1 + 2 * k;                             // first byte of this halfword
+                    h[k] = (bb & 3) == 1 ? (uint16_t)(W[bb >> 2] >> 8) : (uint16_t)((W[bb >> 2] >> 24) | (W[(bb >> 2) + 1] << 8));
+                }
+                r[33] = 0;
+            } else {
+                uint16_t* h = reinterpret_cast<uint16_t*>(r);
+#pragma unroll
+                for (int k = 0; k < 17; ++k) h[k] = (uint16_t)(W[k >> 1] >> (16 * (k & 1)));
+            }
+        }
     }
     // block min / max -> one atomic per value per CTA
 #pragma unroll

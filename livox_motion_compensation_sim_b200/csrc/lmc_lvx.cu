@@ -60,6 +60,13 @@ __global__ void __launch_bounds__(kLvxThreads) k_lvx_v11(const void* __restrict_
     const int phase = (int)(reinterpret_cast<uintptr_t>(out + dst0) & 15);
     uint8_t* img = s_img + phase;                                                     // img[i] <-> out[dst0 + i]; the address is even
 
+    // the points first: K independent loads per thread in flight under the zero fill and the header work
+    const int64_t first = pk0 * kPkPoints;
+    const int npts = (int)min((int64_t)npk * kPkPoints, n - first > 0 ? n - first : 0);
+    constexpr int K = (kPk * kPkPoints + kLvxThreads - 1) / kLvxThreads;
+    RawRow<F64> raw[K];
+    load_rows_strided<F64, K, kLvxThreads>(pts, p0 + first, tid, npts, raw);
+
     for (int i = tid; i < kImg / 16; i += kLvxThreads) reinterpret_cast<uint4*>(s_img)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
 
@@ -76,12 +83,11 @@ __global__ void __launch_bounds__(kLvxThreads) k_lvx_v11(const void* __restrict_
         for (int k = 0; k < 4; ++k) put16(h, 14 + 2 * k, (uint32_t)((uint64_t)ts >> (16 * k)));
     }
     uint32_t fl = 0;
-    const int64_t first = pk0 * kPkPoints;
-    const int npts = (int)min((int64_t)npk * kPkPoints, n - first > 0 ? n - first : 0);
-    for (int j = tid; j < npts; j += kLvxThreads) {
-        Pt p;
-        if constexpr (F64) { const double* s = reinterpret_cast<const double*>(pts) + 4 * (p0 + first + j); ldg256(s, p.x, p.y, p.z, p.w); }
-        else { const float4 v = __ldg(reinterpret_cast<const float4*>(pts) + (p0 + first + j)); p = Pt{ (double)v.x, (double)v.y, (double)v.z, (double)v.w }; }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = tid + k * kLvxThreads;
+        if (j >= npts) break;
+        const Pt p = raw[k].pt();
         const uint32_t x = (uint32_t)q_mm_clip(p.x, fl), y = (uint32_t)q_mm_clip(p.y, fl), z = (uint32_t)q_mm_clip(p.z, fl), r = q_refl(p.w, fl);
         const int off = hdr + (j / kPkPoints) * kPkBytes + 22 + (j % kPkPoints) * 14;
         put16(img, off, x); put16(img, off + 2, x >> 16);

@@ -102,16 +102,21 @@ __global__ void __launch_bounds__(kCsThreads) k_lvx_cs(const __grid_constant__ L
         }
     }
     uint32_t fl = 0;
-    for (int j = tid; j < npts; j += kCsThreads) {
-        const int64_t i = p0 + first + j;
-        Pt p;
-        if constexpr (F64) { const double* s = reinterpret_cast<const double*>(P.pts) + 4 * i; ldg256(s, p.x, p.y, p.z, p.w); }
-        else { const float4 v = __ldg(reinterpret_cast<const float4*>(P.pts) + i); p = Pt{ (double)v.x, (double)v.y, (double)v.z, (double)v.w }; }
+    constexpr int K = kCsChunk / kCsThreads;
+    RawRow<F64> raw[K];
+    uint32_t tg[K];
+    load_rows_strided<F64, K, kCsThreads>(P.pts, p0 + first, tid, npts, raw);
+#pragma unroll
+    for (int k = 0; k < K; ++k) { const int j = tid + k * kCsThreads; tg[k] = (P.tag && j < npts) ? (uint32_t)__ldg(P.tag + (p0 + first + j)) : 0u; }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int j = tid + k * kCsThreads;
+        if (j >= npts) break;
+        const Pt p = raw[k].pt();
         uint32_t x, y, z;
         if (lvx2) { x = (uint32_t)q_mm_noclip(p.x, fl); y = (uint32_t)q_mm_noclip(p.y, fl); z = (uint32_t)q_mm_noclip(p.z, fl); }   // CS:368-372
         else      { x = q_f32_pack(p.x, fl); y = q_f32_pack(p.y, fl); z = q_f32_pack(p.z, fl); }                                     // CS:319
-        const uint32_t t = P.tag ? (uint32_t)__ldg(P.tag + i) : 0u;
-        put_record(img + hdr + 14 * j, x, y, z, q_u8_copy(p.w, fl) | (t << 8));                                                      // CS:373-374 / 320-321
+        put_record(img + hdr + 14 * j, x, y, z, q_u8_copy(p.w, fl) | (tg[k] << 8));                                                  // CS:373-374 / 320-321
     }
     cta_image_out(P.out + (dst0 - phase), s_img, phase, phase + nbytes, tid, kCsThreads);      // TMA bulk store of the aligned body
     if (fl != 0 && P.status != nullptr) atomicOr(P.status, fl);
