@@ -1051,6 +1051,26 @@ def test_las_pf3_file_image():
         mxx, mnx, mxy, mny, mxz, mnz = struct.unpack_from("<6d", b, 179)
         for mx, mn, q, s, o in [(mxx, mnx, X, scale[0], off[0]), (mxy, mny, Y, scale[1], off[1]), (mxz, mnz, Z, scale[2], off[2])]:
             assert abs(mx - (q.max() * s + o)) <= 1e-9 and abs(mn - (q.min() * s + o)) <= 1e-9
+    # f32 rows; a view that starts one row into an allocation breaks the C-ABI's 32-byte alignment contract and is refused
+    rdt = np.dtype([("X", "<i4"), ("Y", "<i4"), ("Z", "<i4"), ("I", "<u2"), ("zero6", "u1", 6), ("gps", "<f8"), ("rgb", "<u2", 3)])
+    p32 = torch.from_numpy(pts.astype(np.float32)).to(DEV)
+    g_d = dev(gps)
+    with pytest.raises(C.LmcError):
+        ops.build_las_pf3(p32[1:], scale=(0.001,) * 3)
+    for k in (0, 2):
+        view, gv = p32[k:], g_d[k:]
+        data, status = ops.build_las_pf3(view, scale=(0.001,) * 3, gps_time=gv)
+        assert int(status.item()) == 0
+        rec = np.frombuffer(data.cpu().numpy().tobytes(), dtype=rdt, offset=227)
+        X, Y, Z, I, _ = orc.C.quantize_las(view.cpu().numpy().astype(np.float64), (0.001,) * 3, (0.0,) * 3, 0)
+        assert np.array_equal(rec["X"], X) and np.array_equal(rec["Y"], Y) and np.array_equal(rec["Z"], Z) and np.array_equal(rec["I"], I)
+        assert not rec["zero6"].any() and not rec["rgb"].any() and np.array_equal(rec["gps"], gps[k:])
+    # a shard's record range [p_begin, p_end) is the same bytes as that range of the whole file (every word phase; an odd
+    # p_begin makes the pair loads 16- but not 32-byte aligned)
+    whole = ops.build_las_pf3(p32, scale=(0.001,) * 3, gps_time=g_d)[0].cpu().numpy()
+    for pb, pe in [(1, n), (2, 70_001), (3, 2051), (40_000, 40_512), (5, 6)]:
+        out, _, status = ops.las_pf3_records(p32, pb, pe, 227 + 34 * pb, scale=(0.001,) * 3, gps_time=g_d)
+        assert int(status.item()) == 0 and np.array_equal(out.cpu().numpy(), whole[227 + 34 * pb:227 + 34 * pe]), (pb, pe)
     data, _ = ops.build_las_pf3(torch.zeros((0, 4), dtype=torch.float64, device=DEV))
     assert data.numel() == 227
 
