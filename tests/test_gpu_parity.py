@@ -1270,6 +1270,84 @@ def test_full_size_1h_stream_properties():
     assert torch.equal(a[:1_000_000], c[:1_000_000])
 
 
+def test_full_size_file_images():
+    """The file writers at BASELINE configs[3] size (3.6e8 points: a 12.2 GB LAS file, 5.2 GB LVX files, 14 GB of PCD text --
+    byte offsets far beyond 2^32): every record of the LVX v1.1 / LVX2 / LAS images is compared with the stand-alone
+    quantiser's buffers (another kernel) by strided views of the whole file, the container fields on sampled frames, and
+    the PCD text through its size, sampled rows formatted by CPython and the line count."""
+    from livox_motion_compensation_sim_b200.lvx import frame_layout
+    F, P = 36_000, 10_000
+    st = synth.make_stream(F, P, 4242, device=DEV, dtype=torch.float32)
+    N = st.n_points
+    raw = st.pts
+    off_d = dev(st.frame_off)
+    q = ops.quantize(raw, ops.ExportSpec(lvx=True, las=True, las_scale=(0.001,) * 3))
+    assert q.flags() == 0
+    rng = np.random.default_rng(5)
+    frames = np.concatenate([[0, 1, F - 1], rng.integers(0, F, 13)])
+
+    # ---- LVX v1.1 (LMC:58-250): 88-byte preamble, per frame 24 + 105 packages of 22 + 96 x 14 bytes (last one zero-padded)
+    _, fpos = frame_layout(st.frame_off)
+    fsz, npk = 24 + 105 * 1366, 105
+    assert int(fpos[-1]) == 88 + F * fsz
+    img, status = ops.build_lvx_v11(raw, off_d, dev(fpos), dev(st.frame_t), dev(np.arange(F, dtype=np.int64)), P, size=int(fpos[-1]))
+    assert int(status.item()) == 0 and img.numel() == int(fpos[-1])
+    pk = img[88:].view(F, fsz)[:, 24:].view(F, npk, 1366)
+    recs = pk[:, :, 22:].reshape(F, npk * 96, 14)
+    assert torch.equal(recs[:, :P].reshape(N, 14), q.lvx14)
+    assert not bool(recs[:, P:].any())                                       # zero-padded tail of the last package (LMC:246-250)
+    hdr = img[88:].view(F, fsz)[:, :24].contiguous().view(torch.int64)
+    assert torch.equal(hdr[:, 0], dev(fpos[:-1])) and torch.equal(hdr[:-1, 1], dev(fpos[1:-1])) and int(hdr[-1, 1]) == 0
+    assert torch.equal(hdr[:, 2], torch.arange(F, device=DEV))
+    for f in frames:
+        ph = pk[int(f), :, :22].cpu().numpy()
+        assert (ph[:, [1, 3, 9, 10]] == [5, 1, 1, 2]).all() and (ph[:, 14:22].copy().view('<u8')[:, 0] == int(st.frame_t[f] * 1e9)).all()
+    del img, pk, recs, hdr
+
+    # ---- LVX2 (CS:269-374): 88-byte prefix, per frame 24 + 21 bytes of headers and P unpadded records
+    ts_ns = (st.frame_t * 1e9).astype(np.int64)
+    img, status = ops.build_lvx_cs(raw, None, off_d, dev(ts_ns), bytes(range(88)), C.LVXCS_LVX2, P)
+    assert int(status.item()) == 0 and img.numel() == 88 + F * (45 + 14 * P)
+    body = img[88:].view(F, 45 + 14 * P)
+    r2 = body[:, 45:].reshape(N, 14)
+    # coordinates as in the type-2 records (nothing here is near the int32 range, so trunc with / without clip agree);
+    # intensity is the VALUE truncated to a byte (CS:373), not value * 255 (LMC:266)
+    assert torch.equal(r2[:, :12], q.lvx14[:, :12]) and torch.equal(r2[:, 12], raw[:, 3].to(torch.uint8)) and not bool(r2[:, 13].any())
+    assert img[:88].cpu().numpy().tobytes() == bytes(range(88))
+    del r2
+    fh = body[:, :45].cpu().numpy()
+    assert (fh[:, 0:4].copy().view('<u4')[:, 0] == np.arange(F)).all() and (fh[:, 4:12].copy().view('<u8')[:, 0] == ts_ns).all()
+    assert (fh[:, 12:16].copy().view('<u4')[:, 0] == P).all() and (fh[:, 37:45].copy().view('<u8')[:, 0] == ts_ns).all()
+    del img, body
+
+    # ---- LAS 1.2 PF3: 227-byte header + 34-byte records
+    img, status = ops.build_las_pf3(raw, scale=(0.001,) * 3)
+    assert int(status.item()) == 0 and img.numel() == 227 + 34 * N
+    rec = img[227:].view(N, 34)
+    xyz = rec[:, :12].contiguous().view(torch.int32)
+    assert torch.equal(xyz[:, 0], q.las_x) and torch.equal(xyz[:, 1], q.las_y) and torch.equal(xyz[:, 2], q.las_z)
+    assert torch.equal(rec[:, 12:14].contiguous().view(torch.int16).view(N), q.las_intensity.view(torch.int16).view(N))
+    assert not bool(rec[:, 14:].any())                                       # no gps_time given: every other field is 0
+    import struct
+    h = img[:227].cpu().numpy().tobytes()
+    mx, mn = struct.unpack_from("<6d", h, 179)[0::2], struct.unpack_from("<6d", h, 179)[1::2]
+    for c, plane in enumerate((q.las_x, q.las_y, q.las_z)):
+        assert abs(mx[c] - int(plane.max()) * 0.001) <= 1e-9 and abs(mn[c] - int(plane.min()) * 0.001) <= 1e-9
+    assert struct.unpack_from("<I", h, 107)[0] == N
+    del img, rec, xyz, q
+
+    # ---- ASCII PCD (LMC:946-947): total size, per-frame offsets, sampled frames against CPython's formatting
+    text, byte_off, status = ops.pcd_ascii_frames(raw, off_d)
+    assert int(status.item()) == 0
+    bo = byte_off.cpu().numpy()
+    assert bo[0] == 0 and bo[-1] == text.numel() and text.numel() > (1 << 33) and (np.diff(bo) > 0).all()
+    assert int((text == 10).sum()) == N                                      # one newline per point
+    for f in frames:
+        rows = raw[int(st.frame_off[f]):int(st.frame_off[f + 1])].cpu().numpy().astype(np.float64)
+        want = "".join(f"{r[0]:.6f} {r[1]:.6f} {r[2]:.6f} {r[3]:.6f}\n" for r in rows).encode()
+        assert text[int(bo[f]):int(bo[f + 1])].cpu().numpy().tobytes() == want, int(f)
+
+
 @pytest.mark.parametrize("mode", ["slerp", "rigid"])
 def test_host_buffer_pipeline_equals_resident(mode):
     """pipeline.StreamingAligner (pinned host in / out, chunked H2D | kernel | D2H on three streams, staging
