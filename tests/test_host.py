@@ -483,3 +483,25 @@ def test_nvtx_spans_are_off_by_default_and_balanced():
             torch.cuda.nvtx.range_push, torch.cuda.nvtx.range_pop = orig
     finally:
         _trace.enable(was)
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's reference arm) needs no GPU: one bounded step of the reference's own code path
+    (oracle/_ref when staged, else the oracle port) -> ONE JSON line with the B200 arm's metric / unit / config.workload."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    base = json.load(open(os.path.join(root, "BASELINE.json")))
+    assert d["impl"] == "reference" and d["steps"] == 1 and d["n_gpus"] == 1 and d["higher_is_better"] is True
+    assert d["unit"] == "points/s" and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["metric"] in base["metric"] or base["metric"] in d["metric"] or "points" in d["metric"]
+    assert "360000000 points" in d["config"]["workload"]
+    cb = d["cpu_baseline"]
+    from oracle import make_ref
+    assert cb["kind"] == ("reference" if make_ref.available() else "port") and cb["cores"] >= 1 and cb["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
