@@ -614,7 +614,10 @@ def main():
             {'lvx_cs': lambda: lvx_cs_fixture(CS, manifest), 'text_rows': lambda: text_rows_fixture(CS, manifest),
              'coord_frames': lambda: coord_frames_fixture(CS, manifest),
              'config2': lambda: config2_fixture(CS, manifest), 'modeb_tiers': lambda: modeb_tiers_fixture(CS, manifest), 'modec_lerp': lambda: modec_lerp_fixture(CS, manifest), 'cs_run': lambda: cs_run_fixture(CS, manifest), 'las': lambda: las_fixture(LMC, CS, manifest),
-             'outputs': lambda: [outputs_fixture(LMC, n, manifest) for n in ['C1a', 'C2a', 'C3']]}[name]()
+             'outputs': lambda: [outputs_fixture(LMC, n, manifest) for n in ['C1a', 'C2a', 'C3']],
+             'lmc_edge': lambda: lmc_edge_fixture(LMC, manifest), 'lvx_type2': lambda: lvx_type2_fixture(LMC, manifest),
+             'lvx_file': lambda: lvx_file_fixture(LMC, manifest), 'modeb': lambda: modeb_fixture(CS, manifest),
+             'coord_chain': lambda: coord_chain_fixture(CS, manifest), 'pcd_ascii': lambda: pcd_fixture(LMC, manifest)}[name]()
         with open(os.path.join(HERE, 'MANIFEST.json'), 'w') as f:
             json.dump(manifest, f, indent=1, sort_keys=True)
         return
