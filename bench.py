@@ -590,6 +590,48 @@ def main_b200(args):
             del sa2
         except Exception as e:                     # noqa: BLE001
             e2e_mode_a = {"error": repr(e)}
+        # the step's own copies without its kernels: the SAME pinned buffers, byte counts and chunking, H2D on one stream || D2H on
+        # another, nothing between them (the 1 GiB-buffer ceiling below can overstate what 18 GB of pinned traffic per rank sustains)
+        try:
+            cur = torch.cuda.current_stream(dev)
+            cuts = sa.cuts
+
+            def raw_step():
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(cur)
+                sa.s_in.wait_event(e0); sa.s_out.wait_event(e0)
+                for ci, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+                    p0, p1 = int(hs.frame_off[a]), int(hs.frame_off[b])
+                    m, sl = p1 - p0, ci % sa.nbuf
+                    with torch.cuda.stream(sa.s_in):
+                        sa.d_pts[sl][:m].copy_(hs.pts[p0:p1], non_blocking=True)
+                        sa.d_ts[sl][:m].copy_(hs.ts_off[p0:p1], non_blocking=True)
+                    with torch.cuda.stream(sa.s_out):
+                        hs.out[p0:p1].copy_(sa.d_out[sl][:m], non_blocking=True)
+                        hs.lvx14[p0:p1].copy_(sa.d_lvx[sl][:m], non_blocking=True)
+                cur.wait_stream(sa.s_in); cur.wait_stream(sa.s_out)
+                e1.record(cur)
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1)
+            best = None
+            for _ in range(3):                               # first pass = warm-up, counted only if fastest
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                ms_raw = raw_step()
+                if world > 1:
+                    t = torch.tensor([ms_raw], dtype=torch.float64, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms_raw = float(t.item())
+                best = ms_raw if best is None else min(best, ms_raw)
+            e2e["copy_ceiling_step_buffers"] = {
+                "ms": best, "points_per_s": world * ne / (best * 1e-3), "h2d_GBps_per_gpu": ne * 20 / (best * 1e-3) / 1e9,
+                "d2h_GBps_per_gpu": ne * 30 / (best * 1e-3) / 1e9,
+                "what": "the step's own cudaMemcpyAsync calls (same pinned buffers, 20 B in + 30 B out per point, same chunks) with no kernels and no "
+                        "dependencies between the two copy streams, every rank at once, max over ranks"}
+            e2e["frac_of_step_buffer_copy_ceiling"] = e2e["value"] / e2e["copy_ceiling_step_buffers"]["points_per_s"]
+        except Exception as e:                     # noqa: BLE001
+            e2e["copy_ceiling_step_buffers_error"] = repr(e)
         del hs, sa
         torch.cuda.empty_cache()
         # raw copy ceiling of this box for the step's byte mix (profiles/pcie_ceiling.py: cudaMemcpyAsync only, every rank at once)
