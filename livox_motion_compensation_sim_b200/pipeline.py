@@ -59,7 +59,7 @@ class StreamingAligner:
     def __init__(self, device, frame_off: np.ndarray, frame_start: np.ndarray, *, mode: str = "slerp",
                  sample_ts: Optional[torch.Tensor] = None, seg: Optional[torch.Tensor] = None,
                  pose_Rt: Optional[torch.Tensor] = None, chunk_points: int = 1 << 24, lvx: bool = True,
-                 pose_samples: Optional[tuple] = None):
+                 pose_samples: Optional[tuple] = None, nbuf: int = 3):
         """pose_samples = (quat_xyzw (S,4) f64, pos (S,3) f64, ts (S) int64) as pinned HOST tensors: the pose stream then
         travels with the points -- every run() uploads it and builds the segment table on the device
         (lmc_build_slerp_table) instead of taking a host-built ``seg``."""
@@ -87,7 +87,7 @@ class StreamingAligner:
         self.max_pts = int(max(self.frame_off[b] - self.frame_off[a] for a, b in zip(cuts[:-1], cuts[1:])))
         self.max_frames = int(max(b - a for a, b in zip(cuts[:-1], cuts[1:])))
         dev = self.device
-        self.nbuf = 3
+        self.nbuf = max(2, int(nbuf))                               # staging buffer sets in flight (H2D | kernel | D2H)
         self.d_pts = [torch.empty((self.max_pts, 4), dtype=torch.float32, device=dev) for _ in range(self.nbuf)]
         self.d_ts = [torch.empty(self.max_pts, dtype=torch.uint32, device=dev) for _ in range(self.nbuf)]
         self.d_out = [torch.empty((self.max_pts, 4), dtype=torch.float32, device=dev) for _ in range(self.nbuf)]
