@@ -12,6 +12,8 @@
  * Conventions
  *   - every data pointer is a caller-owned DEVICE pointer (e.g. torch.Tensor.data_ptr()) unless
  *     the parameter name ends in _host; the library never allocates or frees caller-visible memory.
+ *     ("Device pointer" = any address the GPU can dereference: the UVA address of a pinned host buffer
+ *     works as well -- the kernel then reads / writes it across PCIe)
  *     The lmc_host_* functions are the exception: HOST pointers only, no device work, synchronous
  *     (the host side of the boundary: frame-list packing and the scanner's NumPy noise stream)
  *   - point arrays, record arrays and LAS arrays must be 32-byte aligned at index 0
